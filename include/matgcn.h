@@ -1,0 +1,128 @@
+/*
+ * matgcn.h - C ABI of the B200 (sm_100a) Multi-ATGCN recurrent graph-convolution library.
+ *
+ * This is the drop-in boundary for the one hot path this repository accelerates: the
+ * AGCRN-style cell of the reference's
+ *   libcity/model/traffic_flow_prediction/MultiATGCN.py   ("MA.py" below)
+ * The reference has no native code and no FFI; its "operator API" for
+ * this path is the set of nn.Module.forward methods cited on each entry point, which autograd
+ * differentiates.  Each forward entry point therefore has a hand-written backward twin.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; the library never allocates or frees
+ *    caller-visible memory; scratch comes in through explicit workspace arguments whose sizes
+ *    the *_bytes() queries return;
+ *  - all tensors are float32, dense, row-major with the shapes written next to each argument;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *  - return value 0 = ok, negative = argument/launch error (text via matgcn_last_error());
+ *  - no global mutable state except the thread-local error string; one call at a time per stream.
+ *
+ * Device layouts ("node-major"): activations are [T, N, B, C] (time, node, batch, channel) so that
+ * one time step is an [N, B*C] matrix whose rows the support propagation contracts over.
+ * Base matrices are [Kp, N, ldm] with ldm >= N (row pitch; columns >= N are never read).
+ * K = Kp + 1 counts the implicit identity support T_0 = I.
+ */
+#ifndef MATGCN_H_
+#define MATGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MATGCN_ABI_VERSION 1
+
+/* ABI version of the loaded library (compare with MATGCN_ABI_VERSION). */
+int matgcn_abi_version(void);
+
+/* Last error text of the calling thread ("" if none). */
+const char* matgcn_last_error(void);
+
+/* -------------------------------------------------------------------------------------------
+ * Adaptive adjacency  A = softmax(relu(L * Rt^T), dim=1)
+ * replaces MA.py:80-83 (AGCN.forward): bidirection passes L = Rt = node_emb [N, D];
+ * unidirection passes L = node_vec1 [N, D], Rt = node_vec2^T [N, D].
+ *   A   [N, ldm] out (columns >= N are zero-filled)
+ * ----------------------------------------------------------------------------------------- */
+int matgcn_adaptive_adj_fwd(const float* L, const float* Rt, int N, int D, float* A, int ldm, void* stream);
+
+/* Backward of the above.  dA [N, ldm]; dL, dRt [N, D] are overwritten.
+ * scratch: N*N floats (holds the pre-softmax gradient). For bidirection the caller adds dL + dRt. */
+int matgcn_adaptive_adj_bwd(const float* L, const float* Rt, const float* A, const float* dA, int N, int D,
+                            int ldm, float* dL, float* dRt, float* scratch, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Per-node weight generation from the embedding-indexed pools
+ *   W[n,k,i,o] = c[k] * sum_d E[n,d] * pool[d,k,i,o]        b[n,o] = sum_d E[n,d] * bias_pool[d,o]
+ * replaces MA.py:104-105 (and folds the view weights softmax(weights_g) of MA.py:102-103 into W:
+ * scaling support k by c[k] equals scaling the weights that multiply its output).
+ *   E [N,D]  pool [D,K,I,O]  bias_pool [D,O]  c [K]   ->   W [N,K,I,O]  b [N,O]
+ * ----------------------------------------------------------------------------------------- */
+int matgcn_nodeweights_fwd(const float* E, const float* pool, const float* bias_pool, const float* c,
+                           int N, int D, int K, int I, int O, float* W, float* b, void* stream);
+
+/* Backward: given dW [N,K,I,O], db [N,O] writes dE [N,D], dpool [D,K,I,O], dbias_pool [D,O], dc [K]. */
+int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_pool, const float* c,
+                           const float* dW, const float* db, int N, int D, int K, int I, int O,
+                           float* dE, float* dpool, float* dbias_pool, float* dc, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * One encoder layer over the whole input window.
+ * replaces, for one layer i, the body of ATGRUEncoder.forward MA.py:200-211:
+ *   for t: s = ATGRUCell(x_t, s)            MA.py:120-128 with AGCN MA.py:106-108 for gate/update
+ *          r = GRUCell(x_t, s)              MA.py:142-150 (residual, shared nn.Linear)
+ *          s = mix[t]*s + (1-mix[t])*r      MA.py:208   (mix = sigmoid(weights_gru[i]))
+ * with supports and per-node weights hoisted out of the loop.
+ *
+ * dims: T steps, N nodes, B batch, Cin input channels, H hidden, K supports incl. identity,
+ *       I = Cin + H.
+ *   x      [T, N, B, Cin] with time stride x_tstride (floats); each step block contiguous
+ *   h0     [N, B, H] or NULL (= zeros)
+ *   M      [K-1, N, ldm]  base matrices (unscaled T_k, k >= 1)
+ *   Wg,bg  [N, K, I, 2H], [N, 2H]   gate weights (z first, r second: MA.py:124)
+ *   Wu,bu  [N, K, I, H],  [N, H]    candidate weights
+ *   Rgw,Rgb [2H, I], [2H]; Ruw,Rub [H, I], [H]   residual GRU nn.Linear weights (out x in)
+ *   mix    [T]  already passed through sigmoid
+ *   ws     forward workspace of matgcn_encoder_layer_fwd_ws_bytes(); it holds every saved
+ *          activation and must stay untouched until the matching backward call has run.
+ * The layer output y[t] = hidden state after step t lives INSIDE the workspace at float offset
+ * matgcn_encoder_layer_y_offset() with time stride matgcn_encoder_layer_y_tstride().
+ * ----------------------------------------------------------------------------------------- */
+size_t matgcn_encoder_layer_fwd_ws_bytes(int T, int N, int B, int Cin, int H, int K);
+size_t matgcn_encoder_layer_bwd_ws_bytes(int T, int N, int B, int Cin, int H, int K, int n_adp);
+size_t matgcn_encoder_layer_y_offset(int T, int N, int B, int Cin, int H, int K);
+size_t matgcn_encoder_layer_y_tstride(int T, int N, int B, int Cin, int H, int K);
+
+/* Float offsets of the named workspace slots, for tests/diagnostics.  names: "PX","GX","RX","PH",
+ * "PZ","Z","R","HC","H1","Z2","R2","HC2","ZH2".  Returns (size_t)-1 for an unknown name. */
+size_t matgcn_encoder_layer_slot_offset(const char* name, int T, int N, int B, int Cin, int H, int K);
+
+int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int K, int ldm,
+                             const float* x, long long x_tstride, const float* h0, const float* M,
+                             const float* Wg, const float* bg, const float* Wu, const float* bu,
+                             const float* Rgw, const float* Rgb, const float* Ruw, const float* Rub,
+                             const float* mix, float* ws, void* stream);
+
+/* Backward of one encoder layer (reverse-time BPTT + time-batched parameter gradients).
+ *   dy [T, N, B, H] with time stride dy_tstride: gradient w.r.t. every step's output
+ *   n_adp: the first n_adp base matrices (the adaptive-adjacency slices) receive a gradient
+ * Outputs (all overwritten):
+ *   dx [T, N, B, Cin] contiguous; dh0 [N, B, H] or NULL; dM [K-1, N, ldm] (slices >= n_adp zeroed);
+ *   dWg, dbg, dWu, dbu, dRgw, dRgb, dRuw, dRub as their forward shapes; dmix [T]
+ * ws is the forward workspace (its GX/RX slots are overwritten by the pre-activation gradients),
+ * bws a scratch of matgcn_encoder_layer_bwd_ws_bytes(). */
+int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int K, int ldm, int n_adp,
+                             const float* dy, long long dy_tstride, const float* M,
+                             const float* Wg, const float* Wu, const float* Rgw, const float* Ruw,
+                             const float* mix, float* ws, float* bws,
+                             float* dx, float* dh0, float* dM,
+                             float* dWg, float* dbg, float* dWu, float* dbu,
+                             float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATGCN_H_ */

@@ -1,0 +1,69 @@
+"""ctypes binding of include/matgcn.h.
+
+The product path has no fallback: if ``csrc/libmatgcn.so`` is missing or a call fails,
+the caller gets an exception, never a silent PyTorch/CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmatgcn.so")
+ABI_VERSION = 1
+
+_lib = None
+
+_F = c_void_p  # device float*
+
+_SIGNATURES = {
+    "matgcn_abi_version": (c_int, []),
+    "matgcn_last_error": (c_char_p, []),
+    "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),
+    "matgcn_adaptive_adj_bwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, _F, _F, _F, c_void_p]),
+    "matgcn_nodeweights_fwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, _F, _F, c_void_p]),
+    "matgcn_nodeweights_bwd": (c_int, [_F, _F, _F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int,
+                                       _F, _F, _F, _F, c_void_p]),
+    "matgcn_encoder_layer_fwd_ws_bytes": (c_size_t, [c_int] * 6),
+    "matgcn_encoder_layer_bwd_ws_bytes": (c_size_t, [c_int] * 7),
+    "matgcn_encoder_layer_y_offset": (c_size_t, [c_int] * 6),
+    "matgcn_encoder_layer_y_tstride": (c_size_t, [c_int] * 6),
+    "matgcn_encoder_layer_slot_offset": (c_size_t, [c_char_p] + [c_int] * 6),
+    "matgcn_encoder_layer_fwd": (c_int, [c_int] * 7 + [_F, c_longlong, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F,
+                                                       _F, _F, c_void_p]),
+    "matgcn_encoder_layer_bwd": (c_int, [c_int] * 8 + [_F, c_longlong, _F, _F, _F, _F, _F, _F, _F, _F,
+                                                       _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class MatgcnError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MatgcnError(
+                "CUDA library %s is not built (run `python -m multistgraph_b200.build` or "
+                "__graft_entry__.build()); there is no CPU fallback for the Multi-ATGCN encoder" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        got = handle.matgcn_abi_version()
+        if got != ABI_VERSION:
+            raise MatgcnError("libmatgcn.so ABI %d != expected %d (stale build?)" % (got, ABI_VERSION))
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().matgcn_last_error()
+        raise MatgcnError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

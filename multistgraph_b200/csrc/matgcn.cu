@@ -1,0 +1,772 @@
+// C-ABI entry points of include/matgcn.h: fp32 ("exact mode") path.
+//
+// Each entry point is a host function that enqueues a fixed sequence of kernels on the
+// caller's stream.  The reference lines each one replaces are cited in include/matgcn.h;
+// the decomposition (hoisted supports / weights, time-batched input half, reverse-time BPTT,
+// time-batched parameter gradients) is described in DESIGN.md section 3.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/matgcn.h"
+#include "gemm_simt.cuh"
+
+using namespace matgcn;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(const char* where, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, what);
+    return -1;
+}
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) return fail(__func__, cudaGetErrorString(e_));          \
+    } while (0)
+#define REQUIRE(cond, msg)                          \
+    do {                                            \
+        if (!(cond)) return fail(__func__, msg);    \
+    } while (0)
+
+extern "C" int matgcn_abi_version(void) { return MATGCN_ABI_VERSION; }
+extern "C" const char* matgcn_last_error(void) { return g_err; }
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------------
+// epilogues
+// ------------------------------------------------------------------------------------------
+// C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col]
+struct EpiStore {
+    float* C;
+    long long s1, s2;
+    int ldc;
+    const float* bias;   // may be null
+    long long bias_s1;
+    const float* scale;  // may be null: per column-group scale (view weights)
+    int scale_div;
+    int accumulate;      // 1: C += value
+    const float* add;    // may be null: extra addend with C's indexing (offsets add_s1/add_s2, ld add_ld)
+    long long add_s1, add_s2;
+    int add_ld;
+    __device__ __forceinline__ void operator()(int z1, int z2, int row, int col, float acc) const {
+        float v = acc;
+        if (scale) v *= __ldg(scale + col / scale_div);
+        if (bias) v += __ldg(bias + z1 * bias_s1 + col);
+        if (add) v += add[z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col];
+        float* dst = C + z1 * s1 + z2 * s2 + (long long)row * ldc + col;
+        if (accumulate) v += *dst;
+        *dst = v;
+    }
+};
+static EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
+    EpiStore e;
+    memset(&e, 0, sizeof(e));
+    e.C = C; e.s1 = s1; e.s2 = s2; e.ldc = ldc; e.scale_div = 1;
+    return e;
+}
+
+struct EpiAtomic {  // split-K partial sums into a zeroed C
+    float* C;
+    long long s1, s2;
+    int ldc;
+    __device__ __forceinline__ void operator()(int z1, int z2, int row, int col, float acc) const {
+        atomicAdd(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, acc);
+    }
+};
+
+// Forward step epilogues.  grow = z1*rows_per_z + row indexes (node, batch) pairs; activations
+// are [N*B, H] blocks, pre-activation inputs [N*B, 3H] blocks.
+struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (cols >= H): R
+    const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
+    int rows_per_z, H;
+    __device__ __forceinline__ void operator()(int z1, int, int row, int col, float acc) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float s = sigmoidf_(acc + GX[g * 3 * H + col]);
+        if (col < H) {
+            Z[g * H + col] = s;
+            ZH[g * H + col] = s * Hprev[g * H + col];
+        } else {
+            R[g * H + col - H] = s;
+        }
+    }
+};
+struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
+    const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
+    int rows_per_z, H;
+    __device__ __forceinline__ void operator()(int z1, int, int row, int col, float acc) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float hc = tanhf(acc + GX[g * 3 * H + 2 * H + col]);
+        const float r = R[g * H + col], h = Hprev[g * H + col];
+        HC[g * H + col] = hc;
+        H1[g * H + col] = r * h + (1.f - r) * hc;
+    }
+};
+struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r2)*hc2)
+    const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
+    int H;
+    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+        const long long g = row;
+        const float hc2 = tanhf(acc + RX[g * 3 * H + 2 * H + col]);
+        const float r2 = R2[g * H + col], h1 = H1[g * H + col];
+        const float res = r2 * h1 + (1.f - r2) * hc2;
+        const float m = __ldg(mix_t);
+        HC2[g * H + col] = hc2;
+        Y[g * H + col] = m * h1 + (1.f - m) * res;
+    }
+};
+
+// Backward step epilogues (notation of DESIGN.md section 3 / tests/host_mirror.py).
+struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR[H:2H] = dres*(h1-hc2)*r2(1-r2)
+    float* DH1; float* DR; const float* DRES; const float* H1; const float* Z2; const float* R2; const float* HC2;
+    int H;
+    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+        const long long i = (long long)row * H + col;
+        const float z2 = Z2[i], r2 = R2[i], h1 = H1[i];
+        DH1[i] += acc * z2;
+        DR[(long long)row * 3 * H + col] = acc * h1 * z2 * (1.f - z2);
+        DR[(long long)row * 3 * H + H + col] = DRES[i] * (h1 - HC2[i]) * r2 * (1.f - r2);
+    }
+};
+struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
+    const float* DH1; const float* Hprev; const float* R; const float* HC; float* DHD; float* DG;
+    int H;
+    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+        const long long i = (long long)row * H + col;
+        const float dh1 = DH1[i] + acc;
+        const float r = R[i], hc = HC[i], h = Hprev[i];
+        DHD[i] = dh1 * r;
+        DG[(long long)row * 3 * H + 2 * H + col] = dh1 * (1.f - r) * (1.f - hc * hc);
+        DG[(long long)row * 3 * H + H + col] = dh1 * (h - hc) * r * (1.f - r);
+    }
+};
+struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      (row = node m, col = (b,c))
+    const float* DP0; const float* Hprev; const float* Z; float* DHD; float* DG;
+    int H, BH;  // BH = B*H columns per node
+    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+        const long long i = (long long)row * BH + col;
+        const float dzh = acc + DP0[i];
+        const float z = Z[i];
+        DHD[i] += dzh * z;
+        const long long g = i / H;
+        const int c = (int)(i - g * H);
+        DG[g * 3 * H + c] = dzh * Hprev[i] * z * (1.f - z);
+    }
+};
+
+struct EpiB6 {  // carry = acc + DP0 + DHD
+    const float* DP0; const float* DHD; float* OUT;
+    int BH;
+    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+        const long long i = (long long)row * BH + col;
+        OUT[i] = acc + DP0[i] + DHD[i];
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, u) : v + u;
+    }
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float r = sh[0];
+    for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];
+    return r;
+}
+
+// one CTA per row n: A[n, :] = softmax_m(relu(L[n] . Rt[m]))
+__global__ void adaptive_adj_fwd_kernel(const float* __restrict__ L, const float* __restrict__ Rt, int N, int D,
+                                        float* __restrict__ A, int ldm) {
+    extern __shared__ float sm[];
+    float* row = sm;          // N
+    float* lrow = sm + N;     // D
+    __shared__ float red[32];
+    const int n = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) lrow[d] = L[(long long)n * D + d];
+    __syncthreads();
+    float mx = 0.f;  // relu output is >= 0
+    for (int m = threadIdx.x; m < N; m += blockDim.x) {
+        const float* r = Rt + (long long)m * D;
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s = fmaf(lrow[d], __ldg(r + d), s);
+        s = fmaxf(s, 0.f);
+        row[m] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = block_reduce(mx, red, true);
+    float sum = 0.f;
+    for (int m = threadIdx.x; m < N; m += blockDim.x) {
+        const float e = expf(row[m] - mx);
+        row[m] = e;
+        sum += e;
+    }
+    sum = block_reduce(sum, red, false);
+    const float inv = 1.f / sum;
+    for (int m = threadIdx.x; m < ldm; m += blockDim.x) A[(long long)n * ldm + m] = m < N ? row[m] * inv : 0.f;
+}
+
+// one CTA per row n: dpre[n, m] = [L[n].Rt[m] > 0] * A[n,m] * (dA[n,m] - sum_j dA[n,j] A[n,j])
+__global__ void adaptive_adj_bwd_kernel(const float* __restrict__ L, const float* __restrict__ Rt,
+                                        const float* __restrict__ A, const float* __restrict__ dA, int N, int D,
+                                        int ldm, float* __restrict__ dpre) {
+    extern __shared__ float sm[];
+    float* lrow = sm;  // D
+    __shared__ float red[32];
+    const int n = blockIdx.x;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) lrow[d] = L[(long long)n * D + d];
+    float dot = 0.f;
+    for (int m = threadIdx.x; m < N; m += blockDim.x) dot += A[(long long)n * ldm + m] * dA[(long long)n * ldm + m];
+    dot = block_reduce(dot, red, false);  // also orders the lrow writes before the reads below
+    for (int m = threadIdx.x; m < N; m += blockDim.x) {
+        const float* r = Rt + (long long)m * D;
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s = fmaf(lrow[d], __ldg(r + d), s);
+        const float a = A[(long long)n * ldm + m];
+        dpre[(long long)n * N + m] = s > 0.f ? a * (dA[(long long)n * ldm + m] - dot) : 0.f;
+    }
+}
+
+// out[i] = a[i] * c[(i / div) % K]   (pool scaled by its view weight)
+__global__ void scale_groups_kernel(const float* __restrict__ a, const float* __restrict__ c, long long n, int div,
+                                    int K, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * __ldg(c + (i / div) % K);
+}
+
+// dc[k] = sum_{d,i,o} dpool[d,k,i,o] * pool[d,k,i,o] / c[k]     grid (K, chunks)
+__global__ void view_weight_grad_kernel(const float* __restrict__ dpool, const float* __restrict__ pool,
+                                        const float* __restrict__ c, int D, int K, int IO, float* __restrict__ dc) {
+    __shared__ float red[32];
+    const int k = blockIdx.x;
+    const long long total = (long long)D * IO;
+    float s = 0.f;
+    for (long long j = (long long)blockIdx.y * blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.y * blockDim.x) {
+        const long long d = j / IO, io = j - d * IO;
+        const long long idx = (d * K + k) * IO + io;
+        s += dpool[idx] * pool[idx];
+    }
+    s = block_reduce(s, red, false);
+    if (threadIdx.x == 0) atomicAdd(dc + k, s / c[k]);
+}
+
+// out[z, col] = sum_{t, r} src[t*st + z*sz + r*ld + col]  for col in [0, ncol): grid (Zn, chunks), atomics
+__global__ void colsum_kernel(const float* __restrict__ src, int T, long long st, long long sz, int rows, int ld,
+                              int ncol, float* __restrict__ out, int out_ld) {
+    const int z = blockIdx.x;
+    const int lanes = blockDim.x / ncol;  // row lanes per block
+    const int col = threadIdx.x % ncol, lane = threadIdx.x / ncol;
+    if (lane >= lanes) return;
+    const long long total = (long long)T * rows;
+    float s = 0.f;
+    for (long long j = (long long)blockIdx.y * lanes + lane; j < total; j += (long long)gridDim.y * lanes) {
+        const long long t = j / rows, r = j - t * rows;
+        s += src[t * st + z * sz + r * ld + col];
+    }
+    atomicAdd(out + (long long)z * out_ld + col, s);
+}
+
+// B0: head of the reverse step.  dy = dY[t] + carry ; residual-mix backward up to da3.
+__global__ void bwd_head_kernel(const float* __restrict__ dY, const float* __restrict__ carry,
+                                const float* __restrict__ H1, const float* __restrict__ R2,
+                                const float* __restrict__ HC2, const float* __restrict__ mix_t, long long n, int H,
+                                float* __restrict__ DH1, float* __restrict__ DRES, float* __restrict__ DR,
+                                float* __restrict__ dmix_t) {
+    __shared__ float red[32];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float part = 0.f;
+    if (i < n) {
+        const float g = __ldg(mix_t);
+        const float dy = dY[i] + carry[i];
+        const float h1 = H1[i], r2 = R2[i], hc2 = HC2[i];
+        const float res = r2 * h1 + (1.f - r2) * hc2;
+        part = dy * (h1 - res);
+        const float dres = (1.f - g) * dy;
+        DRES[i] = dres;
+        DH1[i] = g * dy + dres * r2;
+        const long long row = i / H;
+        const int c = (int)(i - row * H);
+        DR[row * 3 * H + 2 * H + c] = dres * (1.f - r2) * (1.f - hc2 * hc2);
+    }
+    part = block_reduce(part, red, false);
+    if (threadIdx.x == 0) atomicAdd(dmix_t, part);
+}
+
+// ------------------------------------------------------------------------------------------
+// adaptive adjacency
+// ------------------------------------------------------------------------------------------
+extern "C" int matgcn_adaptive_adj_fwd(const float* L, const float* Rt, int N, int D, float* A, int ldm, void* stream) {
+    REQUIRE(L && Rt && A, "null pointer");
+    REQUIRE(N > 0 && D > 0 && ldm >= N, "bad dims");
+    const size_t smem = (size_t)(N + D) * sizeof(float);
+    REQUIRE(smem <= 200 * 1024, "N too large for the single-row softmax kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(adaptive_adj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    adaptive_adj_fwd_kernel<<<N, 256, smem, st>>>(L, Rt, N, D, A, ldm);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int matgcn_adaptive_adj_bwd(const float* L, const float* Rt, const float* A, const float* dA, int N, int D,
+                                       int ldm, float* dL, float* dRt, float* scratch, void* stream) {
+    REQUIRE(L && Rt && A && dA && dL && dRt && scratch, "null pointer");
+    REQUIRE(N > 0 && D > 0 && ldm >= N, "bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    adaptive_adj_bwd_kernel<<<N, 256, (size_t)D * sizeof(float), st>>>(L, Rt, A, dA, N, D, ldm, scratch);
+    CK(cudaGetLastError());
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1; p.splits = 1;
+    // dL = dpre [N,N] * Rt [N,D]
+    p.A = scratch; p.lda = N; p.B = Rt; p.ldb = D; p.M = N; p.N = D; p.K = N;
+    CK((launch_gemm<CfgSkinnyN, true, false>(p, epi_store(dL, 0, 0, D), 1, st)));
+    // dRt = dpre^T * L
+    p.A = scratch; p.lda = N; p.B = L; p.ldb = D;
+    CK((launch_gemm<CfgSkinnyN, false, false>(p, epi_store(dRt, 0, 0, D), 1, st)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-node weights
+// ------------------------------------------------------------------------------------------
+extern "C" int matgcn_nodeweights_fwd(const float* E, const float* pool, const float* bias_pool, const float* c,
+                                      int N, int D, int K, int I, int O, float* W, float* b, void* stream) {
+    REQUIRE(E && pool && bias_pool && c && W && b, "null pointer");
+    REQUIRE(N > 0 && D > 0 && K > 0 && I > 0 && O > 0, "bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long KIO = (long long)K * I * O;
+    REQUIRE(KIO < 2147483647LL, "K*I*O overflows int");
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1; p.splits = 1;
+    p.A = E; p.lda = D; p.B = pool; p.ldb = (int)KIO; p.M = N; p.N = (int)KIO; p.K = D;
+    EpiStore e = epi_store(W, 0, 0, (int)KIO);
+    e.scale = c; e.scale_div = I * O;
+    CK((launch_gemm<CfgBig, true, false>(p, e, 1, st)));
+    p.B = bias_pool; p.ldb = O; p.N = O;
+    CK((launch_gemm<CfgMid, true, false>(p, epi_store(b, 0, 0, O), 1, st)));
+    return 0;
+}
+
+extern "C" int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_pool, const float* c,
+                                      const float* dW, const float* db, int N, int D, int K, int I, int O,
+                                      float* dE, float* dpool, float* dbias_pool, float* dc, void* stream) {
+    REQUIRE(E && pool && bias_pool && c && dW && db && dE && dpool && dbias_pool && dc, "null pointer");
+    REQUIRE(N > 0 && D > 0 && K > 0 && I > 0 && O > 0, "bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long KIO = (long long)K * I * O;
+    REQUIRE(KIO < 2147483647LL, "K*I*O overflows int");
+    const long long npool = (long long)D * KIO;
+    CK(cudaMemsetAsync(dE, 0, sizeof(float) * (size_t)N * D, st));
+    CK(cudaMemsetAsync(dc, 0, sizeof(float) * (size_t)K, st));
+    // dpool is first used as scratch for c[k]*pool, consumed by the dE contraction below
+    scale_groups_kernel<<<(unsigned)((npool + 255) / 256), 256, 0, st>>>(pool, c, npool, I * O, K, dpool);
+    CK(cudaGetLastError());
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1;
+    // dE[n,d] = sum_col dW[n,col] * (c*pool)[d,col]   (+ db * bias_pool^T), split-K with atomics
+    p.A = dW; p.lda = (int)KIO; p.B = dpool; p.ldb = (int)KIO; p.M = N; p.N = D; p.K = (int)KIO;
+    p.splits = (int)((KIO + 2047) / 2048);
+    if (p.splits > 128) p.splits = 128;
+    EpiAtomic ea{dE, 0, 0, D};
+    CK((launch_gemm<CfgSkinnyN, true, true>(p, ea, 1, st)));
+    p.A = db; p.lda = O; p.B = bias_pool; p.ldb = O; p.K = O; p.splits = 1;
+    CK((launch_gemm<CfgSkinnyN, true, true>(p, ea, 1, st)));
+    // G[d,col] = sum_n E[n,d] dW[n,col] ; dpool = c[k] * G
+    p.A = E; p.lda = D; p.B = dW; p.ldb = (int)KIO; p.M = D; p.N = (int)KIO; p.K = N; p.splits = 1;
+    EpiStore eg = epi_store(dpool, 0, 0, (int)KIO);
+    eg.scale = c; eg.scale_div = I * O;
+    CK((launch_gemm<CfgSkinnyM, false, false>(p, eg, 1, st)));
+    // dc[k] = sum G * pool = sum dpool * pool / c[k]
+    {
+        dim3 grid(K, 64);
+        view_weight_grad_kernel<<<grid, 256, 0, st>>>(dpool, pool, c, D, K, I * O, dc);
+        CK(cudaGetLastError());
+    }
+    // dbias_pool = E^T db
+    p.A = E; p.lda = D; p.B = db; p.ldb = O; p.M = D; p.N = O; p.K = N;
+    CK((launch_gemm<CfgSkinnyM, false, false>(p, epi_store(dbias_pool, 0, 0, O), 1, st)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// encoder layer: workspace layout
+// ------------------------------------------------------------------------------------------
+struct LayerWs {
+    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, total;
+    size_t U, UX;  // floats of one [N,B,H] / [N,B,Cin] block
+};
+static size_t align64(size_t v) { return (v + 63) / 64 * 64; }
+static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
+    LayerWs w;
+    w.U = (size_t)N * B * H;
+    w.UX = (size_t)N * B * Cin;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o = align64(o + n); return r; };
+    w.PX = take((size_t)T * K * w.UX);
+    w.GX = take((size_t)T * 3 * w.U);
+    w.RX = take((size_t)T * 3 * w.U);
+    w.PH = take(((size_t)T * K + 1) * w.U);
+    w.PZ = take((size_t)T * K * w.U);
+    w.Z = take((size_t)T * w.U);
+    w.R = take((size_t)T * w.U);
+    w.HC = take((size_t)T * w.U);
+    w.H1 = take((size_t)T * w.U);
+    w.Z2 = take((size_t)T * w.U);
+    w.R2 = take((size_t)T * w.U);
+    w.HC2 = take((size_t)T * w.U);
+    w.ZH2 = take((size_t)T * w.U);
+    w.total = o;
+    return w;
+}
+struct LayerBws {
+    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, total;
+};
+static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp) {
+    LayerBws w;
+    const size_t U = (size_t)N * B * H, UX = (size_t)N * B * Cin;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o = align64(o + n); return r; };
+    w.DPX = take((size_t)T * K * UX);
+    w.DPT = take((size_t)K * U);
+    w.DPHA = take((size_t)T * (n_adp > 0 ? n_adp : 0) * U);
+    w.DPZA = take((size_t)T * (n_adp > 0 ? n_adp : 0) * U);
+    w.DH1 = take(U);
+    w.DHD = take(U);
+    w.DHC = take(U);
+    w.DRES = take(U);
+    w.total = o;
+    return w;
+}
+
+extern "C" size_t matgcn_encoder_layer_fwd_ws_bytes(int T, int N, int B, int Cin, int H, int K) {
+    return layer_ws(T, N, B, Cin, H, K).total * sizeof(float);
+}
+extern "C" size_t matgcn_encoder_layer_bwd_ws_bytes(int T, int N, int B, int Cin, int H, int K, int n_adp) {
+    return layer_bws(T, N, B, Cin, H, K, n_adp).total * sizeof(float);
+}
+extern "C" size_t matgcn_encoder_layer_y_offset(int T, int N, int B, int Cin, int H, int K) {
+    const LayerWs w = layer_ws(T, N, B, Cin, H, K);
+    return w.PH + (size_t)K * w.U;  // PH[t+1, 0]
+}
+extern "C" size_t matgcn_encoder_layer_y_tstride(int T, int N, int B, int Cin, int H, int K) {
+    (void)T; (void)Cin;
+    return (size_t)K * N * B * H;
+}
+extern "C" size_t matgcn_encoder_layer_slot_offset(const char* name, int T, int N, int B, int Cin, int H, int K) {
+    const LayerWs w = layer_ws(T, N, B, Cin, H, K);
+    struct { const char* n; size_t v; } tab[] = {{"PX", w.PX}, {"GX", w.GX}, {"RX", w.RX}, {"PH", w.PH}, {"PZ", w.PZ},
+                                                 {"Z", w.Z}, {"R", w.R}, {"HC", w.HC}, {"H1", w.H1}, {"Z2", w.Z2},
+                                                 {"R2", w.R2}, {"HC2", w.HC2}, {"ZH2", w.ZH2}};
+    for (auto& e : tab)
+        if (strcmp(e.n, name) == 0) return e.v;
+    return (size_t)-1;
+}
+
+static int check_layer_dims(int T, int N, int B, int Cin, int H, int K, int ldm) {
+    if (T <= 0 || N <= 0 || B <= 0 || Cin <= 0 || H <= 0 || K < 2) return fail("encoder_layer", "bad dims (need K >= 2)");
+    if (ldm < N) return fail("encoder_layer", "ldm < N");
+    if ((long long)N * B * 3 * H >= 2147483647LL) return fail("encoder_layer", "N*B*3H overflows int (shard the batch)");
+    if ((long long)(K - 1) * N * (long long)ldm >= 2147483647LL) return fail("encoder_layer", "(K-1)*N*ldm overflows int");
+    return 0;
+}
+
+// Support propagation for a block of Z time steps: dst[z][1..K) = M * src[z][0]   (slot stride U)
+static cudaError_t propagate(const float* M, int ldm, int N, int Kp, const float* slot0, long long zstride, int cols,
+                             float* slot1, int Z, cudaStream_t st) {
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1; p.splits = 1;
+    p.A = M; p.lda = ldm; p.M = Kp * N; p.K = N;
+    p.B = slot0; p.ldb = cols; p.N = cols; p.sB1 = zstride;
+    return launch_gemm<CfgBig, true, false>(p, epi_store(slot1, zstride, 0, cols), Z, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// encoder layer forward
+// ------------------------------------------------------------------------------------------
+extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int K, int ldm,
+                                        const float* x, long long x_tstride, const float* h0, const float* M,
+                                        const float* Wg, const float* bg, const float* Wu, const float* bu,
+                                        const float* Rgw, const float* Rgb, const float* Ruw, const float* Rub,
+                                        const float* mix, float* ws, void* stream) {
+    REQUIRE(x && M && Wg && bg && Wu && bu && Rgw && Rgb && Ruw && Rub && mix && ws, "null pointer");
+    if (check_layer_dims(T, N, B, Cin, H, K, ldm)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const LayerWs w = layer_ws(T, N, B, Cin, H, K);
+    const int Kp = K - 1, I = Cin + H;
+    const long long U = (long long)w.U, UX = (long long)w.UX;
+    float* PX = ws + w.PX; float* GX = ws + w.GX; float* RX = ws + w.RX; float* PH = ws + w.PH; float* PZ = ws + w.PZ;
+
+    // x -> slot 0 of PX[t]
+    CK(cudaMemcpy2DAsync(PX, sizeof(float) * K * UX, x, sizeof(float) * x_tstride, sizeof(float) * UX, T,
+                         cudaMemcpyDeviceToDevice, st));
+    // PX[t, 1..K) = M * x_t  (all t at once)
+    CK(propagate(M, ldm, N, Kp, PX, K * UX, B * Cin, PX + UX, T, st));
+
+    GemmP p;
+    // GX[t, n, :, 0:2H] = bg[n] + sum_k PX[t,k,n] * Wg[n,k,0:Cin,:]   z = (n, t), k-batches = k
+    memset(&p, 0, sizeof(p));
+    p.splits = 1; p.Z2 = T; p.KB = K;
+    p.A = PX; p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = K * UX; p.sAk = UX;
+    p.M = B; p.K = Cin;
+    {
+        p.B = Wg; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = 0; p.sBk = (long long)I * 2 * H;
+        EpiStore e = epi_store(GX, (long long)B * 3 * H, 3 * U, 3 * H);
+        e.bias = bg; e.bias_s1 = 2 * H;
+        CK((launch_gemm<CfgMid, true, false>(p, e, N * T, st)));
+        p.B = Wu; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
+        e = epi_store(GX + 2 * H, (long long)B * 3 * H, 3 * U, 3 * H);
+        e.bias = bu; e.bias_s1 = H;
+        CK((launch_gemm<CfgMid, true, false>(p, e, N * T, st)));
+    }
+    // RX[t] = x_t * [Rgw[:, 0:Cin]; Ruw[:, 0:Cin]]^T + [Rgb; Rub]          flat rows (n,b), z = t
+    memset(&p, 0, sizeof(p));
+    p.splits = 1; p.Z2 = 1; p.KB = 1;
+    p.A = PX; p.lda = Cin; p.sA1 = K * UX; p.M = N * B; p.K = Cin;
+    {
+        p.B = Rgw; p.ldb = I; p.N = 2 * H;
+        EpiStore e = epi_store(RX, 3 * U, 0, 3 * H);
+        e.bias = Rgb; e.bias_s1 = 0;
+        CK((launch_gemm<CfgMid, true, true>(p, e, T, st)));
+        p.B = Ruw; p.ldb = I; p.N = H;
+        e = epi_store(RX + 2 * H, 3 * U, 0, 3 * H);
+        e.bias = Rub; e.bias_s1 = 0;
+        CK((launch_gemm<CfgMid, true, true>(p, e, T, st)));
+    }
+    // initial state
+    if (h0) CK(cudaMemcpyAsync(PH, h0, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
+    else CK(cudaMemsetAsync(PH, 0, sizeof(float) * U, st));
+
+    for (int t = 0; t < T; ++t) {
+        float* PHt = PH + (long long)t * K * U;
+        float* PZt = PZ + (long long)t * K * U;
+        float* Zt = ws + w.Z + t * U; float* Rt_ = ws + w.R + t * U; float* HCt = ws + w.HC + t * U;
+        float* H1t = ws + w.H1 + t * U; float* Z2t = ws + w.Z2 + t * U; float* R2t = ws + w.R2 + t * U;
+        float* HC2t = ws + w.HC2 + t * U; float* ZH2t = ws + w.ZH2 + t * U;
+        const float* GXt = GX + (long long)t * 3 * U; const float* RXt = RX + (long long)t * 3 * U;
+        // (a) PH[t,1..] = M * h
+        CK(propagate(M, ldm, N, Kp, PHt, 0, B * H, PHt + U, 1, st));
+        // (b) gate: per node [B, K*H] x [K*H, 2H]
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = 1; p.KB = K;
+        p.A = PHt; p.lda = H; p.sA1 = (long long)B * H; p.sAk = U; p.M = B; p.K = H;
+        p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sBk = (long long)I * 2 * H;
+        CK((launch_gemm<CfgMid, true, false>(p, EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H}, N, st)));
+        // (c) PZ[t,1..] = M * (z*h)
+        CK(propagate(M, ldm, N, Kp, PZt, 0, B * H, PZt + U, 1, st));
+        // (d) candidate
+        p.A = PZt;
+        p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
+        CK((launch_gemm<CfgMid, true, false>(p, EpiCand{GXt, PHt, Rt_, HCt, H1t, B, H}, N, st)));
+        // (e) residual gate: [N*B, H] x Rgw[:, Cin:]^T
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = 1; p.KB = 1;
+        p.A = H1t; p.lda = H; p.M = N * B; p.K = H;
+        p.B = Rgw + Cin; p.ldb = I; p.N = 2 * H;
+        CK((launch_gemm<CfgMid, true, true>(p, EpiGate{RXt, H1t, Z2t, R2t, ZH2t, 0, H}, 1, st)));
+        // (f) residual candidate + mix -> PH[t+1, 0]
+        p.A = ZH2t;
+        p.B = Ruw + Cin; p.ldb = I; p.N = H;
+        CK((launch_gemm<CfgMid, true, true>(p, EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H}, 1, st)));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// encoder layer backward
+// ------------------------------------------------------------------------------------------
+extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int K, int ldm, int n_adp,
+                                        const float* dy, long long dy_tstride, const float* M,
+                                        const float* Wg, const float* Wu, const float* Rgw, const float* Ruw,
+                                        const float* mix, float* ws, float* bws,
+                                        float* dx, float* dh0, float* dM,
+                                        float* dWg, float* dbg, float* dWu, float* dbu,
+                                        float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
+                                        void* stream) {
+    REQUIRE(dy && M && Wg && Wu && Rgw && Ruw && mix && ws && bws, "null pointer");
+    REQUIRE(dx && dM && dWg && dbg && dWu && dbu && dRgw && dRgb && dRuw && dRub && dmix, "null output pointer");
+    if (check_layer_dims(T, N, B, Cin, H, K, ldm)) return -1;
+    REQUIRE(n_adp >= 0 && n_adp <= K - 1, "n_adp out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const LayerWs w = layer_ws(T, N, B, Cin, H, K);
+    const LayerBws bw = layer_bws(T, N, B, Cin, H, K, n_adp);
+    const int Kp = K - 1, I = Cin + H;
+    const long long U = (long long)w.U, UX = (long long)w.UX;
+    float* PX = ws + w.PX; float* DG = ws + w.GX; float* DR = ws + w.RX; float* PH = ws + w.PH; float* PZ = ws + w.PZ;
+    float* DPX = bws + bw.DPX; float* DPT = bws + bw.DPT; float* DPHA = bws + bw.DPHA; float* DPZA = bws + bw.DPZA;
+    float* DH1 = bws + bw.DH1; float* DHD = bws + bw.DHD; float* DHC = bws + bw.DHC; float* DRES = bws + bw.DRES;
+    const int NB = N * B;
+
+    CK(cudaMemsetAsync(DHC, 0, sizeof(float) * U, st));
+    CK(cudaMemsetAsync(dmix, 0, sizeof(float) * T, st));
+    GemmP p;
+    for (int t = T - 1; t >= 0; --t) {
+        const float* PHt = PH + (long long)t * K * U;
+        const float* PZt = PZ + (long long)t * K * U;
+        const float* Zt = ws + w.Z + t * U; const float* Rt_ = ws + w.R + t * U; const float* HCt = ws + w.HC + t * U;
+        const float* H1t = ws + w.H1 + t * U; const float* Z2t = ws + w.Z2 + t * U; const float* R2t = ws + w.R2 + t * U;
+        const float* HC2t = ws + w.HC2 + t * U;
+        float* DGt = DG + (long long)t * 3 * U; float* DRt = DR + (long long)t * 3 * U;
+        (void)PZt;
+        // B0
+        bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t,
+                                                                    mix + t, U, H, DH1, DRES, DRt, dmix + t);
+        CK(cudaGetLastError());
+        // B1: dzh2 = da3 [NB,H] * Ruw[:, Cin:]  (B element (k=o, n=j) at o*I + Cin + j)
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = 1; p.KB = 1;
+        p.A = DRt + 2 * H; p.lda = 3 * H; p.M = NB; p.K = H;
+        p.B = Ruw + Cin; p.ldb = I; p.N = H;
+        CK((launch_gemm<CfgMid, true, false>(p, EpiB1{DH1, DRt, DRES, H1t, Z2t, R2t, HC2t, H}, 1, st)));
+        // B2: dh1 += da2 [NB,2H] * Rgw[:, Cin:]
+        p.A = DRt; p.K = 2 * H;
+        p.B = Rgw + Cin;
+        CK((launch_gemm<CfgMid, true, false>(p, EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H}, 1, st)));
+        // B3: DPT[k][n] = dau[n] [B,H] * Wu[n,k,Cin:,:]^T      z = (n, k)
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = K; p.KB = 1;
+        p.A = DGt + 2 * H; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.sA2 = 0; p.M = B; p.K = H;
+        p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sB2 = (long long)I * H;
+        CK((launch_gemm<CfgMid, true, true>(p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
+        if (n_adp) CK(cudaMemcpyAsync(DPZA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
+        // B4: dzh = DPT[0] + sum_{k>=1} M_k^T DPT[k]
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = 1; p.KB = 1;
+        p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
+        p.B = DPT + U; p.ldb = B * H; p.N = B * H;
+        CK((launch_gemm<CfgBig, false, false>(p, EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H}, 1, st)));
+        // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = K; p.KB = 1;
+        p.A = DGt; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
+        p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = (long long)I * 2 * H;
+        CK((launch_gemm<CfgMid, true, true>(p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
+        if (n_adp) CK(cudaMemcpyAsync(DPHA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
+        // B6: carry = DHD + DPT[0] + sum M_k^T DPT[k]
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = 1; p.KB = 1;
+        p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
+        p.B = DPT + U; p.ldb = B * H; p.N = B * H;
+        CK((launch_gemm<CfgBig, false, false>(p, EpiB6{DPT, DHD, DHC, B * H}, 1, st)));
+    }
+    if (dh0) CK(cudaMemcpyAsync(dh0, DHC, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
+
+    // ---- time-batched parameter gradients ------------------------------------------------
+    // dWg[n,k,Cin:,:] = sum_{t,b} PH[t,k,n]^T DG[t,n][:, 0:2H]        z = (n,k), k-batches = t
+    memset(&p, 0, sizeof(p));
+    p.splits = 1; p.Z2 = K; p.KB = T;
+    p.lda = H; p.sA1 = (long long)B * H; p.sA2 = U; p.sAk = K * U; p.M = H; p.K = B;
+    p.ldb = 3 * H; p.sB1 = (long long)B * 3 * H; p.sB2 = 0; p.sBk = 3 * U;
+    p.A = PH; p.B = DG; p.N = 2 * H;
+    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
+    p.A = PZ; p.B = DG + 2 * H; p.N = H;
+    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWu + (long long)Cin * H, (long long)K * I * H, (long long)I * H, H), N * K, st)));
+    // input rows 0:Cin from PX
+    p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
+    p.A = PX; p.B = DG; p.N = 2 * H;
+    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
+    p.B = DG + 2 * H; p.N = H;
+    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
+    // bias gradients: column sums over (t, b)
+    CK(cudaMemsetAsync(dbg, 0, sizeof(float) * (size_t)N * 2 * H, st));
+    CK(cudaMemsetAsync(dbu, 0, sizeof(float) * (size_t)N * H, st));
+    CK(cudaMemsetAsync(dRgb, 0, sizeof(float) * 2 * H, st));
+    CK(cudaMemsetAsync(dRub, 0, sizeof(float) * H, st));
+    {
+        const int threads = 256;
+        REQUIRE(2 * H <= threads, "hidden size too large for the column-sum kernel");
+        dim3 g1(N, 8);
+        colsum_kernel<<<g1, threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 2 * H, dbg, 2 * H);
+        colsum_kernel<<<g1, threads, 0, st>>>(DG + 2 * H, T, 3 * U, (long long)B * 3 * H, B, 3 * H, H, dbu, H);
+        dim3 g2(1, 1024);
+        colsum_kernel<<<g2, threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 2 * H, dRgb, 2 * H);
+        colsum_kernel<<<g2, threads, 0, st>>>(DR + 2 * H, T, 3 * U, 0, NB, 3 * H, H, dRub, H);
+        CK(cudaGetLastError());
+    }
+    // DPX[t,k,n] = DG[t,n][:,0:2H] * Wg[n,k,0:Cin,:]^T + DG[t,n][:,2H:] * Wu[n,k,0:Cin,:]^T     per k: z = (t, n)
+    for (int k = 0; k < K; ++k) {
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = N; p.KB = 1;
+        p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
+        p.B = Wg + (long long)k * I * 2 * H; p.ldb = 2 * H; p.N = Cin; p.sB1 = 0; p.sB2 = (long long)K * I * 2 * H;
+        EpiStore e = epi_store(DPX + (long long)k * UX, K * UX, (long long)B * Cin, Cin);
+        CK((launch_gemm<CfgMid, true, true>(p, e, T * N, st)));
+        p.A = DG + 2 * H; p.K = H;
+        p.B = Wu + (long long)k * I * H; p.ldb = H; p.sB2 = (long long)K * I * H;
+        e.accumulate = 1;
+        CK((launch_gemm<CfgMid, true, true>(p, e, T * N, st)));
+    }
+    // dx[t] = DPX[t,0] + sum_{k>=1} M_k^T DPX[t,k] + DR[t][:,0:2H]*Rgw[:,0:Cin] + DR[t][:,2H:]*Ruw[:,0:Cin]
+    memset(&p, 0, sizeof(p));
+    p.splits = 1; p.Z2 = 1; p.KB = 1;
+    p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
+    p.B = DPX + UX; p.ldb = B * Cin; p.N = B * Cin; p.sB1 = K * UX;
+    {
+        EpiStore e = epi_store(dx, UX, 0, B * Cin);
+        e.add = DPX; e.add_s1 = K * UX; e.add_ld = B * Cin;
+        CK((launch_gemm<CfgBig, false, false>(p, e, T, st)));
+    }
+    memset(&p, 0, sizeof(p));
+    p.splits = 1; p.Z2 = 1; p.KB = 1;
+    p.A = DR; p.lda = 3 * H; p.sA1 = 3 * U; p.M = NB; p.K = 2 * H;
+    p.B = Rgw; p.ldb = I; p.N = Cin;
+    {
+        EpiStore e = epi_store(dx, UX, 0, Cin);
+        e.accumulate = 1;
+        CK((launch_gemm<CfgMid, true, false>(p, e, T, st)));
+        p.A = DR + 2 * H; p.K = H; p.B = Ruw;
+        CK((launch_gemm<CfgMid, true, false>(p, e, T, st)));
+    }
+    // dM[a] = sum_t DPHA[t,a] PH[t,0]^T + DPZA[t,a] PZ[t,0]^T + DPX[t,a+1] PX[t,0]^T     (split-K, atomics)
+    CK(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)Kp * N * ldm, st));
+    for (int a = 0; a < n_adp; ++a) {
+        EpiAtomic ea{dM + (long long)a * N * ldm, 0, 0, ldm};
+        memset(&p, 0, sizeof(p));
+        p.Z2 = 1; p.KB = T; p.M = N; p.N = N;
+        p.K = B * H; p.lda = B * H; p.ldb = B * H;
+        p.splits = T;
+        p.A = DPHA + (long long)a * U; p.sAk = (long long)n_adp * U; p.B = PH; p.sBk = K * U;
+        CK((launch_gemm<CfgBig, true, true>(p, ea, 1, st)));
+        p.A = DPZA + (long long)a * U; p.B = PZ;
+        CK((launch_gemm<CfgBig, true, true>(p, ea, 1, st)));
+        p.K = B * Cin; p.lda = B * Cin; p.ldb = B * Cin;
+        p.A = DPX + (long long)(a + 1) * UX; p.sAk = K * UX; p.B = PX; p.sBk = K * UX;
+        CK((launch_gemm<CfgBig, true, true>(p, ea, 1, st)));
+    }
+    // residual GRU weights: dRgw[:, Cin:] = sum DR[:,0:2H]^T H1 ; dRgw[:, 0:Cin] = sum DR[:,0:2H]^T x ; same for Ruw
+    CK(cudaMemsetAsync(dRgw, 0, sizeof(float) * (size_t)2 * H * I, st));
+    CK(cudaMemsetAsync(dRuw, 0, sizeof(float) * (size_t)H * I, st));
+    {
+        memset(&p, 0, sizeof(p));
+        p.Z2 = 1; p.KB = T; p.K = NB; p.lda = 3 * H; p.sAk = 3 * U;
+        int splits = (int)(((long long)T * NB + 4095) / 4096);
+        if (splits > 592) splits = 592;
+        if (splits < 1) splits = 1;
+        p.splits = splits;
+        // gate, hidden columns
+        p.A = DR; p.M = 2 * H; p.B = ws + w.H1; p.ldb = H; p.sBk = U; p.N = H;
+        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRgw + Cin, 0, 0, I}, 1, st)));
+        // candidate, hidden columns
+        p.A = DR + 2 * H; p.M = H; p.B = ws + w.ZH2;
+        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRuw + Cin, 0, 0, I}, 1, st)));
+        // input columns
+        p.B = PX; p.ldb = Cin; p.sBk = K * UX; p.N = Cin;
+        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRuw, 0, 0, I}, 1, st)));
+        p.A = DR; p.M = 2 * H;
+        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRgw, 0, 0, I}, 1, st)));
+    }
+    return 0;
+}

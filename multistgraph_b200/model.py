@@ -1,0 +1,327 @@
+"""Drop-in ``MultiATGCN`` for LibCity's model registry, backed by the sm_100a kernels.
+
+Mirrors the public surface of the reference class
+``libcity/model/traffic_flow_prediction/MultiATGCN.py:221-430``:
+
+* ctor ``MultiATGCN(config, data_feature)`` reading the same ``config`` /
+  ``data_feature`` keys with the same defaults,
+* ``forward(batch)`` / ``predict(batch)`` -> ``[B, output_window, N, end_dim-start_dim]``,
+* ``calculate_loss(batch)`` -> masked-MAE scalar on inverse-scaled values,
+* identical parameter names, shapes and registration order, so reference
+  checkpoints (``state_dict``) load unchanged and a seeded construction draws the
+  same initial weights (same RNG consumption order as MA.py:296-348, 356-361).
+
+What differs is *how* the recurrent graph-convolution encoder is evaluated: the
+adaptive adjacency, the support stack and the per-node weights are built once per
+forward (the reference rebuilds them on each of its 96 graph-conv calls), and the
+24-step x L-layer recurrence with its backward pass runs in the CUDA library
+behind ``include/matgcn.h``.  There is no CPU or PyTorch fallback for that part:
+without the compiled library (or on a CPU tensor) the call raises.
+"""
+from __future__ import annotations
+
+from logging import getLogger
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import graph_prep, ops
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class _NodeAdaptiveConvParams(nn.Module):
+    """Parameter holder with the reference's ``AGCN`` names/shapes (MA.py:60-73)."""
+
+    def __init__(self, dim_in, dim_out, cheb_k, embed_dim, adjtype, adpadj):
+        super().__init__()
+        if adjtype == "multi" and adpadj in ("bidirection", "unidirection"):
+            k = 1 + (cheb_k - 1) * 4
+        elif adjtype == "multi" and adpadj == "none":
+            k = 1 + (cheb_k - 1) * 3
+        else:
+            k = cheb_k
+        self.weights_g = nn.Parameter(torch.empty(k, 1, 1))
+        self.weights_pool = nn.Parameter(torch.empty(embed_dim, k, dim_in, dim_out))
+        self.bias_pool = nn.Parameter(torch.empty(embed_dim, dim_out))
+
+
+class _GraphGRUParams(nn.Module):
+    """``ATGRUCell`` holder: ``gate`` (I -> 2H) and ``update`` (I -> H) (MA.py:113-118)."""
+
+    def __init__(self, dim_in, dim_out, cheb_k, embed_dim, adjtype, adpadj):
+        super().__init__()
+        self.gate = _NodeAdaptiveConvParams(dim_in + dim_out, 2 * dim_out, cheb_k, embed_dim, adjtype, adpadj)
+        self.update = _NodeAdaptiveConvParams(dim_in + dim_out, dim_out, cheb_k, embed_dim, adjtype, adpadj)
+
+
+class _DenseGRUParams(nn.Module):
+    """Residual ``GRUCell`` holder: two ``nn.Linear`` shared by all nodes (MA.py:135-140)."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.gate = nn.Linear(dim_in + dim_out, 2 * dim_out)
+        self.update = nn.Linear(dim_in + dim_out, dim_out)
+
+
+class _EncoderParams(nn.Module):
+    """``ATGRUEncoder`` holder (MA.py:157-192): ``weights_gru``, ``agru_cells``, ``res_cells``."""
+
+    def __init__(self, config, feature_final):
+        super().__init__()
+        self.num_nodes = config["num_nodes"]
+        self.hidden_dim = config.get("rnn_units", 64)
+        self.embed_dim_node = 1 if config.get("node_specific_off", False) else config.get("embed_dim_node", 10)
+        self.input_window = config.get("input_window", 1)
+        self.num_layers = config.get("num_layers", 2)
+        self.adjtype = config.get("adjtype", "od")
+        self.adpadj = config.get("adpadj", "bidirection")
+        self.cheb_k = config.get("cheb_order", 2)
+        self.gcn_off = config.get("gcn_off", False)
+        assert self.num_layers >= 1, "At least one DCRNN layer in the Encoder"
+        self.agru_cells = nn.ModuleList()
+        self.res_cells = nn.ModuleList()
+        self.weights_gru = nn.Parameter(torch.empty(self.num_layers, self.input_window))
+        for layer in range(self.num_layers):
+            cin = feature_final if layer == 0 else self.hidden_dim
+            if not self.gcn_off:
+                self.agru_cells.append(_GraphGRUParams(cin, self.hidden_dim, self.cheb_k, self.embed_dim_node,
+                                                       self.adjtype, self.adpadj))
+                self.res_cells.append(_DenseGRUParams(cin, self.hidden_dim))
+            else:
+                self.agru_cells.append(_DenseGRUParams(cin, self.hidden_dim))
+
+
+class MultiATGCN(nn.Module):
+    def __init__(self, config, data_feature):
+        super().__init__()
+        self.data_feature = data_feature
+        g = config.get
+        self.num_nodes = data_feature.get("num_nodes", 1)
+        self.input_window = g("input_window", 1)
+        self.output_window = g("output_window", 1)
+        self.add_time_in_day = g("add_time_in_day", False)
+        self.add_day_in_week = g("add_day_in_week", False)
+        self.node_specific_off = g("node_specific_off", False)
+        self.fnn_off = g("fnn_off", False)
+        self.batch_size = g("batch_size", 64)
+        self.device = g("device", torch.device("cpu"))
+        config["num_nodes"] = self.num_nodes
+        self.embed_dim_node = g("embed_dim_node", 10)
+        self.embed_dim_adj = g("embed_dim_adj", 10)
+        self.adpadj = g("adpadj", "bidirection")
+        self.adjtype = g("adjtype", "od")
+        self.cheb_k = g("cheb_order", 2)
+        self.gcn_off = g("gcn_off", False)
+        self.hidden_dim = g("rnn_units", 64)
+        self.num_layers = g("num_layers", 2)
+        if self.adpadj not in ("bidirection", "unidirection", "none"):
+            raise ValueError("adpadj must be bidirection/unidirection/none, got %r" % (self.adpadj,))
+        n = self.num_nodes
+        self.ldm = _round_up(n, 8)
+
+        # --- static views (host, once): MA.py:238-283 -------------------------------------
+        views = graph_prep.static_views(self.adjtype, data_feature)
+        stat = []
+        for lap in views["laplacians"]:
+            for term in graph_prep.chebyshev_terms(lap, self.cheb_k):
+                padded = np.zeros((n, self.ldm), dtype=np.float32)
+                padded[:, :n] = term
+                stat.append(padded)
+        # not part of the checkpoint, exactly like the reference's plain python list
+        self.register_buffer("static_bases", torch.from_numpy(np.stack(stat, 0)), persistent=False)
+        self.static = data_feature.get("static", None)
+        if self.static is not None:
+            raise NotImplementedError(
+                "data_feature['static'] is set (add_static=true): that branch re-runs a randomised "
+                "torch.pca_lowrank on every forward (MA.py:291, 407) and is outside the accelerated path; "
+                "the shipped default add_static=false passes static=None")
+
+        # --- parameters, in the reference's registration order (MA.py:286-344) -------------
+        self.node_emb = nn.Parameter(torch.randn(n, self.embed_dim_node), requires_grad=True)
+        adj_t = torch.from_numpy(np.ascontiguousarray(views["adj_mx"]))
+        m, p, v = torch.svd(adj_t)
+        da = self.embed_dim_adj
+        self.node_vec1 = nn.Parameter(torch.mm(m[:, :da], torch.diag(p[:da] ** 0.5)), requires_grad=True)
+        self.node_vec2 = nn.Parameter(torch.mm(torch.diag(p[:da] ** 0.5), v[:, :da].t()), requires_grad=True)
+
+        self.start_dim = g("start_dim", 0)
+        self.end_dim = g("end_dim", 1)
+        self.load_dynamic = g("load_dynamic", False)
+        if self.add_time_in_day and self.add_day_in_week:
+            self.time_index_dim = 8
+        elif self.add_time_in_day:
+            self.time_index_dim = 1
+        elif not self.add_day_in_week:
+            self.time_index_dim = 0
+        else:
+            raise ValueError("add_day_in_week without add_time_in_day is undefined in the reference (MA.py:313-318)")
+        self.ext_dim = data_feature.get("ext_dim", 1)
+        self.output_dim = self.end_dim - self.start_dim
+        self.feature_final = self.output_dim + self.ext_dim
+
+        self.len_period = data_feature.get("len_period", 0)
+        self.len_trend = data_feature.get("len_trend", 0)
+        self.len_closeness = data_feature.get("len_closeness", 0)
+        self.len_ts = int((self.len_period + self.len_trend + self.len_closeness) / 24)
+        self.weight_ts = nn.ParameterList(
+            [nn.Parameter(torch.empty(1, 24, n, self.output_dim)) for _ in range(self.len_ts)])
+        self.weight_tsg = nn.Parameter(torch.empty(self.len_ts))
+
+        self.encoder = _EncoderParams(config, self.feature_final)
+        self.end_conv = nn.Conv2d(self.input_window, self.output_window * self.output_dim,
+                                  kernel_size=(1, self.hidden_dim), bias=True)
+        if self.fnn_off:
+            self.end_conv = nn.Conv2d(1, self.output_window * self.output_dim,
+                                      kernel_size=(1, self.hidden_dim), bias=True)
+        self._logger = getLogger()
+        self._scaler = data_feature.get("scaler")
+        self._init_parameters()
+        if self.node_specific_off:
+            self.embed_dim_node = 1
+            self.node_emb = nn.Parameter(torch.ones(n, 1), requires_grad=False)
+
+    def _init_parameters(self):
+        # MA.py:356-361
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+            else:
+                nn.init.uniform_(p)
+
+    # ------------------------------------------------------------------------------------
+    # a14: multi-head closeness / period / trend fusion (MA.py:363-402); tiny, stays torch
+    # ------------------------------------------------------------------------------------
+    def _fuse(self, x_all):
+        src = x_all[:, :, :, self.start_dim:self.end_dim]
+        gate = F.softmax(self.weight_tsg, dim=0)
+        out = 0.0
+        head = 0
+        if self.len_closeness > 0:
+            pos = 0
+            for _ in range(int(self.len_closeness / 24)):
+                out = out + gate[head] * src[:, pos:pos + 24] * self.weight_ts[head]
+                pos += 24
+                head += 1
+        if self.len_period > 0 and self.output_window >= 6:
+            pos = self.len_closeness
+            for _ in range(int(self.len_period / 24)):
+                out = out + gate[head] * src[:, pos:pos + 24] * self.weight_ts[head]
+                pos += 24
+                head += 1
+        if self.len_trend > 0 and self.output_window >= 6:
+            pos = self.len_closeness + self.len_period  # the reference never advances it (MA.py:388-393)
+            for _ in range(int(self.len_trend / 24)):
+                out = out + gate[head] * src[:, pos:pos + 24] * self.weight_ts[head]
+                head += 1
+        if self.add_time_in_day:
+            out = torch.cat((out, x_all[:, 0:self.input_window, :, self.end_dim:self.end_dim + self.time_index_dim]), -1)
+        if self.load_dynamic:
+            out = torch.cat((out, x_all[:, 0:self.input_window, :, self.end_dim + self.time_index_dim:]), -1)
+        return out
+
+    # ------------------------------------------------------------------------------------
+    # a5/a6: base matrices [Kp, N, ldm] = [adaptive T_1.., od.., dist.., cos..], unscaled
+    # ------------------------------------------------------------------------------------
+    def _base_matrices(self):
+        n = self.num_nodes
+        if self.adpadj == "none":
+            return self.static_bases, 0
+        if self.adpadj == "bidirection":
+            adp = ops.adaptive_adjacency(self.node_emb, self.node_emb, self.ldm)
+        else:
+            adp = ops.adaptive_adjacency(self.node_vec1, self.node_vec2.t().contiguous(), self.ldm)
+        terms = [adp]
+        if self.cheb_k > 2:
+            # T_k = 2 A T_{k-1} - T_{k-2}; only ablation configs take this path (library GEMM through autograd)
+            eye = torch.eye(n, device=adp.device, dtype=adp.dtype)
+            prev2, prev1 = eye, adp[:, :n]
+            for _ in range(2, self.cheb_k):
+                nxt = (2 * adp[:, :n]) @ prev1 - prev2
+                terms.append(F.pad(nxt, (0, self.ldm - n)))
+                prev2, prev1 = prev1, nxt
+        n_adp = len(terms)
+        if self.adjtype == "multi":
+            return torch.cat([torch.stack(terms, 0), self.static_bases], 0), n_adp
+        return torch.stack(terms, 0), n_adp
+
+    def _view_weights(self, conv, k_total):
+        """softmax(weights_g) for ``multi`` (MA.py:102-103) else ones, broadcast to the
+        K slots of the stack; also broadcasts the pool over k for the cheb_order=1 quirk."""
+        pool = conv.weights_pool
+        kw = pool.shape[1]
+        if self.adjtype == "multi":
+            c = F.softmax(conv.weights_g, dim=0).reshape(kw)
+        else:
+            c = torch.ones(kw, device=pool.device, dtype=pool.dtype)
+        if kw != k_total:
+            if kw != 1:
+                raise RuntimeError("weight pool has %d supports but the stack has %d" % (kw, k_total))
+            pool = pool.expand(-1, k_total, -1, -1)
+            c = c.expand(k_total)
+        return pool, c
+
+    def _encode(self, x_nm):
+        enc = self.encoder
+        mix = torch.sigmoid(enc.weights_gru)
+        if self.gcn_off:
+            raise NotImplementedError("gcn_off=true (plain GRU ablation) is not on the accelerated path yet")
+        bases, n_adp = self._base_matrices()
+        k_total = bases.shape[0] + 1
+        cur = x_nm
+        for layer in range(self.num_layers):
+            cell, res = enc.agru_cells[layer], enc.res_cells[layer]
+            pool_g, c_g = self._view_weights(cell.gate, k_total)
+            pool_u, c_u = self._view_weights(cell.update, k_total)
+            w_g, b_g = ops.node_weights(self.node_emb, pool_g, cell.gate.bias_pool, c_g)
+            w_u, b_u = ops.node_weights(self.node_emb, pool_u, cell.update.bias_pool, c_u)
+            cur = ops.encoder_layer(cur, None, bases, w_g, b_g, w_u, b_u,
+                                    res.gate.weight, res.gate.bias, res.update.weight, res.update.bias,
+                                    mix[layer], n_adp)
+        return cur
+
+    def forward(self, batch):
+        x_all = batch["X"]
+        fused = self._fuse(x_all)                                   # [B, T, N, C0]
+        assert fused.shape[2] == self.num_nodes
+        if fused.shape[1] > self.input_window:
+            raise ValueError("sequence longer than input_window (weights_gru has %d steps)" % self.input_window)
+        x_nm = fused.permute(1, 2, 0, 3).contiguous()               # node-major [T, N, B, C0]
+        y_nm = self._encode(x_nm)                                   # [T, N, B, H]
+        out = y_nm.permute(2, 0, 1, 3)                              # [B, T, N, H]
+        if self.fnn_off:
+            out = out[:, -1:, :, :]
+        out = F.dropout(out, p=0.1, training=self.training)
+        out = self.end_conv(out)                                    # [B, T_out*C, N, 1]
+        out = out.squeeze(-1).reshape(-1, self.output_window, self.output_dim, self.num_nodes).permute(0, 1, 3, 2)
+        return out
+
+    def predict(self, batch):
+        return self.forward(batch)
+
+    def calculate_loss(self, batch):
+        y_true = batch["y"]
+        y_pred = self.predict(batch)
+        y_true = self._scaler.inverse_transform(y_true[..., self.start_dim:self.end_dim])
+        y_pred = self._scaler.inverse_transform(y_pred)
+        return masked_mae_torch(y_pred, y_true, 0)
+
+
+def masked_mae_torch(preds, labels, null_val=float("nan"), min_s=1e-4):
+    """Same contract as ``libcity/model/loss.py:17-29`` (labels with |v| < min_s count as
+    missing; mask normalised by its mean; NaNs -> 0)."""
+    labels = torch.where(labels.abs() < min_s, torch.zeros_like(labels), labels)
+    if null_val != null_val:
+        mask = ~torch.isnan(labels)
+    else:
+        mask = labels.ne(null_val)
+    mask = mask.float()
+    mask = mask / torch.mean(mask)
+    mask = torch.where(torch.isnan(mask), torch.zeros_like(mask), mask)
+    loss = torch.abs(preds - labels) * mask
+    loss = torch.where(torch.isnan(loss), torch.zeros_like(loss), loss)
+    return torch.mean(loss)

@@ -1,0 +1,168 @@
+"""autograd bindings of the C-ABI operators (include/matgcn.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream and records the
+backward graph; all arithmetic of these three operators runs in ``libmatgcn.so``.
+
+* :func:`adaptive_adjacency`  - softmax(relu(L Rt^T))                     (MA.py:80-83)
+* :func:`node_weights`        - per-node weights/bias from the pools       (MA.py:102-105)
+* :func:`encoder_layer`       - one ATGRUEncoder layer over the window     (MA.py:200-211)
+
+Inputs must be float32 CUDA tensors; anything else raises (no CPU fallback).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _cabi.MatgcnError("%s must be a CUDA tensor: the Multi-ATGCN operators have no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise _cabi.MatgcnError("%s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _AdaptiveAdjFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, L, Rt, ldm):
+        L, Rt = _f32c(L, "L"), _f32c(Rt, "Rt")
+        n, d = L.shape
+        if Rt.shape != (n, d):
+            raise _cabi.MatgcnError("adaptive_adjacency: L and Rt must both be [N, D]")
+        A = torch.empty(n, ldm, device=L.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_adaptive_adj_fwd(_ptr(L), _ptr(Rt), n, d, _ptr(A), ldm, _stream()),
+                    "matgcn_adaptive_adj_fwd")
+        ctx.save_for_backward(L, Rt, A)
+        ctx.ldm = ldm
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        L, Rt, A = ctx.saved_tensors
+        n, d = L.shape
+        dA = _f32c(dA, "dA")
+        dL = torch.empty_like(L)
+        dRt = torch.empty_like(Rt)
+        scratch = torch.empty(n, n, device=L.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_adaptive_adj_bwd(_ptr(L), _ptr(Rt), _ptr(A), _ptr(dA), n, d, ctx.ldm,
+                                                         _ptr(dL), _ptr(dRt), _ptr(scratch), _stream()),
+                    "matgcn_adaptive_adj_bwd")
+        return dL, dRt, None
+
+
+class _NodeWeightsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, pool, bias_pool, c):
+        E, pool, bias_pool, c = _f32c(E, "E"), _f32c(pool, "pool"), _f32c(bias_pool, "bias_pool"), _f32c(c, "c")
+        n, d = E.shape
+        d2, k, i, o = pool.shape
+        if d2 != d or bias_pool.shape != (d, o) or c.shape != (k,):
+            raise _cabi.MatgcnError("node_weights: inconsistent shapes")
+        W = torch.empty(n, k, i, o, device=E.device, dtype=torch.float32)
+        b = torch.empty(n, o, device=E.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_nodeweights_fwd(_ptr(E), _ptr(pool), _ptr(bias_pool), _ptr(c),
+                                                        n, d, k, i, o, _ptr(W), _ptr(b), _stream()),
+                    "matgcn_nodeweights_fwd")
+        ctx.save_for_backward(E, pool, bias_pool, c)
+        return W, b
+
+    @staticmethod
+    def backward(ctx, dW, db):
+        E, pool, bias_pool, c = ctx.saved_tensors
+        n, d = E.shape
+        _, k, i, o = pool.shape
+        dW, db = _f32c(dW, "dW"), _f32c(db, "db")
+        dE = torch.empty_like(E)
+        dpool = torch.empty_like(pool)
+        dbias_pool = torch.empty_like(bias_pool)
+        dc = torch.empty_like(c)
+        _cabi.check(_cabi.lib().matgcn_nodeweights_bwd(_ptr(E), _ptr(pool), _ptr(bias_pool), _ptr(c), _ptr(dW),
+                                                        _ptr(db), n, d, k, i, o, _ptr(dE), _ptr(dpool),
+                                                        _ptr(dbias_pool), _ptr(dc), _stream()),
+                    "matgcn_nodeweights_bwd")
+        return dE, dpool, dbias_pool, dc
+
+
+class _EncoderLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp):
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise _cabi.MatgcnError("encoder_layer: x must be a float32 CUDA tensor (no CPU path)")
+        T, N, B, Cin = x.shape
+        # x may be a strided view over time (the previous layer's output inside its workspace)
+        if x.stride(3) != 1 or x.stride(2) != Cin or x.stride(1) != B * Cin:
+            x = x.contiguous()
+        M, Wg, bg, Wu, bu = (_f32c(M, "M"), _f32c(Wg, "Wg"), _f32c(bg, "bg"), _f32c(Wu, "Wu"), _f32c(bu, "bu"))
+        Rgw, Rgb, Ruw, Rub, mix = (_f32c(Rgw, "Rgw"), _f32c(Rgb, "Rgb"), _f32c(Ruw, "Ruw"), _f32c(Rub, "Rub"),
+                                   _f32c(mix, "mix"))
+        if h0 is not None:
+            h0 = _f32c(h0, "h0")
+        H = Rub.shape[0]
+        Kp, n2, ldm = M.shape
+        K = Kp + 1
+        I = Cin + H
+        if n2 != N or Wg.shape != (N, K, I, 2 * H) or Wu.shape != (N, K, I, H) or Rgw.shape != (2 * H, I) \
+                or Ruw.shape != (H, I) or bg.shape != (N, 2 * H) or bu.shape != (N, H) or mix.shape != (T,):
+            raise _cabi.MatgcnError("encoder_layer: inconsistent shapes")
+        L = _cabi.lib()
+        dims = (T, N, B, Cin, H, K)
+        ws = torch.empty(L.matgcn_encoder_layer_fwd_ws_bytes(*dims) // 4, device=x.device, dtype=torch.float32)
+        _cabi.check(L.matgcn_encoder_layer_fwd(*dims, ldm, _ptr(x), x.stride(0), _ptr(h0), _ptr(M), _ptr(Wg), _ptr(bg),
+                                               _ptr(Wu), _ptr(bu), _ptr(Rgw), _ptr(Rgb), _ptr(Ruw), _ptr(Rub),
+                                               _ptr(mix), _ptr(ws), _stream()), "matgcn_encoder_layer_fwd")
+        y = torch.as_strided(ws, (T, N, B, H), (L.matgcn_encoder_layer_y_tstride(*dims), B * H, H, 1),
+                             L.matgcn_encoder_layer_y_offset(*dims))
+        ctx.save_for_backward(M, Wg, Wu, Rgw, Ruw, mix)
+        ctx.ws = ws
+        ctx.dims, ctx.ldm, ctx.n_adp, ctx.has_h0 = dims, ldm, int(n_adp), h0 is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        M, Wg, Wu, Rgw, Ruw, mix = ctx.saved_tensors
+        T, N, B, Cin, H, K = ctx.dims
+        I = Cin + H
+        dev = dy.device
+        if dy.dtype != torch.float32 or dy.stride(3) != 1 or dy.stride(2) != H or dy.stride(1) != B * H:
+            dy = dy.contiguous().float()
+        L = _cabi.lib()
+        if ctx.ws is None:
+            raise _cabi.MatgcnError("encoder_layer: backward called twice (the saved workspace was released)")
+        bws = torch.empty(L.matgcn_encoder_layer_bwd_ws_bytes(*ctx.dims, ctx.n_adp) // 4, device=dev, dtype=torch.float32)
+        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        dx, dM = new(T, N, B, Cin), new(K - 1, N, ctx.ldm)
+        dh0 = new(N, B, H) if ctx.has_h0 else None
+        dWg, dbg, dWu, dbu = new(N, K, I, 2 * H), new(N, 2 * H), new(N, K, I, H), new(N, H)
+        dRgw, dRgb, dRuw, dRub, dmix = new(2 * H, I), new(2 * H), new(H, I), new(H), new(T)
+        _cabi.check(L.matgcn_encoder_layer_bwd(T, N, B, Cin, H, K, ctx.ldm, ctx.n_adp, _ptr(dy), dy.stride(0), _ptr(M),
+                                               _ptr(Wg), _ptr(Wu), _ptr(Rgw), _ptr(Ruw), _ptr(mix), _ptr(ctx.ws),
+                                               _ptr(bws), _ptr(dx), _ptr(dh0), _ptr(dM), _ptr(dWg), _ptr(dbg),
+                                               _ptr(dWu), _ptr(dbu), _ptr(dRgw), _ptr(dRgb), _ptr(dRuw), _ptr(dRub),
+                                               _ptr(dmix), _stream()), "matgcn_encoder_layer_bwd")
+        ctx.ws = None  # GX/RX slots now hold gradients: the workspace is spent
+        return dx, dh0, dM, dWg, dbg, dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, None
+
+
+def adaptive_adjacency(L, Rt, ldm):
+    """[N, ldm] row-softmax adaptive adjacency; columns >= N are zero."""
+    return _AdaptiveAdjFn.apply(L, Rt, ldm)
+
+
+def node_weights(E, pool, bias_pool, c):
+    """(W [N,K,I,O], b [N,O]) with the view weights c folded into W."""
+    return _NodeWeightsFn.apply(E, pool, bias_pool, c)
+
+
+def encoder_layer(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp):
+    """x [T,N,B,Cin] node-major -> y [T,N,B,H] (a strided view into the layer's workspace)."""
+    return _EncoderLayerFn.apply(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp)
