@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the Multi-ATGCN train step (BASELINE.json metric: train samples/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference
+
+One "step" = one pass of ``TrafficStateExecutor._train_epoch``'s loop body over one batch of
+synthetic input of the named shape: zero_grad -> calculate_loss (forward) -> backward ->
+[gradient all-reduce when N > 1] -> clip_grad_norm_(5) -> Adam step.
+
+* ``value``  : samples/s with the step's inputs already resident in HBM (CUDA-event timed,
+               max over ranks).
+* ``e2e``    : the same metric through the public model API with HOST buffers: every step copies
+               its batch from pinned host memory to the device and reads the loss back.
+* ``roofline``: the dominant kernel (support-propagation GEMM), timed live with CUDA events on
+               the launching stream at the step's exact shape.
+* ``cpu_baseline``: the oracle (a port of the reference's CPU path) timed on this host's cores
+               on a bounded sample of the same workload.
+Multi-GPU: launched by torchrun, one rank per GPU, weak scaling (fixed per-GPU batch).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "multi_atgcn_train_samples_per_s"
+UNIT = "samples/s"
+DEFAULT_WORKLOAD = "baltimore_multi"  # N=403, T=24 -> 24, batch 64 per GPU: the shape the metric is quoted on
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [c.strip() for c in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]  # upper half ~ samples taken under load
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def _dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+    return world, rank, local
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle on host cores
+# ------------------------------------------------------------------------------------------------
+def _oracle_step_time(cfg, df, params, n_nodes, t_out, batch, seed=0):
+    from multistgraph_b200.synthetic import make_batch
+    from oracle.matgcn_oracle import OracleModel
+
+    model = OracleModel(cfg, df, params)
+    b = make_batch(n_nodes, batch, t_out, seed=seed)
+    t0 = time.perf_counter()
+    loss = model.calculate_loss(b)
+    loss.backward()
+    return time.perf_counter() - t0
+
+
+def cpu_reference_run(workload_name: str, steps: int, warmup: int, budget_s: float):
+    """Times the CPU restatement of the reference's train step (forward + backward of
+    calculate_loss; the reference has no GPU-free fast path) on all host threads, on the
+    largest batch <= the workload's that fits ``budget_s``."""
+    from multistgraph_b200.model import MultiATGCN
+    from multistgraph_b200.synthetic import WORKLOADS, workload
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = WORKLOADS[workload_name]
+    cfg, df, _ = workload(workload_name, seed=0, batch=1)
+    torch.manual_seed(0)
+    params = {k: v.detach().clone() for k, v in MultiATGCN(dict(cfg), df).state_dict().items()}
+    t1 = _oracle_step_time(cfg, df, params, w["N"], w["T_out"], 1)           # also warms the thread pool
+    t2 = _oracle_step_time(cfg, df, params, w["N"], w["T_out"], 2)
+    slope = max(t2 - t1, 0.02 * t1)
+    fixed = max(t1 - slope, 0.0)
+    k_eff = max(1, min(steps, 3))
+    w_eff = 1 if warmup > 0 else 0
+    spent = t1 + t2
+    batch = 1
+    for cand in (w["B"], w["B"] // 2, w["B"] // 4, w["B"] // 8, 4, 2, 1):
+        if cand < 1:
+            continue
+        if (k_eff + w_eff) * (fixed + slope * cand) <= max(budget_s - spent, 1.0):
+            batch = cand
+            break
+    for _ in range(w_eff):
+        _oracle_step_time(cfg, df, params, w["N"], w["T_out"], batch)
+    times = [_oracle_step_time(cfg, df, params, w["N"], w["T_out"], batch, seed=i) for i in range(k_eff)]
+    dt = sum(times) / len(times)
+    return {"value": batch / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d timed step(s) of forward+backward at batch %d of %d (N=%d), %.1f s/step, %d torch threads"
+                      % (k_eff, batch, w["B"], w["N"], dt, cores),
+            "steps": k_eff, "warmup": w_eff, "ms_per_step": dt * 1e3, "batch": batch}
+
+
+def run_reference_arm(args):
+    world, rank, _ = _dist_setup(args.gpus)
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.workload, args.steps, args.warmup, budget_s=args.cpu_budget if args.cpu_budget else 200.0)
+    from multistgraph_b200.synthetic import WORKLOADS
+    w = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": _workload_desc(args.workload, w, r["batch"]), "device": "host CPU (no GPU code in the reference)"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def _workload_desc(name, w, batch):
+    return ("%s: N=%d nodes, batch %d per GPU, 24 steps in -> %d out, adjtype=%s adpadj=%s K=5 supports, "
+            "embed_dim=%d, hidden 64, 2 layers" % (name, w["N"], batch, w["T_out"], w["adjtype"], w["adpadj"], w["D"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# dominant-kernel roofline, measured live
+# ------------------------------------------------------------------------------------------------
+def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, iters=20):
+    """Times the support-propagation kernel at the step's shape ([Kp*N, N] x [N, B*H]) with CUDA
+    events on the launching stream; L2 is flushed between launches by rewriting a 256 MB buffer."""
+    from multistgraph_b200 import _cabi
+
+    lib = _cabi.lib()
+    cols = batch * hidden
+    M = torch.randn(kp, n_nodes, ldm, device=device) * 0.05
+    X = torch.randn(n_nodes, cols, device=device)
+    P = torch.empty(kp, n_nodes, cols, device=device)
+    flush = torch.empty(64 * 1024 * 1024, device=device, dtype=torch.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n_nodes, ldm, X.data_ptr(), cols, P.data_ptr(), st), "propagate")
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n_nodes, ldm, X.data_ptr(), cols, P.data_ptr(), st), "propagate")
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    ms = total / iters
+    flops = 2.0 * kp * n_nodes * n_nodes * cols
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops"]
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "gemm_kernel<CfgBig,A_KC,B_NC,EpiStore> (support propagation, fp32 FFMA)",
+            "launch_ms": ms, "flops_per_launch": flops, "peak_source": peaks["source"] + " bf16 dense burst",
+            "note": "fp32 exact-mode kernel measured against the bf16 tensor-core peak"}
+
+
+# ------------------------------------------------------------------------------------------------
+# this repository's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from multistgraph_b200 import _cabi
+    from multistgraph_b200.dp import FlatGradBucket, broadcast_parameters, train_step
+    from multistgraph_b200.model import MultiATGCN
+    from multistgraph_b200.synthetic import WORKLOADS, make_batch, workload
+
+    world, rank, local = _dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the Multi-ATGCN path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
+
+    w = WORKLOADS[args.workload]
+    per_gpu_batch = args.batch if args.batch else w["B"]
+    cfg, df, _ = workload(args.workload, seed=0, batch=per_gpu_batch, device=dev)
+    torch.manual_seed(0)
+    model = MultiATGCN(dict(cfg), df).to(dev).train()
+    broadcast_parameters(model)
+    bucket = FlatGradBucket(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=0.003, eps=1e-8)
+    lib = _cabi.lib()
+
+    # distinct host batches (pinned) so the e2e path really moves fresh data each step
+    n_host = 4
+    host = [make_batch(w["N"], per_gpu_batch, w["T_out"], seed=100 + rank * 16 + i, pin=True) for i in range(n_host)]
+    resident = [{k: v.to(dev, non_blocking=True) for k, v in hb.items()} for hb in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for i in range(args.warmup):
+        train_step(model, resident[i % n_host], opt, bucket)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.matgcn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = train_step(model, resident[i % n_host], opt, bucket)
+    e1.record()
+    barrier()
+    launches = lib.matgcn_launch_count() - l0
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    last_loss = float(loss.item())
+
+    # ---- end-to-end timing: host buffers in, loss out, every step ------------------------------
+    def e2e_step(i):
+        hb = host[i % n_host]
+        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        return float(train_step(model, batch, opt, bucket).item())
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    global_batch = per_gpu_batch * world
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    if rank == 0:
+        peaks = _peaks()
+        roof = propagation_roofline(w["N"], per_gpu_batch, 64, 4, model.ldm, dev, peaks)
+        line = {"metric": METRIC, "value": global_batch / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": _workload_desc(args.workload, w, per_gpu_batch), "global_batch": global_batch,
+                           "step": "zero_grad+forward+backward+allreduce+clip_grad_norm(5)+Adam",
+                           "parallelism": "dp%d (batch-sharded, one flat-bucket all-reduce)" % world,
+                           "l2": "per-step working set (several GB of saved activations) is far larger than the 126 MB L2",
+                           "mode": "exact (fp32 FFMA kernels)"},
+                "clocks": clocks,
+                "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": int(launches), "loss": last_loss, "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                r = cpu_reference_run(args.workload, 1, 0, budget_s=args.cpu_budget if args.cpu_budget else 30.0)
+                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as exc:  # the baseline is informational; never lose the GPU line over it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "failed: %r" % (exc,)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work allowed for the baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

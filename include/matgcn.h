@@ -40,6 +40,9 @@ int matgcn_abi_version(void);
 /* Last error text of the calling thread ("" if none). */
 const char* matgcn_last_error(void);
 
+/* Number of kernels this library has launched in this process (monotonic counter). */
+unsigned long long matgcn_launch_count(void);
+
 /* -------------------------------------------------------------------------------------------
  * Adaptive adjacency  A = softmax(relu(L * Rt^T), dim=1)
  * replaces MA.py:80-83 (AGCN.forward): bidirection passes L = Rt = node_emb [N, D];
@@ -67,6 +70,14 @@ int matgcn_nodeweights_fwd(const float* E, const float* pool, const float* bias_
 int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_pool, const float* c,
                            const float* dW, const float* db, int N, int D, int K, int I, int O,
                            float* dE, float* dpool, float* dbias_pool, float* dc, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Support propagation as a standalone operator (the dominant contraction of the path):
+ *   P[k, n, col] = sum_m M[k, n, m] * X[m, col]
+ * replaces the einsum 'knm,bmc->bknc' of MA.py:106 in node-major layout for the non-identity
+ * supports.   M [Kp, N, ldm]   X [N, cols] (cols = B*C)   ->   P [Kp, N, cols]
+ * ----------------------------------------------------------------------------------------- */
+int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P, void* stream);
 
 /* -------------------------------------------------------------------------------------------
  * One encoder layer over the whole input window.

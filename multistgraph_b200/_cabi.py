@@ -20,6 +20,8 @@ _F = c_void_p  # device float*
 _SIGNATURES = {
     "matgcn_abi_version": (c_int, []),
     "matgcn_last_error": (c_char_p, []),
+    "matgcn_launch_count": (ctypes.c_ulonglong, []),
+    "matgcn_propagate_fwd": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_void_p]),
     "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),
     "matgcn_adaptive_adj_bwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, _F, _F, _F, c_void_p]),
     "matgcn_nodeweights_fwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, _F, _F, c_void_p]),

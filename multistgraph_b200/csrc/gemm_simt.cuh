@@ -12,7 +12,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 namespace matgcn {
+
+// kernels launched by this library in this process (reported by bench.py as gpu_launches)
+inline std::atomic<unsigned long long> g_launches{0};
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct GemmP {
     const float* A;
@@ -172,6 +178,7 @@ inline cudaError_t launch_gemm(const GemmP& p, const Epi& epi, int Z, cudaStream
     if (q.splits < 1) q.splits = 1;
     if (q.Z2 < 1) q.Z2 = 1;
     gemm_kernel<Cfg, A_KC, B_KC, Epi><<<grid, Cfg::NT, 0, st>>>(q, epi, tiles_n, tiles_m * tiles_n);
+    count_launch();
     return cudaGetLastError();
 }
 

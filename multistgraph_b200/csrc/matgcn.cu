@@ -35,6 +35,7 @@ static int fail(const char* where, const char* what) {
 
 extern "C" int matgcn_abi_version(void) { return MATGCN_ABI_VERSION; }
 extern "C" const char* matgcn_last_error(void) { return g_err; }
+extern "C" unsigned long long matgcn_launch_count(void) { return g_launches.load(); }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
@@ -314,6 +315,7 @@ extern "C" int matgcn_adaptive_adj_fwd(const float* L, const float* Rt, int N, i
     cudaStream_t st = (cudaStream_t)stream;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(adaptive_adj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     adaptive_adj_fwd_kernel<<<N, 256, smem, st>>>(L, Rt, N, D, A, ldm);
+    count_launch();
     CK(cudaGetLastError());
     return 0;
 }
@@ -324,6 +326,7 @@ extern "C" int matgcn_adaptive_adj_bwd(const float* L, const float* Rt, const fl
     REQUIRE(N > 0 && D > 0 && ldm >= N, "bad dims");
     cudaStream_t st = (cudaStream_t)stream;
     adaptive_adj_bwd_kernel<<<N, 256, (size_t)D * sizeof(float), st>>>(L, Rt, A, dA, N, D, ldm, scratch);
+    count_launch();
     CK(cudaGetLastError());
     GemmP p;
     memset(&p, 0, sizeof(p));
@@ -372,6 +375,7 @@ extern "C" int matgcn_nodeweights_bwd(const float* E, const float* pool, const f
     CK(cudaMemsetAsync(dc, 0, sizeof(float) * (size_t)K, st));
     // dpool is first used as scratch for c[k]*pool, consumed by the dE contraction below
     scale_groups_kernel<<<(unsigned)((npool + 255) / 256), 256, 0, st>>>(pool, c, npool, I * O, K, dpool);
+    count_launch();
     CK(cudaGetLastError());
     GemmP p;
     memset(&p, 0, sizeof(p));
@@ -393,6 +397,7 @@ extern "C" int matgcn_nodeweights_bwd(const float* E, const float* pool, const f
     {
         dim3 grid(K, 64);
         view_weight_grad_kernel<<<grid, 256, 0, st>>>(dpool, pool, c, D, K, I * O, dc);
+        count_launch();
         CK(cudaGetLastError());
     }
     // dbias_pool = E^T db
@@ -492,6 +497,14 @@ static cudaError_t propagate(const float* M, int ldm, int N, int Kp, const float
     p.A = M; p.lda = ldm; p.M = Kp * N; p.K = N;
     p.B = slot0; p.ldb = cols; p.N = cols; p.sB1 = zstride;
     return launch_gemm<CfgBig, true, false>(p, epi_store(slot1, zstride, 0, cols), Z, st);
+}
+
+extern "C" int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P,
+                                    void* stream) {
+    REQUIRE(M && X && P, "null pointer");
+    REQUIRE(Kp > 0 && N > 0 && cols > 0 && ldm >= N, "bad dims");
+    CK(propagate(M, ldm, N, Kp, X, 0, cols, P, 1, (cudaStream_t)stream));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -624,6 +637,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         // B0
         bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t,
                                                                     mix + t, U, H, DH1, DRES, DRt, dmix + t);
+                                                                    count_launch();
         CK(cudaGetLastError());
         // B1: dzh2 = da3 [NB,H] * Ruw[:, Cin:]  (B element (k=o, n=j) at o*I + Cin + j)
         memset(&p, 0, sizeof(p));
@@ -690,10 +704,14 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         REQUIRE(2 * H <= threads, "hidden size too large for the column-sum kernel");
         dim3 g1(N, 8);
         colsum_kernel<<<g1, threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 2 * H, dbg, 2 * H);
+        count_launch();
         colsum_kernel<<<g1, threads, 0, st>>>(DG + 2 * H, T, 3 * U, (long long)B * 3 * H, B, 3 * H, H, dbu, H);
+        count_launch();
         dim3 g2(1, 1024);
         colsum_kernel<<<g2, threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 2 * H, dRgb, 2 * H);
+        count_launch();
         colsum_kernel<<<g2, threads, 0, st>>>(DR + 2 * H, T, 3 * U, 0, NB, 3 * H, H, dRub, H);
+        count_launch();
         CK(cudaGetLastError());
     }
     // DPX[t,k,n] = DG[t,n][:,0:2H] * Wg[n,k,0:Cin,:]^T + DG[t,n][:,2H:] * Wu[n,k,0:Cin,:]^T     per k: z = (t, n)

@@ -296,8 +296,12 @@ class MultiATGCN(nn.Module):
         if self.fnn_off:
             out = out[:, -1:, :, :]
         out = F.dropout(out, p=0.1, training=self.training)
-        out = self.end_conv(out)                                    # [B, T_out*C, N, 1]
-        out = out.squeeze(-1).reshape(-1, self.output_window, self.output_dim, self.num_nodes).permute(0, 1, 3, 2)
+        # end_conv = Conv2d(T -> T_out*C, kernel (1, H)) (MA.py:340-344, 417): time steps are the
+        # channels, so it is the contraction below.  Written as a matmul so it stays true fp32
+        # (cuDNN convolutions default to TF32, which breaks the 1e-4 parity bound).
+        w = self.end_conv.weight[:, :, 0, :]                        # [T_out*C, T, H]
+        out = torch.einsum("btnh,oth->bon", out, w) + self.end_conv.bias[None, :, None]
+        out = out.reshape(-1, self.output_window, self.output_dim, self.num_nodes).permute(0, 1, 3, 2)
         return out
 
     def predict(self, batch):
