@@ -32,7 +32,11 @@
 extern "C" {
 #endif
 
-#define MATGCN_ABI_VERSION 1
+#define MATGCN_ABI_VERSION 2
+
+/* flags of the contraction-heavy entry points */
+#define MATGCN_FLAG_EXACT 0 /* fp32 FFMA kernels: 1e-4 parity with the reference */
+#define MATGCN_FLAG_TF32 1  /* fast mode: contractions on tcgen05 tensor cores as TF32 (fp32 storage and accumulation) */
 
 /* ABI version of the loaded library (compare with MATGCN_ABI_VERSION). */
 int matgcn_abi_version(void);
@@ -42,6 +46,9 @@ const char* matgcn_last_error(void);
 
 /* Number of kernels this library has launched in this process (monotonic counter). */
 unsigned long long matgcn_launch_count(void);
+
+/* Number of those launches that went to the tcgen05/TMA tensor-core kernel. */
+unsigned long long matgcn_tc_launch_count(void);
 
 /* -------------------------------------------------------------------------------------------
  * Adaptive adjacency  A = softmax(relu(L * Rt^T), dim=1)
@@ -77,7 +84,14 @@ int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_
  * replaces the einsum 'knm,bmc->bknc' of MA.py:106 in node-major layout for the non-identity
  * supports.   M [Kp, N, ldm]   X [N, cols] (cols = B*C)   ->   P [Kp, N, cols]
  * ----------------------------------------------------------------------------------------- */
-int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P, void* stream);
+int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P, int flags,
+                         void* stream);
+
+/* Diagnostics: plain C[M,N] = A*B through the selected engine, for unit tests of the GEMM kernels.
+ * a_kc: A element (m,k) at m*lda+k (else k*lda+m); b_kc: B element (k,n) at n*ldb+k (else k*ldb+n).
+ * splits > 1 exercises the split-K / atomic epilogue. */
+int matgcn_gemm_debug(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                      float* C, int ldc, int splits, int flags, void* stream);
 
 /* -------------------------------------------------------------------------------------------
  * One encoder layer over the whole input window.
@@ -114,7 +128,7 @@ int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int K, int ldm
                              const float* x, long long x_tstride, const float* h0, const float* M,
                              const float* Wg, const float* bg, const float* Wu, const float* bu,
                              const float* Rgw, const float* Rgb, const float* Ruw, const float* Rub,
-                             const float* mix, float* ws, void* stream);
+                             const float* mix, float* ws, int flags, void* stream);
 
 /* Backward of one encoder layer (reverse-time BPTT + time-batched parameter gradients).
  *   dy [T, N, B, H] with time stride dy_tstride: gradient w.r.t. every step's output
@@ -131,7 +145,7 @@ int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int K, int ldm
                              float* dx, float* dh0, float* dM,
                              float* dWg, float* dbg, float* dWu, float* dbu,
                              float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
-                             void* stream);
+                             int flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,9 @@ from ctypes import c_char_p, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmatgcn.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_EXACT = 0
+FLAG_TF32 = 1
 
 _lib = None
 
@@ -21,7 +23,10 @@ _SIGNATURES = {
     "matgcn_abi_version": (c_int, []),
     "matgcn_last_error": (c_char_p, []),
     "matgcn_launch_count": (ctypes.c_ulonglong, []),
-    "matgcn_propagate_fwd": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_void_p]),
+    "matgcn_tc_launch_count": (ctypes.c_ulonglong, []),
+    "matgcn_propagate_fwd": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_int, c_void_p]),
+    "matgcn_gemm_debug": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, c_int, _F, c_int, _F, c_int, c_int, c_int,
+                                  c_void_p]),
     "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),
     "matgcn_adaptive_adj_bwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, _F, _F, _F, c_void_p]),
     "matgcn_nodeweights_fwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, _F, _F, c_void_p]),
@@ -33,9 +38,9 @@ _SIGNATURES = {
     "matgcn_encoder_layer_y_tstride": (c_size_t, [c_int] * 6),
     "matgcn_encoder_layer_slot_offset": (c_size_t, [c_char_p] + [c_int] * 6),
     "matgcn_encoder_layer_fwd": (c_int, [c_int] * 7 + [_F, c_longlong, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F,
-                                                       _F, _F, c_void_p]),
+                                                       _F, _F, c_int, c_void_p]),
     "matgcn_encoder_layer_bwd": (c_int, [c_int] * 8 + [_F, c_longlong, _F, _F, _F, _F, _F, _F, _F, _F,
-                                                       _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
+                                                       _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_int, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,399 @@
+// TMA-fed tcgen05 (5th-gen tensor core) GEMM for sm_100a with TMEM accumulators.
+//
+// "Fast mode" engine: same problem description (GemmP), same epilogue functors and the same
+// semantics as the fp32 SIMT kernel in gemm_simt.cuh, but the products run on the tensor cores
+// as kind::tf32 MMAs (fp32 operands straight from HBM via TMA, truncated to TF32 by the tensor
+// core, fp32 accumulation in tensor memory).  No operand copies or layout changes are needed,
+// so every contraction of the path can be switched between the two engines per call.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor.5d into a STAGES-deep 128B-swizzled smem ring
+//   warp 1   : MMA issuer    - one lane issues tcgen05.mma (M=128, N=BN, K=8), commits to mbarriers
+//   warp 2   : TMEM allocator (2 x BN fp32 columns: double-buffered accumulator)
+//   warps 4-7: epilogue      - tcgen05.ld 32 rows x 32 columns per warp, transpose through padded
+//                              smem so that the epilogue functor sees consecutive columns on
+//                              consecutive lanes (coalesced global access)
+// Tiles: 128 x BN output, 32-element (128 B) K slabs; batching (z1, z2) and k-batches are extra
+// tensor-map dimensions, so one launch covers e.g. all nodes of a node-batched contraction.
+// Out-of-range rows/columns/K are zero-filled by TMA and masked in the epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_simt.cuh"
+
+namespace matgcn {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;  // fp32 elements per K slab = one 128-byte swizzle row
+constexpr int TC_THREADS = 256;
+
+struct TcP {
+    int M, N, K, KB, Z2, splits;
+    int tiles_m, tiles_n;
+    int total_tiles;        // Z * splits * tiles_m * tiles_n
+    int cA1, cA2, cAk;      // 1 if the operand really has that (strided) dimension, else coordinate 0
+    int cB1, cB2, cBk;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (it == 64) t0 = clock64();
+        if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (SM100 UMMA): start address, leading/stride byte offsets (all >> 4),
+// descriptor version 1, 128-byte swizzle.
+// layout_type: 2 = SWIZZLE_128B (16-byte atoms; K-major tiles), 1 = SWIZZLE_128B_BASE32B (32-byte atoms; the only
+// layout the tensor core accepts for MN-major 32-bit operands).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // version = 1 (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+template <int BN>
+struct TcSmem {
+    static constexpr int A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+    static constexpr int B_BYTES = BN * TC_BK * 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
+    static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;  // 4 epilogue warps x [32][33] floats
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool A_KC, bool B_KC, class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p, const Epi epi) {
+    using S = TcSmem<BN>;
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    float* epi_buf = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
+    // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kt_per_kb = (p.K + TC_BK - 1) / TC_BK;
+    const int kt_total = p.KB * kt_per_kb;
+    const int kt_per_split = (kt_total + p.splits - 1) / p.splits;
+    const int tiles_mn = p.tiles_m * p.tiles_n;
+
+    // tile -> (z1, z2, split, m0, n0, kt0, kt1)
+    auto decode = [&](int tile, int& z1, int& z2, int& m0, int& n0, int& kt0, int& kt1) {
+        const int mn = tile % tiles_mn;
+        const int rest = tile / tiles_mn;
+        const int split = rest % p.splits;
+        const int z = rest / p.splits;
+        z1 = z / p.Z2;
+        z2 = z - z1 * p.Z2;
+        m0 = (mn / p.tiles_n) * TC_BM;
+        n0 = (mn % p.tiles_n) * BN;
+        kt0 = split * kt_per_split;
+        kt1 = min(kt_total, kt0 + kt_per_split);
+    };
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int z1, z2, m0, n0, kt0, kt1;
+                decode(tile, z1, z2, m0, n0, kt0, kt1);
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    const int kb = kt / kt_per_kb;
+                    const int k0 = (kt - kb * kt_per_kb) * TC_BK;
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
+                    const uint32_t sb = sa + S::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                    if (A_KC) {
+                        tma_load_5d(sa, &tmA, full_bar(stage), k0, m0, kb * p.cAk, z2 * p.cA2, z1 * p.cA1);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TC_BM / 32; ++j)
+                            tma_load_5d(sa + j * 4096, &tmA, full_bar(stage), m0 + 32 * j, k0, kb * p.cAk, z2 * p.cA2, z1 * p.cA1);
+                    }
+                    if (B_KC) {
+                        tma_load_5d(sb, &tmB, full_bar(stage), k0, n0, kb * p.cBk, z2 * p.cB2, z1 * p.cB1);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j)
+                            tma_load_5d(sb + j * 4096, &tmB, full_bar(stage), n0 + 32 * j, k0, kb * p.cBk, z2 * p.cB2, z1 * p.cB1);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KC ? 0u : 1u) << 15) | ((B_KC ? 0u : 1u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int z1, z2, m0, n0, kt0, kt1;
+                decode(tile, z1, z2, m0, n0, kt0, kt1);
+                if (kt0 >= kt1) continue;  // empty split: nothing to accumulate, epilogue skips it too
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
+                    const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        // K-major : 128B swizzle, 8-row groups 1024 B apart (SBO); a K=8 step advances 32 B inside the row
+                        // MN-major: 128B swizzle with 32B atoms: rows are K indices holding 32 MN-contiguous floats,
+                        //           4-row K groups 512 B apart (SBO), 32-wide MN blocks 4096 B apart (LBO);
+                        //           a K=8 step advances two K groups = 1024 B
+                        const uint64_t da = A_KC ? umma_desc(sa + kk * 32, 16, 1024, 2) : umma_desc(sa + kk * 1024, 4096, 512, 1);
+                        const uint64_t db = B_KC ? umma_desc(sb + kk * 32, 16, 1024, 2) : umma_desc(sb + kk * 1024, 4096, 512, 1);
+                        umma_tf32(tmem_d, da, db, idesc, (kt > kt0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may read: lanes [32q, 32q+32)
+        float* buf = epi_buf + q * (32 * 33);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int z1, z2, m0, n0, kt0, kt1;
+            decode(tile, z1, z2, m0, n0, kt0, kt1);
+            if (kt0 >= kt1) continue;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row_base = m0 + q * 32;
+            if (row_base < p.M) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int col_base = n0 + c * 32;
+                    if (col_base >= p.N) break;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+                    uint32_t r[32];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int col = col_base + lane;
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = row_base + rr;
+                        if (row < p.M && col < p.N) epi(z1, z2, row, col, buf[rr * 33 + lane]);
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = []() -> TmapEncodeFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+        if (q != cudaDriverEntryPointSuccess) return nullptr;
+        return (TmapEncodeFn)p;
+    }();
+    return fn;
+}
+
+inline int sm_count() {
+    static int n = []() {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+}
+
+// Operand as a rank-5 tensor map {inner, outer, KB, Z2, Z1}.  `kc`: K is the contiguous (inner) dimension.
+inline bool make_operand_map(CUtensorMap* map, const float* base, bool kc, int mn, int K, int ld, long long sk, long long s2,
+                             long long s1, int KB, int Z2, int Z1, int box_mn_rows, int* ck, int* c2, int* c1) {
+    TmapEncodeFn enc = tmap_encoder();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3) || (sk & 3) || (s2 & 3) || (s1 & 3)) return false;
+    *ck = (KB > 1 && sk != 0) ? 1 : 0;
+    *c2 = (Z2 > 1 && s2 != 0) ? 1 : 0;
+    *c1 = (Z1 > 1 && s1 != 0) ? 1 : 0;
+    if (KB > 1 && sk == 0) return false;  // a reduction over identical slabs never occurs on this path
+    const cuuint64_t inner = kc ? (cuuint64_t)K : (cuuint64_t)mn;
+    const cuuint64_t outer = kc ? (cuuint64_t)mn : (cuuint64_t)K;
+    const cuuint64_t row_bytes = (cuuint64_t)ld * 4;
+    cuuint64_t dims[5] = {inner, outer, (cuuint64_t)(*ck ? KB : 1), (cuuint64_t)(*c2 ? Z2 : 1), (cuuint64_t)(*c1 ? Z1 : 1)};
+    const cuuint64_t dummy = row_bytes * outer;
+    cuuint64_t strides[4] = {row_bytes, *ck ? (cuuint64_t)sk * 4 : dummy, *c2 ? (cuuint64_t)s2 * 4 : dummy,
+                             *c1 ? (cuuint64_t)s1 * 4 : dummy};
+    for (int i = 0; i < 4; ++i)
+        if (strides[i] == 0 || (strides[i] & 15) || strides[i] >= (1ULL << 40)) return false;
+    cuuint32_t box[5] = {32, (cuuint32_t)(kc ? box_mn_rows : 32), 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kc ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Returns cudaErrorNotSupported when the problem does not meet the TMA alignment rules (caller falls back
+// to the SIMT engine); any other error is a real launch failure.
+template <int BN, bool A_KC, bool B_KC, class Epi>
+inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStream_t st) {
+    if (p.M <= 0 || p.N <= 0 || Z <= 0) return cudaSuccess;
+    const int Z2 = p.Z2 > 0 ? p.Z2 : 1;
+    const int Z1 = (Z + Z2 - 1) / Z2;
+    const int splits = p.splits > 0 ? p.splits : 1;
+    TcP t;
+    t.M = p.M; t.N = p.N; t.K = p.K; t.KB = p.KB; t.Z2 = Z2; t.splits = splits;
+    t.tiles_m = (p.M + TC_BM - 1) / TC_BM;
+    t.tiles_n = (p.N + BN - 1) / BN;
+    const long long total = (long long)t.tiles_m * t.tiles_n * splits * Z;
+    if (total > 2147483647LL) return cudaErrorNotSupported;
+    t.total_tiles = (int)total;
+    CUtensorMap ma, mb;
+    if (!make_operand_map(&ma, p.A, A_KC, p.M, p.K, p.lda, p.sAk, p.sA2, p.sA1, p.KB, Z2, Z1, TC_BM, &t.cAk, &t.cA2, &t.cA1))
+        return cudaErrorNotSupported;
+    if (!make_operand_map(&mb, p.B, B_KC, p.N, p.K, p.ldb, p.sBk, p.sB2, p.sB1, p.KB, Z2, Z1, BN, &t.cBk, &t.cB2, &t.cB1))
+        return cudaErrorNotSupported;
+    using S = TcSmem<BN>;
+    auto kern = gemm_tc_kernel<BN, A_KC, B_KC, Epi>;
+    static bool configured = false;  // one static per template instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int grid = total < sm_count() ? (int)total : sm_count();
+    kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, t, epi);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace matgcn

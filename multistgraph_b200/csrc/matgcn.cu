@@ -11,6 +11,7 @@
 
 #include "../../include/matgcn.h"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 using namespace matgcn;
 
@@ -32,6 +33,21 @@ static int fail(const char* where, const char* what) {
     do {                                            \
         if (!(cond)) return fail(__func__, msg);    \
     } while (0)
+
+// Engine dispatch: fast mode (flags & MATGCN_FLAG_TF32) sends a contraction to the tcgen05/TMA kernel when
+// its operands meet the TMA alignment rules, otherwise (and always in exact mode) to the fp32 SIMT kernel.
+static std::atomic<unsigned long long> g_tc_launches{0};
+template <class Cfg, bool A_KC, bool B_KC, class Epi>
+static cudaError_t gemm_any(bool tc, const GemmP& p, const Epi& epi, int Z, cudaStream_t st) {
+    if (tc && p.K >= 8) {
+        cudaError_t e = (p.N <= 64) ? launch_gemm_tc<64, A_KC, B_KC, Epi>(p, epi, Z, st)
+                                    : launch_gemm_tc<128, A_KC, B_KC, Epi>(p, epi, Z, st);
+        if (e == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != cudaErrorNotSupported) return e;
+    }
+    return launch_gemm<Cfg, A_KC, B_KC, Epi>(p, epi, Z, st);
+}
+extern "C" unsigned long long matgcn_tc_launch_count(void) { return g_tc_launches.load(); }
 
 extern "C" int matgcn_abi_version(void) { return MATGCN_ABI_VERSION; }
 extern "C" const char* matgcn_last_error(void) { return g_err; }
@@ -489,21 +505,50 @@ static int check_layer_dims(int T, int N, int B, int Cin, int H, int K, int ldm)
 }
 
 // Support propagation for a block of Z time steps: dst[z][1..K) = M * src[z][0]   (slot stride U)
-static cudaError_t propagate(const float* M, int ldm, int N, int Kp, const float* slot0, long long zstride, int cols,
+static cudaError_t propagate(bool tc, const float* M, int ldm, int N, int Kp, const float* slot0, long long zstride, int cols,
                              float* slot1, int Z, cudaStream_t st) {
     GemmP p;
     memset(&p, 0, sizeof(p));
     p.KB = 1; p.Z2 = 1; p.splits = 1;
     p.A = M; p.lda = ldm; p.M = Kp * N; p.K = N;
     p.B = slot0; p.ldb = cols; p.N = cols; p.sB1 = zstride;
-    return launch_gemm<CfgBig, true, false>(p, epi_store(slot1, zstride, 0, cols), Z, st);
+    return gemm_any<CfgBig, true, false>(tc, p, epi_store(slot1, zstride, 0, cols), Z, st);
 }
 
 extern "C" int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P,
-                                    void* stream) {
+                                    int flags, void* stream) {
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     REQUIRE(M && X && P, "null pointer");
     REQUIRE(Kp > 0 && N > 0 && cols > 0 && ldm >= N, "bad dims");
-    CK(propagate(M, ldm, N, Kp, X, 0, cols, P, 1, (cudaStream_t)stream));
+    CK(propagate(tc, M, ldm, N, Kp, X, 0, cols, P, 1, (cudaStream_t)stream));
+    return 0;
+}
+
+// Plain C = A*B through either engine, for unit tests of the GEMM kernels (all operand layouts).
+extern "C" int matgcn_gemm_debug(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                                 float* C, int ldc, int splits, int flags, void* stream) {
+    REQUIRE(A && B && C, "null pointer");
+    REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "bad dims");
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1; p.splits = splits;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.M = M; p.N = N; p.K = K;
+    if (splits > 1) {
+        CK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+        EpiAtomic e{C, 0, 0, ldc};
+        if (a_kc && !b_kc) CK((gemm_any<CfgBig, true, false>(tc, p, e, 1, st)));
+        else if (!a_kc && !b_kc) CK((gemm_any<CfgBig, false, false>(tc, p, e, 1, st)));
+        else if (a_kc && b_kc) CK((gemm_any<CfgBig, true, true>(tc, p, e, 1, st)));
+        else return fail(__func__, "layout combination (A M-contiguous, B K-contiguous) is not used on this path");
+    } else {
+        EpiStore e = epi_store(C, 0, 0, ldc);
+        if (a_kc && !b_kc) CK((gemm_any<CfgBig, true, false>(tc, p, e, 1, st)));
+        else if (!a_kc && !b_kc) CK((gemm_any<CfgBig, false, false>(tc, p, e, 1, st)));
+        else if (a_kc && b_kc) CK((gemm_any<CfgBig, true, true>(tc, p, e, 1, st)));
+        else return fail(__func__, "layout combination (A M-contiguous, B K-contiguous) is not used on this path");
+    }
     return 0;
 }
 
@@ -514,7 +559,8 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
                                         const float* x, long long x_tstride, const float* h0, const float* M,
                                         const float* Wg, const float* bg, const float* Wu, const float* bu,
                                         const float* Rgw, const float* Rgb, const float* Ruw, const float* Rub,
-                                        const float* mix, float* ws, void* stream) {
+                                        const float* mix, float* ws, int flags, void* stream) {
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     REQUIRE(x && M && Wg && bg && Wu && bu && Rgw && Rgb && Ruw && Rub && mix && ws, "null pointer");
     if (check_layer_dims(T, N, B, Cin, H, K, ldm)) return -1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -527,7 +573,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     CK(cudaMemcpy2DAsync(PX, sizeof(float) * K * UX, x, sizeof(float) * x_tstride, sizeof(float) * UX, T,
                          cudaMemcpyDeviceToDevice, st));
     // PX[t, 1..K) = M * x_t  (all t at once)
-    CK(propagate(M, ldm, N, Kp, PX, K * UX, B * Cin, PX + UX, T, st));
+    CK(propagate(tc, M, ldm, N, Kp, PX, K * UX, B * Cin, PX + UX, T, st));
 
     GemmP p;
     // GX[t, n, :, 0:2H] = bg[n] + sum_k PX[t,k,n] * Wg[n,k,0:Cin,:]   z = (n, t), k-batches = k
@@ -539,11 +585,11 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         p.B = Wg; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = 0; p.sBk = (long long)I * 2 * H;
         EpiStore e = epi_store(GX, (long long)B * 3 * H, 3 * U, 3 * H);
         e.bias = bg; e.bias_s1 = 2 * H;
-        CK((launch_gemm<CfgMid, true, false>(p, e, N * T, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, e, N * T, st)));
         p.B = Wu; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
         e = epi_store(GX + 2 * H, (long long)B * 3 * H, 3 * U, 3 * H);
         e.bias = bu; e.bias_s1 = H;
-        CK((launch_gemm<CfgMid, true, false>(p, e, N * T, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, e, N * T, st)));
     }
     // RX[t] = x_t * [Rgw[:, 0:Cin]; Ruw[:, 0:Cin]]^T + [Rgb; Rub]          flat rows (n,b), z = t
     memset(&p, 0, sizeof(p));
@@ -553,11 +599,11 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         p.B = Rgw; p.ldb = I; p.N = 2 * H;
         EpiStore e = epi_store(RX, 3 * U, 0, 3 * H);
         e.bias = Rgb; e.bias_s1 = 0;
-        CK((launch_gemm<CfgMid, true, true>(p, e, T, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, e, T, st)));
         p.B = Ruw; p.ldb = I; p.N = H;
         e = epi_store(RX + 2 * H, 3 * U, 0, 3 * H);
         e.bias = Rub; e.bias_s1 = 0;
-        CK((launch_gemm<CfgMid, true, true>(p, e, T, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, e, T, st)));
     }
     // initial state
     if (h0) CK(cudaMemcpyAsync(PH, h0, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
@@ -571,29 +617,29 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         float* HC2t = ws + w.HC2 + t * U; float* ZH2t = ws + w.ZH2 + t * U;
         const float* GXt = GX + (long long)t * 3 * U; const float* RXt = RX + (long long)t * 3 * U;
         // (a) PH[t,1..] = M * h
-        CK(propagate(M, ldm, N, Kp, PHt, 0, B * H, PHt + U, 1, st));
+        CK(propagate(tc, M, ldm, N, Kp, PHt, 0, B * H, PHt + U, 1, st));
         // (b) gate: per node [B, K*H] x [K*H, 2H]
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = K;
         p.A = PHt; p.lda = H; p.sA1 = (long long)B * H; p.sAk = U; p.M = B; p.K = H;
         p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sBk = (long long)I * 2 * H;
-        CK((launch_gemm<CfgMid, true, false>(p, EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H}, N, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H}, N, st)));
         // (c) PZ[t,1..] = M * (z*h)
-        CK(propagate(M, ldm, N, Kp, PZt, 0, B * H, PZt + U, 1, st));
+        CK(propagate(tc, M, ldm, N, Kp, PZt, 0, B * H, PZt + U, 1, st));
         // (d) candidate
         p.A = PZt;
         p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
-        CK((launch_gemm<CfgMid, true, false>(p, EpiCand{GXt, PHt, Rt_, HCt, H1t, B, H}, N, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, EpiCand{GXt, PHt, Rt_, HCt, H1t, B, H}, N, st)));
         // (e) residual gate: [N*B, H] x Rgw[:, Cin:]^T
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = H1t; p.lda = H; p.M = N * B; p.K = H;
         p.B = Rgw + Cin; p.ldb = I; p.N = 2 * H;
-        CK((launch_gemm<CfgMid, true, true>(p, EpiGate{RXt, H1t, Z2t, R2t, ZH2t, 0, H}, 1, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, EpiGate{RXt, H1t, Z2t, R2t, ZH2t, 0, H}, 1, st)));
         // (f) residual candidate + mix -> PH[t+1, 0]
         p.A = ZH2t;
         p.B = Ruw + Cin; p.ldb = I; p.N = H;
-        CK((launch_gemm<CfgMid, true, true>(p, EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H}, 1, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H}, 1, st)));
     }
     return 0;
 }
@@ -608,7 +654,8 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                                         float* dx, float* dh0, float* dM,
                                         float* dWg, float* dbg, float* dWu, float* dbu,
                                         float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
-                                        void* stream) {
+                                        int flags, void* stream) {
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     REQUIRE(dy && M && Wg && Wu && Rgw && Ruw && mix && ws && bws, "null pointer");
     REQUIRE(dx && dM && dWg && dbg && dWu && dbu && dRgw && dRgb && dRuw && dRub && dmix, "null output pointer");
     if (check_layer_dims(T, N, B, Cin, H, K, ldm)) return -1;
@@ -644,37 +691,37 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = DRt + 2 * H; p.lda = 3 * H; p.M = NB; p.K = H;
         p.B = Ruw + Cin; p.ldb = I; p.N = H;
-        CK((launch_gemm<CfgMid, true, false>(p, EpiB1{DH1, DRt, DRES, H1t, Z2t, R2t, HC2t, H}, 1, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, EpiB1{DH1, DRt, DRES, H1t, Z2t, R2t, HC2t, H}, 1, st)));
         // B2: dh1 += da2 [NB,2H] * Rgw[:, Cin:]
         p.A = DRt; p.K = 2 * H;
         p.B = Rgw + Cin;
-        CK((launch_gemm<CfgMid, true, false>(p, EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H}, 1, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H}, 1, st)));
         // B3: DPT[k][n] = dau[n] [B,H] * Wu[n,k,Cin:,:]^T      z = (n, k)
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = K; p.KB = 1;
         p.A = DGt + 2 * H; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.sA2 = 0; p.M = B; p.K = H;
         p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sB2 = (long long)I * H;
-        CK((launch_gemm<CfgMid, true, true>(p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
         if (n_adp) CK(cudaMemcpyAsync(DPZA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
         // B4: dzh = DPT[0] + sum_{k>=1} M_k^T DPT[k]
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
         p.B = DPT + U; p.ldb = B * H; p.N = B * H;
-        CK((launch_gemm<CfgBig, false, false>(p, EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H}, 1, st)));
+        CK((gemm_any<CfgBig, false, false>(tc, p, EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H}, 1, st)));
         // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = K; p.KB = 1;
         p.A = DGt; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
         p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = (long long)I * 2 * H;
-        CK((launch_gemm<CfgMid, true, true>(p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
         if (n_adp) CK(cudaMemcpyAsync(DPHA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
         // B6: carry = DHD + DPT[0] + sum M_k^T DPT[k]
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
         p.B = DPT + U; p.ldb = B * H; p.N = B * H;
-        CK((launch_gemm<CfgBig, false, false>(p, EpiB6{DPT, DHD, DHC, B * H}, 1, st)));
+        CK((gemm_any<CfgBig, false, false>(tc, p, EpiB6{DPT, DHD, DHC, B * H}, 1, st)));
     }
     if (dh0) CK(cudaMemcpyAsync(dh0, DHC, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
 
@@ -685,15 +732,15 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.lda = H; p.sA1 = (long long)B * H; p.sA2 = U; p.sAk = K * U; p.M = H; p.K = B;
     p.ldb = 3 * H; p.sB1 = (long long)B * 3 * H; p.sB2 = 0; p.sBk = 3 * U;
     p.A = PH; p.B = DG; p.N = 2 * H;
-    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
+    CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
     p.A = PZ; p.B = DG + 2 * H; p.N = H;
-    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWu + (long long)Cin * H, (long long)K * I * H, (long long)I * H, H), N * K, st)));
+    CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu + (long long)Cin * H, (long long)K * I * H, (long long)I * H, H), N * K, st)));
     // input rows 0:Cin from PX
     p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
     p.A = PX; p.B = DG; p.N = 2 * H;
-    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
+    CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
     p.B = DG + 2 * H; p.N = H;
-    CK((launch_gemm<CfgMid, false, false>(p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
+    CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
     // bias gradients: column sums over (t, b)
     CK(cudaMemsetAsync(dbg, 0, sizeof(float) * (size_t)N * 2 * H, st));
     CK(cudaMemsetAsync(dbu, 0, sizeof(float) * (size_t)N * H, st));
@@ -721,11 +768,11 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
         p.B = Wg + (long long)k * I * 2 * H; p.ldb = 2 * H; p.N = Cin; p.sB1 = 0; p.sB2 = (long long)K * I * 2 * H;
         EpiStore e = epi_store(DPX + (long long)k * UX, K * UX, (long long)B * Cin, Cin);
-        CK((launch_gemm<CfgMid, true, true>(p, e, T * N, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
         p.A = DG + 2 * H; p.K = H;
         p.B = Wu + (long long)k * I * H; p.ldb = H; p.sB2 = (long long)K * I * H;
         e.accumulate = 1;
-        CK((launch_gemm<CfgMid, true, true>(p, e, T * N, st)));
+        CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
     }
     // dx[t] = DPX[t,0] + sum_{k>=1} M_k^T DPX[t,k] + DR[t][:,0:2H]*Rgw[:,0:Cin] + DR[t][:,2H:]*Ruw[:,0:Cin]
     memset(&p, 0, sizeof(p));
@@ -735,7 +782,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     {
         EpiStore e = epi_store(dx, UX, 0, B * Cin);
         e.add = DPX; e.add_s1 = K * UX; e.add_ld = B * Cin;
-        CK((launch_gemm<CfgBig, false, false>(p, e, T, st)));
+        CK((gemm_any<CfgBig, false, false>(tc, p, e, T, st)));
     }
     memset(&p, 0, sizeof(p));
     p.splits = 1; p.Z2 = 1; p.KB = 1;
@@ -744,9 +791,9 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     {
         EpiStore e = epi_store(dx, UX, 0, Cin);
         e.accumulate = 1;
-        CK((launch_gemm<CfgMid, true, false>(p, e, T, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
         p.A = DR + 2 * H; p.K = H; p.B = Ruw;
-        CK((launch_gemm<CfgMid, true, false>(p, e, T, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
     }
     // dM[a] = sum_t DPHA[t,a] PH[t,0]^T + DPZA[t,a] PZ[t,0]^T + DPX[t,a+1] PX[t,0]^T     (split-K, atomics)
     CK(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)Kp * N * ldm, st));
@@ -757,12 +804,12 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.K = B * H; p.lda = B * H; p.ldb = B * H;
         p.splits = T;
         p.A = DPHA + (long long)a * U; p.sAk = (long long)n_adp * U; p.B = PH; p.sBk = K * U;
-        CK((launch_gemm<CfgBig, true, true>(p, ea, 1, st)));
+        CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
         p.A = DPZA + (long long)a * U; p.B = PZ;
-        CK((launch_gemm<CfgBig, true, true>(p, ea, 1, st)));
+        CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
         p.K = B * Cin; p.lda = B * Cin; p.ldb = B * Cin;
         p.A = DPX + (long long)(a + 1) * UX; p.sAk = K * UX; p.B = PX; p.sBk = K * UX;
-        CK((launch_gemm<CfgBig, true, true>(p, ea, 1, st)));
+        CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
     }
     // residual GRU weights: dRgw[:, Cin:] = sum DR[:,0:2H]^T H1 ; dRgw[:, 0:Cin] = sum DR[:,0:2H]^T x ; same for Ruw
     CK(cudaMemsetAsync(dRgw, 0, sizeof(float) * (size_t)2 * H * I, st));
@@ -776,15 +823,15 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.splits = splits;
         // gate, hidden columns
         p.A = DR; p.M = 2 * H; p.B = ws + w.H1; p.ldb = H; p.sBk = U; p.N = H;
-        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRgw + Cin, 0, 0, I}, 1, st)));
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRgw + Cin, 0, 0, I}, 1, st)));
         // candidate, hidden columns
         p.A = DR + 2 * H; p.M = H; p.B = ws + w.ZH2;
-        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRuw + Cin, 0, 0, I}, 1, st)));
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw + Cin, 0, 0, I}, 1, st)));
         // input columns
         p.B = PX; p.ldb = Cin; p.sBk = K * UX; p.N = Cin;
-        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRuw, 0, 0, I}, 1, st)));
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw, 0, 0, I}, 1, st)));
         p.A = DR; p.M = 2 * H;
-        CK((launch_gemm<CfgMid, false, false>(p, EpiAtomic{dRgw, 0, 0, I}, 1, st)));
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRgw, 0, 0, I}, 1, st)));
     }
     return 0;
 }

@@ -119,6 +119,12 @@ class MultiATGCN(nn.Module):
         self.gcn_off = g("gcn_off", False)
         self.hidden_dim = g("rnn_units", 64)
         self.num_layers = g("num_layers", 2)
+        # extra key of this implementation (absent from the reference): arithmetic of the contractions.
+        # "exact" = fp32 FFMA kernels (1e-4 parity); "tf32"/"fast" = tcgen05 tensor cores, looser bound.
+        mode = g("matgcn_mode", "exact")
+        if mode not in ops.MODES:
+            raise ValueError("matgcn_mode must be one of %s, got %r" % (sorted(ops.MODES), mode))
+        self.matgcn_flags = ops.MODES[mode]
         if self.adpadj not in ("bidirection", "unidirection", "none"):
             raise ValueError("adpadj must be bidirection/unidirection/none, got %r" % (self.adpadj,))
         n = self.num_nodes
@@ -281,7 +287,7 @@ class MultiATGCN(nn.Module):
             w_u, b_u = ops.node_weights(self.node_emb, pool_u, cell.update.bias_pool, c_u)
             cur = ops.encoder_layer(cur, None, bases, w_g, b_g, w_u, b_u,
                                     res.gate.weight, res.gate.bias, res.update.weight, res.update.bias,
-                                    mix[layer], n_adp)
+                                    mix[layer], n_adp, self.matgcn_flags)
         return cur
 
     def forward(self, batch):

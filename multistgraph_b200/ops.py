@@ -95,7 +95,7 @@ class _NodeWeightsFn(torch.autograd.Function):
 
 class _EncoderLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp):
+    def forward(ctx, x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags):
         if not x.is_cuda or x.dtype != torch.float32:
             raise _cabi.MatgcnError("encoder_layer: x must be a float32 CUDA tensor (no CPU path)")
         T, N, B, Cin = x.shape
@@ -119,12 +119,12 @@ class _EncoderLayerFn(torch.autograd.Function):
         ws = torch.empty(L.matgcn_encoder_layer_fwd_ws_bytes(*dims) // 4, device=x.device, dtype=torch.float32)
         _cabi.check(L.matgcn_encoder_layer_fwd(*dims, ldm, _ptr(x), x.stride(0), _ptr(h0), _ptr(M), _ptr(Wg), _ptr(bg),
                                                _ptr(Wu), _ptr(bu), _ptr(Rgw), _ptr(Rgb), _ptr(Ruw), _ptr(Rub),
-                                               _ptr(mix), _ptr(ws), _stream()), "matgcn_encoder_layer_fwd")
+                                               _ptr(mix), _ptr(ws), int(flags), _stream()), "matgcn_encoder_layer_fwd")
         y = torch.as_strided(ws, (T, N, B, H), (L.matgcn_encoder_layer_y_tstride(*dims), B * H, H, 1),
                              L.matgcn_encoder_layer_y_offset(*dims))
         ctx.save_for_backward(M, Wg, Wu, Rgw, Ruw, mix)
         ctx.ws = ws
-        ctx.dims, ctx.ldm, ctx.n_adp, ctx.has_h0 = dims, ldm, int(n_adp), h0 is not None
+        ctx.dims, ctx.ldm, ctx.n_adp, ctx.has_h0, ctx.flags = dims, ldm, int(n_adp), h0 is not None, int(flags)
         return y
 
     @staticmethod
@@ -148,9 +148,9 @@ class _EncoderLayerFn(torch.autograd.Function):
                                                _ptr(Wg), _ptr(Wu), _ptr(Rgw), _ptr(Ruw), _ptr(mix), _ptr(ctx.ws),
                                                _ptr(bws), _ptr(dx), _ptr(dh0), _ptr(dM), _ptr(dWg), _ptr(dbg),
                                                _ptr(dWu), _ptr(dbu), _ptr(dRgw), _ptr(dRgb), _ptr(dRuw), _ptr(dRub),
-                                               _ptr(dmix), _stream()), "matgcn_encoder_layer_bwd")
+                                               _ptr(dmix), ctx.flags, _stream()), "matgcn_encoder_layer_bwd")
         ctx.ws = None  # GX/RX slots now hold gradients: the workspace is spent
-        return dx, dh0, dM, dWg, dbg, dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, None
+        return dx, dh0, dM, dWg, dbg, dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, None, None
 
 
 def adaptive_adjacency(L, Rt, ldm):
@@ -163,6 +163,10 @@ def node_weights(E, pool, bias_pool, c):
     return _NodeWeightsFn.apply(E, pool, bias_pool, c)
 
 
-def encoder_layer(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp):
-    """x [T,N,B,Cin] node-major -> y [T,N,B,H] (a strided view into the layer's workspace)."""
-    return _EncoderLayerFn.apply(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp)
+def encoder_layer(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags=0):
+    """x [T,N,B,Cin] node-major -> y [T,N,B,H] (a strided view into the layer's workspace).
+    flags: _cabi.FLAG_EXACT (fp32 FFMA) or _cabi.FLAG_TF32 (tcgen05 tensor cores)."""
+    return _EncoderLayerFn.apply(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags)
+
+
+MODES = {"exact": _cabi.FLAG_EXACT, "fp32": _cabi.FLAG_EXACT, "fast": _cabi.FLAG_TF32, "tf32": _cabi.FLAG_TF32}

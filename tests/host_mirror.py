@@ -226,7 +226,7 @@ def install(ops_module):
     """Point the three autograd entry points of ``multistgraph_b200.ops`` at the mirror
     (tests only; returns a restore callable)."""
     saved = (ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights)
-    ops_module.encoder_layer = lambda *a: MirrorLayerFn.apply(*a)
+    ops_module.encoder_layer = lambda *a: MirrorLayerFn.apply(*a[:13])
     ops_module.adaptive_adjacency = lambda L, Rt, ldm: MirrorAdjFn.apply(L, Rt, ldm)
     ops_module.node_weights = lambda E, pool, bp, c: MirrorNodeWeightsFn.apply(E, pool, bp, c)
 

@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 ACCEL = [n for n in golden_names() if n != "gcn_off"]
 DEV = "cuda:0"
+FLAGS = 0  # exact mode
 
 
 def _rand(*shape, seed=0, scale=1.0):
@@ -108,7 +109,7 @@ def test_encoder_layer_op_buffers(T, N, B, Cin, H, Kp, n_adp, with_h0):
     ws = torch.zeros(L.matgcn_encoder_layer_fwd_ws_bytes(*dims) // 4, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
     _cabi.check(L.matgcn_encoder_layer_fwd(*dims, ldm, p(xd), xd.stride(0), p(h0d), p(Md), p(Wgd), p(bgd), p(Wud),
-                                           p(bud), p(Rgwd), p(Rgbd), p(Ruwd), p(Rubd), p(mixd), p(ws), st), "fwd")
+                                           p(bud), p(Rgwd), p(Rgbd), p(Ruwd), p(Rubd), p(mixd), p(ws), FLAGS, st), "fwd")
     torch.cuda.synchronize()
 
     def slot(name, shape):
@@ -137,7 +138,7 @@ def test_encoder_layer_op_buffers(T, N, B, Cin, H, Kp, n_adp, with_h0):
     dRgw, dRgb, dRuw, dRub, dmix = new(2 * H, I), new(2 * H), new(H, I), new(H), new(T)
     _cabi.check(L.matgcn_encoder_layer_bwd(*dims, ldm, n_adp, p(dYd), dYd.stride(0), p(Md), p(Wgd), p(Wud), p(Rgwd),
                                            p(Ruwd), p(mixd), p(ws), p(bws), p(dx), p(dh0), p(dM), p(dWg), p(dbg),
-                                           p(dWu), p(dbu), p(dRgw), p(dRgb), p(dRuw), p(dRub), p(dmix), st), "bwd")
+                                           p(dWu), p(dbu), p(dRgw), p(dRgb), p(dRuw), p(dRub), p(dmix), FLAGS, st), "bwd")
     torch.cuda.synchronize()
     errs = {"DG": max_rel_err(slot("GX", (T, N, B, 3 * H)), g_ref["DG"]),
             "DR": max_rel_err(slot("RX", (T, N, B, 3 * H)), g_ref["DR"]),
