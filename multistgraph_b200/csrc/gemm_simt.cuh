@@ -20,6 +20,9 @@ namespace matgcn {
 inline std::atomic<unsigned long long> g_launches{0};
 inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// values an epilogue reads from global memory for one output element (see the epilogue section of matgcn.cu)
+struct EpiIn { float a, b, c, d, e, f; };
+
 struct GemmP {
     const float* A;
     const float* B;

@@ -27,7 +27,8 @@ namespace matgcn {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // fp32 elements per K slab = one 128-byte swizzle row
-constexpr int TC_THREADS = 256;
+constexpr int TC_EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each taking every other 32-column chunk
+constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;
 
 struct TcP {
     int M, N, K, KB, Z2, splits;
@@ -109,7 +110,7 @@ struct TcSmem {
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
-    static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;  // 4 epilogue warps x [32][33] floats
+    static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * 33 * 4;  // per epilogue warp: [32][33] floats
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
@@ -145,7 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);
+            mbar_init(tempty_bar(a), TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -251,8 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may read: lanes [32q, 32q+32)
-        float* buf = epi_buf + q * (32 * 33);
+        const int q = warp & 3;             // TMEM lane quadrant this warp may read: lanes [32q, 32q+32)
+        const int half = (warp - 4) >> 2;   // which of the two warps of that quadrant (column-chunk parity)
+        float* buf = epi_buf + (warp - 4) * (32 * 33);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -264,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int row_base = m0 + q * 32;
             if (row_base < p.M) {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
                     const int col_base = n0 + c * 32;
                     if (col_base >= p.N) break;
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
@@ -283,10 +285,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(r[j]);
                     __syncwarp();
                     const int col = col_base + lane;
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int row = row_base + rr;
-                        if (row < p.M && col < p.N) epi(z1, z2, row, col, buf[rr * 33 + lane]);
+                    const bool col_ok = col < p.N;
+                    // batches of 8 rows: all global reads of the batch are issued before any is consumed
+#pragma unroll 1
+                    for (int rr0 = 0; rr0 < 32; rr0 += 8) {
+                        EpiIn in[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int row = row_base + rr0 + u;
+                            if (col_ok && row < p.M) in[u] = epi.load(z1, z2, row, col);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int row = row_base + rr0 + u;
+                            if (col_ok && row < p.M) epi.store(z1, z2, row, col, buf[(rr0 + u) * 33 + lane], in[u]);
+                        }
                     }
                     __syncwarp();
                 }

@@ -57,8 +57,21 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 
 // ------------------------------------------------------------------------------------------
 // epilogues
+//
+// Every epilogue is split in two phases so that the tensor-core kernel (few epilogue warps, no
+// thread-level parallelism to hide latency) can issue the global loads of a whole batch of output
+// elements before consuming any of them:
+//   EpiIn in = epi.load(z1, z2, row, col);      // every global read the element needs
+//   epi.store(z1, z2, row, col, acc, in);       // arithmetic + global writes
+// operator() = store(load()) is what the SIMT kernel calls.
 // ------------------------------------------------------------------------------------------
-// C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col]
+
+#define EPI_CALL_OPERATOR                                                                              \
+    __device__ __forceinline__ void operator()(int z1, int z2, int row, int col, float acc) const {    \
+        store(z1, z2, row, col, acc, load(z1, z2, row, col));                                          \
+    }
+
+// C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col] + add[...]
 struct EpiStore {
     float* C;
     long long s1, s2;
@@ -71,15 +84,23 @@ struct EpiStore {
     const float* add;    // may be null: extra addend with C's indexing (offsets add_s1/add_s2, ld add_ld)
     long long add_s1, add_s2;
     int add_ld;
-    __device__ __forceinline__ void operator()(int z1, int z2, int row, int col, float acc) const {
-        float v = acc;
-        if (scale) v *= __ldg(scale + col / scale_div);
-        if (bias) v += __ldg(bias + z1 * bias_s1 + col);
-        if (add) v += add[z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col];
-        float* dst = C + z1 * s1 + z2 * s2 + (long long)row * ldc + col;
-        if (accumulate) v += *dst;
-        *dst = v;
+    __device__ __forceinline__ EpiIn load(int z1, int z2, int row, int col) const {
+        EpiIn in;
+        in.a = scale ? __ldg(scale + col / scale_div) : 1.f;
+        in.b = bias ? __ldg(bias + z1 * bias_s1 + col) : 0.f;
+        in.c = add ? add[z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col] : 0.f;
+        in.d = accumulate ? C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] : 0.f;
+        return in;
     }
+    __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn& in) const {
+        float v = acc;
+        if (scale) v *= in.a;
+        if (bias) v += in.b;
+        if (add) v += in.c;
+        if (accumulate) v += in.d;
+        C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = v;
+    }
+    EPI_CALL_OPERATOR
 };
 static EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
     EpiStore e;
@@ -92,97 +113,152 @@ struct EpiAtomic {  // split-K partial sums into a zeroed C
     float* C;
     long long s1, s2;
     int ldc;
-    __device__ __forceinline__ void operator()(int z1, int z2, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int, int, int, int) const { return EpiIn{}; }
+    __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn&) const {
         atomicAdd(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, acc);
     }
+    EPI_CALL_OPERATOR
 };
 
-// Forward step epilogues.  grow = z1*rows_per_z + row indexes (node, batch) pairs; activations
+// Forward step epilogues.  g = z1*rows_per_z + row indexes (node, batch) pairs; activations
 // are [N*B, H] blocks, pre-activation inputs [N*B, 3H] blocks.
 struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (cols >= H): R
     const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
     int rows_per_z, H;
-    __device__ __forceinline__ void operator()(int z1, int, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int z1, int, int row, int col) const {
         const long long g = (long long)z1 * rows_per_z + row;
-        const float s = sigmoidf_(acc + GX[g * 3 * H + col]);
+        EpiIn in;
+        in.a = GX[g * 3 * H + col];
+        in.b = col < H ? Hprev[g * H + col] : 0.f;
+        return in;
+    }
+    __device__ __forceinline__ void store(int z1, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float s = sigmoidf_(acc + in.a);
         if (col < H) {
             Z[g * H + col] = s;
-            ZH[g * H + col] = s * Hprev[g * H + col];
+            ZH[g * H + col] = s * in.b;
         } else {
             R[g * H + col - H] = s;
         }
     }
+    EPI_CALL_OPERATOR
 };
 struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
     int rows_per_z, H;
-    __device__ __forceinline__ void operator()(int z1, int, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int z1, int, int row, int col) const {
         const long long g = (long long)z1 * rows_per_z + row;
-        const float hc = tanhf(acc + GX[g * 3 * H + 2 * H + col]);
-        const float r = R[g * H + col], h = Hprev[g * H + col];
-        HC[g * H + col] = hc;
-        H1[g * H + col] = r * h + (1.f - r) * hc;
+        EpiIn in;
+        in.a = GX[g * 3 * H + 2 * H + col];
+        in.b = R[g * H + col];
+        in.c = Hprev[g * H + col];
+        return in;
     }
+    __device__ __forceinline__ void store(int z1, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float hc = tanhf(acc + in.a);
+        HC[g * H + col] = hc;
+        H1[g * H + col] = in.b * in.c + (1.f - in.b) * hc;
+    }
+    EPI_CALL_OPERATOR
 };
 struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r2)*hc2)
     const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
     int H;
-    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long g = row;
-        const float hc2 = tanhf(acc + RX[g * 3 * H + 2 * H + col]);
-        const float r2 = R2[g * H + col], h1 = H1[g * H + col];
+        EpiIn in;
+        in.a = RX[g * 3 * H + 2 * H + col];
+        in.b = R2[g * H + col];
+        in.c = H1[g * H + col];
+        in.d = __ldg(mix_t);
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long g = row;
+        const float hc2 = tanhf(acc + in.a);
+        const float r2 = in.b, h1 = in.c, m = in.d;
         const float res = r2 * h1 + (1.f - r2) * hc2;
-        const float m = __ldg(mix_t);
         HC2[g * H + col] = hc2;
         Y[g * H + col] = m * h1 + (1.f - m) * res;
     }
+    EPI_CALL_OPERATOR
 };
 
 // Backward step epilogues (notation of DESIGN.md section 3 / tests/host_mirror.py).
 struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR[H:2H] = dres*(h1-hc2)*r2(1-r2)
     float* DH1; float* DR; const float* DRES; const float* H1; const float* Z2; const float* R2; const float* HC2;
     int H;
-    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long i = (long long)row * H + col;
-        const float z2 = Z2[i], r2 = R2[i], h1 = H1[i];
-        DH1[i] += acc * z2;
-        DR[(long long)row * 3 * H + col] = acc * h1 * z2 * (1.f - z2);
-        DR[(long long)row * 3 * H + H + col] = DRES[i] * (h1 - HC2[i]) * r2 * (1.f - r2);
+        EpiIn in;
+        in.a = Z2[i]; in.b = R2[i]; in.c = H1[i]; in.d = DH1[i]; in.e = DRES[i]; in.f = HC2[i];
+        return in;
     }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * H + col;
+        const float z2 = in.a, r2 = in.b, h1 = in.c;
+        DH1[i] = in.d + acc * z2;
+        DR[(long long)row * 3 * H + col] = acc * h1 * z2 * (1.f - z2);
+        DR[(long long)row * 3 * H + H + col] = in.e * (h1 - in.f) * r2 * (1.f - r2);
+    }
+    EPI_CALL_OPERATOR
 };
 struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
     const float* DH1; const float* Hprev; const float* R; const float* HC; float* DHD; float* DG;
     int H;
-    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long i = (long long)row * H + col;
-        const float dh1 = DH1[i] + acc;
-        const float r = R[i], hc = HC[i], h = Hprev[i];
+        EpiIn in;
+        in.a = DH1[i]; in.b = R[i]; in.c = HC[i]; in.d = Hprev[i];
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * H + col;
+        const float dh1 = in.a + acc;
+        const float r = in.b, hc = in.c, h = in.d;
         DHD[i] = dh1 * r;
         DG[(long long)row * 3 * H + 2 * H + col] = dh1 * (1.f - r) * (1.f - hc * hc);
         DG[(long long)row * 3 * H + H + col] = dh1 * (h - hc) * r * (1.f - r);
     }
+    EPI_CALL_OPERATOR
 };
 struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      (row = node m, col = (b,c))
     const float* DP0; const float* Hprev; const float* Z; float* DHD; float* DG;
     int H, BH;  // BH = B*H columns per node
-    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long i = (long long)row * BH + col;
-        const float dzh = acc + DP0[i];
-        const float z = Z[i];
-        DHD[i] += dzh * z;
+        EpiIn in;
+        in.a = DP0[i]; in.b = Z[i]; in.c = DHD[i]; in.d = Hprev[i];
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * BH + col;
+        const float dzh = acc + in.a;
+        const float z = in.b;
+        DHD[i] = in.c + dzh * z;
         const long long g = i / H;
         const int c = (int)(i - g * H);
-        DG[g * 3 * H + c] = dzh * Hprev[i] * z * (1.f - z);
+        DG[g * 3 * H + c] = dzh * in.d * z * (1.f - z);
     }
+    EPI_CALL_OPERATOR
 };
 
 struct EpiB6 {  // carry = acc + DP0 + DHD
     const float* DP0; const float* DHD; float* OUT;
     int BH;
-    __device__ __forceinline__ void operator()(int, int, int row, int col, float acc) const {
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long i = (long long)row * BH + col;
-        OUT[i] = acc + DP0[i] + DHD[i];
+        EpiIn in;
+        in.a = DP0[i]; in.b = DHD[i];
+        return in;
     }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * BH + col;
+        OUT[i] = acc + in.a + in.b;
+    }
+    EPI_CALL_OPERATOR
 };
 
 // ------------------------------------------------------------------------------------------
