@@ -87,6 +87,12 @@ int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_
 int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P, int flags,
                          void* stream);
 
+/* Diagnostics: device buffer (int64, >= 8 per tile of CTA 0) that later tensor-core launches fill with clock64()
+ * stamps [producer start, mma wait, mma start, mma committed, epilogue wait, epilogue start, epilogue end]; NULL disables. */
+int matgcn_debug_set_timeline(long long* buf);
+/* Diagnostics: bit 0 = tensor-core epilogue skips its global stores, bit 1 = skips the smem transpose (results invalid). */
+int matgcn_debug_set_mode(int mode);
+
 /* Diagnostics: plain C[M,N] = A*B through the selected engine, for unit tests of the GEMM kernels.
  * a_kc: A element (m,k) at m*lda+k (else k*lda+m); b_kc: B element (k,n) at n*ldb+k (else k*ldb+n).
  * splits > 1 exercises the split-K / atomic epilogue. */

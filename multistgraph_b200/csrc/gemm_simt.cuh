@@ -11,6 +11,7 @@
 // (the reduction runs over KB strided slabs of inner length K).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include <atomic>
 
@@ -22,6 +23,12 @@ inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed);
 
 // values an epilogue reads from global memory for one output element (see the epilogue section of matgcn.cu)
 struct EpiIn { float a, b, c, d, e, f; };
+// the same for four consecutive output columns (vectorised tensor-core epilogue)
+struct EpiIn4 { float4 a, b, c, d, e, f; };
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 struct GemmP {
     const float* A;

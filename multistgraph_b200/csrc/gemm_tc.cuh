@@ -36,6 +36,9 @@ struct TcP {
     int total_tiles;        // Z * splits * tiles_m * tiles_n
     int cA1, cA2, cAk;      // 1 if the operand really has that (strided) dimension, else coordinate 0
     int cB1, cB2, cBk;
+    int vec;                // 1: N % 4 == 0 and the epilogue's pointers/pitches allow 16-byte accesses
+    int dbg_mode;           // diagnostics only: 1 = skip epilogue stores
+    long long* dbg;         // optional per-tile timeline of CTA 0 (tools/tc_timeline.py); null in production
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -87,6 +90,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -110,7 +121,8 @@ struct TcSmem {
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
-    static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * 33 * 4;  // per epilogue warp: [32][33] floats
+    static constexpr int EPI_LD = 36;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 access
+    static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_LD * 4;  // per epilogue warp: [32][36] floats
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
@@ -123,9 +135,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p, const Epi epi) {
     using S = TcSmem<BN>;
     constexpr int STAGES = S::STAGES;
-    extern __shared__ uint8_t smem_raw[];
-    // 128B-swizzled tiles need 1024-byte alignment
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 128B-swizzled tiles need 1024-byte alignment; keep the pointer derived from the __shared__ symbol so that
+    // the epilogue's staging accesses compile to LDS/STS instead of generic loads/stores
+    uint8_t* smem = smem_raw;
+    if (smem_u32(smem) & 1023u) __trap();
     uint8_t* stage_base = smem;
     float* epi_buf = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
@@ -186,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int z1, z2, m0, n0, kt0, kt1;
                 decode(tile, z1, z2, m0, n0, kt0, kt1);
+                if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
                 for (int kt = kt0; kt < kt1; ++kt) {
                     const int kb = kt / kt_per_kb;
                     const int k0 = (kt - kb * kt_per_kb) * TC_BK;
@@ -225,8 +240,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int z1, z2, m0, n0, kt0, kt1;
                 decode(tile, z1, z2, m0, n0, kt0, kt1);
                 if (kt0 >= kt1) continue;  // empty split: nothing to accumulate, epilogue skips it too
+                if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 1] = clock64();
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
+                if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 2] = clock64();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 for (int kt = kt0; kt < kt1; ++kt) {
                     mbar_wait(full_bar(stage), phase);
@@ -247,6 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tfull_bar(acc));  // accumulator complete
+                if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -254,15 +272,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ================================ epilogue ================================
         const int q = warp & 3;             // TMEM lane quadrant this warp may read: lanes [32q, 32q+32)
         const int half = (warp - 4) >> 2;   // which of the two warps of that quadrant (column-chunk parity)
-        float* buf = epi_buf + (warp - 4) * (32 * 33);
+        float* buf = epi_buf + (warp - 4) * (32 * S::EPI_LD);  // staging tile [32][EPI_LD] of this warp
+        constexpr int LD = S::EPI_LD;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             int z1, z2, m0, n0, kt0, kt1;
             decode(tile, z1, z2, m0, n0, kt0, kt1);
             if (kt0 >= kt1) continue;
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
             const int row_base = m0 + q * 32;
             if (row_base < p.M) {
 #pragma unroll 1
@@ -281,24 +302,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // lane = accumulator row: park the 32 columns of that row in the staging tile
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(buf + lane * LD + 4 * j) =
+                            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                        __uint_as_float(r[4 * j + 3]));
                     __syncwarp();
-                    const int col = col_base + lane;
-                    const bool col_ok = col < p.N;
-                    // batches of 8 rows: all global reads of the batch are issued before any is consumed
+                    if (p.vec) {
+                        // lane -> (row = 4*it + lane/8, columns 4*(lane%8) .. +3): one 16-byte access per lane, 4 rows of
+                        // 128 contiguous bytes per warp instruction; loads of a batch are issued before any is consumed
+                        const int rq = lane >> 3, cq = lane & 7;
+                        const int col = col_base + 4 * cq;
+                        const bool col_ok = col < p.N;
 #pragma unroll 1
-                    for (int rr0 = 0; rr0 < 32; rr0 += 8) {
-                        EpiIn in[8];
+                        for (int it0 = 0; it0 < 8; it0 += 2) {
+                            EpiIn4 in[2];
+                            float4 v[2];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int row = row_base + rr0 + u;
-                            if (col_ok && row < p.M) in[u] = epi.load(z1, z2, row, col);
+                            for (int u = 0; u < 2; ++u) {
+                                const int rl = 4 * (it0 + u) + rq;
+                                v[u] = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
+                                if (col_ok && row_base + rl < p.M) in[u] = epi.load4(z1, z2, row_base + rl, col);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int rl = 4 * (it0 + u) + rq;
+                                if (col_ok && row_base + rl < p.M && !(p.dbg_mode & 1)) epi.store4(z1, z2, row_base + rl, col, v[u], in[u]);
+                            }
                         }
+                    } else {
+                        const int col = col_base + lane;
+                        const bool col_ok = col < p.N;
+#pragma unroll 1
+                        for (int rr0 = 0; rr0 < 32; rr0 += 8) {
+                            EpiIn in[8];
+                            float v[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int row = row_base + rr0 + u;
-                            if (col_ok && row < p.M) epi.store(z1, z2, row, col, buf[(rr0 + u) * 33 + lane], in[u]);
+                            for (int u = 0; u < 8; ++u) {
+                                const int row = row_base + rr0 + u;
+                                v[u] = buf[(rr0 + u) * LD + lane];
+                                if (col_ok && row < p.M) in[u] = epi.load(z1, z2, row, col);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int row = row_base + rr0 + u;
+                                if (col_ok && row < p.M) epi.store(z1, z2, row, col, v[u], in[u]);
+                            }
                         }
                     }
                     __syncwarp();
@@ -306,6 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -335,6 +386,17 @@ inline TmapEncodeFn tmap_encoder() {
         return (TmapEncodeFn)p;
     }();
     return fn;
+}
+
+// Debug hook: when set (matgcn_debug_set_timeline), CTA 0 of every tensor-core launch writes clock64() stamps.
+inline long long*& tc_debug_buffer() {
+    static long long* p = nullptr;
+    return p;
+}
+
+inline int& tc_debug_mode() {
+    static int m = 0;
+    return m;
 }
 
 inline int sm_count() {
@@ -390,6 +452,9 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     const long long total = (long long)t.tiles_m * t.tiles_n * splits * Z;
     if (total > 2147483647LL) return cudaErrorNotSupported;
     t.total_tiles = (int)total;
+    t.vec = ((p.N & 3) == 0 && epi.vec_ok()) ? 1 : 0;
+    t.dbg = tc_debug_buffer();
+    t.dbg_mode = tc_debug_mode();
     CUtensorMap ma, mb;
     if (!make_operand_map(&ma, p.A, A_KC, p.M, p.K, p.lda, p.sAk, p.sA2, p.sA1, p.KB, Z2, Z1, TC_BM, &t.cAk, &t.cA2, &t.cA1))
         return cudaErrorNotSupported;
