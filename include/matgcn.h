@@ -90,6 +90,8 @@ int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X,
 /* Diagnostics: device buffer (int64, >= 8 per tile of CTA 0) that later tensor-core launches fill with clock64()
  * stamps [producer start, mma wait, mma start, mma committed, epilogue wait, epilogue start, epilogue end]; NULL disables. */
 int matgcn_debug_set_timeline(long long* buf);
+/* Diagnostics: record the timeline only for the tensor-core launch that follows `launches` others. */
+int matgcn_debug_set_timeline_skip(int launches);
 /* Diagnostics: bit 0 = tensor-core epilogue skips its global stores, bit 1 = skips the smem transpose (results invalid). */
 int matgcn_debug_set_mode(int mode);
 

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "matgcn_propagate_fwd": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_int, c_void_p]),
     "matgcn_debug_set_timeline": (c_int, [c_void_p]),
     "matgcn_debug_set_mode": (c_int, [c_int]),
+    "matgcn_debug_set_timeline_skip": (c_int, [c_int]),
     "matgcn_gemm_debug": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, c_int, _F, c_int, _F, c_int, c_int, c_int,
                                   c_void_p]),
     "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),

@@ -54,6 +54,13 @@ extern "C" const char* matgcn_last_error(void) { return g_err; }
 extern "C" unsigned long long matgcn_launch_count(void) { return g_launches.load(); }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+// fast-mode activations (SFU approximations, relative error ~2^-11: the same order as the TF32 products they follow)
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float tanh_fast(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------
 // epilogues
@@ -76,8 +83,14 @@ __device__ __forceinline__ float4 operator-(const float4& a, const float4& b) { 
 __device__ __forceinline__ float4 operator*(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 operator*(float a, const float4& b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
 __device__ __forceinline__ float4 one_minus(const float4& a) { return make_float4(1.f - a.x, 1.f - a.y, 1.f - a.z, 1.f - a.w); }
-__device__ __forceinline__ float4 sigmoid4(const float4& a) { return make_float4(sigmoidf_(a.x), sigmoidf_(a.y), sigmoidf_(a.z), sigmoidf_(a.w)); }
-__device__ __forceinline__ float4 tanh4(const float4& a) { return make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w)); }
+__device__ __forceinline__ float4 sigmoid4(const float4& a, int fast) {
+    return fast ? make_float4(sigmoid_fast(a.x), sigmoid_fast(a.y), sigmoid_fast(a.z), sigmoid_fast(a.w))
+                : make_float4(sigmoidf_(a.x), sigmoidf_(a.y), sigmoidf_(a.z), sigmoidf_(a.w));
+}
+__device__ __forceinline__ float4 tanh4(const float4& a, int fast) {
+    return fast ? make_float4(tanh_fast(a.x), tanh_fast(a.y), tanh_fast(a.z), tanh_fast(a.w))
+                : make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
+}
 
 // C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col] + add[...]
 struct EpiStore {
@@ -158,7 +171,7 @@ struct EpiAtomic {  // split-K partial sums into a zeroed C
 // are [N*B, H] blocks, pre-activation inputs [N*B, 3H] blocks.
 struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (cols >= H): R
     const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
-    int rows_per_z, H;
+    int rows_per_z, H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(Z) && aligned16(R) && aligned16(ZH); }
     __device__ __forceinline__ EpiIn load(int z1, int, int row, int col) const {
         const long long g = (long long)z1 * rows_per_z + row;
@@ -169,7 +182,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
     }
     __device__ __forceinline__ void store(int z1, int, int row, int col, float acc, const EpiIn& in) const {
         const long long g = (long long)z1 * rows_per_z + row;
-        const float s = sigmoidf_(acc + in.a);
+        const float s = fast ? sigmoid_fast(acc + in.a) : sigmoidf_(acc + in.a);
         if (col < H) {
             Z[g * H + col] = s;
             ZH[g * H + col] = s * in.b;
@@ -186,7 +199,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
     }
     __device__ __forceinline__ void store4(int z1, int, int row, int col, const float4& acc, const EpiIn4& in) const {
         const long long g = (long long)z1 * rows_per_z + row;
-        const float4 s = sigmoid4(acc + in.a);
+        const float4 s = sigmoid4(acc + in.a, fast);
         if (col < H) {
             st4(Z + g * H + col, s);
             st4(ZH + g * H + col, s * in.b);
@@ -198,7 +211,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
 };
 struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
-    int rows_per_z, H;
+    int rows_per_z, H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(H1); }
     __device__ __forceinline__ EpiIn load(int z1, int, int row, int col) const {
         const long long g = (long long)z1 * rows_per_z + row;
@@ -210,7 +223,7 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     }
     __device__ __forceinline__ void store(int z1, int, int row, int col, float acc, const EpiIn& in) const {
         const long long g = (long long)z1 * rows_per_z + row;
-        const float hc = tanhf(acc + in.a);
+        const float hc = fast ? tanh_fast(acc + in.a) : tanhf(acc + in.a);
         HC[g * H + col] = hc;
         H1[g * H + col] = in.b * in.c + (1.f - in.b) * hc;
     }
@@ -224,7 +237,7 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     }
     __device__ __forceinline__ void store4(int z1, int, int row, int col, const float4& acc, const EpiIn4& in) const {
         const long long g = (long long)z1 * rows_per_z + row;
-        const float4 hc = tanh4(acc + in.a);
+        const float4 hc = tanh4(acc + in.a, fast);
         st4(HC + g * H + col, hc);
         st4(H1 + g * H + col, in.b * in.c + one_minus(in.b) * hc);
     }
@@ -232,7 +245,7 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
 };
 struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r2)*hc2)
     const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
-    int H;
+    int H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(RX) && aligned16(H1) && aligned16(R2) && aligned16(HC2) && aligned16(Y); }
     __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long g = row;
@@ -245,7 +258,7 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
     }
     __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
         const long long g = row;
-        const float hc2 = tanhf(acc + in.a);
+        const float hc2 = fast ? tanh_fast(acc + in.a) : tanhf(acc + in.a);
         const float r2 = in.b, h1 = in.c, m = in.d;
         const float res = r2 * h1 + (1.f - r2) * hc2;
         HC2[g * H + col] = hc2;
@@ -262,7 +275,7 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
     }
     __device__ __forceinline__ void store4(int, int, int row, int col, const float4& acc, const EpiIn4& in) const {
         const long long g = row;
-        const float4 hc2 = tanh4(acc + in.a);
+        const float4 hc2 = tanh4(acc + in.a, fast);
         const float4 res = in.b * in.c + one_minus(in.b) * hc2;
         st4(HC2 + g * H + col, hc2);
         st4(Y + g * H + col, in.d * in.c + one_minus(in.d) * res);
@@ -493,20 +506,85 @@ __global__ void view_weight_grad_kernel(const float* __restrict__ dpool, const f
     if (threadIdx.x == 0) atomicAdd(dc + k, s / c[k]);
 }
 
-// out[z, col] = sum_{t, r} src[t*st + z*sz + r*ld + col]  for col in [0, ncol): grid (Zn, chunks), atomics
+// Column sums of a [T][Z][rows][ld] array over (t, rows) for the first ncol columns; columns < split go to
+// out1[z*ld1 + col], the rest to out2[z*ld2 + col - split].   grid (Z, chunks), partial sums by atomics.
 __global__ void colsum_kernel(const float* __restrict__ src, int T, long long st, long long sz, int rows, int ld,
-                              int ncol, float* __restrict__ out, int out_ld) {
+                              int ncol, int split, float* __restrict__ out1, int ld1, float* __restrict__ out2, int ld2) {
     const int z = blockIdx.x;
     const int lanes = blockDim.x / ncol;  // row lanes per block
     const int col = threadIdx.x % ncol, lane = threadIdx.x / ncol;
     if (lane >= lanes) return;
     const long long total = (long long)T * rows;
-    float s = 0.f;
-    for (long long j = (long long)blockIdx.y * lanes + lane; j < total; j += (long long)gridDim.y * lanes) {
-        const long long t = j / rows, r = j - t * rows;
-        s += src[t * st + z * sz + r * ld + col];
+    float s0 = 0.f, s1 = 0.f;
+    long long j = (long long)blockIdx.y * lanes + lane;
+    const long long step = (long long)gridDim.y * lanes;
+    for (; j + step < total; j += 2 * step) {  // two independent loads in flight
+        const long long t0 = j / rows, r0 = j - t0 * rows;
+        const long long j1 = j + step, t1 = j1 / rows, r1 = j1 - t1 * rows;
+        s0 += src[t0 * st + z * sz + r0 * ld + col];
+        s1 += src[t1 * st + z * sz + r1 * ld + col];
     }
-    atomicAdd(out + (long long)z * out_ld + col, s);
+    if (j < total) {
+        const long long t0 = j / rows, r0 = j - t0 * rows;
+        s0 += src[t0 * st + z * sz + r0 * ld + col];
+    }
+    const float s = s0 + s1;
+    if (col < split) atomicAdd(out1 + (long long)z * ld1 + col, s);
+    else atomicAdd(out2 + (long long)z * ld2 + col - split, s);
+}
+
+// Weight gradient of the input rows when Cin is tiny (layer 0: Cin = 2), fused with the bias gradient:
+//   dWg[n,k,i,o] (o < 2H) / dWu[n,k,i,o-2H] = sum_{t,b} PX[t,k,n,b,i] * DG[t,n,b,o]      dbg/dbu[n,o] = sum_{t,b} DG[t,n,b,o]
+// One CTA per node, one thread per output column o in [0, 3H): DG[n] is streamed exactly once.
+constexpr int DWX_KMAX = 9, DWX_CMAX = 4;
+__global__ void dwx_small_kernel(const float* __restrict__ PX, const float* __restrict__ DG, int T, int N, int B, int Cin,
+                                 int H, int K, float* __restrict__ dWg, float* __restrict__ dWu, float* __restrict__ dbg,
+                                 float* __restrict__ dbu) {
+    extern __shared__ float xs[];  // [K][B][Cin] slab of PX for the current t
+    const int n = blockIdx.x, o = threadIdx.x;
+    const int I = Cin + H;
+    const long long UX = (long long)N * B * Cin, U3 = (long long)N * B * 3 * H;
+    float acc[DWX_KMAX][DWX_CMAX];
+#pragma unroll
+    for (int k = 0; k < DWX_KMAX; ++k)
+#pragma unroll
+        for (int i = 0; i < DWX_CMAX; ++i) acc[k][i] = 0.f;
+    float bsum = 0.f;
+    for (int t = 0; t < T; ++t) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < K * B * Cin; j += blockDim.x) {
+            const int k = j / (B * Cin), r = j - k * (B * Cin);
+            xs[j] = PX[((long long)t * K + k) * UX + (long long)n * B * Cin + r];
+        }
+        __syncthreads();
+        if (o < 3 * H) {
+            const float* dg = DG + t * U3 + (long long)n * B * 3 * H + o;
+            for (int b = 0; b < B; ++b) {
+                const float d = dg[(long long)b * 3 * H];
+                bsum += d;
+#pragma unroll
+                for (int k = 0; k < DWX_KMAX; ++k)
+                    if (k < K) {
+#pragma unroll
+                        for (int i = 0; i < DWX_CMAX; ++i)
+                            if (i < Cin) acc[k][i] = fmaf(xs[(k * B + b) * Cin + i], d, acc[k][i]);
+                    }
+            }
+        }
+    }
+    if (o >= 3 * H) return;
+    if (o < 2 * H) dbg[(long long)n * 2 * H + o] = bsum;
+    else dbu[(long long)n * H + o - 2 * H] = bsum;
+#pragma unroll
+    for (int k = 0; k < DWX_KMAX; ++k)
+        if (k < K) {
+#pragma unroll
+            for (int i = 0; i < DWX_CMAX; ++i)
+                if (i < Cin) {
+                    if (o < 2 * H) dWg[(((long long)n * K + k) * I + i) * 2 * H + o] = acc[k][i];
+                    else dWu[(((long long)n * K + k) * I + i) * H + o - 2 * H] = acc[k][i];
+                }
+        }
 }
 
 // B0: head of the reverse step.  dy = dY[t] + carry ; residual-mix backward up to da3.
@@ -641,7 +719,7 @@ extern "C" int matgcn_nodeweights_bwd(const float* E, const float* pool, const f
 // encoder layer: workspace layout
 // ------------------------------------------------------------------------------------------
 struct LayerWs {
-    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, total;
+    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, total;
     size_t U, UX;  // floats of one [N,B,H] / [N,B,Cin] block
 };
 static size_t align64(size_t v) { return (v + 63) / 64 * 64; }
@@ -664,6 +742,8 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.R2 = take((size_t)T * w.U);
     w.HC2 = take((size_t)T * w.U);
     w.ZH2 = take((size_t)T * w.U);
+    w.RGH = take((size_t)2 * H * H);  // Rgw[:, Cin:] and Ruw[:, Cin:] repacked densely (16-byte aligned rows for TMA)
+    w.RUH = take((size_t)H * H);
     w.total = o;
     return w;
 }
@@ -745,8 +825,13 @@ extern "C" int matgcn_debug_set_mode(int mode) {
     tc_debug_mode() = mode;
     return 0;
 }
+extern "C" int matgcn_debug_set_timeline_skip(int launches) {
+    tc_debug_countdown() = launches;
+    return 0;
+}
 extern "C" int matgcn_debug_set_timeline(long long* buf) {
     tc_debug_buffer() = buf;
+    tc_debug_countdown() = 0;
     return 0;
 }
 
@@ -831,6 +916,10 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         e.bias = Rub; e.bias_s1 = 0;
         CK((gemm_any<CfgMid, true, true>(tc, p, e, T, st)));
     }
+    // dense, aligned copies of the hidden-state columns of the residual GRU weights
+    float* RgH = ws + w.RGH; float* RuH = ws + w.RUH;
+    CK(cudaMemcpy2DAsync(RgH, sizeof(float) * H, Rgw + Cin, sizeof(float) * I, sizeof(float) * H, 2 * H, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(RuH, sizeof(float) * H, Ruw + Cin, sizeof(float) * I, sizeof(float) * H, H, cudaMemcpyDeviceToDevice, st));
     // initial state
     if (h0) CK(cudaMemcpyAsync(PH, h0, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
     else CK(cudaMemsetAsync(PH, 0, sizeof(float) * U, st));
@@ -849,23 +938,23 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         p.splits = 1; p.Z2 = 1; p.KB = K;
         p.A = PHt; p.lda = H; p.sA1 = (long long)B * H; p.sAk = U; p.M = B; p.K = H;
         p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sBk = (long long)I * 2 * H;
-        CK((gemm_any<CfgMid, true, false>(tc, p, EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H}, N, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H, tc ? 1 : 0}, N, st)));
         // (c) PZ[t,1..] = M * (z*h)
         CK(propagate(tc, M, ldm, N, Kp, PZt, 0, B * H, PZt + U, 1, st));
         // (d) candidate
         p.A = PZt;
         p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
-        CK((gemm_any<CfgMid, true, false>(tc, p, EpiCand{GXt, PHt, Rt_, HCt, H1t, B, H}, N, st)));
+        CK((gemm_any<CfgMid, true, false>(tc, p, EpiCand{GXt, PHt, Rt_, HCt, H1t, B, H, tc ? 1 : 0}, N, st)));
         // (e) residual gate: [N*B, H] x Rgw[:, Cin:]^T
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = H1t; p.lda = H; p.M = N * B; p.K = H;
-        p.B = Rgw + Cin; p.ldb = I; p.N = 2 * H;
-        CK((gemm_any<CfgMid, true, true>(tc, p, EpiGate{RXt, H1t, Z2t, R2t, ZH2t, 0, H}, 1, st)));
+        p.B = RgH; p.ldb = H; p.N = 2 * H;
+        CK((gemm_any<CfgMid, true, true>(tc, p, EpiGate{RXt, H1t, Z2t, R2t, ZH2t, 0, H, tc ? 1 : 0}, 1, st)));
         // (f) residual candidate + mix -> PH[t+1, 0]
         p.A = ZH2t;
-        p.B = Ruw + Cin; p.ldb = I; p.N = H;
-        CK((gemm_any<CfgMid, true, true>(tc, p, EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H}, 1, st)));
+        p.B = RuH; p.ldb = H; p.N = H;
+        CK((gemm_any<CfgMid, true, true>(tc, p, EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H, tc ? 1 : 0}, 1, st)));
     }
     return 0;
 }
@@ -916,11 +1005,11 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = DRt + 2 * H; p.lda = 3 * H; p.M = NB; p.K = H;
-        p.B = Ruw + Cin; p.ldb = I; p.N = H;
+        p.B = ws + w.RUH; p.ldb = H; p.N = H;
         CK((gemm_any<CfgMid, true, false>(tc, p, EpiB1{DH1, DRt, DRES, H1t, Z2t, R2t, HC2t, H}, 1, st)));
         // B2: dh1 += da2 [NB,2H] * Rgw[:, Cin:]
         p.A = DRt; p.K = 2 * H;
-        p.B = Rgw + Cin;
+        p.B = ws + w.RGH;
         CK((gemm_any<CfgMid, true, false>(tc, p, EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H}, 1, st)));
         // B3: DPT[k][n] = dau[n] [B,H] * Wu[n,k,Cin:,:]^T      z = (n, k)
         memset(&p, 0, sizeof(p));
@@ -961,29 +1050,32 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
     p.A = PZ; p.B = DG + 2 * H; p.N = H;
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu + (long long)Cin * H, (long long)K * I * H, (long long)I * H, H), N * K, st)));
-    // input rows 0:Cin from PX
-    p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
-    p.A = PX; p.B = DG; p.N = 2 * H;
-    CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
-    p.B = DG + 2 * H; p.N = H;
-    CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
-    // bias gradients: column sums over (t, b)
-    CK(cudaMemsetAsync(dbg, 0, sizeof(float) * (size_t)N * 2 * H, st));
-    CK(cudaMemsetAsync(dbu, 0, sizeof(float) * (size_t)N * H, st));
+    // input rows 0:Cin from PX, and the bias gradients (column sums of DG over (t, b))
     CK(cudaMemsetAsync(dRgb, 0, sizeof(float) * 2 * H, st));
     CK(cudaMemsetAsync(dRub, 0, sizeof(float) * H, st));
-    {
-        const int threads = 256;
-        REQUIRE(2 * H <= threads, "hidden size too large for the column-sum kernel");
+    const int cs_threads = 3 * H <= 256 ? 256 : 3 * H;
+    REQUIRE(3 * H <= 1024, "hidden size too large for the column-sum kernels");
+    if (Cin <= DWX_CMAX && K <= DWX_KMAX) {
+        const int threads = (3 * H + 31) / 32 * 32;
+        dwx_small_kernel<<<N, threads, sizeof(float) * (size_t)K * B * Cin, st>>>(PX, DG, T, N, B, Cin, H, K, dWg, dWu, dbg, dbu);
+        count_launch();
+        CK(cudaGetLastError());
+    } else {
+        p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
+        p.A = PX; p.B = DG; p.N = 2 * H;
+        CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
+        p.B = DG + 2 * H; p.N = H;
+        CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
+        CK(cudaMemsetAsync(dbg, 0, sizeof(float) * (size_t)N * 2 * H, st));
+        CK(cudaMemsetAsync(dbu, 0, sizeof(float) * (size_t)N * H, st));
         dim3 g1(N, 8);
-        colsum_kernel<<<g1, threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 2 * H, dbg, 2 * H);
+        colsum_kernel<<<g1, cs_threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
         count_launch();
-        colsum_kernel<<<g1, threads, 0, st>>>(DG + 2 * H, T, 3 * U, (long long)B * 3 * H, B, 3 * H, H, dbu, H);
-        count_launch();
-        dim3 g2(1, 1024);
-        colsum_kernel<<<g2, threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 2 * H, dRgb, 2 * H);
-        count_launch();
-        colsum_kernel<<<g2, threads, 0, st>>>(DR + 2 * H, T, 3 * U, 0, NB, 3 * H, H, dRub, H);
+        CK(cudaGetLastError());
+    }
+    {
+        dim3 g2(1, 1184);
+        colsum_kernel<<<g2, cs_threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
         count_launch();
         CK(cudaGetLastError());
     }

@@ -1,0 +1,49 @@
+"""Timeline of one chosen tensor-core launch inside an encoder-layer fwd+bwd at the Baltimore shape."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from multistgraph_b200 import _cabi
+lib = _cabi.lib()
+dev = "cuda:0"
+T, N, B, Cin, H, Kp, n_adp = 2, 403, 64, 64, 64, 4, 1
+K, I = Kp + 1, Cin + H
+ldm = (N + 7) // 8 * 8
+g = torch.Generator().manual_seed(0)
+R = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev)
+x, M = R(T, N, B, Cin), R(Kp, N, ldm, sc=0.05)
+Wg, Wu = R(N, K, I, 2 * H, sc=0.05), R(N, K, I, H, sc=0.05)
+bg, bu, Rgw, Ruw, Rgb, Rub = R(N, 2 * H), R(N, H), R(2 * H, I, sc=0.1), R(H, I, sc=0.1), R(2 * H), R(H)
+mix, dY = torch.sigmoid(R(T)), R(T, N, B, H)
+dims = (T, N, B, Cin, H, K)
+p = lambda t: None if t is None else t.data_ptr()
+st = torch.cuda.current_stream().cuda_stream
+names = ["prod_start", "mma_wait", "mma_start", "mma_commit", "epi_wait", "epi_start", "epi_end"]
+
+def run(skip):
+    ws = torch.zeros(lib.matgcn_encoder_layer_fwd_ws_bytes(*dims) // 4, device=dev)
+    bws = torch.zeros(lib.matgcn_encoder_layer_bwd_ws_bytes(*dims, n_adp) // 4, device=dev)
+    new = lambda *s: torch.zeros(*s, device=dev)
+    outs = [new(T, N, B, Cin), None, new(Kp, N, ldm), new(N, K, I, 2 * H), new(N, 2 * H), new(N, K, I, H), new(N, H),
+            new(2 * H, I), new(2 * H), new(H, I), new(H), new(T)]
+    buf = torch.zeros(8 * 128, dtype=torch.int64, device=dev)
+    if skip >= 0:
+        lib.matgcn_debug_set_timeline(buf.data_ptr())
+        lib.matgcn_debug_set_timeline_skip(skip)
+    _cabi.check(lib.matgcn_encoder_layer_fwd(*dims, ldm, p(x), x.stride(0), None, p(M), p(Wg), p(bg), p(Wu), p(bu), p(Rgw),
+                                             p(Rgb), p(Ruw), p(Rub), p(mix), p(ws), 1, st), "fwd")
+    _cabi.check(lib.matgcn_encoder_layer_bwd(*dims, ldm, n_adp, p(dY), dY.stride(0), p(M), p(Wg), p(Wu), p(Rgw), p(Ruw), p(mix),
+                                             p(ws), p(bws), *[p(o) for o in outs], 1, st), "bwd")
+    torch.cuda.synchronize()
+    lib.matgcn_debug_set_timeline(None)
+    return buf.cpu().view(-1, 8)
+
+run(-1)
+for label, skip in [("fwd gate (per-node)", 5 + 1), ("bwd B3 (per-node NT)", 5 + 6 * T + 2), ("bwd B5", 5 + 6 * T + 4)]:
+    b = run(skip)
+    t0 = b[0, 0].item()
+    print("==", label)
+    for i in range(16):
+        if b[i, 0].item() == 0:
+            break
+        print(" tile %2d: " % i + " ".join("%s=%d" % (nm, b[i, j].item() - t0) for j, nm in enumerate(names)))
