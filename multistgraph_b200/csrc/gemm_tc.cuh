@@ -57,6 +57,7 @@ struct TcP {
     FastDiv d_mn, d_splits, d_z2, d_tn;
     int cA1, cA2, cAk;      // 1 if the operand really has that (strided) dimension, else coordinate 0
     int cB1, cB2, cBk;
+    int m64;                // 1: issue M=64 MMAs (tile rows 0..63 only; 16 accumulator rows per TMEM lane quadrant)
     int vec;                // 1: N % 4 == 0 and the epilogue's pointers/pitches allow 16-byte accesses
     int dbg_mode;           // diagnostics only: 1 = skip epilogue stores
     long long* dbg;         // optional per-tile timeline of CTA 0 (tools/tc_timeline.py); null in production
@@ -253,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KC ? 0u : 1u) << 15) | ((B_KC ? 0u : 1u) << 16) |
-                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((p.m64 ? 64 : TC_BM) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -306,8 +307,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
-            const int row_base = m0 + q * 32;
-            if (row_base < p.M) {
+            // M=128: accumulator row r lives in TMEM lane r.  M=64: row r lives in lane 32*(r/16) + r%16, i.e. every
+            // lane quadrant holds 16 rows, so all epilogue warps stay busy on the half-height tiles of this path.
+            const int rows_per_q = p.m64 ? 16 : 32;
+            const int row_base = m0 + q * rows_per_q;
+            const int row_lim = (p.dbg_mode & 4) ? (m0 + 128) : min(p.M, row_base + rows_per_q);  // bit 2: raw lane dump
+            if (row_base < row_lim) {
 #pragma unroll 1
                 for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
                     const int col_base = n0 + c * 32;
@@ -345,12 +350,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int u = 0; u < 2; ++u) {
                                 const int rl = 4 * (it0 + u) + rq;
                                 v[u] = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
-                                if (col_ok && row_base + rl < p.M) in[u] = epi.load4(z1, z2, row_base + rl, col);
+                                if (col_ok && row_base + rl < row_lim) in[u] = epi.load4(z1, z2, row_base + rl, col);
                             }
 #pragma unroll
                             for (int u = 0; u < 2; ++u) {
                                 const int rl = 4 * (it0 + u) + rq;
-                                if (col_ok && row_base + rl < p.M && !(p.dbg_mode & 1)) epi.store4(z1, z2, row_base + rl, col, v[u], in[u]);
+                                if (col_ok && row_base + rl < row_lim && !(p.dbg_mode & 1)) epi.store4(z1, z2, row_base + rl, col, v[u], in[u]);
                             }
                         }
                     } else {
@@ -364,12 +369,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int u = 0; u < 8; ++u) {
                                 const int row = row_base + rr0 + u;
                                 v[u] = buf[(rr0 + u) * LD + lane];
-                                if (col_ok && row < p.M) in[u] = epi.load(z1, z2, row, col);
+                                if (col_ok && row < row_lim) in[u] = epi.load(z1, z2, row, col);
                             }
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
                                 const int row = row_base + rr0 + u;
-                                if (col_ok && row < p.M) epi.store(z1, z2, row, col, v[u], in[u]);
+                                if (col_ok && row < row_lim) epi.store(z1, z2, row, col, v[u], in[u]);
                             }
                         }
                     }
@@ -484,6 +489,10 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     t.d_z2 = make_fastdiv((uint32_t)Z2);
     t.d_tn = make_fastdiv((uint32_t)t.tiles_n);
     t.vec = ((p.N & 3) == 0 && epi.vec_ok()) ? 1 : 0;
+    // M <= 64 (every node-batched contraction at batch 64): M=64 MMAs, whose accumulator spreads 16 rows over each
+    // TMEM lane quadrant (layout verified on hardware by tools/m64_probe.py), halve the MMA work and keep all
+    // epilogue warps busy
+    t.m64 = (p.M <= 64 || (tc_debug_mode() & 8)) ? 1 : 0;
     t.dbg = (tc_debug_buffer() && tc_debug_countdown()-- == 0) ? tc_debug_buffer() : nullptr;
     t.dbg_mode = tc_debug_mode();
     CUtensorMap ma, mb;
