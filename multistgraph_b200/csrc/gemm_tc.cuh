@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "gemm_simt.cuh"
 
@@ -194,6 +196,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
+    // previous kernel in the stream; from here on its results are needed.  No-ops for an ordinary launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int kt_per_kb = (p.K + TC_BK - 1) / TC_BK;
     const int kt_total = p.KB * kt_per_kb;
@@ -431,6 +437,15 @@ inline int& tc_debug_mode() {
     return m;
 }
 
+// Programmatic dependent launch of the tensor-core kernels (MATGCN_PDL=0 disables it).
+inline bool tc_use_pdl() {
+    static bool on = []() {
+        const char* e = getenv("MATGCN_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 inline int sm_count() {
     static int n = []() {
         int dev = 0, v = 0;
@@ -509,9 +524,20 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
         configured = true;
     }
     const int grid = total < sm_count() ? (int)total : sm_count();
-    kern<<<grid, TC_THREADS, S::TOTAL, st>>>(ma, mb, t, epi);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tc_use_pdl() ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, t, epi);
     count_launch();
-    return cudaGetLastError();
+    return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 }  // namespace matgcn

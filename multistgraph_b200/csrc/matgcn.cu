@@ -515,20 +515,24 @@ __global__ void colsum_kernel(const float* __restrict__ src, int T, long long st
     const int col = threadIdx.x % ncol, lane = threadIdx.x / ncol;
     if (lane >= lanes) return;
     const long long total = (long long)T * rows;
-    float s0 = 0.f, s1 = 0.f;
+    float s = 0.f;
     long long j = (long long)blockIdx.y * lanes + lane;
     const long long step = (long long)gridDim.y * lanes;
-    for (; j + step < total; j += 2 * step) {  // two independent loads in flight
-        const long long t0 = j / rows, r0 = j - t0 * rows;
-        const long long j1 = j + step, t1 = j1 / rows, r1 = j1 - t1 * rows;
-        s0 += src[t0 * st + z * sz + r0 * ld + col];
-        s1 += src[t1 * st + z * sz + r1 * ld + col];
+    for (; j < total; j += 8 * step) {  // eight independent loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long ju = j + u * step;
+            if (ju < total) {
+                const long long t = ju / rows, r = ju - t * rows;
+                v[u] = src[t * st + z * sz + r * ld + col];
+            } else {
+                v[u] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
     }
-    if (j < total) {
-        const long long t0 = j / rows, r0 = j - t0 * rows;
-        s0 += src[t0 * st + z * sz + r0 * ld + col];
-    }
-    const float s = s0 + s1;
     if (col < split) atomicAdd(out1 + (long long)z * ld1 + col, s);
     else atomicAdd(out2 + (long long)z * ld2 + col - split, s);
 }
@@ -559,16 +563,22 @@ __global__ void dwx_small_kernel(const float* __restrict__ PX, const float* __re
         __syncthreads();
         if (o < 3 * H) {
             const float* dg = DG + t * U3 + (long long)n * B * 3 * H + o;
-            for (int b = 0; b < B; ++b) {
-                const float d = dg[(long long)b * 3 * H];
-                bsum += d;
+            for (int b0 = 0; b0 < B; b0 += 8) {
+                float d[8];
 #pragma unroll
-                for (int k = 0; k < DWX_KMAX; ++k)
-                    if (k < K) {
+                for (int u = 0; u < 8; ++u) d[u] = (b0 + u < B) ? dg[(long long)(b0 + u) * 3 * H] : 0.f;  // 8 loads in flight
 #pragma unroll
-                        for (int i = 0; i < DWX_CMAX; ++i)
-                            if (i < Cin) acc[k][i] = fmaf(xs[(k * B + b) * Cin + i], d, acc[k][i]);
-                    }
+                for (int u = 0; u < 8; ++u) {
+                    if (b0 + u >= B) break;
+                    bsum += d[u];
+#pragma unroll
+                    for (int k = 0; k < DWX_KMAX; ++k)
+                        if (k < K) {
+#pragma unroll
+                            for (int i = 0; i < DWX_CMAX; ++i)
+                                if (i < Cin) acc[k][i] = fmaf(xs[(k * B + b0 + u) * Cin + i], d[u], acc[k][i]);
+                        }
+                }
             }
         }
     }
