@@ -49,6 +49,50 @@ static cudaError_t gemm_any(bool tc, const GemmP& p, const Epi& epi, int Z, cuda
 }
 extern "C" unsigned long long matgcn_tc_launch_count(void) { return g_tc_launches.load(); }
 
+// Optional per-launch tracing (MATGCN_TRACE=1): a CUDA event after every enqueued operation of the encoder
+// entry points; on exit the entry point synchronises and prints the time spent between consecutive events,
+// aggregated by source line, to stderr.  Diagnostics only - it serialises host and device.
+#include <map>
+#include <string>
+#include <vector>
+struct Tracer {
+    bool on;
+    cudaStream_t st;
+    std::vector<std::pair<int, cudaEvent_t>> ev;
+    explicit Tracer(cudaStream_t s) : st(s) {
+        static const bool enabled = []() { const char* e = getenv("MATGCN_TRACE"); return e && e[0] == '1'; }();
+        on = enabled;
+        if (on) mark(0);
+    }
+    void mark(int line) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back({line, e});
+    }
+    void report(const char* what) {
+        if (!on || ev.size() < 2) return;
+        cudaEventSynchronize(ev.back().second);
+        std::map<int, std::pair<int, float>> agg;
+        float total = 0.f;
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            agg[ev[i].first].first++;
+            agg[ev[i].first].second += ms;
+            total += ms;
+        }
+        fprintf(stderr, "[matgcn trace] %s: total %.3f ms\n", what, total);
+        for (auto& kv : agg)
+            fprintf(stderr, "[matgcn trace]   line %4d: %4d x  %8.3f ms total  %7.1f us avg\n", kv.first, kv.second.first,
+                    kv.second.second, 1e3f * kv.second.second / kv.second.first);
+        for (auto& e : ev) cudaEventDestroy(e.second);
+        ev.clear();
+    }
+};
+#define TR() tr.mark(__LINE__)
+
 extern "C" int matgcn_abi_version(void) { return MATGCN_ABI_VERSION; }
 extern "C" const char* matgcn_last_error(void) { return g_err; }
 extern "C" unsigned long long matgcn_launch_count(void) { return g_launches.load(); }
@@ -623,6 +667,247 @@ __global__ void bwd_head_kernel(const float* __restrict__ dY, const float* __res
     if (threadIdx.x == 0) atomicAdd(dmix_t, part);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Input-side kernels for a tiny channel count (layer 0: Cin = 2).  With K*Cin <= 10 the contractions over the
+// input rows are a handful of FMAs per output element, so GEMM tiles would be >90% padding; these kernels
+// stream the big [T,N,B,3H] arrays exactly once instead.
+// ------------------------------------------------------------------------------------------
+constexpr int XS_KC = 10;  // max K*Cin
+constexpr int XS_J = 6;    // max ceil(3H/32)
+static bool xside_small_ok(int Cin, int H, int K) { return Cin <= 4 && K * Cin <= XS_KC && 3 * H <= 32 * XS_J; }
+
+// GX[t,n,b,o] = bias3[n,o] + sum_{k,i} PX[t,k,n,b,i] * W3[n,k,i,o] ;  RX[t,n,b,o] = rbias3[o] + sum_i x[t,n,b,i] * Rx3[o,i]
+// (W3 = [Wg | Wu] input rows, Rx3 = [Rgw ; Ruw][:, 0:Cin]).   grid (N, T), thread = output column o.
+__global__ void xside_fwd_small_kernel(const float* __restrict__ PX, const float* __restrict__ Wg, const float* __restrict__ bg,
+                                       const float* __restrict__ Wu, const float* __restrict__ bu,
+                                       const float* __restrict__ Rgw, const float* __restrict__ Rgb,
+                                       const float* __restrict__ Ruw, const float* __restrict__ Rub, int T, int N, int B, int Cin,
+                                       int H, int K, float* __restrict__ GX, float* __restrict__ RX) {
+    extern __shared__ float xs[];  // [K][B][Cin]
+    const int n = blockIdx.x, t = blockIdx.y, o = threadIdx.x;
+    const int I = Cin + H, KC = K * Cin;
+    const long long UX = (long long)N * B * Cin;
+    for (int j = threadIdx.x; j < K * B * Cin; j += blockDim.x) {
+        const int k = j / (B * Cin), r = j - k * (B * Cin);
+        xs[j] = PX[((long long)t * K + k) * UX + (long long)n * B * Cin + r];
+    }
+    float w[XS_KC], rw[4], bias = 0.f, rb = 0.f;
+    if (o < 3 * H) {
+#pragma unroll
+        for (int kc = 0; kc < XS_KC; ++kc)
+            if (kc < KC) {
+                const int k = kc / Cin, i = kc - k * Cin;
+                w[kc] = o < 2 * H ? Wg[(((long long)n * K + k) * I + i) * 2 * H + o] : Wu[(((long long)n * K + k) * I + i) * H + o - 2 * H];
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < Cin) rw[i] = o < 2 * H ? Rgw[(long long)o * I + i] : Ruw[(long long)(o - 2 * H) * I + i];
+        bias = o < 2 * H ? bg[(long long)n * 2 * H + o] : bu[(long long)n * H + o - 2 * H];
+        rb = o < 2 * H ? Rgb[o] : Rub[o - 2 * H];
+    }
+    __syncthreads();
+    if (o >= 3 * H) return;
+    float* gx = GX + (((long long)t * N + n) * B) * 3 * H + o;
+    float* rx = RX + (((long long)t * N + n) * B) * 3 * H + o;
+    for (int b = 0; b < B; ++b) {
+        float g = bias, r = rb;
+#pragma unroll
+        for (int kc = 0; kc < XS_KC; ++kc)
+            if (kc < KC) {
+                const int k = kc / Cin, i = kc - k * Cin;
+                g = fmaf(w[kc], xs[(k * B + b) * Cin + i], g);
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < Cin) r = fmaf(rw[i], xs[b * Cin + i], r);
+        gx[(long long)b * 3 * H] = g;
+        rx[(long long)b * 3 * H] = r;
+    }
+}
+
+// One pass over DG[:, n]: weight gradient of the input rows, bias gradient, and the input-side data gradient
+//   dW3[n,k,i,o] = sum_{t,b} PX[t,k,n,b,i] * DG[t,n,b,o]     db3[n,o] = sum_{t,b} DG[t,n,b,o]
+//   DPX[t,k,n,b,i] = sum_o DG[t,n,b,o] * W3[n,k,i,o]
+// grid (N), 8 warps; a warp takes every 8th (t,b) row, lane l owns columns l, l+32, ...
+__global__ void __launch_bounds__(256) xside_bwd_dg_small_kernel(
+    const float* __restrict__ PX, const float* __restrict__ DG, const float* __restrict__ Wg, const float* __restrict__ Wu, int T,
+    int N, int B, int Cin, int H, int K, float* __restrict__ dWg, float* __restrict__ dWu, float* __restrict__ dbg,
+    float* __restrict__ dbu, float* __restrict__ DPX) {
+    __shared__ float w3[XS_KC][32 * XS_J];
+    __shared__ float red[32 * XS_J][XS_KC + 1];
+    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int I = Cin + H, KC = K * Cin, H3 = 3 * H;
+    const long long UX = (long long)N * B * Cin;
+    for (int j = threadIdx.x; j < XS_KC * 32 * XS_J; j += blockDim.x) {
+        const int kc = j / (32 * XS_J), o = j - kc * (32 * XS_J);
+        float v = 0.f;
+        if (kc < KC && o < H3) {
+            const int k = kc / Cin, i = kc - k * Cin;
+            v = o < 2 * H ? Wg[(((long long)n * K + k) * I + i) * 2 * H + o] : Wu[(((long long)n * K + k) * I + i) * H + o - 2 * H];
+        }
+        w3[kc][o] = v;
+    }
+    for (int j = threadIdx.x; j < 32 * XS_J * (XS_KC + 1); j += blockDim.x) (&red[0][0])[j] = 0.f;
+    __syncthreads();
+    float acc[XS_J][XS_KC], bsum[XS_J];
+#pragma unroll
+    for (int j = 0; j < XS_J; ++j) {
+        bsum[j] = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < XS_KC; ++kc) acc[j][kc] = 0.f;
+    }
+    const int rows = T * B;
+    for (int r = warp; r < rows; r += 8) {
+        const int t = r / B, b = r - t * B;
+        const float* dgp = DG + (((long long)t * N + n) * B + b) * H3;
+        float dg[XS_J];
+#pragma unroll
+        for (int j = 0; j < XS_J; ++j) dg[j] = (lane + 32 * j < H3) ? dgp[lane + 32 * j] : 0.f;
+        float xv = 0.f;
+        if (lane < KC) {
+            const int k = lane / Cin, i = lane - k * Cin;
+            xv = PX[((long long)t * K + k) * UX + ((long long)n * B + b) * Cin + i];
+        }
+        float part[XS_KC];
+#pragma unroll
+        for (int kc = 0; kc < XS_KC; ++kc) {
+            const float x = __shfl_sync(0xffffffffu, xv, kc);
+            float pp = 0.f;
+#pragma unroll
+            for (int j = 0; j < XS_J; ++j) {
+                acc[j][kc] = fmaf(x, dg[j], acc[j][kc]);
+                pp = fmaf(dg[j], w3[kc][lane + 32 * j], pp);
+            }
+            part[kc] = pp;
+        }
+#pragma unroll
+        for (int j = 0; j < XS_J; ++j) bsum[j] += dg[j];
+#pragma unroll
+        for (int kc = 0; kc < XS_KC; ++kc) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part[kc] += __shfl_xor_sync(0xffffffffu, part[kc], off);
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < XS_KC; ++kc)
+            if (lane == kc) mine = part[kc];
+        if (lane < KC) {
+            const int k = lane / Cin, i = lane - k * Cin;
+            DPX[((long long)t * K + k) * UX + ((long long)n * B + b) * Cin + i] = mine;
+        }
+    }
+    // cross-warp reduction through shared memory, one warp at a time
+    for (int wsel = 0; wsel < 8; ++wsel) {
+        if (warp == wsel) {
+#pragma unroll
+            for (int j = 0; j < XS_J; ++j) {
+#pragma unroll
+                for (int kc = 0; kc < XS_KC; ++kc) red[lane + 32 * j][kc] += acc[j][kc];
+                red[lane + 32 * j][XS_KC] += bsum[j];
+            }
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < H3 * (KC + 1); j += blockDim.x) {
+        const int kc = j / H3, o = j - kc * H3;
+        if (kc == KC) {
+            const float v = red[o][XS_KC];
+            if (o < 2 * H) dbg[(long long)n * 2 * H + o] = v;
+            else dbu[(long long)n * H + o - 2 * H] = v;
+        } else {
+            const int k = kc / Cin, i = kc - k * Cin;
+            const float v = red[o][kc];
+            if (o < 2 * H) dWg[(((long long)n * K + k) * I + i) * 2 * H + o] = v;
+            else dWu[(((long long)n * K + k) * I + i) * H + o - 2 * H] = v;
+        }
+    }
+}
+
+// One pass over DR (flat rows (t,n,b)): residual-GRU input-column weight gradient, bias gradient, and the
+// residual path's share of the input gradient, added into DPX[t,0]:
+//   dRx3[o,i] += sum_rows DR[row,o] * x[row,i]    drb3[o] += sum_rows DR[row,o]    DPX[t,0,n,b,i] += sum_o DR[row,o] * Rx3[o,i]
+// grid (chunks), 8 warps, warp per row; outputs are pre-zeroed and receive one atomic per CTA and element.
+__global__ void __launch_bounds__(256) xside_bwd_dr_small_kernel(
+    const float* __restrict__ PX, const float* __restrict__ DR, const float* __restrict__ Rgw, const float* __restrict__ Ruw,
+    int T, int N, int B, int Cin, int H, int K, float* __restrict__ dRgw, float* __restrict__ dRuw, float* __restrict__ dRgb,
+    float* __restrict__ dRub, float* __restrict__ DPX) {
+    __shared__ float rx3[4][32 * XS_J];
+    __shared__ float red[32 * XS_J][5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int I = Cin + H, H3 = 3 * H;
+    const long long UX = (long long)N * B * Cin, NB = (long long)N * B;
+    for (int j = threadIdx.x; j < 4 * 32 * XS_J; j += blockDim.x) {
+        const int i = j / (32 * XS_J), o = j - i * (32 * XS_J);
+        float v = 0.f;
+        if (i < Cin && o < H3) v = o < 2 * H ? Rgw[(long long)o * I + i] : Ruw[(long long)(o - 2 * H) * I + i];
+        rx3[i][o] = v;
+    }
+    for (int j = threadIdx.x; j < 32 * XS_J * 5; j += blockDim.x) (&red[0][0])[j] = 0.f;
+    __syncthreads();
+    float acc[XS_J][4], bsum[XS_J];
+#pragma unroll
+    for (int j = 0; j < XS_J; ++j) {
+        bsum[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    }
+    const long long rows = (long long)T * NB;
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+        const long long t = r / NB, nb = r - t * NB;
+        const float* drp = DR + r * H3;
+        float dr[XS_J];
+#pragma unroll
+        for (int j = 0; j < XS_J; ++j) dr[j] = (lane + 32 * j < H3) ? drp[lane + 32 * j] : 0.f;
+        float* x0 = DPX + t * K * UX + nb * Cin;          // DPX[t,0,n,b,:]
+        const float* xin = PX + t * K * UX + nb * Cin;    // PX[t,0,n,b,:] = x
+        float xv = lane < Cin ? xin[lane] : 0.f;
+        float part[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x = __shfl_sync(0xffffffffu, xv, i);
+            float pp = 0.f;
+#pragma unroll
+            for (int j = 0; j < XS_J; ++j) {
+                acc[j][i] = fmaf(x, dr[j], acc[j][i]);
+                pp = fmaf(dr[j], rx3[i][lane + 32 * j], pp);
+            }
+            part[i] = pp;
+        }
+#pragma unroll
+        for (int j = 0; j < XS_J; ++j) bsum[j] += dr[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part[i] += __shfl_xor_sync(0xffffffffu, part[i], off);
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (lane == i) mine = part[i];
+        if (lane < Cin) x0[lane] += mine;
+    }
+    for (int wsel = 0; wsel < 8; ++wsel) {
+        if (warp == wsel) {
+#pragma unroll
+            for (int j = 0; j < XS_J; ++j) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) red[lane + 32 * j][i] += acc[j][i];
+                red[lane + 32 * j][4] += bsum[j];
+            }
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < H3 * (Cin + 1); j += blockDim.x) {
+        const int i = j / H3, o = j - i * H3;
+        if (i == Cin) {
+            atomicAdd(o < 2 * H ? dRgb + o : dRub + (o - 2 * H), red[o][4]);
+        } else {
+            atomicAdd(o < 2 * H ? dRgw + (long long)o * I + i : dRuw + (long long)(o - 2 * H) * I + i, red[o][i]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // adaptive adjacency
 // ------------------------------------------------------------------------------------------
@@ -885,6 +1170,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     REQUIRE(x && M && Wg && bg && Wu && bu && Rgw && Rgb && Ruw && Rub && mix && ws, "null pointer");
     if (check_layer_dims(T, N, B, Cin, H, K, ldm)) return -1;
     cudaStream_t st = (cudaStream_t)stream;
+    Tracer tr(st);
     const LayerWs w = layer_ws(T, N, B, Cin, H, K);
     const int Kp = K - 1, I = Cin + H;
     const long long U = (long long)w.U, UX = (long long)w.UX;
@@ -895,8 +1181,19 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
                          cudaMemcpyDeviceToDevice, st));
     // PX[t, 1..K) = M * x_t  (all t at once)
     CK(propagate(tc, M, ldm, N, Kp, PX, K * UX, B * Cin, PX + UX, T, st));
+    TR();
 
     GemmP p;
+    if (xside_small_ok(Cin, H, K)) {
+        // tiny channel count (layer 0): one streaming kernel writes GX and RX
+        dim3 grid(N, T);
+        const int threads = (3 * H + 31) / 32 * 32;
+        xside_fwd_small_kernel<<<grid, threads, sizeof(float) * (size_t)K * B * Cin, st>>>(PX, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, T, N,
+                                                                                      B, Cin, H, K, GX, RX);
+        count_launch();
+        TR();
+        CK(cudaGetLastError());
+    } else {
     // GX[t, n, :, 0:2H] = bg[n] + sum_k PX[t,k,n] * Wg[n,k,0:Cin,:]   z = (n, t), k-batches = k
     memset(&p, 0, sizeof(p));
     p.splits = 1; p.Z2 = T; p.KB = K;
@@ -907,10 +1204,12 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         EpiStore e = epi_store(GX, (long long)B * 3 * H, 3 * U, 3 * H);
         e.bias = bg; e.bias_s1 = 2 * H;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, N * T, st)));
+        TR();
         p.B = Wu; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
         e = epi_store(GX + 2 * H, (long long)B * 3 * H, 3 * U, 3 * H);
         e.bias = bu; e.bias_s1 = H;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, N * T, st)));
+        TR();
     }
     // RX[t] = x_t * [Rgw[:, 0:Cin]; Ruw[:, 0:Cin]]^T + [Rgb; Rub]          flat rows (n,b), z = t
     memset(&p, 0, sizeof(p));
@@ -921,15 +1220,20 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         EpiStore e = epi_store(RX, 3 * U, 0, 3 * H);
         e.bias = Rgb; e.bias_s1 = 0;
         CK((gemm_any<CfgMid, true, true>(tc, p, e, T, st)));
+        TR();
         p.B = Ruw; p.ldb = I; p.N = H;
         e = epi_store(RX + 2 * H, 3 * U, 0, 3 * H);
         e.bias = Rub; e.bias_s1 = 0;
         CK((gemm_any<CfgMid, true, true>(tc, p, e, T, st)));
+        TR();
+    }
     }
     // dense, aligned copies of the hidden-state columns of the residual GRU weights
     float* RgH = ws + w.RGH; float* RuH = ws + w.RUH;
     CK(cudaMemcpy2DAsync(RgH, sizeof(float) * H, Rgw + Cin, sizeof(float) * I, sizeof(float) * H, 2 * H, cudaMemcpyDeviceToDevice, st));
+    TR();
     CK(cudaMemcpy2DAsync(RuH, sizeof(float) * H, Ruw + Cin, sizeof(float) * I, sizeof(float) * H, H, cudaMemcpyDeviceToDevice, st));
+    TR();
     // initial state
     if (h0) CK(cudaMemcpyAsync(PH, h0, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
     else CK(cudaMemsetAsync(PH, 0, sizeof(float) * U, st));
@@ -943,29 +1247,36 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         const float* GXt = GX + (long long)t * 3 * U; const float* RXt = RX + (long long)t * 3 * U;
         // (a) PH[t,1..] = M * h
         CK(propagate(tc, M, ldm, N, Kp, PHt, 0, B * H, PHt + U, 1, st));
+        TR();
         // (b) gate: per node [B, K*H] x [K*H, 2H]
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = K;
         p.A = PHt; p.lda = H; p.sA1 = (long long)B * H; p.sAk = U; p.M = B; p.K = H;
         p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sBk = (long long)I * 2 * H;
         CK((gemm_any<CfgMid, true, false>(tc, p, EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H, tc ? 1 : 0}, N, st)));
+        TR();
         // (c) PZ[t,1..] = M * (z*h)
         CK(propagate(tc, M, ldm, N, Kp, PZt, 0, B * H, PZt + U, 1, st));
+        TR();
         // (d) candidate
         p.A = PZt;
         p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
         CK((gemm_any<CfgMid, true, false>(tc, p, EpiCand{GXt, PHt, Rt_, HCt, H1t, B, H, tc ? 1 : 0}, N, st)));
+        TR();
         // (e) residual gate: [N*B, H] x Rgw[:, Cin:]^T
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = H1t; p.lda = H; p.M = N * B; p.K = H;
         p.B = RgH; p.ldb = H; p.N = 2 * H;
         CK((gemm_any<CfgMid, true, true>(tc, p, EpiGate{RXt, H1t, Z2t, R2t, ZH2t, 0, H, tc ? 1 : 0}, 1, st)));
+        TR();
         // (f) residual candidate + mix -> PH[t+1, 0]
         p.A = ZH2t;
         p.B = RuH; p.ldb = H; p.N = H;
         CK((gemm_any<CfgMid, true, true>(tc, p, EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H, tc ? 1 : 0}, 1, st)));
+        TR();
     }
+    tr.report("encoder_layer_fwd");
     return 0;
 }
 
@@ -986,6 +1297,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     if (check_layer_dims(T, N, B, Cin, H, K, ldm)) return -1;
     REQUIRE(n_adp >= 0 && n_adp <= K - 1, "n_adp out of range");
     cudaStream_t st = (cudaStream_t)stream;
+    Tracer tr(st);
     const LayerWs w = layer_ws(T, N, B, Cin, H, K);
     const LayerBws bw = layer_bws(T, N, B, Cin, H, K, n_adp);
     const int Kp = K - 1, I = Cin + H;
@@ -996,7 +1308,9 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     const int NB = N * B;
 
     CK(cudaMemsetAsync(DHC, 0, sizeof(float) * U, st));
+    TR();
     CK(cudaMemsetAsync(dmix, 0, sizeof(float) * T, st));
+    TR();
     GemmP p;
     for (int t = T - 1; t >= 0; --t) {
         const float* PHt = PH + (long long)t * K * U;
@@ -1010,6 +1324,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t,
                                                                     mix + t, U, H, DH1, DRES, DRt, dmix + t);
                                                                     count_launch();
+                                                                    TR();
         CK(cudaGetLastError());
         // B1: dzh2 = da3 [NB,H] * Ruw[:, Cin:]  (B element (k=o, n=j) at o*I + Cin + j)
         memset(&p, 0, sizeof(p));
@@ -1017,36 +1332,44 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.A = DRt + 2 * H; p.lda = 3 * H; p.M = NB; p.K = H;
         p.B = ws + w.RUH; p.ldb = H; p.N = H;
         CK((gemm_any<CfgMid, true, false>(tc, p, EpiB1{DH1, DRt, DRES, H1t, Z2t, R2t, HC2t, H}, 1, st)));
+        TR();
         // B2: dh1 += da2 [NB,2H] * Rgw[:, Cin:]
         p.A = DRt; p.K = 2 * H;
         p.B = ws + w.RGH;
         CK((gemm_any<CfgMid, true, false>(tc, p, EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H}, 1, st)));
+        TR();
         // B3: DPT[k][n] = dau[n] [B,H] * Wu[n,k,Cin:,:]^T      z = (n, k)
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = K; p.KB = 1;
         p.A = DGt + 2 * H; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.sA2 = 0; p.M = B; p.K = H;
         p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sB2 = (long long)I * H;
         CK((gemm_any<CfgMid, true, true>(tc, p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
+        TR();
         if (n_adp) CK(cudaMemcpyAsync(DPZA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
+        TR();
         // B4: dzh = DPT[0] + sum_{k>=1} M_k^T DPT[k]
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
         p.B = DPT + U; p.ldb = B * H; p.N = B * H;
         CK((gemm_any<CfgBig, false, false>(tc, p, EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H}, 1, st)));
+        TR();
         // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = K; p.KB = 1;
         p.A = DGt; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
         p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = (long long)I * 2 * H;
         CK((gemm_any<CfgMid, true, true>(tc, p, epi_store(DPT, (long long)B * H, U, H), N * K, st)));
+        TR();
         if (n_adp) CK(cudaMemcpyAsync(DPHA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
+        TR();
         // B6: carry = DHD + DPT[0] + sum M_k^T DPT[k]
         memset(&p, 0, sizeof(p));
         p.splits = 1; p.Z2 = 1; p.KB = 1;
         p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
         p.B = DPT + U; p.ldb = B * H; p.N = B * H;
         CK((gemm_any<CfgBig, false, false>(tc, p, EpiB6{DPT, DHD, DHC, B * H}, 1, st)));
+        TR();
     }
     if (dh0) CK(cudaMemcpyAsync(dh0, DHC, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
 
@@ -1058,49 +1381,69 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.ldb = 3 * H; p.sB1 = (long long)B * 3 * H; p.sB2 = 0; p.sBk = 3 * U;
     p.A = PH; p.B = DG; p.N = 2 * H;
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
+    TR();
     p.A = PZ; p.B = DG + 2 * H; p.N = H;
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu + (long long)Cin * H, (long long)K * I * H, (long long)I * H, H), N * K, st)));
-    // input rows 0:Cin from PX, and the bias gradients (column sums of DG over (t, b))
+    TR();
+    // residual-GRU weight gradients accumulate by atomics: clear them first
+    CK(cudaMemsetAsync(dRgw, 0, sizeof(float) * (size_t)2 * H * I, st));
+    TR();
+    CK(cudaMemsetAsync(dRuw, 0, sizeof(float) * (size_t)H * I, st));
+    TR();
     CK(cudaMemsetAsync(dRgb, 0, sizeof(float) * 2 * H, st));
+    TR();
     CK(cudaMemsetAsync(dRub, 0, sizeof(float) * H, st));
+    TR();
+    const bool small_x = xside_small_ok(Cin, H, K);
     const int cs_threads = 3 * H <= 256 ? 256 : 3 * H;
     REQUIRE(3 * H <= 1024, "hidden size too large for the column-sum kernels");
-    if (Cin <= DWX_CMAX && K <= DWX_KMAX) {
-        const int threads = (3 * H + 31) / 32 * 32;
-        dwx_small_kernel<<<N, threads, sizeof(float) * (size_t)K * B * Cin, st>>>(PX, DG, T, N, B, Cin, H, K, dWg, dWu, dbg, dbu);
+    if (small_x) {
+        // tiny channel count (layer 0): one pass over DG (input-row weight gradient, bias gradient, DPX) and one pass
+        // over DR (residual input-column gradients, residual bias gradient, residual share of dx into DPX[t,0])
+        xside_bwd_dg_small_kernel<<<N, 256, 0, st>>>(PX, DG, Wg, Wu, T, N, B, Cin, H, K, dWg, dWu, dbg, dbu, DPX);
         count_launch();
+        TR();
+        xside_bwd_dr_small_kernel<<<592, 256, 0, st>>>(PX, DR, Rgw, Ruw, T, N, B, Cin, H, K, dRgw, dRuw, dRgb, dRub, DPX);
+        count_launch();
+        TR();
         CK(cudaGetLastError());
     } else {
+        // input rows 0:Cin from PX, and the bias gradients (column sums of DG over (t, b))
         p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
         p.A = PX; p.B = DG; p.N = 2 * H;
         CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
+        TR();
         p.B = DG + 2 * H; p.N = H;
         CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
+        TR();
         CK(cudaMemsetAsync(dbg, 0, sizeof(float) * (size_t)N * 2 * H, st));
+        TR();
         CK(cudaMemsetAsync(dbu, 0, sizeof(float) * (size_t)N * H, st));
+        TR();
         dim3 g1(N, 8);
         colsum_kernel<<<g1, cs_threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
         count_launch();
-        CK(cudaGetLastError());
-    }
-    {
+        TR();
         dim3 g2(1, 1184);
         colsum_kernel<<<g2, cs_threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
         count_launch();
+        TR();
         CK(cudaGetLastError());
-    }
-    // DPX[t,k,n] = DG[t,n][:,0:2H] * Wg[n,k,0:Cin,:]^T + DG[t,n][:,2H:] * Wu[n,k,0:Cin,:]^T     per k: z = (t, n)
-    for (int k = 0; k < K; ++k) {
-        memset(&p, 0, sizeof(p));
-        p.splits = 1; p.Z2 = N; p.KB = 1;
-        p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
-        p.B = Wg + (long long)k * I * 2 * H; p.ldb = 2 * H; p.N = Cin; p.sB1 = 0; p.sB2 = (long long)K * I * 2 * H;
-        EpiStore e = epi_store(DPX + (long long)k * UX, K * UX, (long long)B * Cin, Cin);
-        CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
-        p.A = DG + 2 * H; p.K = H;
-        p.B = Wu + (long long)k * I * H; p.ldb = H; p.sB2 = (long long)K * I * H;
-        e.accumulate = 1;
-        CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
+        // DPX[t,k,n] = DG[t,n][:,0:2H] * Wg[n,k,0:Cin,:]^T + DG[t,n][:,2H:] * Wu[n,k,0:Cin,:]^T     per k: z = (t, n)
+        for (int k = 0; k < K; ++k) {
+            memset(&p, 0, sizeof(p));
+            p.splits = 1; p.Z2 = N; p.KB = 1;
+            p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
+            p.B = Wg + (long long)k * I * 2 * H; p.ldb = 2 * H; p.N = Cin; p.sB1 = 0; p.sB2 = (long long)K * I * 2 * H;
+            EpiStore e = epi_store(DPX + (long long)k * UX, K * UX, (long long)B * Cin, Cin);
+            CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
+            TR();
+            p.A = DG + 2 * H; p.K = H;
+            p.B = Wu + (long long)k * I * H; p.ldb = H; p.sB2 = (long long)K * I * H;
+            e.accumulate = 1;
+            CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
+            TR();
+        }
     }
     // dx[t] = DPX[t,0] + sum_{k>=1} M_k^T DPX[t,k] + DR[t][:,0:2H]*Rgw[:,0:Cin] + DR[t][:,2H:]*Ruw[:,0:Cin]
     memset(&p, 0, sizeof(p));
@@ -1111,20 +1454,24 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         EpiStore e = epi_store(dx, UX, 0, B * Cin);
         e.add = DPX; e.add_s1 = K * UX; e.add_ld = B * Cin;
         CK((gemm_any<CfgBig, false, false>(tc, p, e, T, st)));
+        TR();
     }
     memset(&p, 0, sizeof(p));
     p.splits = 1; p.Z2 = 1; p.KB = 1;
     p.A = DR; p.lda = 3 * H; p.sA1 = 3 * U; p.M = NB; p.K = 2 * H;
     p.B = Rgw; p.ldb = I; p.N = Cin;
-    {
+    if (!small_x) {
         EpiStore e = epi_store(dx, UX, 0, Cin);
         e.accumulate = 1;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
+        TR();
         p.A = DR + 2 * H; p.K = H; p.B = Ruw;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
+        TR();
     }
     // dM[a] = sum_t DPHA[t,a] PH[t,0]^T + DPZA[t,a] PZ[t,0]^T + DPX[t,a+1] PX[t,0]^T     (split-K, atomics)
     CK(cudaMemsetAsync(dM, 0, sizeof(float) * (size_t)Kp * N * ldm, st));
+    TR();
     for (int a = 0; a < n_adp; ++a) {
         EpiAtomic ea{dM + (long long)a * N * ldm, 0, 0, ldm};
         memset(&p, 0, sizeof(p));
@@ -1133,15 +1480,16 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.splits = T;
         p.A = DPHA + (long long)a * U; p.sAk = (long long)n_adp * U; p.B = PH; p.sBk = K * U;
         CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
+        TR();
         p.A = DPZA + (long long)a * U; p.B = PZ;
         CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
+        TR();
         p.K = B * Cin; p.lda = B * Cin; p.ldb = B * Cin;
         p.A = DPX + (long long)(a + 1) * UX; p.sAk = K * UX; p.B = PX; p.sBk = K * UX;
         CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
+        TR();
     }
     // residual GRU weights: dRgw[:, Cin:] = sum DR[:,0:2H]^T H1 ; dRgw[:, 0:Cin] = sum DR[:,0:2H]^T x ; same for Ruw
-    CK(cudaMemsetAsync(dRgw, 0, sizeof(float) * (size_t)2 * H * I, st));
-    CK(cudaMemsetAsync(dRuw, 0, sizeof(float) * (size_t)H * I, st));
     {
         memset(&p, 0, sizeof(p));
         p.Z2 = 1; p.KB = T; p.K = NB; p.lda = 3 * H; p.sAk = 3 * U;
@@ -1152,14 +1500,21 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         // gate, hidden columns
         p.A = DR; p.M = 2 * H; p.B = ws + w.H1; p.ldb = H; p.sBk = U; p.N = H;
         CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRgw + Cin, 0, 0, I}, 1, st)));
+        TR();
         // candidate, hidden columns
         p.A = DR + 2 * H; p.M = H; p.B = ws + w.ZH2;
         CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw + Cin, 0, 0, I}, 1, st)));
+        TR();
         // input columns
-        p.B = PX; p.ldb = Cin; p.sBk = K * UX; p.N = Cin;
-        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw, 0, 0, I}, 1, st)));
-        p.A = DR; p.M = 2 * H;
-        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRgw, 0, 0, I}, 1, st)));
+        if (!small_x) {
+            p.B = PX; p.ldb = Cin; p.sBk = K * UX; p.N = Cin;
+            CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw, 0, 0, I}, 1, st)));
+            TR();
+            p.A = DR; p.M = 2 * H;
+            CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRgw, 0, 0, I}, 1, st)));
+            TR();
+        }
     }
+    tr.report("encoder_layer_bwd");
     return 0;
 }
