@@ -221,10 +221,18 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
     flops = 2.0 * kp * n_nodes * n_nodes * cols
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r1_prop_kernel_ncu.json")
+    if flags and os.path.exists(prof):
+        with open(prof) as f:
+            pj = json.load(f)
+        if pj["shape"] == {"Kp": kp, "N": n_nodes, "cols": cols}:  # the ncu --set full capture of this very shape
+            traffic = pj["dram_bytes_read"] + pj["dram_bytes_write"]
     kern = ("gemm_tc_kernel<128,A_KC,B_NC,EpiStore> (support propagation, tcgen05 kind::tf32 + TMA)" if flags
             else "gemm_kernel<CfgBig,A_KC,B_NC,EpiStore> (support propagation, fp32 FFMA)")
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": kern, "launch_ms": ms, "flops_per_launch": flops,
+            "traffic": traffic, "kernel": kern, "launch_ms": ms, "flops_per_launch": flops,
+            "algorithmic_bytes_per_launch": 4.0 * (kp * n_nodes * ldm + n_nodes * cols + kp * n_nodes * cols),
             "peak_source": peaks["source"] + " bf16 dense burst",
             "note": "peak is the measured bf16 cuBLAS figure; TF32 tensor-core peak is half of it, the fp32 FFMA "
                     "kernel of exact mode cannot approach either"}

@@ -581,66 +581,6 @@ __global__ void colsum_kernel(const float* __restrict__ src, int T, long long st
     else atomicAdd(out2 + (long long)z * ld2 + col - split, s);
 }
 
-// Weight gradient of the input rows when Cin is tiny (layer 0: Cin = 2), fused with the bias gradient:
-//   dWg[n,k,i,o] (o < 2H) / dWu[n,k,i,o-2H] = sum_{t,b} PX[t,k,n,b,i] * DG[t,n,b,o]      dbg/dbu[n,o] = sum_{t,b} DG[t,n,b,o]
-// One CTA per node, one thread per output column o in [0, 3H): DG[n] is streamed exactly once.
-constexpr int DWX_KMAX = 9, DWX_CMAX = 4;
-__global__ void dwx_small_kernel(const float* __restrict__ PX, const float* __restrict__ DG, int T, int N, int B, int Cin,
-                                 int H, int K, float* __restrict__ dWg, float* __restrict__ dWu, float* __restrict__ dbg,
-                                 float* __restrict__ dbu) {
-    extern __shared__ float xs[];  // [K][B][Cin] slab of PX for the current t
-    const int n = blockIdx.x, o = threadIdx.x;
-    const int I = Cin + H;
-    const long long UX = (long long)N * B * Cin, U3 = (long long)N * B * 3 * H;
-    float acc[DWX_KMAX][DWX_CMAX];
-#pragma unroll
-    for (int k = 0; k < DWX_KMAX; ++k)
-#pragma unroll
-        for (int i = 0; i < DWX_CMAX; ++i) acc[k][i] = 0.f;
-    float bsum = 0.f;
-    for (int t = 0; t < T; ++t) {
-        __syncthreads();
-        for (int j = threadIdx.x; j < K * B * Cin; j += blockDim.x) {
-            const int k = j / (B * Cin), r = j - k * (B * Cin);
-            xs[j] = PX[((long long)t * K + k) * UX + (long long)n * B * Cin + r];
-        }
-        __syncthreads();
-        if (o < 3 * H) {
-            const float* dg = DG + t * U3 + (long long)n * B * 3 * H + o;
-            for (int b0 = 0; b0 < B; b0 += 8) {
-                float d[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) d[u] = (b0 + u < B) ? dg[(long long)(b0 + u) * 3 * H] : 0.f;  // 8 loads in flight
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (b0 + u >= B) break;
-                    bsum += d[u];
-#pragma unroll
-                    for (int k = 0; k < DWX_KMAX; ++k)
-                        if (k < K) {
-#pragma unroll
-                            for (int i = 0; i < DWX_CMAX; ++i)
-                                if (i < Cin) acc[k][i] = fmaf(xs[(k * B + b0 + u) * Cin + i], d[u], acc[k][i]);
-                        }
-                }
-            }
-        }
-    }
-    if (o >= 3 * H) return;
-    if (o < 2 * H) dbg[(long long)n * 2 * H + o] = bsum;
-    else dbu[(long long)n * H + o - 2 * H] = bsum;
-#pragma unroll
-    for (int k = 0; k < DWX_KMAX; ++k)
-        if (k < K) {
-#pragma unroll
-            for (int i = 0; i < DWX_CMAX; ++i)
-                if (i < Cin) {
-                    if (o < 2 * H) dWg[(((long long)n * K + k) * I + i) * 2 * H + o] = acc[k][i];
-                    else dWu[(((long long)n * K + k) * I + i) * H + o - 2 * H] = acc[k][i];
-                }
-        }
-}
-
 // B0: head of the reverse step.  dy = dY[t] + carry ; residual-mix backward up to da3.
 __global__ void bwd_head_kernel(const float* __restrict__ dY, const float* __restrict__ carry,
                                 const float* __restrict__ H1, const float* __restrict__ R2,
