@@ -87,6 +87,10 @@ int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_
 int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P, int flags,
                          void* stream);
 
+/* Experimental: run each layer's recurrence as one persistent cooperative kernel (fast mode only) instead of one
+ * launch per contraction.  Returns the previous setting.  Default off (or MATGCN_MULTI=1 in the environment). */
+int matgcn_set_persistent(int on);
+
 /* Diagnostics: device buffer (int64, >= 8 per tile of CTA 0) that later tensor-core launches fill with clock64()
  * stamps [producer start, mma wait, mma start, mma committed, epilogue wait, epilogue start, epilogue end]; NULL disables. */
 int matgcn_debug_set_timeline(long long* buf);

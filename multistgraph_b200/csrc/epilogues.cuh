@@ -1,0 +1,372 @@
+// Epilogue functors shared by the SIMT engine (gemm_simt.cuh) and the tensor-core engines (gemm_tc*.cuh):
+// all the elementwise GRU algebra of the path (forward gating, reverse-step chain rule) lives here.
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include "gemm_simt.cuh"
+
+namespace matgcn {
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+// fast-mode activations (SFU approximations, relative error ~2^-11: the same order as the TF32 products they follow)
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float tanh_fast(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogues
+//
+// Every epilogue is split in two phases so that the tensor-core kernel (few epilogue warps, no
+// thread-level parallelism to hide latency) can issue the global loads of a whole batch of output
+// elements before consuming any of them:
+//   EpiIn in = epi.load(z1, z2, row, col);      // every global read the element needs
+//   epi.store(z1, z2, row, col, acc, in);       // arithmetic + global writes
+// operator() = store(load()) is what the SIMT kernel calls.  load4/store4 are the same for four
+// consecutive columns (col % 4 == 0) with 16-byte accesses; vec_ok() tells the host whether every
+// pointer/pitch involved allows that.
+// ------------------------------------------------------------------------------------------
+#define EPI_CALL_OPERATOR                                                                              \
+    __device__ __forceinline__ void operator()(int z1, int z2, int row, int col, float acc) const {    \
+        store(z1, z2, row, col, acc, load(z1, z2, row, col));                                          \
+    }
+__device__ __forceinline__ float4 operator+(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator*(float a, const float4& b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
+__device__ __forceinline__ float4 one_minus(const float4& a) { return make_float4(1.f - a.x, 1.f - a.y, 1.f - a.z, 1.f - a.w); }
+__device__ __forceinline__ float4 sigmoid4(const float4& a, int fast) {
+    return fast ? make_float4(sigmoid_fast(a.x), sigmoid_fast(a.y), sigmoid_fast(a.z), sigmoid_fast(a.w))
+                : make_float4(sigmoidf_(a.x), sigmoidf_(a.y), sigmoidf_(a.z), sigmoidf_(a.w));
+}
+__device__ __forceinline__ float4 tanh4(const float4& a, int fast) {
+    return fast ? make_float4(tanh_fast(a.x), tanh_fast(a.y), tanh_fast(a.z), tanh_fast(a.w))
+                : make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w));
+}
+
+// C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col] + add[...]
+struct EpiStore {
+    float* C;
+    long long s1, s2;
+    int ldc;
+    const float* bias;   // may be null
+    long long bias_s1;
+    const float* scale;  // may be null: per column-group scale (view weights)
+    int scale_div;
+    int accumulate;      // 1: C += value
+    const float* add;    // may be null: extra addend with C's indexing (offsets add_s1/add_s2, ld add_ld)
+    long long add_s1, add_s2;
+    int add_ld;
+    bool vec_ok() const {
+        return aligned16(C) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3) && (!bias || (aligned16(bias) && !(bias_s1 & 3))) &&
+               (!scale || !(scale_div & 3)) && (!add || (aligned16(add) && !(add_s1 & 3) && !(add_s2 & 3) && !(add_ld & 3)));
+    }
+    __device__ __forceinline__ EpiIn load(int z1, int z2, int row, int col) const {
+        EpiIn in;
+        in.a = scale ? __ldg(scale + col / scale_div) : 1.f;
+        in.b = bias ? __ldg(bias + z1 * bias_s1 + col) : 0.f;
+        in.c = add ? add[z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col] : 0.f;
+        in.d = accumulate ? C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] : 0.f;
+        return in;
+    }
+    __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn& in) const {
+        float v = acc;
+        if (scale) v *= in.a;
+        if (bias) v += in.b;
+        if (add) v += in.c;
+        if (accumulate) v += in.d;
+        C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = v;
+    }
+    __device__ __forceinline__ EpiIn4 load4(int z1, int z2, int row, int col) const {
+        EpiIn4 in;
+        in.a = f4(scale ? __ldg(scale + col / scale_div) : 1.f);
+        in.b = bias ? ld4(bias + z1 * bias_s1 + col) : f4(0.f);
+        in.c = add ? ld4(add + z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col) : f4(0.f);
+        in.d = accumulate ? ld4(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col) : f4(0.f);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4& in) const {
+        float4 v = acc;
+        if (scale) v = v * in.a;
+        if (bias) v = v + in.b;
+        if (add) v = v + in.c;
+        if (accumulate) v = v + in.d;
+        st4(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
+    }
+    EPI_CALL_OPERATOR
+};
+inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
+    EpiStore e;
+    memset(&e, 0, sizeof(e));
+    e.C = C; e.s1 = s1; e.s2 = s2; e.ldc = ldc; e.scale_div = 1;
+    return e;
+}
+
+struct EpiAtomic {  // split-K partial sums into a zeroed C
+    float* C;
+    long long s1, s2;
+    int ldc;
+    bool vec_ok() const { return true; }
+    __device__ __forceinline__ EpiIn load(int, int, int, int) const { return EpiIn{}; }
+    __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn&) const {
+        atomicAdd(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, acc);
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int, int) const { return EpiIn4{}; }
+    __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4&) const {
+        float* d = C + z1 * s1 + z2 * s2 + (long long)row * ldc + col;
+        atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+    }
+    EPI_CALL_OPERATOR
+};
+
+// Forward step epilogues.  g = z1*rows_per_z + row indexes (node, batch) pairs; activations
+// are [N*B, H] blocks, pre-activation inputs [N*B, 3H] blocks.
+struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (cols >= H): R
+    const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
+    int rows_per_z, H, fast;
+    bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(Z) && aligned16(R) && aligned16(ZH); }
+    __device__ __forceinline__ EpiIn load(int z1, int, int row, int col) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        EpiIn in;
+        in.a = GX[g * 3 * H + col];
+        in.b = col < H ? Hprev[g * H + col] : 0.f;
+        return in;
+    }
+    __device__ __forceinline__ void store(int z1, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float s = fast ? sigmoid_fast(acc + in.a) : sigmoidf_(acc + in.a);
+        if (col < H) {
+            Z[g * H + col] = s;
+            ZH[g * H + col] = s * in.b;
+        } else {
+            R[g * H + col - H] = s;
+        }
+    }
+    __device__ __forceinline__ EpiIn4 load4(int z1, int, int row, int col) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        EpiIn4 in;
+        in.a = ld4(GX + g * 3 * H + col);
+        in.b = col < H ? ld4(Hprev + g * H + col) : f4(0.f);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int z1, int, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float4 s = sigmoid4(acc + in.a, fast);
+        if (col < H) {
+            st4(Z + g * H + col, s);
+            st4(ZH + g * H + col, s * in.b);
+        } else {
+            st4(R + g * H + col - H, s);
+        }
+    }
+    EPI_CALL_OPERATOR
+};
+struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
+    const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
+    int rows_per_z, H, fast;
+    bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(H1); }
+    __device__ __forceinline__ EpiIn load(int z1, int, int row, int col) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        EpiIn in;
+        in.a = GX[g * 3 * H + 2 * H + col];
+        in.b = R[g * H + col];
+        in.c = Hprev[g * H + col];
+        return in;
+    }
+    __device__ __forceinline__ void store(int z1, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float hc = fast ? tanh_fast(acc + in.a) : tanhf(acc + in.a);
+        HC[g * H + col] = hc;
+        H1[g * H + col] = in.b * in.c + (1.f - in.b) * hc;
+    }
+    __device__ __forceinline__ EpiIn4 load4(int z1, int, int row, int col) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        EpiIn4 in;
+        in.a = ld4(GX + g * 3 * H + 2 * H + col);
+        in.b = ld4(R + g * H + col);
+        in.c = ld4(Hprev + g * H + col);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int z1, int, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        const float4 hc = tanh4(acc + in.a, fast);
+        st4(HC + g * H + col, hc);
+        st4(H1 + g * H + col, in.b * in.c + one_minus(in.b) * hc);
+    }
+    EPI_CALL_OPERATOR
+};
+struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r2)*hc2)
+    const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
+    int H, fast;
+    bool vec_ok() const { return !(H & 3) && aligned16(RX) && aligned16(H1) && aligned16(R2) && aligned16(HC2) && aligned16(Y); }
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
+        const long long g = row;
+        EpiIn in;
+        in.a = RX[g * 3 * H + 2 * H + col];
+        in.b = R2[g * H + col];
+        in.c = H1[g * H + col];
+        in.d = __ldg(mix_t);
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long g = row;
+        const float hc2 = fast ? tanh_fast(acc + in.a) : tanhf(acc + in.a);
+        const float r2 = in.b, h1 = in.c, m = in.d;
+        const float res = r2 * h1 + (1.f - r2) * hc2;
+        HC2[g * H + col] = hc2;
+        Y[g * H + col] = m * h1 + (1.f - m) * res;
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
+        const long long g = row;
+        EpiIn4 in;
+        in.a = ld4(RX + g * 3 * H + 2 * H + col);
+        in.b = ld4(R2 + g * H + col);
+        in.c = ld4(H1 + g * H + col);
+        in.d = f4(__ldg(mix_t));
+        return in;
+    }
+    __device__ __forceinline__ void store4(int, int, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const long long g = row;
+        const float4 hc2 = tanh4(acc + in.a, fast);
+        const float4 res = in.b * in.c + one_minus(in.b) * hc2;
+        st4(HC2 + g * H + col, hc2);
+        st4(Y + g * H + col, in.d * in.c + one_minus(in.d) * res);
+    }
+    EPI_CALL_OPERATOR
+};
+
+// Backward step epilogues (notation of DESIGN.md section 3 / tests/host_mirror.py).
+struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR[H:2H] = dres*(h1-hc2)*r2(1-r2)
+    float* DH1; float* DR; const float* DRES; const float* H1; const float* Z2; const float* R2; const float* HC2;
+    int H;
+    bool vec_ok() const {
+        return !(H & 3) && aligned16(DH1) && aligned16(DR) && aligned16(DRES) && aligned16(H1) && aligned16(Z2) && aligned16(R2) && aligned16(HC2);
+    }
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
+        const long long i = (long long)row * H + col;
+        EpiIn in;
+        in.a = Z2[i]; in.b = R2[i]; in.c = H1[i]; in.d = DH1[i]; in.e = DRES[i]; in.f = HC2[i];
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * H + col;
+        const float z2 = in.a, r2 = in.b, h1 = in.c;
+        DH1[i] = in.d + acc * z2;
+        DR[(long long)row * 3 * H + col] = acc * h1 * z2 * (1.f - z2);
+        DR[(long long)row * 3 * H + H + col] = in.e * (h1 - in.f) * r2 * (1.f - r2);
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
+        const long long i = (long long)row * H + col;
+        EpiIn4 in;
+        in.a = ld4(Z2 + i); in.b = ld4(R2 + i); in.c = ld4(H1 + i); in.d = ld4(DH1 + i); in.e = ld4(DRES + i); in.f = ld4(HC2 + i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int, int, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const long long i = (long long)row * H + col;
+        st4(DH1 + i, in.d + acc * in.a);
+        st4(DR + (long long)row * 3 * H + col, acc * in.c * in.a * one_minus(in.a));
+        st4(DR + (long long)row * 3 * H + H + col, in.e * (in.c - in.f) * in.b * one_minus(in.b));
+    }
+    EPI_CALL_OPERATOR
+};
+struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
+    const float* DH1; const float* Hprev; const float* R; const float* HC; float* DHD; float* DG;
+    int H;
+    bool vec_ok() const { return !(H & 3) && aligned16(DH1) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(DHD) && aligned16(DG); }
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
+        const long long i = (long long)row * H + col;
+        EpiIn in;
+        in.a = DH1[i]; in.b = R[i]; in.c = HC[i]; in.d = Hprev[i];
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * H + col;
+        const float dh1 = in.a + acc;
+        const float r = in.b, hc = in.c, h = in.d;
+        DHD[i] = dh1 * r;
+        DG[(long long)row * 3 * H + 2 * H + col] = dh1 * (1.f - r) * (1.f - hc * hc);
+        DG[(long long)row * 3 * H + H + col] = dh1 * (h - hc) * r * (1.f - r);
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
+        const long long i = (long long)row * H + col;
+        EpiIn4 in;
+        in.a = ld4(DH1 + i); in.b = ld4(R + i); in.c = ld4(HC + i); in.d = ld4(Hprev + i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int, int, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const long long i = (long long)row * H + col;
+        const float4 dh1 = in.a + acc;
+        st4(DHD + i, dh1 * in.b);
+        st4(DG + (long long)row * 3 * H + 2 * H + col, dh1 * one_minus(in.b) * one_minus(in.c * in.c));
+        st4(DG + (long long)row * 3 * H + H + col, dh1 * (in.d - in.c) * in.b * one_minus(in.b));
+    }
+    EPI_CALL_OPERATOR
+};
+struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      (row = node m, col = (b,c))
+    const float* DP0; const float* Hprev; const float* Z; float* DHD; float* DG;
+    int H, BH;  // BH = B*H columns per node
+    bool vec_ok() const { return !(H & 3) && !(BH & 3) && aligned16(DP0) && aligned16(Hprev) && aligned16(Z) && aligned16(DHD) && aligned16(DG); }
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
+        const long long i = (long long)row * BH + col;
+        EpiIn in;
+        in.a = DP0[i]; in.b = Z[i]; in.c = DHD[i]; in.d = Hprev[i];
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * BH + col;
+        const float dzh = acc + in.a;
+        const float z = in.b;
+        DHD[i] = in.c + dzh * z;
+        const long long g = i / H;
+        const int c = (int)(i - g * H);
+        DG[g * 3 * H + c] = dzh * in.d * z * (1.f - z);
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
+        const long long i = (long long)row * BH + col;
+        EpiIn4 in;
+        in.a = ld4(DP0 + i); in.b = ld4(Z + i); in.c = ld4(DHD + i); in.d = ld4(Hprev + i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int, int, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const long long i = (long long)row * BH + col;
+        const float4 dzh = acc + in.a;
+        st4(DHD + i, in.c + dzh * in.b);
+        const long long g = i / H;
+        const int c = (int)(i - g * H);
+        st4(DG + g * 3 * H + c, dzh * in.d * in.b * one_minus(in.b));
+    }
+    EPI_CALL_OPERATOR
+};
+
+struct EpiB6 {  // carry = acc + DP0 + DHD
+    const float* DP0; const float* DHD; float* OUT;
+    int BH;
+    bool vec_ok() const { return !(BH & 3) && aligned16(DP0) && aligned16(DHD) && aligned16(OUT); }
+    __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
+        const long long i = (long long)row * BH + col;
+        EpiIn in;
+        in.a = DP0[i]; in.b = DHD[i];
+        return in;
+    }
+    __device__ __forceinline__ void store(int, int, int row, int col, float acc, const EpiIn& in) const {
+        const long long i = (long long)row * BH + col;
+        OUT[i] = acc + in.a + in.b;
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
+        const long long i = (long long)row * BH + col;
+        EpiIn4 in;
+        in.a = ld4(DP0 + i); in.b = ld4(DHD + i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int, int, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const long long i = (long long)row * BH + col;
+        st4(OUT + i, acc + in.a + in.b);
+    }
+    EPI_CALL_OPERATOR
+};
+
+
+}  // namespace matgcn

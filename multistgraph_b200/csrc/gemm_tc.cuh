@@ -27,6 +27,7 @@
 
 namespace matgcn {
 
+constexpr int TC_EPI_LD = 36;  // epilogue staging row pitch (floats)
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;  // fp32 elements per K slab = one 128-byte swizzle row
 constexpr int TC_EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each taking every other 32-column chunk
@@ -59,6 +60,7 @@ struct TcP {
     FastDiv d_mn, d_splits, d_z2, d_tn;
     int cA1, cA2, cAk;      // 1 if the operand really has that (strided) dimension, else coordinate 0
     int cB1, cB2, cBk;
+    int tA_dim, tB_dim, t;  // persistent kernel: which coordinate (2..4, 0 = none) carries the time step, and its value
     int m64;                // 1: issue M=64 MMAs (tile rows 0..63 only; 16 accumulator rows per TMEM lane quadrant)
     int vec;                // 1: N % 4 == 0 and the epilogue's pointers/pitches allow 16-byte accesses
     int dbg_mode;           // diagnostics only: 1 = skip epilogue stores
@@ -145,11 +147,95 @@ struct TcSmem {
     static constexpr int B_BYTES = BN * TC_BK * 4;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
-    static constexpr int EPI_LD = 36;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 access
+    static constexpr int EPI_LD = TC_EPI_LD;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 access
     static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_LD * 4;  // per epilogue warp: [32][36] floats
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
+
+// Epilogue of one output tile, run by one epilogue warp: TMEM -> registers -> staging tile -> epilogue functor.
+//   tmem_acc: TMEM address of the accumulator (lane 0, first column); bn: tile width; q: lane quadrant of this warp;
+//   half: which of the two warps of the quadrant (takes every other 32-column chunk); buf: [32][EPI_LD] staging tile.
+template <class Epi>
+__device__ __forceinline__ void tc_epilogue_tile(const Epi& epi, const TcP& p, uint32_t tmem_acc, int bn, int q, int half,
+                                                 float* buf, int lane, int z1, int z2, int m0, int n0) {
+    constexpr int LD = TC_EPI_LD;
+    const int pM = p.M, pN = p.N, pvec = p.vec, pm64 = p.m64, pdbg = p.dbg_mode;  // hoisted: p may sit in memory
+    // M=128: accumulator row r lives in TMEM lane r.  M=64: row r lives in lane 32*(r/16) + r%16, i.e. every
+    // lane quadrant holds 16 rows, so all epilogue warps stay busy on the half-height tiles of this path.
+    const int rows_per_q = pm64 ? 16 : 32;
+    const int row_base = m0 + q * rows_per_q;
+    const int row_lim = (pdbg & 4) ? (m0 + 128) : min(pM, row_base + rows_per_q);  // bit 2: raw lane dump
+    if (row_base < row_lim) {
+#pragma unroll 1
+        for (int c = half; c < bn / 32; c += TC_EPI_WARPS / 4) {
+            const int col_base = n0 + c * 32;
+            if (col_base >= pN) break;
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            uint32_t r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // lane = accumulator row: park the 32 columns of that row in the staging tile
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(buf + lane * LD + 4 * j) =
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+            __syncwarp();
+            if (pvec) {
+                // lane -> (row = 4*it + lane/8, columns 4*(lane%8) .. +3): one 16-byte access per lane, 4 rows of
+                // 128 contiguous bytes per warp instruction; loads of a batch are issued before any is consumed
+                const int rq = lane >> 3, cq = lane & 7;
+                const int col = col_base + 4 * cq;
+                const bool col_ok = col < pN;
+#pragma unroll 1
+                for (int it0 = 0; it0 < 8; it0 += 2) {
+                    EpiIn4 in[2];
+                    float4 v[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int rl = 4 * (it0 + u) + rq;
+                        v[u] = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
+                        if (col_ok && row_base + rl < row_lim) in[u] = epi.load4(z1, z2, row_base + rl, col);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int rl = 4 * (it0 + u) + rq;
+                        if (col_ok && row_base + rl < row_lim && !(pdbg & 1)) epi.store4(z1, z2, row_base + rl, col, v[u], in[u]);
+                    }
+                }
+            } else {
+                const int col = col_base + lane;
+                const bool col_ok = col < pN;
+#pragma unroll 1
+                for (int rr0 = 0; rr0 < 32; rr0 += 8) {
+                    EpiIn in[8];
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int row = row_base + rr0 + u;
+                        v[u] = buf[(rr0 + u) * LD + lane];
+                        if (col_ok && row < row_lim) in[u] = epi.load(z1, z2, row, col);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int row = row_base + rr0 + u;
+                        if (col_ok && row < row_lim) epi.store(z1, z2, row, col, v[u], in[u]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
@@ -302,7 +388,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;             // TMEM lane quadrant this warp may read: lanes [32q, 32q+32)
         const int half = (warp - 4) >> 2;   // which of the two warps of that quadrant (column-chunk parity)
         float* buf = epi_buf + (warp - 4) * (32 * S::EPI_LD);  // staging tile [32][EPI_LD] of this warp
-        constexpr int LD = S::EPI_LD;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -313,80 +398,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
-            // M=128: accumulator row r lives in TMEM lane r.  M=64: row r lives in lane 32*(r/16) + r%16, i.e. every
-            // lane quadrant holds 16 rows, so all epilogue warps stay busy on the half-height tiles of this path.
-            const int rows_per_q = p.m64 ? 16 : 32;
-            const int row_base = m0 + q * rows_per_q;
-            const int row_lim = (p.dbg_mode & 4) ? (m0 + 128) : min(p.M, row_base + rows_per_q);  // bit 2: raw lane dump
-            if (row_base < row_lim) {
-#pragma unroll 1
-                for (int c = half; c < BN / 32; c += TC_EPI_WARPS / 4) {
-                    const int col_base = n0 + c * 32;
-                    if (col_base >= p.N) break;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-                    uint32_t r[32];
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // lane = accumulator row: park the 32 columns of that row in the staging tile
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(buf + lane * LD + 4 * j) =
-                            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                        __uint_as_float(r[4 * j + 3]));
-                    __syncwarp();
-                    if (p.vec) {
-                        // lane -> (row = 4*it + lane/8, columns 4*(lane%8) .. +3): one 16-byte access per lane, 4 rows of
-                        // 128 contiguous bytes per warp instruction; loads of a batch are issued before any is consumed
-                        const int rq = lane >> 3, cq = lane & 7;
-                        const int col = col_base + 4 * cq;
-                        const bool col_ok = col < p.N;
-#pragma unroll 1
-                        for (int it0 = 0; it0 < 8; it0 += 2) {
-                            EpiIn4 in[2];
-                            float4 v[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int rl = 4 * (it0 + u) + rq;
-                                v[u] = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
-                                if (col_ok && row_base + rl < row_lim) in[u] = epi.load4(z1, z2, row_base + rl, col);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int rl = 4 * (it0 + u) + rq;
-                                if (col_ok && row_base + rl < row_lim && !(p.dbg_mode & 1)) epi.store4(z1, z2, row_base + rl, col, v[u], in[u]);
-                            }
-                        }
-                    } else {
-                        const int col = col_base + lane;
-                        const bool col_ok = col < p.N;
-#pragma unroll 1
-                        for (int rr0 = 0; rr0 < 32; rr0 += 8) {
-                            EpiIn in[8];
-                            float v[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int row = row_base + rr0 + u;
-                                v[u] = buf[(rr0 + u) * LD + lane];
-                                if (col_ok && row < row_lim) in[u] = epi.load(z1, z2, row, col);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int row = row_base + rr0 + u;
-                                if (col_ok && row < row_lim) epi.store(z1, z2, row, col, v[u], in[u]);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
+            tc_epilogue_tile(epi, p, tmem_base + (uint32_t)(acc * BN), BN, q, half, buf, lane, z1, z2, m0, n0);
             tc_fence_before();
             __syncwarp();
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
@@ -457,11 +469,14 @@ inline int sm_count() {
 }
 
 // Operand as a rank-5 tensor map {inner, outer, KB, Z2, Z1}.  `kc`: K is the contiguous (inner) dimension.
+// Optional time dimension (persistent recurrence kernel): when nT > 1 and st != 0 one of the unused outer
+// dimensions becomes the time step (size nT, stride st floats) and *tdim tells which coordinate carries t.
 inline bool make_operand_map(CUtensorMap* map, const float* base, bool kc, int mn, int K, int ld, long long sk, long long s2,
-                             long long s1, int KB, int Z2, int Z1, int box_mn_rows, int* ck, int* c2, int* c1) {
+                             long long s1, int KB, int Z2, int Z1, int box_mn_rows, int* ck, int* c2, int* c1,
+                             long long st = 0, int nT = 1, int* tdim = nullptr) {
     TmapEncodeFn enc = tmap_encoder();
     if (!enc) return false;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3) || (sk & 3) || (s2 & 3) || (s1 & 3)) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3) || (sk & 3) || (s2 & 3) || (s1 & 3) || (st & 3) || st < 0) return false;
     *ck = (KB > 1 && sk != 0) ? 1 : 0;
     *c2 = (Z2 > 1 && s2 != 0) ? 1 : 0;
     *c1 = (Z1 > 1 && s1 != 0) ? 1 : 0;
@@ -473,6 +488,14 @@ inline bool make_operand_map(CUtensorMap* map, const float* base, bool kc, int m
     const cuuint64_t dummy = row_bytes * outer;
     cuuint64_t strides[4] = {row_bytes, *ck ? (cuuint64_t)sk * 4 : dummy, *c2 ? (cuuint64_t)s2 * 4 : dummy,
                              *c1 ? (cuuint64_t)s1 * 4 : dummy};
+    if (tdim) *tdim = 0;
+    if (nT > 1 && st != 0) {
+        int d = !*ck ? 2 : (!*c2 ? 3 : (!*c1 ? 4 : -1));
+        if (d < 0 || !tdim) return false;
+        dims[d] = (cuuint64_t)nT;
+        strides[d - 1] = (cuuint64_t)st * 4;
+        *tdim = d;
+    }
     for (int i = 0; i < 4; ++i)
         if (strides[i] == 0 || (strides[i] & 15) || strides[i] >= (1ULL << 40)) return false;
     cuuint32_t box[5] = {32, (cuuint32_t)(kc ? box_mn_rows : 32), 1, 1, 1};
@@ -503,6 +526,7 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     t.d_splits = make_fastdiv((uint32_t)splits);
     t.d_z2 = make_fastdiv((uint32_t)Z2);
     t.d_tn = make_fastdiv((uint32_t)t.tiles_n);
+    t.tA_dim = t.tB_dim = t.t = 0;
     t.vec = ((p.N & 3) == 0 && epi.vec_ok()) ? 1 : 0;
     // M <= 64 (every node-batched contraction at batch 64): M=64 MMAs, whose accumulator spreads 16 rows over each
     // TMEM lane quadrant (layout verified on hardware by tools/m64_probe.py), halve the MMA work and keep all

@@ -91,3 +91,36 @@ def test_model_fast_mode_matches_oracle(N, B, adjtype, adpadj, D, tout):
     print("[fast N=%d] " % N + ", ".join("%s=%.2e" % kv for kv in errs.items()))
     bad = {k: v for k, v in errs.items() if not (v < MODEL_TOL)}
     assert not bad, bad
+
+
+def test_persistent_recurrence_kernel_matches_per_phase_launches():
+    """The experimental persistent multi-phase kernel (one cooperative launch per layer recurrence) must give the
+    same forecasts and gradients as the default one-launch-per-contraction path."""
+    N, B, tout = 70, 8, 12
+    cfg = make_config(adjtype="multi", adpadj="bidirection", embed_dim=10, output_window=tout, batch_size=B,
+                      device=torch.device(DEV), matgcn_mode="tf32")
+    df = make_data_feature(N, seed=9)
+    batch = make_batch(N, B, tout, seed=9)
+    torch.manual_seed(1)
+    model = MultiATGCN(dict(cfg), df).to(DEV).eval()
+    lib = _cabi.lib()
+
+    def run(persistent):
+        prev = lib.matgcn_set_persistent(1 if persistent else 0)
+        try:
+            model.zero_grad(set_to_none=True)
+            y = model.predict(clone_batch(batch, DEV))
+            model.calculate_loss(clone_batch(batch, DEV)).backward()
+            torch.cuda.synchronize()
+            return y.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        finally:
+            lib.matgcn_set_persistent(prev)
+
+    y0, g0 = run(False)
+    n0 = lib.matgcn_launch_count()
+    y1, g1 = run(True)
+    n1 = lib.matgcn_launch_count() - n0
+    assert max_rel_err(y1, y0) < 1e-5
+    for k in g0:
+        assert max_rel_err(g1[k], g0[k]) < 1e-4, k   # split-K atomics reorder sums slightly
+    assert n1 < 300, "persistent mode should need far fewer launches (got %d)" % n1
