@@ -275,12 +275,23 @@ __global__ void xside_fwd_small_kernel(const float* __restrict__ PX, const float
         xs[j] = PX[((long long)t * K + k) * UX + (long long)n * B * Cin + r];
     }
     float w[XS_KC], rw[4], bias = 0.f, rb = 0.f;
+    int xo[XS_KC];  // smem offset of x[k][b=0][i] for each (k,i) pair: no index arithmetic in the inner loop
+#pragma unroll
+    for (int kc = 0; kc < XS_KC; ++kc) {
+        const int k = kc / Cin, i = kc - k * Cin;
+        xo[kc] = k * B * Cin + i;
+        w[kc] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rw[i] = 0.f;
     if (o < 3 * H) {
 #pragma unroll
         for (int kc = 0; kc < XS_KC; ++kc)
             if (kc < KC) {
                 const int k = kc / Cin, i = kc - k * Cin;
                 w[kc] = o < 2 * H ? Wg[(((long long)n * K + k) * I + i) * 2 * H + o] : Wu[(((long long)n * K + k) * I + i) * H + o - 2 * H];
+            } else {
+                xo[kc] = 0;  // weight 0: any valid slot
             }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -292,17 +303,14 @@ __global__ void xside_fwd_small_kernel(const float* __restrict__ PX, const float
     if (o >= 3 * H) return;
     float* gx = GX + (((long long)t * N + n) * B) * 3 * H + o;
     float* rx = RX + (((long long)t * N + n) * B) * 3 * H + o;
+    const int cin_m1 = Cin - 1;
     for (int b = 0; b < B; ++b) {
+        const float* xb = xs + b * Cin;
         float g = bias, r = rb;
 #pragma unroll
-        for (int kc = 0; kc < XS_KC; ++kc)
-            if (kc < KC) {
-                const int k = kc / Cin, i = kc - k * Cin;
-                g = fmaf(w[kc], xs[(k * B + b) * Cin + i], g);
-            }
+        for (int kc = 0; kc < XS_KC; ++kc) g = fmaf(w[kc], xb[xo[kc]], g);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i < Cin) r = fmaf(rw[i], xs[b * Cin + i], r);
+        for (int i = 0; i < 4; ++i) r = fmaf(rw[i], xb[min(i, cin_m1)], r);
         gx[(long long)b * 3 * H] = g;
         rx[(long long)b * 3 * H] = r;
     }
