@@ -159,6 +159,23 @@ int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int K, int ldm
                              float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
                              int flags, void* stream);
 
+/* -------------------------------------------------------------------------------------------
+ * gcn_off ablation layer: a plain GRU whose nn.Linear weights are shared by all nodes,
+ * replaces GRUCell.forward MA.py:142-150 used as the main cell (MA.py:187-192, 204) over the whole window.
+ *   x [T, N, B, Cin] (time stride x_tstride), h0 [N, B, H] or NULL, Gw/Gb [2H, I]/[2H] (gate), Uw/Ub [H, I]/[H]
+ * The output y[t] lives in the workspace at float offset matgcn_dense_gru_layer_y_offset(), time stride N*B*H.
+ * Backward overwrites dx [T,N,B,Cin], dh0 (or NULL), dGw, dGb, dUw, dUb.
+ * ----------------------------------------------------------------------------------------- */
+size_t matgcn_dense_gru_layer_fwd_ws_bytes(int T, int N, int B, int Cin, int H);
+size_t matgcn_dense_gru_layer_bwd_ws_bytes(int T, int N, int B, int Cin, int H);
+size_t matgcn_dense_gru_layer_y_offset(int T, int N, int B, int Cin, int H);
+int matgcn_dense_gru_layer_fwd(int T, int N, int B, int Cin, int H, const float* x, long long x_tstride, const float* h0,
+                               const float* Gw, const float* Gb, const float* Uw, const float* Ub, float* ws, int flags,
+                               void* stream);
+int matgcn_dense_gru_layer_bwd(int T, int N, int B, int Cin, int H, const float* dy, long long dy_tstride, const float* x,
+                               long long x_tstride, const float* Gw, const float* Uw, float* ws, float* bws, float* dx,
+                               float* dh0, float* dGw, float* dGb, float* dUw, float* dUb, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

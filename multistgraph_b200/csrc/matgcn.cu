@@ -1169,3 +1169,170 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     tr.report("encoder_layer_bwd");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// gcn_off ablation: the layer is a plain GRU whose two nn.Linear are shared by all nodes (MA.py:134-153 used as
+// the main cell, MA.py:187-192).  It is the residual-GRU half of the full layer with the hidden state itself
+// as input, so it reuses the same epilogues (with a constant mix of 0: y = GRU(x, h)).
+//   workspace: RX [T,NB,3H] (-> DR in backward) | HS [T+1,NB,H] (HS[0] = h0, HS[t+1] = h_t) | Z2,R2,HC2,ZH2 [T,NB,H]
+//              | GH [2H,H] | UH [H,H] | zero, scratch
+// ------------------------------------------------------------------------------------------
+struct DenseWs {
+    size_t RX, HS, Z2, R2, HC2, ZH2, GH, UH, ZERO, total;
+};
+static DenseWs dense_ws(int T, int N, int B, int H) {
+    DenseWs w;
+    const size_t U = (size_t)N * B * H;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o = align64(o + n); return r; };
+    w.RX = take((size_t)T * 3 * U);
+    w.HS = take((size_t)(T + 1) * U);
+    w.Z2 = take((size_t)T * U);
+    w.R2 = take((size_t)T * U);
+    w.HC2 = take((size_t)T * U);
+    w.ZH2 = take((size_t)T * U);
+    w.GH = take((size_t)2 * H * H);
+    w.UH = take((size_t)H * H);
+    w.ZERO = take(64);
+    w.total = o;
+    return w;
+}
+extern "C" size_t matgcn_dense_gru_layer_fwd_ws_bytes(int T, int N, int B, int Cin, int H) {
+    (void)Cin;
+    return dense_ws(T, N, B, H).total * sizeof(float);
+}
+extern "C" size_t matgcn_dense_gru_layer_bwd_ws_bytes(int T, int N, int B, int Cin, int H) {
+    (void)T; (void)Cin;
+    return (align64((size_t)N * B * H) * 3 + 64) * sizeof(float);
+}
+extern "C" size_t matgcn_dense_gru_layer_y_offset(int T, int N, int B, int Cin, int H) {
+    (void)Cin;
+    return dense_ws(T, N, B, H).HS + (size_t)N * B * H;
+}
+
+extern "C" int matgcn_dense_gru_layer_fwd(int T, int N, int B, int Cin, int H, const float* x, long long x_tstride,
+                                          const float* h0, const float* Gw, const float* Gb, const float* Uw, const float* Ub,
+                                          float* ws, int flags, void* stream) {
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
+    REQUIRE(x && Gw && Gb && Uw && Ub && ws, "null pointer");
+    REQUIRE(T > 0 && N > 0 && B > 0 && Cin > 0 && H > 0, "bad dims");
+    REQUIRE((long long)N * B * 3 * H < 2147483647LL, "N*B*3H overflows int (shard the batch)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const DenseWs w = dense_ws(T, N, B, H);
+    const int I = Cin + H, NB = N * B;
+    const long long U = (long long)NB * H;
+    float* RX = ws + w.RX; float* HS = ws + w.HS; float* GH = ws + w.GH; float* UH = ws + w.UH;
+    CK(cudaMemsetAsync(ws + w.ZERO, 0, sizeof(float) * 64, st));
+    CK(cudaMemcpy2DAsync(GH, sizeof(float) * H, Gw + Cin, sizeof(float) * I, sizeof(float) * H, 2 * H, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(UH, sizeof(float) * H, Uw + Cin, sizeof(float) * I, sizeof(float) * H, H, cudaMemcpyDeviceToDevice, st));
+    if (h0) CK(cudaMemcpyAsync(HS, h0, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
+    else CK(cudaMemsetAsync(HS, 0, sizeof(float) * U, st));
+    GemmP p;
+    // input half for all t: RX[t] = x_t * [Gw[:, :Cin]; Uw[:, :Cin]]^T + [Gb; Ub]
+    memset(&p, 0, sizeof(p));
+    p.splits = 1; p.Z2 = 1; p.KB = 1;
+    p.A = x; p.lda = Cin; p.sA1 = x_tstride; p.M = NB; p.K = Cin;
+    {
+        p.B = Gw; p.ldb = I; p.N = 2 * H;
+        EpiStore e = epi_store(RX, 3 * U, 0, 3 * H);
+        e.bias = Gb;
+        CK((gemm_any<CfgMid, true, true>(tc, p, e, T, st)));
+        p.B = Uw; p.N = H;
+        e = epi_store(RX + 2 * H, 3 * U, 0, 3 * H);
+        e.bias = Ub;
+        CK((gemm_any<CfgMid, true, true>(tc, p, e, T, st)));
+    }
+    for (int t = 0; t < T; ++t) {
+        const float* Ht = HS + t * U;
+        const float* RXt = RX + (long long)t * 3 * U;
+        float* Z2t = ws + w.Z2 + t * U; float* R2t = ws + w.R2 + t * U; float* HC2t = ws + w.HC2 + t * U; float* ZH2t = ws + w.ZH2 + t * U;
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = 1; p.KB = 1;
+        p.A = Ht; p.lda = H; p.M = NB; p.K = H;
+        p.B = GH; p.ldb = H; p.N = 2 * H;
+        CK((gemm_any<CfgMid, true, true>(tc, p, EpiGate{RXt, Ht, Z2t, R2t, ZH2t, 0, H, tc ? 1 : 0}, 1, st)));
+        p.A = ZH2t; p.B = UH; p.N = H;
+        CK((gemm_any<CfgMid, true, true>(tc, p, EpiResCand{RXt, Ht, R2t, HC2t, HS + (t + 1) * U, ws + w.ZERO, H, tc ? 1 : 0}, 1, st)));
+    }
+    return 0;
+}
+
+extern "C" int matgcn_dense_gru_layer_bwd(int T, int N, int B, int Cin, int H, const float* dy, long long dy_tstride,
+                                          const float* x, long long x_tstride, const float* Gw, const float* Uw, float* ws,
+                                          float* bws, float* dx, float* dh0, float* dGw, float* dGb, float* dUw, float* dUb,
+                                          int flags, void* stream) {
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
+    REQUIRE(dy && x && Gw && Uw && ws && bws && dx && dGw && dGb && dUw && dUb, "null pointer");
+    REQUIRE(T > 0 && N > 0 && B > 0 && Cin > 0 && H > 0, "bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    const DenseWs w = dense_ws(T, N, B, H);
+    const int I = Cin + H, NB = N * B;
+    const long long U = (long long)NB * H, UX = (long long)NB * Cin;
+    float* DR = ws + w.RX; const float* HS = ws + w.HS;
+    const size_t Ua = align64((size_t)U);
+    float* DH1 = bws; float* DRES = bws + Ua; float* DHC = bws + 2 * Ua; float* scratch = bws + 3 * Ua;
+    CK(cudaMemsetAsync(DHC, 0, sizeof(float) * U, st));
+    CK(cudaMemsetAsync(scratch, 0, sizeof(float) * 64, st));
+    GemmP p;
+    for (int t = T - 1; t >= 0; --t) {
+        const float* Ht = HS + t * U;
+        const float* Z2t = ws + w.Z2 + t * U; const float* R2t = ws + w.R2 + t * U; const float* HC2t = ws + w.HC2 + t * U;
+        float* DRt = DR + (long long)t * 3 * U;
+        bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dy + (long long)t * dy_tstride, DHC, Ht, R2t, HC2t, ws + w.ZERO, U, H,
+                                                                    DH1, DRES, DRt, scratch);
+        count_launch();
+        CK(cudaGetLastError());
+        memset(&p, 0, sizeof(p));
+        p.splits = 1; p.Z2 = 1; p.KB = 1;
+        p.A = DRt + 2 * H; p.lda = 3 * H; p.M = NB; p.K = H;
+        p.B = ws + w.UH; p.ldb = H; p.N = H;
+        CK((gemm_any<CfgMid, true, false>(tc, p, EpiB1{DH1, DRt, DRES, Ht, Z2t, R2t, HC2t, H}, 1, st)));
+        p.A = DRt; p.K = 2 * H; p.B = ws + w.GH;
+        {
+            EpiStore e = epi_store(DHC, 0, 0, H);   // carry = dh1 (direct) + da2 * Gw[:, Cin:]
+            e.add = DH1; e.add_ld = H;
+            CK((gemm_any<CfgMid, true, false>(tc, p, e, 1, st)));
+        }
+    }
+    if (dh0) CK(cudaMemcpyAsync(dh0, DHC, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
+    // parameter gradients over all steps
+    CK(cudaMemsetAsync(dGw, 0, sizeof(float) * (size_t)2 * H * I, st));
+    CK(cudaMemsetAsync(dUw, 0, sizeof(float) * (size_t)H * I, st));
+    CK(cudaMemsetAsync(dGb, 0, sizeof(float) * 2 * H, st));
+    CK(cudaMemsetAsync(dUb, 0, sizeof(float) * H, st));
+    {
+        REQUIRE(3 * H <= 1024, "hidden size too large for the column-sum kernels");
+        const int cs_threads = 3 * H <= 256 ? 256 : 3 * H;
+        dim3 g2(1, 1184);
+        colsum_kernel<<<g2, cs_threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 3 * H, 2 * H, dGb, 2 * H, dUb, H);
+        count_launch();
+        CK(cudaGetLastError());
+        memset(&p, 0, sizeof(p));
+        p.Z2 = 1; p.KB = T; p.K = NB; p.lda = 3 * H; p.sAk = 3 * U;
+        int splits = (int)(((long long)T * NB + 4095) / 4096);
+        if (splits > 592) splits = 592;
+        if (splits < 1) splits = 1;
+        p.splits = splits;
+        p.A = DR; p.M = 2 * H; p.B = HS; p.ldb = H; p.sBk = U; p.N = H;
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dGw + Cin, 0, 0, I}, 1, st)));
+        p.A = DR + 2 * H; p.M = H; p.B = ws + w.ZH2;
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dUw + Cin, 0, 0, I}, 1, st)));
+        p.B = x; p.ldb = Cin; p.sBk = x_tstride; p.N = Cin;
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dUw, 0, 0, I}, 1, st)));
+        p.A = DR; p.M = 2 * H;
+        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dGw, 0, 0, I}, 1, st)));
+    }
+    // dx[t] = DR[t][:, :2H] * Gw[:, :Cin] + DR[t][:, 2H:] * Uw[:, :Cin]
+    memset(&p, 0, sizeof(p));
+    p.splits = 1; p.Z2 = 1; p.KB = 1;
+    p.A = DR; p.lda = 3 * H; p.sA1 = 3 * U; p.M = NB; p.K = 2 * H;
+    p.B = Gw; p.ldb = I; p.N = Cin;
+    {
+        EpiStore e = epi_store(dx, UX, 0, Cin);
+        CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
+        e.accumulate = 1;
+        p.A = DR + 2 * H; p.K = H; p.B = Uw;
+        CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
+    }
+    return 0;
+}

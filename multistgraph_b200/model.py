@@ -275,7 +275,14 @@ class MultiATGCN(nn.Module):
         enc = self.encoder
         mix = torch.sigmoid(enc.weights_gru)
         if self.gcn_off:
-            raise NotImplementedError("gcn_off=true (plain GRU ablation) is not on the accelerated path yet")
+            # ablation: the main cell is a plain GRU with node-shared Linear weights, no residual cell, no mixing
+            # (MA.py:187-192, 204-209)
+            cur = x_nm
+            for layer in range(self.num_layers):
+                cell = enc.agru_cells[layer]
+                cur = ops.dense_gru_layer(cur, None, cell.gate.weight, cell.gate.bias, cell.update.weight,
+                                          cell.update.bias, self.matgcn_flags)
+            return cur
         bases, n_adp = self._base_matrices()
         k_total = bases.shape[0] + 1
         cur = x_nm

@@ -153,6 +153,59 @@ class _EncoderLayerFn(torch.autograd.Function):
         return dx, dh0, dM, dWg, dbg, dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, None, None
 
 
+class _DenseGRULayerFn(torch.autograd.Function):
+    """gcn_off ablation: plain GRU layer with node-shared nn.Linear weights (MA.py:142-150 as the main cell)."""
+
+    @staticmethod
+    def forward(ctx, x, h0, Gw, Gb, Uw, Ub, flags):
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise _cabi.MatgcnError("dense_gru_layer: x must be a float32 CUDA tensor (no CPU path)")
+        T, N, B, Cin = x.shape
+        if x.stride(3) != 1 or x.stride(2) != Cin or x.stride(1) != B * Cin:
+            x = x.contiguous()
+        Gw, Gb, Uw, Ub = _f32c(Gw, "Gw"), _f32c(Gb, "Gb"), _f32c(Uw, "Uw"), _f32c(Ub, "Ub")
+        if h0 is not None:
+            h0 = _f32c(h0, "h0")
+        H = Ub.shape[0]
+        if Gw.shape != (2 * H, Cin + H) or Uw.shape != (H, Cin + H) or Gb.shape != (2 * H,):
+            raise _cabi.MatgcnError("dense_gru_layer: inconsistent shapes")
+        L = _cabi.lib()
+        dims = (T, N, B, Cin, H)
+        ws = torch.empty(L.matgcn_dense_gru_layer_fwd_ws_bytes(*dims) // 4, device=x.device, dtype=torch.float32)
+        _cabi.check(L.matgcn_dense_gru_layer_fwd(*dims, _ptr(x), x.stride(0), _ptr(h0), _ptr(Gw), _ptr(Gb), _ptr(Uw),
+                                                 _ptr(Ub), _ptr(ws), int(flags), _stream()), "matgcn_dense_gru_layer_fwd")
+        y = torch.as_strided(ws, (T, N, B, H), (N * B * H, B * H, H, 1), L.matgcn_dense_gru_layer_y_offset(*dims))
+        ctx.save_for_backward(x, Gw, Uw)
+        ctx.ws, ctx.dims, ctx.has_h0, ctx.flags = ws, dims, h0 is not None, int(flags)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Gw, Uw = ctx.saved_tensors
+        T, N, B, Cin, H = ctx.dims
+        dev = dy.device
+        if dy.dtype != torch.float32 or dy.stride(3) != 1 or dy.stride(2) != H or dy.stride(1) != B * H:
+            dy = dy.contiguous().float()
+        L = _cabi.lib()
+        if ctx.ws is None:
+            raise _cabi.MatgcnError("dense_gru_layer: backward called twice (the saved workspace was released)")
+        bws = torch.empty(L.matgcn_dense_gru_layer_bwd_ws_bytes(*ctx.dims) // 4, device=dev, dtype=torch.float32)
+        new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        dx = new(T, N, B, Cin)
+        dh0 = new(N, B, H) if ctx.has_h0 else None
+        dGw, dGb, dUw, dUb = new(2 * H, Cin + H), new(2 * H), new(H, Cin + H), new(H)
+        _cabi.check(L.matgcn_dense_gru_layer_bwd(T, N, B, Cin, H, _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(Gw),
+                                                 _ptr(Uw), _ptr(ctx.ws), _ptr(bws), _ptr(dx), _ptr(dh0), _ptr(dGw), _ptr(dGb),
+                                                 _ptr(dUw), _ptr(dUb), ctx.flags, _stream()), "matgcn_dense_gru_layer_bwd")
+        ctx.ws = None
+        return dx, dh0, dGw, dGb, dUw, dUb, None
+
+
+def dense_gru_layer(x, h0, Gw, Gb, Uw, Ub, flags=0):
+    """gcn_off layer: x [T,N,B,Cin] node-major -> y [T,N,B,H]."""
+    return _DenseGRULayerFn.apply(x, h0, Gw, Gb, Uw, Ub, flags)
+
+
 def adaptive_adjacency(L, Rt, ldm):
     """[N, ldm] row-softmax adaptive adjacency; columns >= N are zero."""
     return _AdaptiveAdjFn.apply(L, Rt, ldm)

@@ -222,14 +222,32 @@ class MirrorNodeWeightsFn(torch.autograd.Function):
         return node_weights_bwd(*ctx.saved_tensors, dW, db)
 
 
+def dense_gru_layer_mirror(x, h0, Gw, Gb, Uw, Ub, flags=0):
+    """gcn_off layer as plain torch autograd (node-major layout)."""
+    T, N, B, Cin = x.shape
+    H = Ub.shape[0]
+    h = torch.zeros(N, B, H, dtype=x.dtype) if h0 is None else h0
+    ys = []
+    for t in range(T):
+        zr = sig(torch.cat((x[t], h), -1) @ Gw.T + Gb)
+        z, r = zr[..., :H], zr[..., H:]
+        hc = torch.tanh(torch.cat((x[t], z * h), -1) @ Uw.T + Ub)
+        h = r * h + (1 - r) * hc
+        ys.append(h)
+    return torch.stack(ys, 0)
+
+
 def install(ops_module):
     """Point the three autograd entry points of ``multistgraph_b200.ops`` at the mirror
     (tests only; returns a restore callable)."""
     saved = (ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights)
+    saved_dense = ops_module.dense_gru_layer
+    ops_module.dense_gru_layer = dense_gru_layer_mirror
     ops_module.encoder_layer = lambda *a: MirrorLayerFn.apply(*a[:13])
     ops_module.adaptive_adjacency = lambda L, Rt, ldm: MirrorAdjFn.apply(L, Rt, ldm)
     ops_module.node_weights = lambda E, pool, bp, c: MirrorNodeWeightsFn.apply(E, pool, bp, c)
 
     def restore():
         ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights = saved
+        ops_module.dense_gru_layer = saved_dense
     return restore

@@ -18,7 +18,7 @@ from tests.util import clone_batch, golden_names, load_golden, max_rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-ACCEL = [n for n in golden_names() if n != "gcn_off"]
+ACCEL = golden_names()
 DEV = "cuda:0"
 FLAGS = 0  # exact mode
 

@@ -16,7 +16,7 @@ from oracle import matgcn_oracle
 from tests import host_mirror
 from tests.util import clone_batch, golden_names, load_golden, max_rel_err
 
-ACCEL = [n for n in golden_names() if n != "gcn_off"]
+ACCEL = golden_names()
 
 
 @pytest.fixture()
