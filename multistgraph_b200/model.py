@@ -243,11 +243,12 @@ class MultiATGCN(nn.Module):
             adp = ops.adaptive_adjacency(self.node_vec1, self.node_vec2.t().contiguous(), self.ldm)
         terms = [adp]
         if self.cheb_k > 2:
-            # T_k = 2 A T_{k-1} - T_{k-2}; only ablation configs take this path (library GEMM through autograd)
+            # T_k = 2 A T_{k-1} - T_{k-2} (MA.py:98-99); only ablation configs have cheb_order > 2
             eye = torch.eye(n, device=adp.device, dtype=adp.dtype)
-            prev2, prev1 = eye, adp[:, :n]
+            a1 = adp[:, :n].contiguous()
+            prev2, prev1 = eye, a1
             for _ in range(2, self.cheb_k):
-                nxt = (2 * adp[:, :n]) @ prev1 - prev2
+                nxt = 2 * ops.matmul(a1, prev1.contiguous(), self.matgcn_flags) - prev2
                 terms.append(F.pad(nxt, (0, self.ldm - n)))
                 prev2, prev1 = prev1, nxt
         n_adp = len(terms)

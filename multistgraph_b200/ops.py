@@ -206,6 +206,44 @@ def dense_gru_layer(x, h0, Gw, Gb, Uw, Ub, flags=0):
     return _DenseGRULayerFn.apply(x, h0, Gw, Gb, Uw, Ub, flags)
 
 
+class _MatmulFn(torch.autograd.Function):
+    """C = A @ B for 2-D row-major float32 CUDA tensors through the library's GEMM engines (used by the
+    Chebyshev recurrence T_k = 2 A T_{k-1} - T_{k-2} of the adaptive view when cheb_order > 2, MA.py:98-99)."""
+
+    @staticmethod
+    def _gemm(a_kc, b_kc, M, N, K, A, lda, Bm, ldb, flags):
+        C = torch.empty(M, N, device=A.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_gemm_debug(a_kc, b_kc, M, N, K, _ptr(A), lda, _ptr(Bm), ldb, _ptr(C), N, 1,
+                                                  int(flags), _stream()), "matgcn_gemm")
+        return C
+
+    @staticmethod
+    def forward(ctx, A, B, flags):
+        A, B = _f32c(A, "A"), _f32c(B, "B")
+        M, K = A.shape
+        K2, N = B.shape
+        if K != K2:
+            raise _cabi.MatgcnError("matmul: inner dimensions differ")
+        ctx.save_for_backward(A, B)
+        ctx.flags = int(flags)
+        return _MatmulFn._gemm(1, 0, M, N, K, A, K, B, N, flags)
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B = ctx.saved_tensors
+        dC = _f32c(dC, "dC")
+        M, K = A.shape
+        N = B.shape[1]
+        dA = _MatmulFn._gemm(1, 1, M, K, N, dC, N, B, N, ctx.flags)   # dC [M,N] x B^T : B read as [n'=k][k'=n]
+        dB = _MatmulFn._gemm(0, 0, K, N, M, A, K, dC, N, ctx.flags)   # A^T [K,M] x dC [M,N]
+        return dA, dB, None
+
+
+def matmul(A, B, flags=0):
+    """A [M,K] @ B [K,N] on the library's GEMM engines, differentiable."""
+    return _MatmulFn.apply(A, B, flags)
+
+
 def adaptive_adjacency(L, Rt, ldm):
     """[N, ldm] row-softmax adaptive adjacency; columns >= N are zero."""
     return _AdaptiveAdjFn.apply(L, Rt, ldm)

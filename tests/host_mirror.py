@@ -241,13 +241,14 @@ def install(ops_module):
     """Point the three autograd entry points of ``multistgraph_b200.ops`` at the mirror
     (tests only; returns a restore callable)."""
     saved = (ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights)
-    saved_dense = ops_module.dense_gru_layer
+    saved_dense, saved_mm = ops_module.dense_gru_layer, ops_module.matmul
     ops_module.dense_gru_layer = dense_gru_layer_mirror
+    ops_module.matmul = lambda A, B, flags=0: A @ B
     ops_module.encoder_layer = lambda *a: MirrorLayerFn.apply(*a[:13])
     ops_module.adaptive_adjacency = lambda L, Rt, ldm: MirrorAdjFn.apply(L, Rt, ldm)
     ops_module.node_weights = lambda E, pool, bp, c: MirrorNodeWeightsFn.apply(E, pool, bp, c)
 
     def restore():
         ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights = saved
-        ops_module.dense_gru_layer = saved_dense
+        ops_module.dense_gru_layer, ops_module.matmul = saved_dense, saved_mm
     return restore
