@@ -49,6 +49,7 @@ __device__ __forceinline__ float4 tanh4(const float4& a, int fast) {
 
 // C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col] + add[...]
 struct EpiStore {
+    static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     float* C;
     long long s1, s2;
     int ldc;
@@ -106,6 +107,7 @@ inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
 }
 
 struct EpiAtomic {  // split-K partial sums into a zeroed C
+    static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     float* C;
     long long s1, s2;
     int ldc;
@@ -125,6 +127,7 @@ struct EpiAtomic {  // split-K partial sums into a zeroed C
 // Forward step epilogues.  g = z1*rows_per_z + row indexes (node, batch) pairs; activations
 // are [N*B, H] blocks, pre-activation inputs [N*B, 3H] blocks.
 struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (cols >= H): R
+    static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
     int rows_per_z, H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(Z) && aligned16(R) && aligned16(ZH); }
@@ -165,6 +168,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
     EPI_CALL_OPERATOR
 };
 struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
+    static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
     int rows_per_z, H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(H1); }
@@ -199,6 +203,7 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     EPI_CALL_OPERATOR
 };
 struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r2)*hc2)
+    static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
     int H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(RX) && aligned16(H1) && aligned16(R2) && aligned16(HC2) && aligned16(Y); }
@@ -240,6 +245,7 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
 
 // Backward step epilogues (notation of DESIGN.md section 3 / tests/host_mirror.py).
 struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR[H:2H] = dres*(h1-hc2)*r2(1-r2)
+    static constexpr int kBatch = 2;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     float* DH1; float* DR; const float* DRES; const float* H1; const float* Z2; const float* R2; const float* HC2;
     int H;
     bool vec_ok() const {
@@ -273,6 +279,7 @@ struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR
     EPI_CALL_OPERATOR
 };
 struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
+    static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* DH1; const float* Hprev; const float* R; const float* HC; float* DHD; float* DG;
     int H;
     bool vec_ok() const { return !(H & 3) && aligned16(DH1) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(DHD) && aligned16(DG); }
@@ -306,6 +313,7 @@ struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
     EPI_CALL_OPERATOR
 };
 struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      (row = node m, col = (b,c))
+    static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* DP0; const float* Hprev; const float* Z; float* DHD; float* DG;
     int H, BH;  // BH = B*H columns per node
     bool vec_ok() const { return !(H & 3) && !(BH & 3) && aligned16(DP0) && aligned16(Hprev) && aligned16(Z) && aligned16(DHD) && aligned16(DG); }
@@ -342,6 +350,7 @@ struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      
 };
 
 struct EpiB6 {  // carry = acc + DP0 + DHD
+    static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* DP0; const float* DHD; float* OUT;
     int BH;
     bool vec_ok() const { return !(BH & 3) && aligned16(DP0) && aligned16(DHD) && aligned16(OUT); }

@@ -196,18 +196,19 @@ __device__ __forceinline__ void tc_epilogue_tile(const Epi& epi, const TcP& p, u
                 const int rq = lane >> 3, cq = lane & 7;
                 const int col = col_base + 4 * cq;
                 const bool col_ok = col < pN;
+                constexpr int NBATCH = Epi::kBatch;
 #pragma unroll 1
-                for (int it0 = 0; it0 < 8; it0 += 2) {
-                    EpiIn4 in[2];
-                    float4 v[2];
+                for (int it0 = 0; it0 < 8; it0 += NBATCH) {
+                    EpiIn4 in[NBATCH];
+                    float4 v[NBATCH];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < NBATCH; ++u) {
                         const int rl = 4 * (it0 + u) + rq;
                         v[u] = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
                         if (col_ok && row_base + rl < row_lim) in[u] = epi.load4(z1, z2, row_base + rl, col);
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < NBATCH; ++u) {
                         const int rl = 4 * (it0 + u) + rq;
                         if (col_ok && row_base + rl < row_lim && !(pdbg & 1)) epi.store4(z1, z2, row_base + rl, col, v[u], in[u]);
                     }
