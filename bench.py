@@ -205,15 +205,26 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
     P = torch.empty(kp, n_nodes, cols, device=device)
     flush = torch.empty(64 * 1024 * 1024, device=device, dtype=torch.float32)
     st = torch.cuda.current_stream().cuda_stream
+    bf16 = bool(flags & _cabi.FLAG_BF16)
+    if bf16:
+        M16, X16 = M.bfloat16(), X.bfloat16()
+
+        def launch():
+            _cabi.check(lib.matgcn_propagate_fwd_bf16(M16.data_ptr(), kp, n_nodes, ldm, X16.data_ptr(), cols, P.data_ptr(), st),
+                        "propagate_bf16")
+    else:
+        def launch():
+            _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n_nodes, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st),
+                        "propagate")
     for _ in range(3):
-        _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n_nodes, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st), "propagate")
+        launch()
     torch.cuda.synchronize()
     total = 0.0
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n_nodes, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st), "propagate")
+        launch()
         e1.record()
         e1.synchronize()
         total += e0.elapsed_time(e1)
@@ -223,16 +234,17 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
     peak = peaks["bf16_tflops"]
     traffic = None
     prof = os.path.join(ROOT, "profiles", "r1_prop_kernel_ncu.json")
-    if flags and os.path.exists(prof):
+    if flags == _cabi.FLAG_TF32 and os.path.exists(prof):
         with open(prof) as f:
             pj = json.load(f)
         if pj["shape"] == {"Kp": kp, "N": n_nodes, "cols": cols}:  # the ncu --set full capture of this very shape
             traffic = pj["dram_bytes_read"] + pj["dram_bytes_write"]
-    kern = ("gemm_tc_kernel<128,A_KC,B_NC,EpiStore> (support propagation, tcgen05 kind::tf32 + TMA)" if flags
+    kern = ("gemm_tc_kernel<128,A_KC,B_NC,BF16,EpiStore> (support propagation, tcgen05 kind::f16 bf16 + TMA)" if bf16
+            else "gemm_tc_kernel<128,A_KC,B_NC,EpiStore> (support propagation, tcgen05 kind::tf32 + TMA)" if flags
             else "gemm_kernel<CfgBig,A_KC,B_NC,EpiStore> (support propagation, fp32 FFMA)")
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "kernel": kern, "launch_ms": ms, "flops_per_launch": flops,
-            "algorithmic_bytes_per_launch": 4.0 * (kp * n_nodes * ldm + n_nodes * cols + kp * n_nodes * cols),
+            "algorithmic_bytes_per_launch": (2.0 if bf16 else 4.0) * (kp * n_nodes * ldm + n_nodes * cols) + 4.0 * kp * n_nodes * cols,
             "peak_source": peaks["source"] + " bf16 dense burst",
             "note": "peak is the measured bf16 cuBLAS figure; TF32 tensor-core peak is half of it, the fp32 FFMA "
                     "kernel of exact mode cannot approach either"}
@@ -332,13 +344,15 @@ def run_ours(args):
         roof = propagation_roofline(w["N"], per_gpu_batch, 64, 4, model.ldm, dev, peaks, model.matgcn_flags)
         line = {"metric": METRIC, "value": global_batch / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if model.matgcn_flags else "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "tf32", 3: "bf16+tf32"}.get(model.matgcn_flags, "tf32"), "data": "synthetic",
                 "config": {"workload": _workload_desc(args.workload, w, per_gpu_batch), "global_batch": global_batch,
                            "step": "zero_grad+forward+backward+allreduce+clip_grad_norm(5)+Adam",
                            "parallelism": "dp%d (batch-sharded, one flat-bucket all-reduce)" % world,
                            "l2": "per-step working set (several GB of saved activations) is far larger than the 126 MB L2",
-                           "mode": ("fast: contractions on tcgen05 tensor cores as TF32, fp32 storage and accumulation"
-                                    if model.matgcn_flags else "exact: fp32 FFMA kernels (1e-4 parity)")},
+                           "mode": {0: "exact: fp32 FFMA kernels (1e-4 parity)",
+                                    1: "fast: contractions on tcgen05 tensor cores as TF32, fp32 storage and accumulation",
+                                    3: "fast: tcgen05 tensor cores; support propagation on bf16 operand twins, the rest TF32; "
+                                       "fp32 storage of the state and fp32 accumulation"}[model.matgcn_flags]},
                 "clocks": clocks,
                 "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world},
@@ -363,7 +377,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--mode", default="tf32", choices=["tf32", "exact"],
+    ap.add_argument("--mode", default="tf32", choices=["tf32", "bf16", "exact"],
                     help="tf32: tcgen05 tensor cores (headline); exact: fp32 FFMA kernels")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work allowed for the baseline")

@@ -37,6 +37,7 @@ extern "C" {
 /* flags of the contraction-heavy entry points */
 #define MATGCN_FLAG_EXACT 0 /* fp32 FFMA kernels: 1e-4 parity with the reference */
 #define MATGCN_FLAG_TF32 1  /* fast mode: contractions on tcgen05 tensor cores as TF32 (fp32 storage and accumulation) */
+#define MATGCN_FLAG_BF16 2  /* with TF32: the support-propagation contractions read bf16 twins of their operands (kind::f16 MMAs) */
 
 /* ABI version of the loaded library (compare with MATGCN_ABI_VERSION). */
 int matgcn_abi_version(void);
@@ -91,6 +92,10 @@ int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X,
  * launch per contraction.  Returns the previous setting.  Default off (or MATGCN_MULTI=1 in the environment). */
 int matgcn_set_persistent(int on);
 
+/* The same contraction with bf16 twins of M and X (device arrays of __nv_bfloat16), float32 output: the kernel the
+ * layer entry points launch for the propagation when MATGCN_FLAG_BF16 is set. */
+int matgcn_propagate_fwd_bf16(const void* M16, int Kp, int N, int ldm, const void* X16, int cols, float* P, void* stream);
+
 /* Diagnostics: device buffer (int64, >= 8 per tile of CTA 0) that later tensor-core launches fill with clock64()
  * stamps [producer start, mma wait, mma start, mma committed, epilogue wait, epilogue start, epilogue end]; NULL disables. */
 int matgcn_debug_set_timeline(long long* buf);
@@ -104,6 +109,10 @@ int matgcn_debug_set_mode(int mode);
  * splits > 1 exercises the split-K / atomic epilogue. */
 int matgcn_gemm_debug(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                       float* C, int ldc, int splits, int flags, void* stream);
+
+/* Diagnostics: the same product with bf16 operands (device arrays of __nv_bfloat16) on the bf16 tensor-core engine. */
+int matgcn_gemm_debug_bf16(int a_kc, int b_kc, int M, int N, int K, const void* A16, int lda, const void* B16, int ldb,
+                           float* C, int ldc, int splits, void* stream);
 
 /* -------------------------------------------------------------------------------------------
  * One encoder layer over the whole input window.

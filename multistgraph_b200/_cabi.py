@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmatgcn.so")
 ABI_VERSION = 2
 FLAG_EXACT = 0
 FLAG_TF32 = 1
+FLAG_BF16 = 2
 
 _lib = None
 
@@ -31,6 +32,8 @@ _SIGNATURES = {
     "matgcn_debug_set_timeline_skip": (c_int, [c_int]),
     "matgcn_gemm_debug": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, c_int, _F, c_int, _F, c_int, c_int, c_int,
                                   c_void_p]),
+    "matgcn_propagate_fwd_bf16": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_void_p]),
+    "matgcn_gemm_debug_bf16": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, c_int, _F, c_int, _F, c_int, c_int, c_void_p]),
     "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),
     "matgcn_adaptive_adj_bwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, _F, _F, _F, c_void_p]),
     "matgcn_nodeweights_fwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, _F, _F, c_void_p]),

@@ -61,8 +61,9 @@ struct EpiStore {
     const float* add;    // may be null: extra addend with C's indexing (offsets add_s1/add_s2, ld add_ld)
     long long add_s1, add_s2;
     int add_ld;
+    __nv_bfloat16* C16;  // may be null: bf16 twin of C (same indexing), operand of a later bf16 contraction
     bool vec_ok() const {
-        return aligned16(C) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3) && (!bias || (aligned16(bias) && !(bias_s1 & 3))) &&
+        return aligned16(C) && (!C16 || aligned16(C16)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3) && (!bias || (aligned16(bias) && !(bias_s1 & 3))) &&
                (!scale || !(scale_div & 3)) && (!add || (aligned16(add) && !(add_s1 & 3) && !(add_s2 & 3) && !(add_ld & 3)));
     }
     __device__ __forceinline__ EpiIn load(int z1, int z2, int row, int col) const {
@@ -80,6 +81,7 @@ struct EpiStore {
         if (add) v += in.c;
         if (accumulate) v += in.d;
         C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = v;
+        if (C16) C16[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = __float2bfloat16_rn(v);
     }
     __device__ __forceinline__ EpiIn4 load4(int z1, int z2, int row, int col) const {
         EpiIn4 in;
@@ -96,6 +98,7 @@ struct EpiStore {
         if (add) v = v + in.c;
         if (accumulate) v = v + in.d;
         st4(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
+        if (C16) st4_bf16(C16 + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
     }
     EPI_CALL_OPERATOR
 };
@@ -130,6 +133,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
     int rows_per_z, H, fast;
+    __nv_bfloat16* ZH16;  // may be null: bf16 twin of ZH
     bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(Z) && aligned16(R) && aligned16(ZH); }
     __device__ __forceinline__ EpiIn load(int z1, int, int row, int col) const {
         const long long g = (long long)z1 * rows_per_z + row;
@@ -144,6 +148,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
         if (col < H) {
             Z[g * H + col] = s;
             ZH[g * H + col] = s * in.b;
+            if (ZH16) ZH16[g * H + col] = __float2bfloat16_rn(s * in.b);
         } else {
             R[g * H + col - H] = s;
         }
@@ -161,6 +166,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
         if (col < H) {
             st4(Z + g * H + col, s);
             st4(ZH + g * H + col, s * in.b);
+            if (ZH16) st4_bf16(ZH16 + g * H + col, s * in.b);
         } else {
             st4(R + g * H + col - H, s);
         }
@@ -206,6 +212,7 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
     int H, fast;
+    __nv_bfloat16* Y16;  // may be null: bf16 twin of Y
     bool vec_ok() const { return !(H & 3) && aligned16(RX) && aligned16(H1) && aligned16(R2) && aligned16(HC2) && aligned16(Y); }
     __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long g = row;
@@ -223,6 +230,7 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
         const float res = r2 * h1 + (1.f - r2) * hc2;
         HC2[g * H + col] = hc2;
         Y[g * H + col] = m * h1 + (1.f - m) * res;
+        if (Y16) Y16[g * H + col] = __float2bfloat16_rn(m * h1 + (1.f - m) * res);
     }
     __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
         const long long g = row;
@@ -238,7 +246,9 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
         const float4 hc2 = tanh4(acc + in.a, fast);
         const float4 res = in.b * in.c + one_minus(in.b) * hc2;
         st4(HC2 + g * H + col, hc2);
-        st4(Y + g * H + col, in.d * in.c + one_minus(in.d) * res);
+        const float4 y = in.d * in.c + one_minus(in.d) * res;
+        st4(Y + g * H + col, y);
+        if (Y16) st4_bf16(Y16 + g * H + col, y);
     }
     EPI_CALL_OPERATOR
 };

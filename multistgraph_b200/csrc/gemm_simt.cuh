@@ -10,6 +10,7 @@
 // through three knobs: operand layouts, a two-level batch index z = (z1, z2) and "k-batches"
 // (the reduction runs over KB strided slabs of inner length K).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,11 +29,22 @@ struct EpiIn4 { float4 a, b, c, d, e, f; };
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+// four floats -> four bf16 (round to nearest even), one 8-byte store; p must be 8-byte aligned
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const float4& v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+}
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 struct GemmP {
     const float* A;
     const float* B;
+    // optional bf16 twins of the operands (same logical layout and strides): used by the bf16 tensor-core engine
+    const __nv_bfloat16* A16;
+    const __nv_bfloat16* B16;
     int M, N, K;  // K: inner reduction length of one k-batch
     int KB;       // number of k-batches
     int lda, ldb;

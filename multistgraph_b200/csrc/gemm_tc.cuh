@@ -141,10 +141,35 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// Operand element traits: TF32 reads fp32 operands (32 per 128-byte slab, K = 8 per MMA), BF16 reads bf16 twins
+// (64 per slab, K = 16 per MMA).  MN-major tiles: rows are K indices holding MN_BLOCK contiguous elements;
+// 32-bit operands need the 32-byte-atom swizzle (4-row K groups), 16-bit ones the plain 128-byte swizzle (8-row groups).
+template <bool BF16>
+struct TcElem {
+    static constexpr int ESIZE = BF16 ? 2 : 4;
+    static constexpr int BK = 128 / ESIZE;            // elements per 128-byte K slab
+    static constexpr int UMMA_K = 32 / ESIZE;         // K per tcgen05.mma
+    static constexpr int MN_BLOCK = 128 / ESIZE;      // MN elements per swizzle row of an MN-major tile
+    static constexpr int MN_BOX_BYTES = BK * 128;     // one MN-major TMA box: BK rows of 128 bytes
+    static constexpr int MN_KSTEP_BYTES = UMMA_K * 128;
+    static constexpr int MN_SBO = BF16 ? 1024 : 512;  // K-group stride
+    static constexpr int MN_LAYOUT = BF16 ? 2 : 1;    // SWIZZLE_128B : SWIZZLE_128B_BASE32B
+    static constexpr uint32_t FMT = BF16 ? 1u : 2u;   // instruction-descriptor operand format
+};
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 template <int BN>
 struct TcSmem {
-    static constexpr int A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
-    static constexpr int B_BYTES = BN * TC_BK * 4;
+    static constexpr int A_BYTES = TC_BM * 128;  // 16 KB: 128 rows of one 128-byte slab
+    static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
     static constexpr int EPI_LD = TC_EPI_LD;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 access
@@ -241,11 +266,13 @@ __device__ __forceinline__ void tc_epilogue_tile(const Epi& epi, const TcP& p, u
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_KC, bool B_KC, class Epi>
+template <int BN, bool A_KC, bool B_KC, bool BF16, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p, const Epi epi) {
     using S = TcSmem<BN>;
+    using E = TcElem<BF16>;
     constexpr int STAGES = S::STAGES;
+    constexpr int BK = E::BK;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte alignment; keep the pointer derived from the __shared__ symbol so that
     // the epilogue's staging accesses compile to LDS/STS instead of generic loads/stores
@@ -288,7 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    const int kt_per_kb = (p.K + TC_BK - 1) / TC_BK;
+    const int kt_per_kb = (p.K + BK - 1) / BK;
     const int kt_total = p.KB * kt_per_kb;
     const int kt_per_split = (kt_total + p.splits - 1) / p.splits;
     const int tiles_mn = p.tiles_m * p.tiles_n;
@@ -319,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
                 for (int kt = kt0; kt < kt1; ++kt) {
                     const int kb = kt / kt_per_kb;
-                    const int k0 = (kt - kb * kt_per_kb) * TC_BK;
+                    const int k0 = (kt - kb * kt_per_kb) * BK;
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
                     const uint32_t sb = sa + S::A_BYTES;
@@ -328,15 +355,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_5d(sa, &tmA, full_bar(stage), k0, m0, kb * p.cAk, z2 * p.cA2, z1 * p.cA1);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < TC_BM / 32; ++j)
-                            tma_load_5d(sa + j * 4096, &tmA, full_bar(stage), m0 + 32 * j, k0, kb * p.cAk, z2 * p.cA2, z1 * p.cA1);
+                        for (int j = 0; j < TC_BM / E::MN_BLOCK; ++j)
+                            tma_load_5d(sa + j * E::MN_BOX_BYTES, &tmA, full_bar(stage), m0 + E::MN_BLOCK * j, k0, kb * p.cAk, z2 * p.cA2,
+                                        z1 * p.cA1);
                     }
                     if (B_KC) {
                         tma_load_5d(sb, &tmB, full_bar(stage), k0, n0, kb * p.cBk, z2 * p.cB2, z1 * p.cB1);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j)
-                            tma_load_5d(sb + j * 4096, &tmB, full_bar(stage), n0 + 32 * j, k0, kb * p.cBk, z2 * p.cB2, z1 * p.cB1);
+                        for (int j = 0; j < BN / E::MN_BLOCK; ++j)
+                            tma_load_5d(sb + j * E::MN_BOX_BYTES, &tmB, full_bar(stage), n0 + E::MN_BLOCK * j, k0, kb * p.cBk, z2 * p.cB2,
+                                        z1 * p.cB1);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -346,7 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ================================ MMA issuer ================================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KC ? 0u : 1u) << 15) | ((B_KC ? 0u : 1u) << 16) |
+            const uint32_t idesc = (1u << 4) | (E::FMT << 7) | (E::FMT << 10) | ((A_KC ? 0u : 1u) << 15) | ((B_KC ? 0u : 1u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((p.m64 ? 64 : TC_BM) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -367,14 +396,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
                     const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                        // K-major : 128B swizzle, 8-row groups 1024 B apart (SBO); a K=8 step advances 32 B inside the row
-                        // MN-major: 128B swizzle with 32B atoms: rows are K indices holding 32 MN-contiguous floats,
-                        //           4-row K groups 512 B apart (SBO), 32-wide MN blocks 4096 B apart (LBO);
-                        //           a K=8 step advances two K groups = 1024 B
-                        const uint64_t da = A_KC ? umma_desc(sa + kk * 32, 16, 1024, 2) : umma_desc(sa + kk * 1024, 4096, 512, 1);
-                        const uint64_t db = B_KC ? umma_desc(sb + kk * 32, 16, 1024, 2) : umma_desc(sb + kk * 1024, 4096, 512, 1);
-                        umma_tf32(tmem_d, da, db, idesc, (kt > kt0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < BK / E::UMMA_K; ++kk) {
+                        // K-major : 128B swizzle, 8-row groups 1024 B apart (SBO); one MMA step advances 32 B inside the row
+                        // MN-major: rows are K indices holding MN_BLOCK contiguous elements; K groups MN_SBO apart,
+                        //           MN blocks one TMA box (MN_BOX_BYTES) apart (LBO); one MMA step advances UMMA_K rows
+                        const uint64_t da = A_KC ? umma_desc(sa + kk * 32, 16, 1024, 2)
+                                                 : umma_desc(sa + kk * E::MN_KSTEP_BYTES, E::MN_BOX_BYTES, E::MN_SBO, E::MN_LAYOUT);
+                        const uint64_t db = B_KC ? umma_desc(sb + kk * 32, 16, 1024, 2)
+                                                 : umma_desc(sb + kk * E::MN_KSTEP_BYTES, E::MN_BOX_BYTES, E::MN_SBO, E::MN_LAYOUT);
+                        if (BF16) umma_bf16(tmem_d, da, db, idesc, (kt > kt0 || kk > 0) ? 1u : 0u);
+                        else umma_tf32(tmem_d, da, db, idesc, (kt > kt0 || kk > 0) ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -472,37 +503,41 @@ inline int sm_count() {
 // Operand as a rank-5 tensor map {inner, outer, KB, Z2, Z1}.  `kc`: K is the contiguous (inner) dimension.
 // Optional time dimension (persistent recurrence kernel): when nT > 1 and st != 0 one of the unused outer
 // dimensions becomes the time step (size nT, stride st floats) and *tdim tells which coordinate carries t.
-inline bool make_operand_map(CUtensorMap* map, const float* base, bool kc, int mn, int K, int ld, long long sk, long long s2,
+inline bool make_operand_map(CUtensorMap* map, const void* base, bool kc, int mn, int K, int ld, long long sk, long long s2,
                              long long s1, int KB, int Z2, int Z1, int box_mn_rows, int* ck, int* c2, int* c1,
-                             long long st = 0, int nT = 1, int* tdim = nullptr) {
+                             long long st = 0, int nT = 1, int* tdim = nullptr, bool bf16 = false) {
     TmapEncodeFn enc = tmap_encoder();
     if (!enc) return false;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3) || (sk & 3) || (s2 & 3) || (s1 & 3) || (st & 3) || st < 0) return false;
+    const int es = bf16 ? 2 : 4;            // element size
+    const int am = 16 / es - 1;             // strides (in elements) must keep 16-byte alignment
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & am) || (sk & am) || (s2 & am) || (s1 & am) || (st & am) || st < 0) return false;
     *ck = (KB > 1 && sk != 0) ? 1 : 0;
     *c2 = (Z2 > 1 && s2 != 0) ? 1 : 0;
     *c1 = (Z1 > 1 && s1 != 0) ? 1 : 0;
     if (KB > 1 && sk == 0) return false;  // a reduction over identical slabs never occurs on this path
     const cuuint64_t inner = kc ? (cuuint64_t)K : (cuuint64_t)mn;
     const cuuint64_t outer = kc ? (cuuint64_t)mn : (cuuint64_t)K;
-    const cuuint64_t row_bytes = (cuuint64_t)ld * 4;
+    const cuuint64_t row_bytes = (cuuint64_t)ld * es;
     cuuint64_t dims[5] = {inner, outer, (cuuint64_t)(*ck ? KB : 1), (cuuint64_t)(*c2 ? Z2 : 1), (cuuint64_t)(*c1 ? Z1 : 1)};
     const cuuint64_t dummy = row_bytes * outer;
-    cuuint64_t strides[4] = {row_bytes, *ck ? (cuuint64_t)sk * 4 : dummy, *c2 ? (cuuint64_t)s2 * 4 : dummy,
-                             *c1 ? (cuuint64_t)s1 * 4 : dummy};
+    cuuint64_t strides[4] = {row_bytes, *ck ? (cuuint64_t)sk * es : dummy, *c2 ? (cuuint64_t)s2 * es : dummy,
+                             *c1 ? (cuuint64_t)s1 * es : dummy};
     if (tdim) *tdim = 0;
     if (nT > 1 && st != 0) {
         int d = !*ck ? 2 : (!*c2 ? 3 : (!*c1 ? 4 : -1));
         if (d < 0 || !tdim) return false;
         dims[d] = (cuuint64_t)nT;
-        strides[d - 1] = (cuuint64_t)st * 4;
+        strides[d - 1] = (cuuint64_t)st * es;
         *tdim = d;
     }
     for (int i = 0; i < 4; ++i)
         if (strides[i] == 0 || (strides[i] & 15) || strides[i] >= (1ULL << 40)) return false;
-    cuuint32_t box[5] = {32, (cuuint32_t)(kc ? box_mn_rows : 32), 1, 1, 1};
+    const cuuint32_t slab = (cuuint32_t)(128 / es);  // elements per 128-byte row
+    cuuint32_t box[5] = {slab, (cuuint32_t)(kc ? box_mn_rows : slab), 1, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, kc ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     (kc || bf16) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -510,7 +545,7 @@ inline bool make_operand_map(CUtensorMap* map, const float* base, bool kc, int m
 
 // Returns cudaErrorNotSupported when the problem does not meet the TMA alignment rules (caller falls back
 // to the SIMT engine); any other error is a real launch failure.
-template <int BN, bool A_KC, bool B_KC, class Epi>
+template <int BN, bool A_KC, bool B_KC, class Epi, bool BF16 = false>
 inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStream_t st) {
     if (p.M <= 0 || p.N <= 0 || Z <= 0) return cudaSuccess;
     const int Z2 = p.Z2 > 0 ? p.Z2 : 1;
@@ -536,12 +571,17 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     t.dbg = (tc_debug_buffer() && tc_debug_countdown()-- == 0) ? tc_debug_buffer() : nullptr;
     t.dbg_mode = tc_debug_mode();
     CUtensorMap ma, mb;
-    if (!make_operand_map(&ma, p.A, A_KC, p.M, p.K, p.lda, p.sAk, p.sA2, p.sA1, p.KB, Z2, Z1, TC_BM, &t.cAk, &t.cA2, &t.cA1))
+    const void* Aop = BF16 ? (const void*)p.A16 : (const void*)p.A;
+    const void* Bop = BF16 ? (const void*)p.B16 : (const void*)p.B;
+    if (!Aop || !Bop) return cudaErrorNotSupported;
+    if (!make_operand_map(&ma, Aop, A_KC, p.M, p.K, p.lda, p.sAk, p.sA2, p.sA1, p.KB, Z2, Z1, TC_BM, &t.cAk, &t.cA2, &t.cA1, 0, 1,
+                          nullptr, BF16))
         return cudaErrorNotSupported;
-    if (!make_operand_map(&mb, p.B, B_KC, p.N, p.K, p.ldb, p.sBk, p.sB2, p.sB1, p.KB, Z2, Z1, BN, &t.cBk, &t.cB2, &t.cB1))
+    if (!make_operand_map(&mb, Bop, B_KC, p.N, p.K, p.ldb, p.sBk, p.sB2, p.sB1, p.KB, Z2, Z1, BN, &t.cBk, &t.cB2, &t.cB1, 0, 1,
+                          nullptr, BF16))
         return cudaErrorNotSupported;
     using S = TcSmem<BN>;
-    auto kern = gemm_tc_kernel<BN, A_KC, B_KC, Epi>;
+    auto kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi>;
     static bool configured = false;  // one static per template instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);

@@ -41,6 +41,13 @@ static int fail(const char* where, const char* what) {
 static std::atomic<unsigned long long> g_tc_launches{0};
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
 static cudaError_t gemm_any(bool tc, const GemmP& p, const Epi& epi, int Z, cudaStream_t st) {
+    if (tc && p.K >= 8 && p.A16 && p.B16) {
+        // bf16 twins of both operands are available: bf16 MMAs (half the operand traffic, twice the MMA rate)
+        cudaError_t e = (p.N <= 64) ? launch_gemm_tc<64, A_KC, B_KC, Epi, true>(p, epi, Z, st)
+                                    : launch_gemm_tc<128, A_KC, B_KC, Epi, true>(p, epi, Z, st);
+        if (e == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != cudaErrorNotSupported) return e;
+    }
     if (tc && p.K >= 8) {
         cudaError_t e = (p.N <= 64) ? launch_gemm_tc<64, A_KC, B_KC, Epi>(p, epi, Z, st)
                                     : launch_gemm_tc<128, A_KC, B_KC, Epi>(p, epi, Z, st);
@@ -498,6 +505,26 @@ __global__ void __launch_bounds__(256) xside_bwd_dr_small_kernel(
     }
 }
 
+
+// fp32 -> bf16 twins (round to nearest even).  2-D form: `rows` blocks of `n` floats, source/destination pitches in elements.
+__global__ void to_bf16_kernel(const float* __restrict__ src, long long spitch, __nv_bfloat16* __restrict__ dst, long long dpitch,
+                               long long n, int rows) {
+    const long long total = n * rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n, c = i - r * n;
+        dst[r * dpitch + c] = __float2bfloat16_rn(src[r * spitch + c]);
+    }
+}
+static cudaError_t to_bf16(const float* src, long long spitch, __nv_bfloat16* dst, long long dpitch, long long n, int rows, cudaStream_t st) {
+    const long long total = n * rows;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    to_bf16_kernel<<<blocks, 256, 0, st>>>(src, spitch, dst, dpitch, n, rows);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // adaptive adjacency
 // ------------------------------------------------------------------------------------------
@@ -635,7 +662,7 @@ static GemmP prop_params(const float* M, int ldm, int N, int Kp, const float* sl
 // encoder layer: workspace layout
 // ------------------------------------------------------------------------------------------
 struct LayerWs {
-    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, MPH, total;
+    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, MPH, M16, PH16, PZ16, PX16, total;
     size_t U, UX;  // floats of one [N,B,H] / [N,B,Cin] block
 };
 static size_t align64(size_t v) { return (v + 63) / 64 * 64; }
@@ -661,11 +688,16 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.RGH = take((size_t)2 * H * H);  // Rgw[:, Cin:] and Ruw[:, Cin:] repacked densely (16-byte aligned rows for TMA)
     w.RUH = take((size_t)H * H);
     w.MPH = take((sizeof(MPhase) * (size_t)(6 * T + 2) + 256) / 4);  // phase list + grid-barrier counter of the persistent kernel
+    // bf16 twins (sizes in floats = elements / 2): base matrices, h_{t-1} per step, z*h per step, x (PX layout)
+    w.M16 = take(((size_t)(K - 1) * N * 8 * ((N + 7) / 8 + 1)) / 2 + 64);
+    w.PH16 = take(((size_t)(T + 1) * w.U) / 2 + 64);
+    w.PZ16 = take(((size_t)T * w.U) / 2 + 64);
+    w.PX16 = take(((size_t)T * K * w.UX) / 2 + 64);
     w.total = o;
     return w;
 }
 struct LayerBws {
-    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, total;
+    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, total;
 };
 static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp) {
     LayerBws w;
@@ -681,6 +713,8 @@ static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp)
     w.DHC = take(U);
     w.DRES = take(U);
     w.MPH = take((sizeof(MPhase) * (size_t)(7 * T + 2) + 256) / 4);
+    w.DPT16 = take(((size_t)K * U) / 2 + 64);
+    w.DPX16 = take(((size_t)T * K * UX) / 2 + 64);
     w.total = o;
     return w;
 }
@@ -753,6 +787,22 @@ extern "C" int matgcn_debug_set_timeline(long long* buf) {
     return 0;
 }
 
+// bf16 form of matgcn_propagate_fwd: M16 [Kp, N, ldm] and X16 [N, cols] are bf16 twins, P is float32.
+extern "C" int matgcn_propagate_fwd_bf16(const void* M16, int Kp, int N, int ldm, const void* X16, int cols, float* P, void* stream) {
+    REQUIRE(M16 && X16 && P, "null pointer");
+    REQUIRE(Kp > 0 && N > 0 && cols > 0 && ldm >= N, "bad dims");
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1; p.splits = 1;
+    p.A16 = (const __nv_bfloat16*)M16; p.lda = ldm; p.M = Kp * N; p.K = N;
+    p.B16 = (const __nv_bfloat16*)X16; p.ldb = cols; p.N = cols;
+    cudaError_t e = launch_gemm_tc<128, true, false, EpiStore, true>(p, epi_store(P, 0, 0, cols), 1, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(__func__, "operands do not meet the TMA alignment rules");
+    CK(e);
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 // Plain C = A*B through either engine, for unit tests of the GEMM kernels (all operand layouts).
 extern "C" int matgcn_gemm_debug(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                                  float* C, int ldc, int splits, int flags, void* stream) {
@@ -781,6 +831,36 @@ extern "C" int matgcn_gemm_debug(int a_kc, int b_kc, int M, int N, int K, const 
     return 0;
 }
 
+// Same with bf16 operands (A16/B16 are bf16 device arrays in the layouts above; C is float32).
+extern "C" int matgcn_gemm_debug_bf16(int a_kc, int b_kc, int M, int N, int K, const void* A16, int lda, const void* B16,
+                                      int ldb, float* C, int ldc, int splits, void* stream) {
+    REQUIRE(A16 && B16 && C, "null pointer");
+    REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1; p.splits = splits;
+    p.A16 = (const __nv_bfloat16*)A16; p.B16 = (const __nv_bfloat16*)B16;
+    p.lda = lda; p.ldb = ldb; p.M = M; p.N = N; p.K = K;
+    cudaError_t e = cudaErrorNotSupported;
+    if (splits > 1) {
+        CK(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+        EpiAtomic ep{C, 0, 0, ldc};
+        if (a_kc && !b_kc) e = launch_gemm_tc<128, true, false, EpiAtomic, true>(p, ep, 1, st);
+        else if (!a_kc && !b_kc) e = launch_gemm_tc<128, false, false, EpiAtomic, true>(p, ep, 1, st);
+        else if (a_kc && b_kc) e = launch_gemm_tc<128, true, true, EpiAtomic, true>(p, ep, 1, st);
+    } else {
+        EpiStore ep = epi_store(C, 0, 0, ldc);
+        if (a_kc && !b_kc) e = launch_gemm_tc<128, true, false, EpiStore, true>(p, ep, 1, st);
+        else if (!a_kc && !b_kc) e = launch_gemm_tc<128, false, false, EpiStore, true>(p, ep, 1, st);
+        else if (a_kc && b_kc) e = launch_gemm_tc<128, true, true, EpiStore, true>(p, ep, 1, st);
+    }
+    if (e == cudaErrorNotSupported) return fail(__func__, "operands do not meet the TMA alignment rules (or unused layout)");
+    CK(e);
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // encoder layer forward
 // ------------------------------------------------------------------------------------------
@@ -799,11 +879,27 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     const long long U = (long long)w.U, UX = (long long)w.UX;
     float* PX = ws + w.PX; float* GX = ws + w.GX; float* RX = ws + w.RX; float* PH = ws + w.PH; float* PZ = ws + w.PZ;
 
+    // bf16 propagation (flags & MATGCN_FLAG_BF16): bf16 twins of the base matrices and of every propagated tensor
+    const size_t m16_cap = ((size_t)Kp * N * 8 * ((N + 7) / 8 + 1));
+    const bool bf = tc && (flags & MATGCN_FLAG_BF16) != 0 && (size_t)Kp * N * ldm <= m16_cap;
+    __nv_bfloat16* M16 = reinterpret_cast<__nv_bfloat16*>(ws + w.M16);
+    __nv_bfloat16* PH16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PH16);
+    __nv_bfloat16* PZ16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PZ16);
+    __nv_bfloat16* PX16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PX16);
     // x -> slot 0 of PX[t]
     CK(cudaMemcpy2DAsync(PX, sizeof(float) * K * UX, x, sizeof(float) * x_tstride, sizeof(float) * UX, T,
                          cudaMemcpyDeviceToDevice, st));
+    if (bf) {
+        CK(to_bf16(M, 0, M16, 0, (long long)Kp * N * ldm, 1, st));
+        CK(to_bf16(x, x_tstride, PX16, K * UX, UX, T, st));
+    }
     // PX[t, 1..K) = M * x_t  (all t at once)
-    CK(propagate(tc, M, ldm, N, Kp, PX, K * UX, B * Cin, PX + UX, T, st));
+    {
+        GemmP pp = prop_params(M, ldm, N, Kp, PX, B * Cin);
+        pp.sB1 = K * UX;
+        if (bf) { pp.A16 = M16; pp.B16 = PX16; }
+        CK((gemm_any<CfgBig, true, false>(tc, pp, epi_store(PX + UX, K * UX, 0, B * Cin), T, st)));
+    }
     TR();
 
     GemmP p;
@@ -860,6 +956,10 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     // initial state
     if (h0) CK(cudaMemcpyAsync(PH, h0, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
     else CK(cudaMemsetAsync(PH, 0, sizeof(float) * U, st));
+    if (bf) {
+        if (h0) CK(to_bf16(h0, 0, PH16, 0, U, 1, st));
+        else CK(cudaMemsetAsync(PH16, 0, sizeof(__nv_bfloat16) * U, st));
+    }
 
     bool use_multi = tc && multi_enabled();
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -873,16 +973,18 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             const float* GXt = GX + (long long)t * 3 * U; const float* RXt = RX + (long long)t * 3 * U;
             // (a) PH[t,1..] = M * h
             p = prop_params(M, ldm, N, Kp, PHt, B * H);
+            if (bf) { p.A16 = M16; p.B16 = PH16 + (long long)t * U; }
             STEP_GEMM(0, CfgBig, true, false, p, epi_store(PHt + U, 0, 0, B * H), 1);
             // (b) gate: per node [B, K*H] x [K*H, 2H]
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = 1; p.KB = K;
             p.A = PHt; p.lda = H; p.sA1 = (long long)B * H; p.sAk = U; p.M = B; p.K = H;
             p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sBk = (long long)I * 2 * H;
-            STEP_GEMM(1, CfgMid, true, false, p, (EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H, tc ? 1 : 0}), N);
+            STEP_GEMM(1, CfgMid, true, false, p, (EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H, tc ? 1 : 0, bf ? PZ16 + (long long)t * U : nullptr}), N);
             // (c) PZ[t,1..] = M * (z*h)
             {
                 GemmP pp = prop_params(M, ldm, N, Kp, PZt, B * H);
+                if (bf) { pp.A16 = M16; pp.B16 = PZ16 + (long long)t * U; }
                 STEP_GEMM(2, CfgBig, true, false, pp, epi_store(PZt + U, 0, 0, B * H), 1);
             }
             // (d) candidate
@@ -898,7 +1000,8 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             // (f) residual candidate + mix -> PH[t+1, 0]
             p.A = ZH2t;
             p.B = RuH; p.ldb = H; p.N = H;
-            STEP_GEMM(5, CfgMid, true, true, p, (EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H, tc ? 1 : 0}), 1);
+            STEP_GEMM(5, CfgMid, true, true, p,
+                      (EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H, tc ? 1 : 0, bf ? PH16 + (long long)(t + 1) * U : nullptr}), 1);
         }
         if (!use_multi) break;
         float* mph = ws + w.MPH;
@@ -942,6 +1045,11 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     float* DH1 = bws + bw.DH1; float* DHD = bws + bw.DHD; float* DHC = bws + bw.DHC; float* DRES = bws + bw.DRES;
     const int NB = N * B;
 
+    const size_t m16_cap = ((size_t)Kp * N * 8 * ((N + 7) / 8 + 1));
+    const bool bf = tc && (flags & MATGCN_FLAG_BF16) != 0 && (size_t)Kp * N * ldm <= m16_cap;
+    const __nv_bfloat16* M16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.M16);  // written by the forward pass
+    __nv_bfloat16* DPT16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.DPT16);
+    __nv_bfloat16* DPX16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.DPX16);
     CK(cudaMemsetAsync(DHC, 0, sizeof(float) * U, st));
     TR();
     CK(cudaMemsetAsync(dmix, 0, sizeof(float) * T, st));
@@ -981,7 +1089,11 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.splits = 1; p.Z2 = K; p.KB = 1;
             p.A = DGt + 2 * H; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.sA2 = 0; p.M = B; p.K = H;
             p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sB2 = (long long)I * H;
-            STEP_GEMM(2, CfgMid, true, true, p, epi_store(DPT, (long long)B * H, U, H), N * K);
+            {
+                EpiStore e = epi_store(DPT, (long long)B * H, U, H);
+                if (bf) e.C16 = DPT16;
+                STEP_GEMM(2, CfgMid, true, true, p, e, N * K);
+            }
             if (n_adp && !use_multi) {
                 CK(cudaMemcpyAsync(DPZA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
                 TR();
@@ -991,6 +1103,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.splits = 1; p.Z2 = 1; p.KB = 1;
             p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
+            if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
             STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPZA + (long long)t * n_adp * U, (long long)n_adp * U);
             // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
@@ -998,7 +1111,11 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.splits = 1; p.Z2 = K; p.KB = 1;
             p.A = DGt; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
             p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = (long long)I * 2 * H;
-            STEP_GEMM(4, CfgMid, true, true, p, epi_store(DPT, (long long)B * H, U, H), N * K);
+            {
+                EpiStore e = epi_store(DPT, (long long)B * H, U, H);
+                if (bf) e.C16 = DPT16;
+                STEP_GEMM(4, CfgMid, true, true, p, e, N * K);
+            }
             if (n_adp && !use_multi) {
                 CK(cudaMemcpyAsync(DPHA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
                 TR();
@@ -1008,6 +1125,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.splits = 1; p.Z2 = 1; p.KB = 1;
             p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
+            if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
             STEP_GEMM(5, CfgBig, false, false, p, (EpiB6{DPT, DHD, DHC, B * H}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPHA + (long long)t * n_adp * U, (long long)n_adp * U);
         }
@@ -1087,6 +1205,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
             p.B = Wg + (long long)k * I * 2 * H; p.ldb = 2 * H; p.N = Cin; p.sB1 = 0; p.sB2 = (long long)K * I * 2 * H;
             EpiStore e = epi_store(DPX + (long long)k * UX, K * UX, (long long)B * Cin, Cin);
+            if (bf && k >= 1) e.C16 = DPX16 + (long long)k * UX;  // (the accumulating second launch writes the final twin)
             CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
             TR();
             p.A = DG + 2 * H; p.K = H;
@@ -1101,6 +1220,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.splits = 1; p.Z2 = 1; p.KB = 1;
     p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
     p.B = DPX + UX; p.ldb = B * Cin; p.N = B * Cin; p.sB1 = K * UX;
+    if (bf && !small_x) { p.A16 = M16; p.B16 = DPX16 + UX; }
     {
         EpiStore e = epi_store(dx, UX, 0, B * Cin);
         e.add = DPX; e.add_s1 = K * UX; e.add_ld = B * Cin;

@@ -120,7 +120,8 @@ class MultiATGCN(nn.Module):
         self.hidden_dim = g("rnn_units", 64)
         self.num_layers = g("num_layers", 2)
         # extra key of this implementation (absent from the reference): arithmetic of the contractions.
-        # "exact" = fp32 FFMA kernels (1e-4 parity); "tf32"/"fast" = tcgen05 tensor cores, looser bound.
+        # "exact" = fp32 FFMA kernels (1e-4 parity); "tf32"/"fast" = tcgen05 tensor cores, looser bound;
+        # "bf16" = tf32 plus bf16 operands for the support-propagation contractions.
         mode = g("matgcn_mode", "exact")
         if mode not in ops.MODES:
             raise ValueError("matgcn_mode must be one of %s, got %r" % (sorted(ops.MODES), mode))

@@ -260,4 +260,5 @@ def encoder_layer(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flag
     return _EncoderLayerFn.apply(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags)
 
 
-MODES = {"exact": _cabi.FLAG_EXACT, "fp32": _cabi.FLAG_EXACT, "fast": _cabi.FLAG_TF32, "tf32": _cabi.FLAG_TF32}
+MODES = {"exact": _cabi.FLAG_EXACT, "fp32": _cabi.FLAG_EXACT, "fast": _cabi.FLAG_TF32, "tf32": _cabi.FLAG_TF32,
+         "bf16": _cabi.FLAG_TF32 | _cabi.FLAG_BF16}

@@ -63,11 +63,15 @@ def test_gemm_engine_tf32(a_kc, b_kc, M, N, K, splits):
     assert max_rel_err(C2[:, :N], ref) < 1e-5
 
 
+BF16_TOL = 3e-2  # bf16 keeps 8 mantissa bits of the propagated operands
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
 @pytest.mark.parametrize("N,B,adjtype,adpadj,D,tout", [(45, 8, "multi", "bidirection", 20, 24),
                                                         (130, 4, "od", "bidirection", 10, 3)])
-def test_model_fast_mode_matches_oracle(N, B, adjtype, adpadj, D, tout):
+def test_model_fast_mode_matches_oracle(N, B, adjtype, adpadj, D, tout, mode):
     cfg = make_config(adjtype=adjtype, adpadj=adpadj, embed_dim=D, output_window=tout, batch_size=B,
-                      device=torch.device(DEV), matgcn_mode="tf32")
+                      device=torch.device(DEV), matgcn_mode=mode)
     df = make_data_feature(N, seed=5)
     batch = make_batch(N, B, tout, seed=5)
     torch.manual_seed(0)
@@ -88,8 +92,9 @@ def test_model_fast_mode_matches_oracle(N, B, adjtype, adpadj, D, tout):
     for k, p in model.named_parameters():
         if grads.get(k) is not None and p.grad is not None:
             errs["d" + k] = max_rel_err(p.grad, grads[k])
-    print("[fast N=%d] " % N + ", ".join("%s=%.2e" % kv for kv in errs.items()))
-    bad = {k: v for k, v in errs.items() if not (v < MODEL_TOL)}
+    print("[fast %s N=%d] " % (mode, N) + ", ".join("%s=%.2e" % kv for kv in errs.items()))
+    tol = MODEL_TOL if mode == "tf32" else BF16_TOL
+    bad = {k: v for k, v in errs.items() if not (v < tol)}
     assert not bad, bad
 
 
@@ -124,3 +129,35 @@ def test_persistent_recurrence_kernel_matches_per_phase_launches():
     for k in g0:
         assert max_rel_err(g1[k], g0[k]) < 1e-4, k   # split-K atomics reorder sums slightly
     assert n1 < 300, "persistent mode should need far fewer launches (got %d)" % n1
+
+
+@pytest.mark.parametrize("a_kc,b_kc", [(1, 0), (0, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K,splits", [(128, 128, 64, 1), (403, 4096, 403, 1), (64, 64, 320, 1), (1612, 520, 403, 1),
+                                          (37, 72, 100, 1), (403, 403, 4096, 4)])
+def test_gemm_engine_bf16(a_kc, b_kc, M, N, K, splits):
+    """bf16 operand twins on the bf16 tcgen05 engine (kind::f16), fp32 accumulation; compared with the fp64 product
+    of the SAME bf16-rounded operands, so only accumulation order differs."""
+    lib = _cabi.lib()
+    pad = lambda v: (v + 7) // 8 * 8  # noqa: E731  (16-byte row pitches in bf16)
+    A = _rand(M, K, seed=1).bfloat16()
+    B = _rand(K, N, seed=2).bfloat16()
+    ref = A.double() @ B.double()
+    if a_kc:
+        Ad = torch.zeros(M, pad(K), dtype=torch.bfloat16); Ad[:, :K] = A; lda = pad(K)
+    else:
+        Ad = torch.zeros(K, pad(M), dtype=torch.bfloat16); Ad[:, :M] = A.t(); lda = pad(M)
+    if b_kc:
+        Bd = torch.zeros(N, pad(K), dtype=torch.bfloat16); Bd[:, :K] = B.t(); ldb = pad(K)
+    else:
+        Bd = torch.zeros(K, pad(N), dtype=torch.bfloat16); Bd[:, :N] = B; ldb = pad(N)
+    Ad, Bd = Ad.to(DEV), Bd.to(DEV)
+    ldc = N + 3
+    C = torch.full((M, ldc), float("nan"), device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _cabi.check(lib.matgcn_gemm_debug_bf16(a_kc, b_kc, M, N, K, Ad.data_ptr(), lda, Bd.data_ptr(), ldb, C.data_ptr(), ldc,
+                                           splits, st), "gemm_debug_bf16")
+    torch.cuda.synchronize()
+    err = max_rel_err(C[:, :N], ref)
+    print("[bf16 gemm a_kc=%d b_kc=%d %dx%dx%d s=%d] err=%.2e" % (a_kc, b_kc, M, N, K, splits, err))
+    assert err < 1e-5
+    assert torch.isnan(C[:, N:]).all()
