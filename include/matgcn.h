@@ -92,6 +92,11 @@ int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X,
  * launch per contraction.  Returns the previous setting.  Default off (or MATGCN_MULTI=1 in the environment). */
 int matgcn_set_persistent(int on);
 
+/* Fused tail of the forward step (candidate contraction + residual GRU cell + mix in one launch; tensor-core engine,
+ * rnn_units = 64).  on = 0 selects the three separate contractions.  Returns the previous setting.  Default on
+ * (or MATGCN_FUSED_TAIL=0 in the environment). */
+int matgcn_set_fused_tail(int on);
+
 /* The same contraction with bf16 twins of M and X (device arrays of __nv_bfloat16), float32 output: the kernel the
  * layer entry points launch for the propagation when MATGCN_FLAG_BF16 is set. */
 int matgcn_propagate_fwd_bf16(const void* M16, int Kp, int N, int ldm, const void* X16, int cols, float* P, void* stream);

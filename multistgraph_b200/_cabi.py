@@ -32,6 +32,7 @@ _SIGNATURES = {
     "matgcn_debug_set_timeline_skip": (c_int, [c_int]),
     "matgcn_gemm_debug": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, c_int, _F, c_int, _F, c_int, c_int, c_int,
                                   c_void_p]),
+    "matgcn_set_fused_tail": (c_int, [c_int]),
     "matgcn_propagate_fwd_bf16": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_void_p]),
     "matgcn_gemm_debug_bf16": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, c_int, _F, c_int, _F, c_int, c_int, c_void_p]),
     "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),

@@ -50,6 +50,7 @@ __device__ __forceinline__ float4 tanh4(const float4& a, int fast) {
 // C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col] + add[...]
 struct EpiStore {
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     float* C;
     long long s1, s2;
     int ldc;
@@ -100,6 +101,30 @@ struct EpiStore {
         st4(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
         if (C16) st4_bf16(C16 + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
     }
+    // cursor form (tensor-core epilogue): the position is computed once per 32-column chunk and bumped row by row
+    struct Cur { long long off, aoff; float4 bias; float scale; };
+    __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
+        Cur c;
+        c.off = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
+        c.aoff = add ? z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col : 0;
+        c.bias = bias ? ld4(bias + z1 * bias_s1 + col) : f4(0.f);
+        c.scale = scale ? __ldg(scale + col / scale_div) : 1.f;
+        return c;
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ldc; c.aoff += (long long)rows * add_ld; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.c = add ? ld4(add + c.aoff) : f4(0.f);
+        in.d = accumulate ? ld4(C + c.off) : f4(0.f);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        float4 v = c.scale * acc + c.bias;
+        if (add) v = v + in.c;
+        if (accumulate) v = v + in.d;
+        st4(C + c.off, v);
+        if (C16) st4_bf16(C16 + c.off, v);
+    }
     EPI_CALL_OPERATOR
 };
 inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
@@ -111,6 +136,7 @@ inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
 
 struct EpiAtomic {  // split-K partial sums into a zeroed C
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 8;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     float* C;
     long long s1, s2;
     int ldc;
@@ -124,6 +150,14 @@ struct EpiAtomic {  // split-K partial sums into a zeroed C
         float* d = C + z1 * s1 + z2 * s2 + (long long)row * ldc + col;
         atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
     }
+    struct Cur { long long off; };
+    __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const { return Cur{z1 * s1 + z2 * s2 + (long long)row * ldc + col}; }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ldc; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur&) const { return EpiIn4{}; }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4&) const {
+        float* d = C + c.off;
+        atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+    }
     EPI_CALL_OPERATOR
 };
 
@@ -131,6 +165,7 @@ struct EpiAtomic {  // split-K partial sums into a zeroed C
 // are [N*B, H] blocks, pre-activation inputs [N*B, 3H] blocks.
 struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (cols >= H): R
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
     int rows_per_z, H, fast;
     __nv_bfloat16* ZH16;  // may be null: bf16 twin of ZH
@@ -171,10 +206,38 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
             st4(R + g * H + col - H, s);
         }
     }
+    // i: offset into the [rows, H] blocks (column already reduced by H for the r half), j: offset into GX [rows, 3H]
+    struct Cur { long long i, j; int is_z; };
+    __device__ __forceinline__ Cur begin4(int z1, int, int row, int col) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        Cur c;
+        c.is_z = col < H;
+        c.i = g * H + (c.is_z ? col : col - H);
+        c.j = g * 3 * H + col;
+        return c;
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.i += (long long)rows * H; c.j += (long long)rows * 3 * H; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.a = ld4(GX + c.j);
+        in.b = c.is_z ? ld4(Hprev + c.i) : f4(0.f);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        const float4 s = sigmoid4(acc + in.a, fast);
+        if (c.is_z) {
+            st4(Z + c.i, s);
+            st4(ZH + c.i, s * in.b);
+            if (ZH16) st4_bf16(ZH16 + c.i, s * in.b);
+        } else {
+            st4(R + c.i, s);
+        }
+    }
     EPI_CALL_OPERATOR
 };
 struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
     int rows_per_z, H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(H1); }
@@ -206,10 +269,27 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
         st4(HC + g * H + col, hc);
         st4(H1 + g * H + col, in.b * in.c + one_minus(in.b) * hc);
     }
+    struct Cur { long long i, j; };
+    __device__ __forceinline__ Cur begin4(int z1, int, int row, int col) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        return Cur{g * H + col, g * 3 * H + 2 * H + col};
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.i += (long long)rows * H; c.j += (long long)rows * 3 * H; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.a = ld4(GX + c.j); in.b = ld4(R + c.i); in.c = ld4(Hprev + c.i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        const float4 hc = tanh4(acc + in.a, fast);
+        st4(HC + c.i, hc);
+        st4(H1 + c.i, in.b * in.c + one_minus(in.b) * hc);
+    }
     EPI_CALL_OPERATOR
 };
 struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r2)*hc2)
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
     int H, fast;
     __nv_bfloat16* Y16;  // may be null: bf16 twin of Y
@@ -250,12 +330,54 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
         st4(Y + g * H + col, y);
         if (Y16) st4_bf16(Y16 + g * H + col, y);
     }
+    struct Cur { long long i, j; float m; };
+    __device__ __forceinline__ Cur begin4(int, int, int row, int col) const {
+        return Cur{(long long)row * H + col, (long long)row * 3 * H + 2 * H + col, __ldg(mix_t)};
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.i += (long long)rows * H; c.j += (long long)rows * 3 * H; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.a = ld4(RX + c.j); in.b = ld4(R2 + c.i); in.c = ld4(H1 + c.i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        const float4 hc2 = tanh4(acc + in.a, fast);
+        const float4 res = in.b * in.c + one_minus(in.b) * hc2;
+        st4(HC2 + c.i, hc2);
+        const float4 y = c.m * in.c + (1.f - c.m) * res;
+        st4(Y + c.i, y);
+        if (Y16) st4_bf16(Y16 + c.i, y);
+    }
     EPI_CALL_OPERATOR
 };
+
+// Fused tail of the forward step (tensor-core engine only, H = 64): the candidate contraction's epilogue
+// (EpiCand) followed, for the same (node, batch) rows, by the whole residual GRU cell and the mix
+// (EpiGate on RX / EpiResCand) - the two small [rows, 64] x [64, 192] products run as warp-level mma.sync
+// inside the epilogue warps (gemm_tc.cuh: tc_epilogue_tile_candres), so one launch replaces three.
+struct EpiCandRes {
+    static constexpr bool kFusedRes = true;
+    // candidate part (EpiCand)
+    const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
+    int rows_per_z, H, fast;
+    // residual cell + mix (EpiGate on RX, EpiResCand)
+    const float* RX; float* Z2; float* R2; float* ZH2; float* HC2; float* Y; const float* mix_t;
+    __nv_bfloat16* Y16;   // may be null: bf16 twin of Y
+    const float* RgH;     // [2H, H] dense: Rgw[:, Cin:]
+    const float* RuH;     // [H, H]  dense: Ruw[:, Cin:]
+    bool vec_ok() const {
+        return H == 64 && aligned16(GX) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(H1) && aligned16(RX) &&
+               aligned16(Z2) && aligned16(R2) && aligned16(ZH2) && aligned16(HC2) && aligned16(Y) && aligned16(RgH) && aligned16(RuH) &&
+               (!Y16 || aligned16(Y16));
+    }
+};
+template <class E, class = void> struct IsFusedRes { static constexpr bool value = false; };
+template <class E> struct IsFusedRes<E, decltype((void)E::kFusedRes)> { static constexpr bool value = true; };
 
 // Backward step epilogues (notation of DESIGN.md section 3 / tests/host_mirror.py).
 struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR[H:2H] = dres*(h1-hc2)*r2(1-r2)
     static constexpr int kBatch = 2;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 1;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     float* DH1; float* DR; const float* DRES; const float* H1; const float* Z2; const float* R2; const float* HC2;
     int H;
     bool vec_ok() const {
@@ -286,10 +408,24 @@ struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR
         st4(DR + (long long)row * 3 * H + col, acc * in.c * in.a * one_minus(in.a));
         st4(DR + (long long)row * 3 * H + H + col, in.e * (in.c - in.f) * in.b * one_minus(in.b));
     }
+    struct Cur { long long i, j; };
+    __device__ __forceinline__ Cur begin4(int, int, int row, int col) const { return Cur{(long long)row * H + col, (long long)row * 3 * H + col}; }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.i += (long long)rows * H; c.j += (long long)rows * 3 * H; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.a = ld4(Z2 + c.i); in.b = ld4(R2 + c.i); in.c = ld4(H1 + c.i); in.d = ld4(DH1 + c.i); in.e = ld4(DRES + c.i); in.f = ld4(HC2 + c.i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        st4(DH1 + c.i, in.d + acc * in.a);
+        st4(DR + c.j, acc * in.c * in.a * one_minus(in.a));
+        st4(DR + c.j + H, in.e * (in.c - in.f) * in.b * one_minus(in.b));
+    }
     EPI_CALL_OPERATOR
 };
 struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 2;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     const float* DH1; const float* Hprev; const float* R; const float* HC; float* DHD; float* DG;
     int H;
     bool vec_ok() const { return !(H & 3) && aligned16(DH1) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(DHD) && aligned16(DG); }
@@ -320,10 +456,25 @@ struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
         st4(DG + (long long)row * 3 * H + 2 * H + col, dh1 * one_minus(in.b) * one_minus(in.c * in.c));
         st4(DG + (long long)row * 3 * H + H + col, dh1 * (in.d - in.c) * in.b * one_minus(in.b));
     }
+    struct Cur { long long i, j; };
+    __device__ __forceinline__ Cur begin4(int, int, int row, int col) const { return Cur{(long long)row * H + col, (long long)row * 3 * H + col}; }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.i += (long long)rows * H; c.j += (long long)rows * 3 * H; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.a = ld4(DH1 + c.i); in.b = ld4(R + c.i); in.c = ld4(HC + c.i); in.d = ld4(Hprev + c.i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        const float4 dh1 = in.a + acc;
+        st4(DHD + c.i, dh1 * in.b);
+        st4(DG + c.j + 2 * H, dh1 * one_minus(in.b) * one_minus(in.c * in.c));
+        st4(DG + c.j + H, dh1 * (in.d - in.c) * in.b * one_minus(in.b));
+    }
     EPI_CALL_OPERATOR
 };
 struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      (row = node m, col = (b,c))
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 2;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     const float* DP0; const float* Hprev; const float* Z; float* DHD; float* DG;
     int H, BH;  // BH = B*H columns per node
     bool vec_ok() const { return !(H & 3) && !(BH & 3) && aligned16(DP0) && aligned16(Hprev) && aligned16(Z) && aligned16(DHD) && aligned16(DG); }
@@ -356,11 +507,29 @@ struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      
         const int c = (int)(i - g * H);
         st4(DG + g * 3 * H + c, dzh * in.d * in.b * one_minus(in.b));
     }
+    struct Cur { long long i, j; };  // j: position of the same element in the [rows, 3H] gradient block
+    __device__ __forceinline__ Cur begin4(int, int, int row, int col) const {
+        const long long i = (long long)row * BH + col;
+        const long long g = i / H;
+        return Cur{i, g * 3 * H + (i - g * H)};
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.i += (long long)rows * BH; c.j += (long long)rows * 3 * BH; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.a = ld4(DP0 + c.i); in.b = ld4(Z + c.i); in.c = ld4(DHD + c.i); in.d = ld4(Hprev + c.i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        const float4 dzh = acc + in.a;
+        st4(DHD + c.i, in.c + dzh * in.b);
+        st4(DG + c.j, dzh * in.d * in.b * one_minus(in.b));
+    }
     EPI_CALL_OPERATOR
 };
 
 struct EpiB6 {  // carry = acc + DP0 + DHD
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
+    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
     const float* DP0; const float* DHD; float* OUT;
     int BH;
     bool vec_ok() const { return !(BH & 3) && aligned16(DP0) && aligned16(DHD) && aligned16(OUT); }
@@ -384,6 +553,15 @@ struct EpiB6 {  // carry = acc + DP0 + DHD
         const long long i = (long long)row * BH + col;
         st4(OUT + i, acc + in.a + in.b);
     }
+    struct Cur { long long i; };
+    __device__ __forceinline__ Cur begin4(int, int, int row, int col) const { return Cur{(long long)row * BH + col}; }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.i += (long long)rows * BH; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        in.a = ld4(DP0 + c.i); in.b = ld4(DHD + c.i);
+        return in;
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const { st4(OUT + c.i, acc + in.a + in.b); }
     EPI_CALL_OPERATOR
 };
 

@@ -166,16 +166,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
-template <int BN>
+constexpr int TC_RES_LD = 68;  // row pitch (floats) of the residual-cell weight tiles in shared memory: conflict-free B fragments
+template <int BN, bool FUSED = false>
 struct TcSmem {
     static constexpr int A_BYTES = TC_BM * 128;  // 16 KB: 128 rows of one 128-byte slab
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128 ? 5 : 3);
+    static constexpr int STAGES = FUSED ? 5 : ((BN <= 64) ? 6 : (BN <= 128 ? 5 : 3));
     static constexpr int EPI_LD = TC_EPI_LD;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 access
     static constexpr int EPI_BYTES = TC_EPI_WARPS * 32 * EPI_LD * 4;  // per epilogue warp: [32][36] floats
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
+    static constexpr int EXTRA_BYTES = FUSED ? (3 * 64) * TC_RES_LD * 4 : 0;  // fused tail: Rg_h [128][68] + Ru_h [64][68]
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + EXTRA_BYTES + 1024;  // + alignment slack
 };
 
 // Epilogue of one output tile, run by one epilogue warp: TMEM -> registers -> staging tile -> epilogue functor.
@@ -263,13 +265,327 @@ __device__ __forceinline__ void tc_epilogue_tile(const Epi& epi, const TcP& p, u
     }
 }
 
+// Compile-time step index and ping-pong recursion for the software-pipelined epilogue: every step sees its two
+// register buffers under fixed names, so they are never indexed dynamically (which would put them in local memory).
+template <int V> struct IntC { static constexpr int value = V; };
+template <int S, int N, class F>
+__device__ __forceinline__ void tc_pingpong_steps(F& f, EpiIn4* cur, EpiIn4* nxt) {
+    if constexpr (S < N) {
+        f(IntC<S>{}, cur, nxt);
+        tc_pingpong_steps<S + 1, N>(f, nxt, cur);
+    }
+}
+
+// Software-pipelined form of the vectorised epilogue (p.vec): the epilogue functor's global reads do not depend on the
+// accumulator, so the reads of step s+1 are issued before step s is computed (double-buffered registers), and those of
+// the first step before the accumulator is even complete (the wait on `tfull` sits inside).  Positions are cursors
+// (Epi::Cur) computed once per 32-column chunk and bumped by four rows per access - no per-element index arithmetic.
+// A step = Epi::kPipe accesses per lane; a 32x32 chunk = 8 accesses per lane (lane -> row 4*it + lane/8, columns 4*(lane%8)..+3).
+template <int BN, class Epi>
+__device__ __forceinline__ void tc_epilogue_tile_pipe(const Epi& epi, const TcP& p, uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_parity,
+                                                      int q, int half, float* buf, int lane, int z1, int z2, int m0, int n0) {
+    constexpr int LD = TC_EPI_LD;
+    constexpr int NB = Epi::kPipe;
+    constexpr int NCH = (BN / 32 + 1) / 2;  // 32-column chunks per warp (two warps share a TMEM lane quadrant)
+    constexpr int SPC = 8 / NB;             // steps per chunk
+    constexpr int STEPS = NCH * SPC;
+    static_assert(8 % NB == 0, "kPipe must divide 8");
+    const int pM = p.M, pN = p.N, pdbg = p.dbg_mode;
+    const int rows_per_q = p.m64 ? 16 : 32;  // see tc_epilogue_tile
+    const int row_base = m0 + q * rows_per_q;
+    const int row_lim = min(pM, row_base + rows_per_q);
+    const int rq = lane >> 3, cq = lane & 7;
+    const int col0 = n0 + half * 32 + 4 * cq;  // this lane's first column in chunk 0; chunk ci is 64*ci further
+    const bool any_row = row_base < row_lim;
+
+    typename Epi::Cur lc = epi.begin4(z1, z2, row_base + rq, col0);  // load cursor (runs one step ahead)
+    typename Epi::Cur sc = lc;                                        // store cursor
+    EpiIn4 bufA[NB], bufB[NB];
+    if (any_row && col0 < pN) {
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            if (row_base + 4 * u + rq < row_lim) bufA[u] = epi.load4(lc);
+            epi.advance4(lc, 4);
+        }
+    }
+    mbar_wait(tfull, tfull_parity);
+    tc_fence_after();
+    if (!any_row) return;
+    auto step = [&](auto S_, EpiIn4* cur, EpiIn4* nxt) {
+        constexpr int s = decltype(S_)::value;
+        constexpr int ci = s / SPC, b = s % SPC;
+        const int col = col0 + 64 * ci;
+        const bool chunk_ok = n0 + (half + 2 * ci) * 32 < pN;  // warp-uniform
+        if (b == 0 && chunk_ok) {
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((half + 2 * ci) * 32);
+            uint32_t r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ci > 0) __syncwarp();  // every lane is done reading the previous chunk from the staging tile
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(buf + lane * LD + 4 * j) =
+                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+            __syncwarp();
+        }
+        if (b == 0 && ci > 0) sc = epi.begin4(z1, z2, row_base + rq, col);
+        // reads of the next step
+        if constexpr (s + 1 < STEPS) {
+            constexpr int ci1 = (s + 1) / SPC, b1 = (s + 1) % SPC;
+            const int col1 = col0 + 64 * ci1;
+            if (b1 == 0) lc = epi.begin4(z1, z2, row_base + rq, col1);
+            if (col1 < pN) {
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    if (row_base + 4 * (b1 * NB + u) + rq < row_lim) nxt[u] = epi.load4(lc);
+                    epi.advance4(lc, 4);
+                }
+            }
+        }
+        // arithmetic + writes of this step
+        if (chunk_ok) {
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int rl = 4 * (b * NB + u) + rq;
+                const float4 v = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
+                if (col < pN && row_base + rl < row_lim && !(pdbg & 1)) epi.store4(sc, v, cur[u]);
+                epi.advance4(sc, 4);
+            }
+        }
+    };
+    tc_pingpong_steps<0, STEPS>(step, bufA, bufB);
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused tail of the forward step (EpiCandRes; BN = H = 64, one 32-column chunk per epilogue warp).
+// Phase 1 is the candidate epilogue in the coalesced layout; h1 goes back into the staging tile, where the two warps
+// of a TMEM lane quadrant (columns 0..31 / 32..63 of the same rows) find the full 64-wide rows.  Phases 2/3 are the
+// residual gate and candidate products as mma.sync m16n8k8 TF32 (A fragments from the staging tiles, B fragments from
+// the weight tiles in shared memory) with their elementwise epilogues in the accumulator-fragment layout.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+
+template <class Epi>
+__device__ __forceinline__ void tc_epilogue_tile_candres(const Epi& e, const TcP& p, uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_parity,
+                                                         int q, int half, float* buf, float* buf_other, const float* wg_s,
+                                                         const float* wu_s, int lane, int z1, int m0) {
+    constexpr int LD = TC_EPI_LD;
+    constexpr int H = 64;
+    constexpr int WL = TC_RES_LD;
+    const int rows_per_q = p.m64 ? 16 : 32;
+    const int row_base = m0 + q * rows_per_q;           // row inside the node's [B, H] block
+    const int row_lim = min(p.M, row_base + rows_per_q);
+    const bool any_row = row_base < row_lim;            // same for both warps of the quadrant
+    const int fast = e.fast;
+    const long long g0 = (long long)z1 * e.rows_per_z;  // first (node, batch) row of this node
+
+    // ---------------- phase 1: hc = tanh(acc + GX[2H:3H]); h1 = r*h + (1-r)*hc ----------------
+    const int rq = lane >> 3, cq = lane & 7;
+    const int col = half * 32 + 4 * cq;
+    long long i = (g0 + row_base + rq) * H + col;
+    long long j = (g0 + row_base + rq) * 3 * H + 2 * H + col;
+    float4 gx[4], rr[4], hh[4];
+    if (any_row) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (row_base + 4 * u + rq < row_lim) {
+                gx[u] = ld4(e.GX + j + (long long)u * 12 * H);
+                rr[u] = ld4(e.R + i + (long long)u * 4 * H);
+                hh[u] = ld4(e.Hprev + i + (long long)u * 4 * H);
+            }
+    }
+    mbar_wait(tfull, tfull_parity);
+    tc_fence_after();
+    if (!any_row) return;
+    {
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+            *reinterpret_cast<float4*>(buf + lane * LD + 4 * jj) =
+                make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]), __uint_as_float(r[4 * jj + 2]),
+                            __uint_as_float(r[4 * jj + 3]));
+        __syncwarp();
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        if (16 * b >= rows_per_q) break;  // half-height tiles keep 16 rows per quadrant
+        if (b == 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (row_base + 16 + 4 * u + rq < row_lim) {
+                    gx[u] = ld4(e.GX + j + (long long)(4 + u) * 12 * H);
+                    rr[u] = ld4(e.R + i + (long long)(4 + u) * 4 * H);
+                    hh[u] = ld4(e.Hprev + i + (long long)(4 + u) * 4 * H);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rl = 16 * b + 4 * u + rq;
+            if (row_base + rl < row_lim) {
+                float* sp = buf + rl * LD + 4 * cq;
+                const float4 acc = *reinterpret_cast<const float4*>(sp);
+                const float4 hc = tanh4(acc + gx[u], fast);
+                const float4 h1 = rr[u] * hh[u] + one_minus(rr[u]) * hc;
+                st4(e.HC + i + (long long)(4 * b + u) * 4 * H, hc);
+                st4(e.H1 + i + (long long)(4 * b + u) * 4 * H, h1);
+                *reinterpret_cast<float4*>(sp) = h1;
+            }
+        }
+    }
+    pair_sync(q);  // both 32-column halves of h1 are in the two staging tiles
+
+    // ---------------- phases 2/3: residual GRU cell on h1, mix ----------------
+    const int g = lane >> 2, tig = lane & 3;
+    const float* k_lo = half == 0 ? buf : buf_other;   // columns (= reduction index) 0..31 of the rows
+    const float* k_hi = half == 0 ? buf_other : buf;   // columns 32..63
+    const float m = __ldg(e.mix_t);
+    for (int mb = 0; mb * 16 < rows_per_q; ++mb) {
+        const int ra = 16 * mb + g, rb = ra + 8;       // staging rows of this thread's fragments
+        const bool va = row_base + ra < row_lim, vb = row_base + rb < row_lim;
+        const long long ga = g0 + row_base + ra, gb = ga + 8;
+        const int c0 = 32 * half + 2 * tig;            // first of this thread's output columns (+ 8*nt)
+        // pre-activation inputs of the residual gate (issued before the products)
+        float2 xz[4][2], xr[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            if (va) { xz[nt][0] = ld2(e.RX + ga * 3 * H + c0 + 8 * nt); xr[nt][0] = ld2(e.RX + ga * 3 * H + H + c0 + 8 * nt); }
+            if (vb) { xz[nt][1] = ld2(e.RX + gb * 3 * H + c0 + 8 * nt); xr[nt][1] = ld2(e.RX + gb * 3 * H + H + c0 + 8 * nt); }
+        }
+        float cz[4][4], cr[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { cz[nt][x] = 0.f; cr[nt][x] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const float* src = (ks < 4 ? k_lo : k_hi) + (ks & 3) * 8 + tig;
+            uint32_t a[4];
+            a[0] = __float_as_uint(src[ra * LD]); a[1] = __float_as_uint(src[rb * LD]);
+            a[2] = __float_as_uint(src[ra * LD + 4]); a[3] = __float_as_uint(src[rb * LD + 4]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float* wz = wg_s + (32 * half + 8 * nt + g) * WL + 8 * ks + tig;
+                mma_tf32_16x8x8(cz[nt], a, __float_as_uint(wz[0]), __float_as_uint(wz[4]));
+                const float* wr = wz + 64 * WL;
+                mma_tf32_16x8x8(cr[nt], a, __float_as_uint(wr[0]), __float_as_uint(wr[4]));
+            }
+        }
+        float h1v[4][4], r2v[4][4], zhv[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float2 ha = *reinterpret_cast<const float2*>(buf + ra * LD + 8 * nt + 2 * tig);
+            const float2 hb = *reinterpret_cast<const float2*>(buf + rb * LD + 8 * nt + 2 * tig);
+            h1v[nt][0] = ha.x; h1v[nt][1] = ha.y; h1v[nt][2] = hb.x; h1v[nt][3] = hb.y;
+            float z2[4];
+            z2[0] = cz[nt][0] + xz[nt][0].x; z2[1] = cz[nt][1] + xz[nt][0].y; z2[2] = cz[nt][2] + xz[nt][1].x; z2[3] = cz[nt][3] + xz[nt][1].y;
+            r2v[nt][0] = cr[nt][0] + xr[nt][0].x; r2v[nt][1] = cr[nt][1] + xr[nt][0].y;
+            r2v[nt][2] = cr[nt][2] + xr[nt][1].x; r2v[nt][3] = cr[nt][3] + xr[nt][1].y;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                z2[x] = fast ? sigmoid_fast(z2[x]) : sigmoidf_(z2[x]);
+                r2v[nt][x] = fast ? sigmoid_fast(r2v[nt][x]) : sigmoidf_(r2v[nt][x]);
+                zhv[nt][x] = z2[x] * h1v[nt][x];
+            }
+            const int c = c0 + 8 * nt;
+            if (va) { st2(e.Z2 + ga * H + c, z2[0], z2[1]); st2(e.R2 + ga * H + c, r2v[nt][0], r2v[nt][1]); st2(e.ZH2 + ga * H + c, zhv[nt][0], zhv[nt][1]); }
+            if (vb) { st2(e.Z2 + gb * H + c, z2[2], z2[3]); st2(e.R2 + gb * H + c, r2v[nt][2], r2v[nt][3]); st2(e.ZH2 + gb * H + c, zhv[nt][2], zhv[nt][3]); }
+        }
+        // candidate pre-activation inputs (in flight during the exchange below)
+        float2 xu[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            if (va) xu[nt][0] = ld2(e.RX + ga * 3 * H + 2 * H + c0 + 8 * nt);
+            if (vb) xu[nt][1] = ld2(e.RX + gb * 3 * H + 2 * H + c0 + 8 * nt);
+        }
+        pair_sync(q);  // both warps are done reading h1 from the staging tiles
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<float2*>(buf + ra * LD + 8 * nt + 2 * tig) = make_float2(zhv[nt][0], zhv[nt][1]);
+            *reinterpret_cast<float2*>(buf + rb * LD + 8 * nt + 2 * tig) = make_float2(zhv[nt][2], zhv[nt][3]);
+        }
+        pair_sync(q);  // z2*h1 is in place
+        float cf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) cf[nt][x] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const float* src = (ks < 4 ? k_lo : k_hi) + (ks & 3) * 8 + tig;
+            uint32_t a[4];
+            a[0] = __float_as_uint(src[ra * LD]); a[1] = __float_as_uint(src[rb * LD]);
+            a[2] = __float_as_uint(src[ra * LD + 4]); a[3] = __float_as_uint(src[rb * LD + 4]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float* wu = wu_s + (32 * half + 8 * nt + g) * WL + 8 * ks + tig;
+                mma_tf32_16x8x8(cf[nt], a, __float_as_uint(wu[0]), __float_as_uint(wu[4]));
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float hc2[4], y[4];
+            hc2[0] = cf[nt][0] + xu[nt][0].x; hc2[1] = cf[nt][1] + xu[nt][0].y; hc2[2] = cf[nt][2] + xu[nt][1].x; hc2[3] = cf[nt][3] + xu[nt][1].y;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                hc2[x] = fast ? tanh_fast(hc2[x]) : tanhf(hc2[x]);
+                const float res = r2v[nt][x] * h1v[nt][x] + (1.f - r2v[nt][x]) * hc2[x];
+                y[x] = m * h1v[nt][x] + (1.f - m) * res;
+            }
+            const int c = c0 + 8 * nt;
+            if (va) {
+                st2(e.HC2 + ga * H + c, hc2[0], hc2[1]);
+                st2(e.Y + ga * H + c, y[0], y[1]);
+                if (e.Y16) *reinterpret_cast<__nv_bfloat162*>(e.Y16 + ga * H + c) = __floats2bfloat162_rn(y[0], y[1]);
+            }
+            if (vb) {
+                st2(e.HC2 + gb * H + c, hc2[2], hc2[3]);
+                st2(e.Y + gb * H + c, y[2], y[3]);
+                if (e.Y16) *reinterpret_cast<__nv_bfloat162*>(e.Y16 + gb * H + c) = __floats2bfloat162_rn(y[2], y[3]);
+            }
+        }
+    }
+    pair_sync(q);  // the partner is done reading this warp's staging tile: the next tile may overwrite it
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_KC, bool B_KC, bool BF16, class Epi>
+// VEC: the vectorised, software-pipelined epilogue (N % 4 == 0 and 16-byte aligned epilogue operands); the scalar
+// epilogue is a separate instantiation because ptxas spills when both live in one kernel.
+template <int BN, bool A_KC, bool B_KC, bool BF16, class Epi, bool VEC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p, const Epi epi) {
-    using S = TcSmem<BN>;
+    constexpr bool FUSED = IsFusedRes<Epi>::value;
+    using S = TcSmem<BN, FUSED>;
     using E = TcElem<BF16>;
     constexpr int STAGES = S::STAGES;
     constexpr int BK = E::BK;
@@ -283,6 +599,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
     // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base slot
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* res_w = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES + S::BAR_BYTES);  // FUSED only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -335,6 +652,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         kt1 = min(kt_total, kt0 + kt_per_split);
     };
 
+    // Register re-partition between the warpgroups: the producer / MMA / allocator warps (warpgroup 0) need few
+    // registers, the two epilogue warpgroups hold double-buffered epilogue inputs (128*56 + 256*224 = 384*168).
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
@@ -420,6 +739,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;             // TMEM lane quadrant this warp may read: lanes [32q, 32q+32)
         const int half = (warp - 4) >> 2;   // which of the two warps of that quadrant (column-chunk parity)
         float* buf = epi_buf + (warp - 4) * (32 * S::EPI_LD);  // staging tile [32][EPI_LD] of this warp
+        if constexpr (FUSED) {
+            // residual-cell weights Rg_h [128][64] and Ru_h [64][64] -> padded tiles in shared memory, once per CTA
+            const int et = threadIdx.x - 128;
+            for (int idx = et; idx < 3 * 64 * 16; idx += TC_EPI_WARPS * 32) {
+                const int n = idx >> 4, k4 = (idx & 15) * 4;
+                const float4 v = n < 128 ? ld4(epi.RgH + n * 64 + k4) : ld4(epi.RuH + (n - 128) * 64 + k4);
+                *reinterpret_cast<float4*>(res_w + n * TC_RES_LD + k4) = v;
+            }
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -427,10 +756,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             decode(tile, z1, z2, m0, n0, kt0, kt1);
             if (kt0 >= kt1) continue;
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
-            tc_epilogue_tile(epi, p, tmem_base + (uint32_t)(acc * BN), BN, q, half, buf, lane, z1, z2, m0, n0);
+            if constexpr (FUSED) {
+                tc_epilogue_tile_candres(epi, p, tmem_base + (uint32_t)(acc * BN), tfull_bar(acc), acc_phase, q, half, buf,
+                                         epi_buf + ((warp - 4) ^ 4) * (32 * S::EPI_LD), res_w, res_w + 128 * TC_RES_LD, lane, z1, m0);
+            } else if constexpr (VEC) {
+                // the wait on the accumulator is inside: the first global reads of the epilogue are issued before it
+                tc_epilogue_tile_pipe<BN>(epi, p, tmem_base + (uint32_t)(acc * BN), tfull_bar(acc), acc_phase, q, half, buf, lane,
+                                          z1, z2, m0, n0);
+            } else {
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                tc_epilogue_tile(epi, p, tmem_base + (uint32_t)(acc * BN), BN, q, half, buf, lane, z1, z2, m0, n0);
+            }
             tc_fence_before();
             __syncwarp();
             if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
@@ -580,13 +917,20 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     if (!make_operand_map(&mb, Bop, B_KC, p.N, p.K, p.ldb, p.sBk, p.sB2, p.sB1, p.KB, Z2, Z1, BN, &t.cBk, &t.cB2, &t.cB1, 0, 1,
                           nullptr, BF16))
         return cudaErrorNotSupported;
-    using S = TcSmem<BN>;
-    auto kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi>;
-    static bool configured = false;  // one static per template instantiation
-    if (!configured) {
+    constexpr bool FUSED = IsFusedRes<Epi>::value;
+    using S = TcSmem<BN, FUSED>;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const TcP, const Epi);
+    if constexpr (FUSED) {
+        if (!t.vec || BN != 64 || p.N != 64 || t.tiles_n != 1) return cudaErrorNotSupported;  // caller launches the three unfused contractions
+        kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true>;
+    } else {
+        kern = t.vec ? gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true> : gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, false>;
+    }
+    static bool configured[2] = {false, false};  // per template instantiation and epilogue flavour
+    if (!configured[t.vec]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[t.vec] = true;
     }
     const int grid = total < sm_count() ? (int)total : sm_count();
     cudaLaunchConfig_t cfg;

@@ -638,6 +638,18 @@ extern "C" int matgcn_set_persistent(int on) {
     multi_flag() = on ? 1 : 0;
     return prev;
 }
+// Fused tail of the forward step (candidate + residual cell + mix in one launch); MATGCN_FUSED_TAIL=0 or
+// matgcn_set_fused_tail(0) selects the three separate contractions (A/B comparisons, tests).
+static int& fused_tail_flag() {
+    static int f = []() { const char* e = getenv("MATGCN_FUSED_TAIL"); return (e && e[0] == '0') ? 0 : 1; }();
+    return f;
+}
+static bool fused_tail_enabled() { return fused_tail_flag() != 0; }
+extern "C" int matgcn_set_fused_tail(int on) {
+    const int prev = fused_tail_flag();
+    fused_tail_flag() = on ? 1 : 0;
+    return prev;
+}
 // One contraction of a recurrence step: queued as a phase of the persistent kernel, or launched on its own.
 #define STEP_GEMM(SLOT, Cfg, AKC, BKC, P, EPI, Z)                            \
     do {                                                                     \
@@ -990,6 +1002,18 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             // (d) candidate
             p.A = PZt;
             p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
+            // (d)+(e)+(f) in one launch when the fused tail applies (tensor-core engine, H = 64): see EpiCandRes
+            if (tc && !use_multi && H == 64 && fused_tail_enabled()) {
+                EpiCandRes ef{GXt, PHt, Rt_, HCt, H1t, B, H, 1, RXt, Z2t, R2t, ZH2t, HC2t, PHt + (long long)K * U, mix + t,
+                              bf ? PH16 + (long long)(t + 1) * U : nullptr, RgH, RuH};
+                const cudaError_t fe = launch_gemm_tc<64, true, false, EpiCandRes>(p, ef, N, st);
+                if (fe == cudaSuccess) {
+                    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+                    TR();
+                    continue;
+                }
+                if (fe != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(fe));
+            }
             STEP_GEMM(3, CfgMid, true, false, p, (EpiCand{GXt, PHt, Rt_, HCt, H1t, B, H, tc ? 1 : 0}), N);
             // (e) residual gate: [N*B, H] x Rgw[:, Cin:]^T
             memset(&p, 0, sizeof(p));

@@ -131,6 +131,43 @@ def test_persistent_recurrence_kernel_matches_per_phase_launches():
     assert n1 < 300, "persistent mode should need far fewer launches (got %d)" % n1
 
 
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("N,B", [(70, 8), (37, 64), (21, 100)])
+def test_fused_step_tail_matches_separate_contractions(N, B, mode):
+    """The fused tail of the forward step (candidate contraction + residual GRU cell + mix in one launch, the residual
+    products as mma.sync inside the epilogue warps) against the three separate tensor-core contractions: same
+    forecasts and gradients up to TF32 rounding of the residual products (RNA in mma.sync vs truncation in tcgen05).
+    B = 8 / 64 exercise the half-height (M = 64) tiles, B = 100 the full-height ones with a ragged last quadrant."""
+    tout = 6
+    cfg = make_config(adjtype="multi", adpadj="bidirection", embed_dim=10, output_window=tout, batch_size=B,
+                      device=torch.device(DEV), matgcn_mode=mode)
+    df = make_data_feature(N, seed=11)
+    batch = make_batch(N, B, tout, seed=11)
+    torch.manual_seed(2)
+    model = MultiATGCN(dict(cfg), df).to(DEV).eval()
+    lib = _cabi.lib()
+
+    def run(fused):
+        prev = lib.matgcn_set_fused_tail(1 if fused else 0)
+        try:
+            model.zero_grad(set_to_none=True)
+            n0 = lib.matgcn_launch_count()
+            y = model.predict(clone_batch(batch, DEV))
+            n = lib.matgcn_launch_count() - n0
+            model.calculate_loss(clone_batch(batch, DEV)).backward()
+            torch.cuda.synchronize()
+            return y.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}, n
+        finally:
+            lib.matgcn_set_fused_tail(prev)
+
+    y0, g0, n0 = run(False)
+    y1, g1, n1 = run(True)
+    assert n0 - n1 == 2 * 24 * 2, "fused tail should save two launches per step and layer (%d vs %d)" % (n1, n0)
+    assert max_rel_err(y1, y0) < 2e-3
+    for k in g0:
+        assert max_rel_err(g1[k], g0[k]) < MODEL_TOL, k
+
+
 @pytest.mark.parametrize("a_kc,b_kc", [(1, 0), (0, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K,splits", [(128, 128, 64, 1), (403, 4096, 403, 1), (64, 64, 320, 1), (1612, 520, 403, 1),
                                           (37, 72, 100, 1), (403, 403, 4096, 4)])
