@@ -10,12 +10,13 @@ namespace matgcn {
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 // fast-mode activations (SFU approximations, relative error ~2^-11: the same order as the TF32 products they follow)
-__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 __device__ __forceinline__ float tanh_fast(float v) {
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
+// sigma(v) = (1 + tanh(v/2)) / 2: one SFU operation instead of exp + reciprocal (the SFU pipe bounds the epilogues)
+__device__ __forceinline__ float sigmoid_fast(float v) { return fmaf(tanh_fast(0.5f * v), 0.5f, 0.5f); }
 
 // ------------------------------------------------------------------------------------------
 // epilogues
@@ -33,6 +34,9 @@ __device__ __forceinline__ float tanh_fast(float v) {
     __device__ __forceinline__ void operator()(int z1, int z2, int row, int col, float acc) const {    \
         store(z1, z2, row, col, acc, load(z1, z2, row, col));                                          \
     }
+// L2 prefetch of the 128-byte line holding *p (tensor-core engine: a spare warp runs one tile ahead of the epilogue
+// warps and pulls their global inputs into L2, see gemm_tc.cuh)
+__device__ __forceinline__ void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 operator+(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 operator-(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 __device__ __forceinline__ float4 operator*(const float4& a, const float4& b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
@@ -50,7 +54,7 @@ __device__ __forceinline__ float4 tanh4(const float4& a, int fast) {
 // C[z1*s1 + z2*s2 + row*ldc + col] (=|+=) acc * scale[(col / scale_div)] + bias[z1*bias_s1 + col] + add[...]
 struct EpiStore {
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 8;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     float* C;
     long long s1, s2;
     int ldc;
@@ -118,6 +122,10 @@ struct EpiStore {
         in.d = accumulate ? ld4(C + c.off) : f4(0.f);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const {
+        if (add) pf_l2(add + c.aoff);
+        if (accumulate) pf_l2(C + c.off);
+    }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
         float4 v = c.scale * acc + c.bias;
         if (add) v = v + in.c;
@@ -136,7 +144,7 @@ inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
 
 struct EpiAtomic {  // split-K partial sums into a zeroed C
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 8;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 1;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     float* C;
     long long s1, s2;
     int ldc;
@@ -154,6 +162,7 @@ struct EpiAtomic {  // split-K partial sums into a zeroed C
     __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const { return Cur{z1 * s1 + z2 * s2 + (long long)row * ldc + col}; }
     __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ldc; }
     __device__ __forceinline__ EpiIn4 load4(const Cur&) const { return EpiIn4{}; }
+    __device__ __forceinline__ void prefetch4(const Cur&) const {}
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4&) const {
         float* d = C + c.off;
         atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
@@ -165,7 +174,7 @@ struct EpiAtomic {  // split-K partial sums into a zeroed C
 // are [N*B, H] blocks, pre-activation inputs [N*B, 3H] blocks.
 struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (cols >= H): R
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 8;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     const float* GX; const float* Hprev; float* Z; float* R; float* ZH;
     int rows_per_z, H, fast;
     __nv_bfloat16* ZH16;  // may be null: bf16 twin of ZH
@@ -223,6 +232,10 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
         in.b = c.is_z ? ld4(Hprev + c.i) : f4(0.f);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const {
+        pf_l2(GX + c.j);
+        if (c.is_z) pf_l2(Hprev + c.i);
+    }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
         const float4 s = sigmoid4(acc + in.a, fast);
         if (c.is_z) {
@@ -237,7 +250,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
 };
 struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 8;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     const float* GX; const float* Hprev; const float* R; float* HC; float* H1;
     int rows_per_z, H, fast;
     bool vec_ok() const { return !(H & 3) && aligned16(GX) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(H1); }
@@ -280,6 +293,7 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
         in.a = ld4(GX + c.j); in.b = ld4(R + c.i); in.c = ld4(Hprev + c.i);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const { pf_l2(GX + c.j); pf_l2(R + c.i); pf_l2(Hprev + c.i); }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
         const float4 hc = tanh4(acc + in.a, fast);
         st4(HC + c.i, hc);
@@ -289,7 +303,7 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
 };
 struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r2)*hc2)
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 8;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     const float* RX; const float* H1; const float* R2; float* HC2; float* Y; const float* mix_t;
     int H, fast;
     __nv_bfloat16* Y16;  // may be null: bf16 twin of Y
@@ -340,6 +354,7 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
         in.a = ld4(RX + c.j); in.b = ld4(R2 + c.i); in.c = ld4(H1 + c.i);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const { pf_l2(RX + c.j); pf_l2(R2 + c.i); pf_l2(H1 + c.i); }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
         const float4 hc2 = tanh4(acc + in.a, fast);
         const float4 res = in.b * in.c + one_minus(in.b) * hc2;
@@ -370,6 +385,16 @@ struct EpiCandRes {
                aligned16(Z2) && aligned16(R2) && aligned16(ZH2) && aligned16(HC2) && aligned16(Y) && aligned16(RgH) && aligned16(RuH) &&
                (!Y16 || aligned16(Y16));
     }
+    // only the prefetch warp uses cursors here (col < 64: one 128-byte line per stream and 32-column chunk)
+    struct Cur { long long i, j; };
+    __device__ __forceinline__ Cur begin4(int z1, int, int row, int col) const {
+        const long long g = (long long)z1 * rows_per_z + row;
+        return Cur{g * H + col, g * 3 * H + col};
+    }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const {
+        pf_l2(GX + c.j + 2 * H); pf_l2(R + c.i); pf_l2(Hprev + c.i);
+        pf_l2(RX + c.j); pf_l2(RX + c.j + H); pf_l2(RX + c.j + 2 * H);
+    }
 };
 template <class E, class = void> struct IsFusedRes { static constexpr bool value = false; };
 template <class E> struct IsFusedRes<E, decltype((void)E::kFusedRes)> { static constexpr bool value = true; };
@@ -377,7 +402,7 @@ template <class E> struct IsFusedRes<E, decltype((void)E::kFusedRes)> { static c
 // Backward step epilogues (notation of DESIGN.md section 3 / tests/host_mirror.py).
 struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR[H:2H] = dres*(h1-hc2)*r2(1-r2)
     static constexpr int kBatch = 2;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 1;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 2;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     float* DH1; float* DR; const float* DRES; const float* H1; const float* Z2; const float* R2; const float* HC2;
     int H;
     bool vec_ok() const {
@@ -416,6 +441,9 @@ struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR
         in.a = ld4(Z2 + c.i); in.b = ld4(R2 + c.i); in.c = ld4(H1 + c.i); in.d = ld4(DH1 + c.i); in.e = ld4(DRES + c.i); in.f = ld4(HC2 + c.i);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const {
+        pf_l2(Z2 + c.i); pf_l2(R2 + c.i); pf_l2(H1 + c.i); pf_l2(DH1 + c.i); pf_l2(DRES + c.i); pf_l2(HC2 + c.i);
+    }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
         st4(DH1 + c.i, in.d + acc * in.a);
         st4(DR + c.j, acc * in.c * in.a * one_minus(in.a));
@@ -425,9 +453,10 @@ struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR
 };
 struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 2;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 4;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     const float* DH1; const float* Hprev; const float* R; const float* HC; float* DHD; float* DG;
     int H;
+    __nv_bfloat16* DG16;  // may be null: bf16 twin of the current step's DG block (same [rows, 3H] layout)
     bool vec_ok() const { return !(H & 3) && aligned16(DH1) && aligned16(Hprev) && aligned16(R) && aligned16(HC) && aligned16(DHD) && aligned16(DG); }
     __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long i = (long long)row * H + col;
@@ -440,8 +469,13 @@ struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
         const float dh1 = in.a + acc;
         const float r = in.b, hc = in.c, h = in.d;
         DHD[i] = dh1 * r;
-        DG[(long long)row * 3 * H + 2 * H + col] = dh1 * (1.f - r) * (1.f - hc * hc);
-        DG[(long long)row * 3 * H + H + col] = dh1 * (h - hc) * r * (1.f - r);
+        const float gu = dh1 * (1.f - r) * (1.f - hc * hc), gr = dh1 * (h - hc) * r * (1.f - r);
+        DG[(long long)row * 3 * H + 2 * H + col] = gu;
+        DG[(long long)row * 3 * H + H + col] = gr;
+        if (DG16) {
+            DG16[(long long)row * 3 * H + 2 * H + col] = __float2bfloat16_rn(gu);
+            DG16[(long long)row * 3 * H + H + col] = __float2bfloat16_rn(gr);
+        }
     }
     __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
         const long long i = (long long)row * H + col;
@@ -453,8 +487,13 @@ struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
         const long long i = (long long)row * H + col;
         const float4 dh1 = in.a + acc;
         st4(DHD + i, dh1 * in.b);
-        st4(DG + (long long)row * 3 * H + 2 * H + col, dh1 * one_minus(in.b) * one_minus(in.c * in.c));
-        st4(DG + (long long)row * 3 * H + H + col, dh1 * (in.d - in.c) * in.b * one_minus(in.b));
+        const float4 gu = dh1 * one_minus(in.b) * one_minus(in.c * in.c), gr = dh1 * (in.d - in.c) * in.b * one_minus(in.b);
+        st4(DG + (long long)row * 3 * H + 2 * H + col, gu);
+        st4(DG + (long long)row * 3 * H + H + col, gr);
+        if (DG16) {
+            st4_bf16(DG16 + (long long)row * 3 * H + 2 * H + col, gu);
+            st4_bf16(DG16 + (long long)row * 3 * H + H + col, gr);
+        }
     }
     struct Cur { long long i, j; };
     __device__ __forceinline__ Cur begin4(int, int, int row, int col) const { return Cur{(long long)row * H + col, (long long)row * 3 * H + col}; }
@@ -464,19 +503,26 @@ struct EpiB2 {  // dh1 = DH1 + acc ; cell backward elementwise
         in.a = ld4(DH1 + c.i); in.b = ld4(R + c.i); in.c = ld4(HC + c.i); in.d = ld4(Hprev + c.i);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const { pf_l2(DH1 + c.i); pf_l2(R + c.i); pf_l2(HC + c.i); pf_l2(Hprev + c.i); }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
         const float4 dh1 = in.a + acc;
         st4(DHD + c.i, dh1 * in.b);
-        st4(DG + c.j + 2 * H, dh1 * one_minus(in.b) * one_minus(in.c * in.c));
-        st4(DG + c.j + H, dh1 * (in.d - in.c) * in.b * one_minus(in.b));
+        const float4 gu = dh1 * one_minus(in.b) * one_minus(in.c * in.c), gr = dh1 * (in.d - in.c) * in.b * one_minus(in.b);
+        st4(DG + c.j + 2 * H, gu);
+        st4(DG + c.j + H, gr);
+        if (DG16) {
+            st4_bf16(DG16 + c.j + 2 * H, gu);
+            st4_bf16(DG16 + c.j + H, gr);
+        }
     }
     EPI_CALL_OPERATOR
 };
 struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      (row = node m, col = (b,c))
     static constexpr int kBatch = 4;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 2;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 4;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     const float* DP0; const float* Hprev; const float* Z; float* DHD; float* DG;
     int H, BH;  // BH = B*H columns per node
+    __nv_bfloat16* DG16;  // may be null: bf16 twin of the current step's DG block
     bool vec_ok() const { return !(H & 3) && !(BH & 3) && aligned16(DP0) && aligned16(Hprev) && aligned16(Z) && aligned16(DHD) && aligned16(DG); }
     __device__ __forceinline__ EpiIn load(int, int, int row, int col) const {
         const long long i = (long long)row * BH + col;
@@ -491,7 +537,9 @@ struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      
         DHD[i] = in.c + dzh * z;
         const long long g = i / H;
         const int c = (int)(i - g * H);
-        DG[g * 3 * H + c] = dzh * in.d * z * (1.f - z);
+        const float gz = dzh * in.d * z * (1.f - z);
+        DG[g * 3 * H + c] = gz;
+        if (DG16) DG16[g * 3 * H + c] = __float2bfloat16_rn(gz);
     }
     __device__ __forceinline__ EpiIn4 load4(int, int, int row, int col) const {
         const long long i = (long long)row * BH + col;
@@ -505,7 +553,9 @@ struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      
         st4(DHD + i, in.c + dzh * in.b);
         const long long g = i / H;
         const int c = (int)(i - g * H);
-        st4(DG + g * 3 * H + c, dzh * in.d * in.b * one_minus(in.b));
+        const float4 gz = dzh * in.d * in.b * one_minus(in.b);
+        st4(DG + g * 3 * H + c, gz);
+        if (DG16) st4_bf16(DG16 + g * 3 * H + c, gz);
     }
     struct Cur { long long i, j; };  // j: position of the same element in the [rows, 3H] gradient block
     __device__ __forceinline__ Cur begin4(int, int, int row, int col) const {
@@ -519,17 +569,20 @@ struct EpiB4 {  // dzh = acc + DP0 ; DHD += dzh*z ; DG[0:H] = dzh*h*z(1-z)      
         in.a = ld4(DP0 + c.i); in.b = ld4(Z + c.i); in.c = ld4(DHD + c.i); in.d = ld4(Hprev + c.i);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const { pf_l2(DP0 + c.i); pf_l2(Z + c.i); pf_l2(DHD + c.i); pf_l2(Hprev + c.i); }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
         const float4 dzh = acc + in.a;
         st4(DHD + c.i, in.c + dzh * in.b);
-        st4(DG + c.j, dzh * in.d * in.b * one_minus(in.b));
+        const float4 gz = dzh * in.d * in.b * one_minus(in.b);
+        st4(DG + c.j, gz);
+        if (DG16) st4_bf16(DG16 + c.j, gz);
     }
     EPI_CALL_OPERATOR
 };
 
 struct EpiB6 {  // carry = acc + DP0 + DHD
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 4;   // float4 rows per software-pipelined step of the tensor-core epilogue (double-buffered)
+    static constexpr int kPipe = 8;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     const float* DP0; const float* DHD; float* OUT;
     int BH;
     bool vec_ok() const { return !(BH & 3) && aligned16(DP0) && aligned16(DHD) && aligned16(OUT); }
@@ -561,6 +614,7 @@ struct EpiB6 {  // carry = acc + DP0 + DHD
         in.a = ld4(DP0 + c.i); in.b = ld4(DHD + c.i);
         return in;
     }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const { pf_l2(DP0 + c.i); pf_l2(DHD + c.i); }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const { st4(OUT + c.i, acc + in.a + in.b); }
     EPI_CALL_OPERATOR
 };

@@ -45,6 +45,7 @@ struct GemmP {
     // optional bf16 twins of the operands (same logical layout and strides): used by the bf16 tensor-core engine
     const __nv_bfloat16* A16;
     const __nv_bfloat16* B16;
+    int keepB;    // tensor-core engine: load B with the L2 evict-last policy (an operand re-read by every step of a recurrence)
     int M, N, K;  // K: inner reduction length of one k-batch
     int KB;       // number of k-batches
     int lda, ldb;

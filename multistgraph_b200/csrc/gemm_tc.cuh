@@ -62,6 +62,7 @@ struct TcP {
     int cB1, cB2, cBk;
     int tA_dim, tB_dim, t;  // persistent kernel: which coordinate (2..4, 0 = none) carries the time step, and its value
     int m64;                // 1: issue M=64 MMAs (tile rows 0..63 only; 16 accumulator rows per TMEM lane quadrant)
+    int keepB;              // 1: B operand loads carry the L2 evict-last policy
     int vec;                // 1: N % 4 == 0 and the epilogue's pointers/pitches allow 16-byte accesses
     int dbg_mode;           // diagnostics only: 1 = skip epilogue stores
     long long* dbg;         // optional per-tile timeline of CTA 0 (tools/tc_timeline.py); null in production
@@ -104,6 +105,19 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
+}
+// same with an L2 cache policy (createpolicy) attached to the load
+__device__ __forceinline__ void tma_load_5d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3, int c4, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -265,31 +279,31 @@ __device__ __forceinline__ void tc_epilogue_tile(const Epi& epi, const TcP& p, u
     }
 }
 
-// Compile-time step index and ping-pong recursion for the software-pipelined epilogue: every step sees its two
-// register buffers under fixed names, so they are never indexed dynamically (which would put them in local memory).
+// Compile-time row index for the software-pipelined epilogue: every access to the register ring below uses a
+// constant index, so the ring is never indexed dynamically (which would put it in local memory).
 template <int V> struct IntC { static constexpr int value = V; };
 template <int S, int N, class F>
-__device__ __forceinline__ void tc_pingpong_steps(F& f, EpiIn4* cur, EpiIn4* nxt) {
+__device__ __forceinline__ void tc_static_for(F& f) {
     if constexpr (S < N) {
-        f(IntC<S>{}, cur, nxt);
-        tc_pingpong_steps<S + 1, N>(f, nxt, cur);
+        f(IntC<S>{});
+        tc_static_for<S + 1, N>(f);
     }
 }
 
-// Software-pipelined form of the vectorised epilogue (p.vec): the epilogue functor's global reads do not depend on the
-// accumulator, so the reads of step s+1 are issued before step s is computed (double-buffered registers), and those of
-// the first step before the accumulator is even complete (the wait on `tfull` sits inside).  Positions are cursors
-// (Epi::Cur) computed once per 32-column chunk and bumped by four rows per access - no per-element index arithmetic.
-// A step = Epi::kPipe accesses per lane; a 32x32 chunk = 8 accesses per lane (lane -> row 4*it + lane/8, columns 4*(lane%8)..+3).
+// Software-pipelined form of the vectorised epilogue (p.vec).  The epilogue functor's global reads do not depend on
+// the accumulator and an L2 hit costs ~1000 cycles here, so they run Epi::kPipe accesses ahead of their use through a
+// ring of registers: the first kPipe are issued before the accumulator is even complete (the wait on `tfull` sits
+// inside), then every access consumes its ring slot and refills it with the access kPipe further on.
+// Positions are cursors (Epi::Cur) computed once per 32-column chunk and bumped by four rows per access - no
+// per-element index arithmetic.  A 32x32 chunk = 8 accesses per lane (lane -> row 4*it + lane/8, columns 4*(lane%8)..+3).
 template <int BN, class Epi>
 __device__ __forceinline__ void tc_epilogue_tile_pipe(const Epi& epi, const TcP& p, uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_parity,
                                                       int q, int half, float* buf, int lane, int z1, int z2, int m0, int n0) {
     constexpr int LD = TC_EPI_LD;
-    constexpr int NB = Epi::kPipe;
+    constexpr int R = Epi::kPipe;           // ring size = prefetch distance in accesses
     constexpr int NCH = (BN / 32 + 1) / 2;  // 32-column chunks per warp (two warps share a TMEM lane quadrant)
-    constexpr int SPC = 8 / NB;             // steps per chunk
-    constexpr int STEPS = NCH * SPC;
-    static_assert(8 % NB == 0, "kPipe must divide 8");
+    constexpr int ACC = NCH * 8;            // accesses per lane and tile
+    static_assert(R >= 1 && R <= 8, "kPipe out of range");
     const int pM = p.M, pN = p.N, pdbg = p.dbg_mode;
     const int rows_per_q = p.m64 ? 16 : 32;  // see tc_epilogue_tile
     const int row_base = m0 + q * rows_per_q;
@@ -297,26 +311,32 @@ __device__ __forceinline__ void tc_epilogue_tile_pipe(const Epi& epi, const TcP&
     const int rq = lane >> 3, cq = lane & 7;
     const int col0 = n0 + half * 32 + 4 * cq;  // this lane's first column in chunk 0; chunk ci is 64*ci further
     const bool any_row = row_base < row_lim;
+    const bool do_loads = !(pdbg & 32);        // debug mode bit 5: no epilogue global reads (A/B measurements)
 
-    typename Epi::Cur lc = epi.begin4(z1, z2, row_base + rq, col0);  // load cursor (runs one step ahead)
+    typename Epi::Cur lc = epi.begin4(z1, z2, row_base + rq, col0);  // load cursor (runs R accesses ahead)
     typename Epi::Cur sc = lc;                                        // store cursor
-    EpiIn4 bufA[NB], bufB[NB];
-    if (any_row && col0 < pN) {
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            if (row_base + 4 * u + rq < row_lim) bufA[u] = epi.load4(lc);
+    EpiIn4 ring[R];
+    // access a (compile time) = chunk a / 8, row 4 * (a % 8) + rq of the quadrant
+    auto issue = [&](auto A_) {
+        constexpr int a = decltype(A_)::value;
+        if constexpr (a < ACC) {
+            constexpr int ci = a / 8, it = a % 8;
+            const int col = col0 + 64 * ci;
+            if (it == 0 && ci > 0) lc = epi.begin4(z1, z2, row_base + rq, col);
+            if (col < pN && row_base + 4 * it + rq < row_lim && do_loads) ring[a % R] = epi.load4(lc);
             epi.advance4(lc, 4);
         }
-    }
+    };
+    if (any_row) tc_static_for<0, R>(issue);
     mbar_wait(tfull, tfull_parity);
     tc_fence_after();
     if (!any_row) return;
-    auto step = [&](auto S_, EpiIn4* cur, EpiIn4* nxt) {
-        constexpr int s = decltype(S_)::value;
-        constexpr int ci = s / SPC, b = s % SPC;
+    auto step = [&](auto A_) {
+        constexpr int a = decltype(A_)::value;
+        constexpr int ci = a / 8, it = a % 8;
         const int col = col0 + 64 * ci;
         const bool chunk_ok = n0 + (half + 2 * ci) * 32 < pN;  // warp-uniform
-        if (b == 0 && chunk_ok) {
+        if (it == 0 && chunk_ok) {
             const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((half + 2 * ci) * 32);
             uint32_t r[32];
             asm volatile(
@@ -337,32 +357,17 @@ __device__ __forceinline__ void tc_epilogue_tile_pipe(const Epi& epi, const TcP&
                                 __uint_as_float(r[4 * j + 3]));
             __syncwarp();
         }
-        if (b == 0 && ci > 0) sc = epi.begin4(z1, z2, row_base + rq, col);
-        // reads of the next step
-        if constexpr (s + 1 < STEPS) {
-            constexpr int ci1 = (s + 1) / SPC, b1 = (s + 1) % SPC;
-            const int col1 = col0 + 64 * ci1;
-            if (b1 == 0) lc = epi.begin4(z1, z2, row_base + rq, col1);
-            if (col1 < pN) {
-#pragma unroll
-                for (int u = 0; u < NB; ++u) {
-                    if (row_base + 4 * (b1 * NB + u) + rq < row_lim) nxt[u] = epi.load4(lc);
-                    epi.advance4(lc, 4);
-                }
-            }
-        }
-        // arithmetic + writes of this step
+        if (it == 0 && ci > 0) sc = epi.begin4(z1, z2, row_base + rq, col);
+        // arithmetic + writes of this access, then its ring slot is refilled with the access R further on
         if (chunk_ok) {
-#pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                const int rl = 4 * (b * NB + u) + rq;
-                const float4 v = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
-                if (col < pN && row_base + rl < row_lim && !(pdbg & 1)) epi.store4(sc, v, cur[u]);
-                epi.advance4(sc, 4);
-            }
+            const int rl = 4 * it + rq;
+            const float4 v = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
+            if (col < pN && row_base + rl < row_lim && !(pdbg & 1)) epi.store4(sc, v, ring[a % R]);
         }
+        epi.advance4(sc, 4);
+        issue(IntC<a + R>{});
     };
-    tc_pingpong_steps<0, STEPS>(step, bufA, bufB);
+    tc_static_for<0, ACC>(step);
     __syncwarp();
 }
 
@@ -659,6 +664,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const bool keepB = p.keepB != 0;
+            const uint64_t polB = l2_policy_evict_last();
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int z1, z2, m0, n0, kt0, kt1;
                 decode(tile, z1, z2, m0, n0, kt0, kt1);
@@ -679,12 +686,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         z1 * p.cA1);
                     }
                     if (B_KC) {
-                        tma_load_5d(sb, &tmB, full_bar(stage), k0, n0, kb * p.cBk, z2 * p.cB2, z1 * p.cB1);
+                        if (keepB) tma_load_5d_hint(sb, &tmB, full_bar(stage), k0, n0, kb * p.cBk, z2 * p.cB2, z1 * p.cB1, polB);
+                        else tma_load_5d(sb, &tmB, full_bar(stage), k0, n0, kb * p.cBk, z2 * p.cB2, z1 * p.cB1);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN / E::MN_BLOCK; ++j)
-                            tma_load_5d(sb + j * E::MN_BOX_BYTES, &tmB, full_bar(stage), n0 + E::MN_BLOCK * j, k0, kb * p.cBk, z2 * p.cB2,
-                                        z1 * p.cB1);
+                        for (int j = 0; j < BN / E::MN_BLOCK; ++j) {
+                            if (keepB)
+                                tma_load_5d_hint(sb + j * E::MN_BOX_BYTES, &tmB, full_bar(stage), n0 + E::MN_BLOCK * j, k0, kb * p.cBk,
+                                                 z2 * p.cB2, z1 * p.cB1, polB);
+                            else
+                                tma_load_5d(sb + j * E::MN_BOX_BYTES, &tmB, full_bar(stage), n0 + E::MN_BLOCK * j, k0, kb * p.cBk, z2 * p.cB2,
+                                            z1 * p.cB1);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -732,6 +745,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_commit(tfull_bar(acc));  // accumulator complete
                 if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ epilogue-input prefetch ================================
+        // The epilogue's global reads (saved activations, pre-activations: mostly HBM-resident) queue behind the
+        // operand stream when they are issued on demand; this warp touches them tile by tile right away, so that
+        // the epilogue warps find them in L2.
+        if ((VEC || FUSED) && !(p.dbg_mode & 16)) {  // debug mode bit 4: no prefetch (A/B measurements)
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int z1, z2, m0, n0, kt0, kt1;
+                decode(tile, z1, z2, m0, n0, kt0, kt1);
+                if (kt0 >= kt1) continue;
+                const int rows = min(p.m64 ? 64 : TC_BM, p.M - m0);
+                constexpr int CH = BN / 32;
+                for (int idx = lane; idx < rows * CH; idx += 32) {
+                    const int row = m0 + idx / CH, col = n0 + (idx % CH) * 32;
+                    if (col < p.N) epi.prefetch4(epi.begin4(z1, z2, row, col));
+                }
             }
         }
     } else if (warp >= 4) {
@@ -900,6 +931,7 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     t.d_z2 = make_fastdiv((uint32_t)Z2);
     t.d_tn = make_fastdiv((uint32_t)t.tiles_n);
     t.tA_dim = t.tB_dim = t.t = 0;
+    t.keepB = p.keepB;
     t.vec = ((p.N & 3) == 0 && epi.vec_ok()) ? 1 : 0;
     // M <= 64 (every node-batched contraction at batch 64): M=64 MMAs, whose accumulator spreads 16 rows over each
     // TMEM lane quadrant (layout verified on hardware by tools/m64_probe.py), halve the MMA work and keep all

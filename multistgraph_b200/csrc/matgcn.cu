@@ -674,7 +674,7 @@ static GemmP prop_params(const float* M, int ldm, int N, int Kp, const float* sl
 // encoder layer: workspace layout
 // ------------------------------------------------------------------------------------------
 struct LayerWs {
-    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, MPH, M16, PH16, PZ16, PX16, total;
+    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, MPH, M16, PH16, PZ16, PX16, WG16, WU16, total;
     size_t U, UX;  // floats of one [N,B,H] / [N,B,Cin] block
 };
 static size_t align64(size_t v) { return (v + 63) / 64 * 64; }
@@ -700,16 +700,19 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.RGH = take((size_t)2 * H * H);  // Rgw[:, Cin:] and Ruw[:, Cin:] repacked densely (16-byte aligned rows for TMA)
     w.RUH = take((size_t)H * H);
     w.MPH = take((sizeof(MPhase) * (size_t)(6 * T + 2) + 256) / 4);  // phase list + grid-barrier counter of the persistent kernel
-    // bf16 twins (sizes in floats = elements / 2): base matrices, h_{t-1} per step, z*h per step, x (PX layout)
+    // bf16 twins (sizes in floats = elements / 2): base matrices, PH / PZ / PX (same layouts as the fp32 arrays: slot 0 =
+    // the state itself, slots 1.. = its propagated copies) and the per-node weights
     w.M16 = take(((size_t)(K - 1) * N * 8 * ((N + 7) / 8 + 1)) / 2 + 64);
-    w.PH16 = take(((size_t)(T + 1) * w.U) / 2 + 64);
-    w.PZ16 = take(((size_t)T * w.U) / 2 + 64);
+    w.PH16 = take((((size_t)T * K + 1) * w.U) / 2 + 64);
+    w.PZ16 = take(((size_t)T * K * w.U) / 2 + 64);
     w.PX16 = take(((size_t)T * K * w.UX) / 2 + 64);
+    w.WG16 = take(((size_t)N * K * (Cin + H) * 2 * H) / 2 + 64);
+    w.WU16 = take(((size_t)N * K * (Cin + H) * H) / 2 + 64);
     w.total = o;
     return w;
 }
 struct LayerBws {
-    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, total;
+    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, total;
 };
 static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp) {
     LayerBws w;
@@ -727,6 +730,7 @@ static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp)
     w.MPH = take((sizeof(MPhase) * (size_t)(7 * T + 2) + 256) / 4);
     w.DPT16 = take(((size_t)K * U) / 2 + 64);
     w.DPX16 = take(((size_t)T * K * UX) / 2 + 64);
+    w.DG16 = take(((size_t)3 * U) / 2 + 64);  // bf16 twin of the current step's pre-activation gradients [N*B, 3H]
     w.total = o;
     return w;
 }
@@ -898,12 +902,18 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     __nv_bfloat16* PH16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PH16);
     __nv_bfloat16* PZ16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PZ16);
     __nv_bfloat16* PX16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PX16);
+    __nv_bfloat16* WG16 = reinterpret_cast<__nv_bfloat16*>(ws + w.WG16);
+    __nv_bfloat16* WU16 = reinterpret_cast<__nv_bfloat16*>(ws + w.WU16);
     // x -> slot 0 of PX[t]
     CK(cudaMemcpy2DAsync(PX, sizeof(float) * K * UX, x, sizeof(float) * x_tstride, sizeof(float) * UX, T,
                          cudaMemcpyDeviceToDevice, st));
     if (bf) {
         CK(to_bf16(M, 0, M16, 0, (long long)Kp * N * ldm, 1, st));
         CK(to_bf16(x, x_tstride, PX16, K * UX, UX, T, st));
+        // per-node weights: 2-byte twins are what the step contractions stream (and, marked evict-last, what stays in L2
+        // across the 24 steps: 49 MB per layer at the Baltimore size instead of 99 MB of fp32 from HBM every step)
+        CK(to_bf16(Wg, 0, WG16, 0, (long long)N * K * I * 2 * H, 1, st));
+        CK(to_bf16(Wu, 0, WU16, 0, (long long)N * K * I * H, 1, st));
     }
     // PX[t, 1..K) = M * x_t  (all t at once)
     {
@@ -985,28 +995,38 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             const float* GXt = GX + (long long)t * 3 * U; const float* RXt = RX + (long long)t * 3 * U;
             // (a) PH[t,1..] = M * h
             p = prop_params(M, ldm, N, Kp, PHt, B * H);
-            if (bf) { p.A16 = M16; p.B16 = PH16 + (long long)t * U; }
-            STEP_GEMM(0, CfgBig, true, false, p, epi_store(PHt + U, 0, 0, B * H), 1);
+            __nv_bfloat16* PH16t = PH16 + (long long)t * K * U;
+            __nv_bfloat16* PZ16t = PZ16 + (long long)t * K * U;
+            {
+                EpiStore e = epi_store(PHt + U, 0, 0, B * H);
+                if (bf) { p.A16 = M16; p.B16 = PH16t; e.C16 = PH16t + U; }
+                STEP_GEMM(0, CfgBig, true, false, p, e, 1);
+            }
             // (b) gate: per node [B, K*H] x [K*H, 2H]
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = 1; p.KB = K;
             p.A = PHt; p.lda = H; p.sA1 = (long long)B * H; p.sAk = U; p.M = B; p.K = H;
             p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sBk = (long long)I * 2 * H;
-            STEP_GEMM(1, CfgMid, true, false, p, (EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H, tc ? 1 : 0, bf ? PZ16 + (long long)t * U : nullptr}), N);
+            if (bf) { p.A16 = PH16t; p.B16 = WG16 + (long long)Cin * 2 * H; p.keepB = 1; }
+            STEP_GEMM(1, CfgMid, true, false, p, (EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H, tc ? 1 : 0, bf ? PZ16t : nullptr}), N);
             // (c) PZ[t,1..] = M * (z*h)
             {
                 GemmP pp = prop_params(M, ldm, N, Kp, PZt, B * H);
-                if (bf) { pp.A16 = M16; pp.B16 = PZ16 + (long long)t * U; }
-                STEP_GEMM(2, CfgBig, true, false, pp, epi_store(PZt + U, 0, 0, B * H), 1);
+                EpiStore e = epi_store(PZt + U, 0, 0, B * H);
+                if (bf) { pp.A16 = M16; pp.B16 = PZ16t; e.C16 = PZ16t + U; }
+                STEP_GEMM(2, CfgBig, true, false, pp, e, 1);
             }
             // (d) candidate
             p.A = PZt;
             p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
+            if (bf) { p.A16 = PZ16t; p.B16 = WU16 + (long long)Cin * H; p.keepB = 1; }
             // (d)+(e)+(f) in one launch when the fused tail applies (tensor-core engine, H = 64): see EpiCandRes
             if (tc && !use_multi && H == 64 && fused_tail_enabled()) {
                 EpiCandRes ef{GXt, PHt, Rt_, HCt, H1t, B, H, 1, RXt, Z2t, R2t, ZH2t, HC2t, PHt + (long long)K * U, mix + t,
-                              bf ? PH16 + (long long)(t + 1) * U : nullptr, RgH, RuH};
-                const cudaError_t fe = launch_gemm_tc<64, true, false, EpiCandRes>(p, ef, N, st);
+                              bf ? PH16t + (long long)K * U : nullptr, RgH, RuH};
+                cudaError_t fe = cudaErrorNotSupported;
+                if (bf) fe = launch_gemm_tc<64, true, false, EpiCandRes, true>(p, ef, N, st);
+                if (fe == cudaErrorNotSupported) fe = launch_gemm_tc<64, true, false, EpiCandRes>(p, ef, N, st);
                 if (fe == cudaSuccess) {
                     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
                     TR();
@@ -1025,7 +1045,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             p.A = ZH2t;
             p.B = RuH; p.ldb = H; p.N = H;
             STEP_GEMM(5, CfgMid, true, true, p,
-                      (EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H, tc ? 1 : 0, bf ? PH16 + (long long)(t + 1) * U : nullptr}), 1);
+                      (EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H, tc ? 1 : 0, bf ? PH16t + (long long)K * U : nullptr}), 1);
         }
         if (!use_multi) break;
         float* mph = ws + w.MPH;
@@ -1074,6 +1094,9 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     const __nv_bfloat16* M16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.M16);  // written by the forward pass
     __nv_bfloat16* DPT16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.DPT16);
     __nv_bfloat16* DPX16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.DPX16);
+    __nv_bfloat16* DG16 = bf ? reinterpret_cast<__nv_bfloat16*>(bws + bw.DG16) : nullptr;
+    const __nv_bfloat16* WG16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.WG16);  // written by the forward pass
+    const __nv_bfloat16* WU16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.WU16);
     CK(cudaMemsetAsync(DHC, 0, sizeof(float) * U, st));
     TR();
     CK(cudaMemsetAsync(dmix, 0, sizeof(float) * T, st));
@@ -1107,12 +1130,13 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             // B2: dh1 += da2 [NB,2H] * Rgw[:, Cin:]
             p.A = DRt; p.K = 2 * H;
             p.B = ws + w.RGH;
-            STEP_GEMM(1, CfgMid, true, false, p, (EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H}), 1);
+            STEP_GEMM(1, CfgMid, true, false, p, (EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H, DG16}), 1);
             // B3: DPT[k][n] = dau[n] [B,H] * Wu[n,k,Cin:,:]^T      z = (n, k)
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = K; p.KB = 1;
             p.A = DGt + 2 * H; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.sA2 = 0; p.M = B; p.K = H;
             p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sB2 = (long long)I * H;
+            if (bf) { p.A16 = DG16 + 2 * H; p.B16 = WU16 + (long long)Cin * H; p.keepB = 1; }
             {
                 EpiStore e = epi_store(DPT, (long long)B * H, U, H);
                 if (bf) e.C16 = DPT16;
@@ -1128,13 +1152,14 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
             if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
-            STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H}), 1);
+            STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H, DG16}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPZA + (long long)t * n_adp * U, (long long)n_adp * U);
             // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = K; p.KB = 1;
             p.A = DGt; p.lda = 3 * H; p.sA1 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
             p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = (long long)I * 2 * H;
+            if (bf) { p.A16 = DG16; p.B16 = WG16 + (long long)Cin * 2 * H; p.keepB = 1; }
             {
                 EpiStore e = epi_store(DPT, (long long)B * H, U, H);
                 if (bf) e.C16 = DPT16;

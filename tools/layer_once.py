@@ -17,6 +17,7 @@ mix, dY = torch.sigmoid(R(T)), R(T, N, B, H)
 dims = (T, N, B, Cin, H, K)
 p = lambda t: None if t is None else t.data_ptr()
 st = torch.cuda.current_stream().cuda_stream
+FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 for rep in range(2):
     ws = torch.zeros(lib.matgcn_encoder_layer_fwd_ws_bytes(*dims) // 4, device=dev)
     bws = torch.zeros(lib.matgcn_encoder_layer_bwd_ws_bytes(*dims, n_adp) // 4, device=dev)
@@ -24,8 +25,8 @@ for rep in range(2):
     outs = [new(T, N, B, Cin), None, new(Kp, N, ldm), new(N, K, I, 2 * H), new(N, 2 * H), new(N, K, I, H), new(N, H),
             new(2 * H, I), new(2 * H), new(H, I), new(H), new(T)]
     _cabi.check(lib.matgcn_encoder_layer_fwd(*dims, ldm, p(x), x.stride(0), None, p(M), p(Wg), p(bg), p(Wu), p(bu), p(Rgw),
-                                             p(Rgb), p(Ruw), p(Rub), p(mix), p(ws), 1, st), "fwd")
+                                             p(Rgb), p(Ruw), p(Rub), p(mix), p(ws), FLAGS, st), "fwd")
     _cabi.check(lib.matgcn_encoder_layer_bwd(*dims, ldm, n_adp, p(dY), dY.stride(0), p(M), p(Wg), p(Wu), p(Rgw), p(Ruw), p(mix),
-                                             p(ws), p(bws), *[p(o) for o in outs], 1, st), "bwd")
+                                             p(ws), p(bws), *[p(o) for o in outs], FLAGS, st), "bwd")
     torch.cuda.synchronize()
 print("ok")

@@ -38,8 +38,11 @@ def run(skip):
     lib.matgcn_debug_set_timeline(None)
     return buf.cpu().view(-1, 8)
 
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+lib.matgcn_debug_set_mode(mode)
+print('debug mode', mode)
 run(-1)
-for label, skip in [("fwd gate (per-node)", 5 + 1), ("bwd B3 (per-node NT)", 5 + 6 * T + 2), ("bwd B5", 5 + 6 * T + 4)]:
+for label, skip in [("fwd prop", 5 + 0), ("fwd gate (per-node)", 5 + 1), ("fwd fused tail (cand + residual cell)", 5 + 3), ("bwd B1", 5 + 4 * T + 0), ("bwd B2", 5 + 4 * T + 1), ("bwd B3 (per-node NT)", 5 + 4 * T + 2), ("bwd B4", 5 + 4 * T + 3), ("bwd B5", 5 + 4 * T + 4)]:
     b = run(skip)
     t0 = b[0, 0].item()
     print("==", label)

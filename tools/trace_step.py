@@ -5,7 +5,7 @@ from multistgraph_b200.model import MultiATGCN
 from multistgraph_b200.synthetic import workload
 dev = torch.device("cuda:0")
 cfg, df, batch = workload("baltimore_multi", seed=0, device=dev)
-cfg["matgcn_mode"] = "tf32"
+cfg["matgcn_mode"] = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 torch.manual_seed(0)
 model = MultiATGCN(dict(cfg), df).to(dev).train()
 for i in range(3):
