@@ -67,8 +67,10 @@ struct EpiStore {
     long long add_s1, add_s2;
     int add_ld;
     __nv_bfloat16* C16;  // may be null: bf16 twin of C (same indexing), operand of a later bf16 contraction
+    float* D2;           // may be null: second copy of the blocks z2 in [d2_lo, d2_hi), at D2 + z1*s1 + (z2-d2_lo)*s2 + row*ldc + col
+    int d2_lo, d2_hi;
     bool vec_ok() const {
-        return aligned16(C) && (!C16 || aligned16(C16)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3) && (!bias || (aligned16(bias) && !(bias_s1 & 3))) &&
+        return aligned16(C) && (!D2 || aligned16(D2)) && (!C16 || aligned16(C16)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3) && (!bias || (aligned16(bias) && !(bias_s1 & 3))) &&
                (!scale || !(scale_div & 3)) && (!add || (aligned16(add) && !(add_s1 & 3) && !(add_s2 & 3) && !(add_ld & 3)));
     }
     __device__ __forceinline__ EpiIn load(int z1, int z2, int row, int col) const {
@@ -87,6 +89,7 @@ struct EpiStore {
         if (accumulate) v += in.d;
         C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = v;
         if (C16) C16[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = __float2bfloat16_rn(v);
+        if (D2 && z2 >= d2_lo && z2 < d2_hi) D2[z1 * s1 + (z2 - d2_lo) * s2 + (long long)row * ldc + col] = v;
     }
     __device__ __forceinline__ EpiIn4 load4(int z1, int z2, int row, int col) const {
         EpiIn4 in;
@@ -104,18 +107,25 @@ struct EpiStore {
         if (accumulate) v = v + in.d;
         st4(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
         if (C16) st4_bf16(C16 + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
+        if (D2 && z2 >= d2_lo && z2 < d2_hi) st4(D2 + z1 * s1 + (z2 - d2_lo) * s2 + (long long)row * ldc + col, v);
     }
-    // cursor form (tensor-core epilogue): the position is computed once per 32-column chunk and bumped row by row
-    struct Cur { long long off, aoff; float4 bias; float scale; };
+    // cursor form (tensor-core epilogue only: always the fast activations, which keeps the unrolled epilogue code small -
+    // these short kernels start with a cold instruction cache): the position is computed once per 32-column chunk and
+    // bumped row by row
+    struct Cur { long long off, aoff, off2; float4 bias; float scale; };
     __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
         Cur c;
         c.off = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
+        c.off2 = (D2 && z2 >= d2_lo && z2 < d2_hi) ? z1 * s1 + (z2 - d2_lo) * s2 + (long long)row * ldc + col : -1;
         c.aoff = add ? z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col : 0;
         c.bias = bias ? ld4(bias + z1 * bias_s1 + col) : f4(0.f);
         c.scale = scale ? __ldg(scale + col / scale_div) : 1.f;
         return c;
     }
-    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ldc; c.aoff += (long long)rows * add_ld; }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const {
+        c.off += (long long)rows * ldc; c.aoff += (long long)rows * add_ld;
+        if (c.off2 >= 0) c.off2 += (long long)rows * ldc;
+    }
     __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
         EpiIn4 in;
         in.c = add ? ld4(add + c.aoff) : f4(0.f);
@@ -132,6 +142,7 @@ struct EpiStore {
         if (accumulate) v = v + in.d;
         st4(C + c.off, v);
         if (C16) st4_bf16(C16 + c.off, v);
+        if (c.off2 >= 0) st4(D2 + c.off2, v);
     }
     EPI_CALL_OPERATOR
 };
@@ -139,6 +150,55 @@ inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
     EpiStore e;
     memset(&e, 0, sizeof(e));
     e.C = C; e.s1 = s1; e.s2 = s2; e.ldc = ldc; e.scale_div = 1;
+    return e;
+}
+
+// Lean form of EpiStore for the contractions of the recurrence (support propagation, the per-node products of the
+// reverse step): C = acc, optionally with a bf16 twin and a second copy of the blocks z2 in [d2_lo, d2_hi).
+// (EpiStore's optional bias / scale / addend / accumulate paths cost code even when unused, and every launch of these
+// short kernels starts with a cold instruction cache.)
+struct EpiPlain {
+    static constexpr int kBatch = 8;
+    static constexpr int kPipe = 1;   // no global reads
+    float* C;
+    long long s1, s2;
+    int ldc;
+    __nv_bfloat16* C16;  // may be null
+    float* D2;           // may be null: see EpiStore
+    int d2_lo, d2_hi;
+    bool vec_ok() const { return aligned16(C) && (!C16 || aligned16(C16)) && (!D2 || aligned16(D2)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3); }
+    __device__ __forceinline__ EpiIn load(int, int, int, int) const { return EpiIn{}; }
+    __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn&) const {
+        const long long o = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
+        C[o] = acc;
+        if (C16) C16[o] = __float2bfloat16_rn(acc);
+        if (D2 && z2 >= d2_lo && z2 < d2_hi) D2[o - (long long)d2_lo * s2] = acc;
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int, int) const { return EpiIn4{}; }
+    __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4&) const {
+        const long long o = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
+        st4(C + o, acc);
+        if (C16) st4_bf16(C16 + o, acc);
+        if (D2 && z2 >= d2_lo && z2 < d2_hi) st4(D2 + o - (long long)d2_lo * s2, acc);
+    }
+    struct Cur { long long off; int dup; };
+    __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
+        return Cur{z1 * s1 + z2 * s2 + (long long)row * ldc + col, (D2 && z2 >= d2_lo && z2 < d2_hi) ? 1 : 0};
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ldc; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur&) const { return EpiIn4{}; }
+    __device__ __forceinline__ void prefetch4(const Cur&) const {}
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4&) const {
+        st4(C + c.off, acc);
+        if (C16) st4_bf16(C16 + c.off, acc);
+        if (c.dup) st4(D2 + c.off - (long long)d2_lo * s2, acc);
+    }
+    EPI_CALL_OPERATOR
+};
+inline EpiPlain epi_plain(float* C, long long s1, long long s2, int ldc) {
+    EpiPlain e;
+    memset(&e, 0, sizeof(e));
+    e.C = C; e.s1 = s1; e.s2 = s2; e.ldc = ldc;
     return e;
 }
 
@@ -237,7 +297,7 @@ struct EpiGate {  // sigma(acc + GX[:, 0:2H]) -> z (cols < H): Z, ZH = z*h ; r (
         if (c.is_z) pf_l2(Hprev + c.i);
     }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
-        const float4 s = sigmoid4(acc + in.a, fast);
+        const float4 s = sigmoid4(acc + in.a, 1);
         if (c.is_z) {
             st4(Z + c.i, s);
             st4(ZH + c.i, s * in.b);
@@ -295,7 +355,7 @@ struct EpiCand {  // hc = tanh(acc + GX[:, 2H:3H]); h1 = r*h + (1-r)*hc
     }
     __device__ __forceinline__ void prefetch4(const Cur& c) const { pf_l2(GX + c.j); pf_l2(R + c.i); pf_l2(Hprev + c.i); }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
-        const float4 hc = tanh4(acc + in.a, fast);
+        const float4 hc = tanh4(acc + in.a, 1);
         st4(HC + c.i, hc);
         st4(H1 + c.i, in.b * in.c + one_minus(in.b) * hc);
     }
@@ -356,7 +416,7 @@ struct EpiResCand {  // residual candidate + mix: y = g*h1 + (1-g)*(r2*h1 + (1-r
     }
     __device__ __forceinline__ void prefetch4(const Cur& c) const { pf_l2(RX + c.j); pf_l2(R2 + c.i); pf_l2(H1 + c.i); }
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
-        const float4 hc2 = tanh4(acc + in.a, fast);
+        const float4 hc2 = tanh4(acc + in.a, 1);
         const float4 res = in.b * in.c + one_minus(in.b) * hc2;
         st4(HC2 + c.i, hc2);
         const float4 y = c.m * in.c + (1.f - c.m) * res;
@@ -402,7 +462,7 @@ template <class E> struct IsFusedRes<E, decltype((void)E::kFusedRes)> { static c
 // Backward step epilogues (notation of DESIGN.md section 3 / tests/host_mirror.py).
 struct EpiB1 {  // acc = dzh2 ; DH1 += dzh2*z2 ; DR[0:H] = dzh2*h1*z2(1-z2) ; DR[H:2H] = dres*(h1-hc2)*r2(1-r2)
     static constexpr int kBatch = 2;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
-    static constexpr int kPipe = 2;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
+    static constexpr int kPipe = 4;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead
     float* DH1; float* DR; const float* DRES; const float* H1; const float* Z2; const float* R2; const float* HC2;
     int H;
     bool vec_ok() const {

@@ -290,85 +290,125 @@ __device__ __forceinline__ void tc_static_for(F& f) {
     }
 }
 
-// Software-pipelined form of the vectorised epilogue (p.vec).  The epilogue functor's global reads do not depend on
-// the accumulator and an L2 hit costs ~1000 cycles here, so they run Epi::kPipe accesses ahead of their use through a
-// ring of registers: the first kPipe are issued before the accumulator is even complete (the wait on `tfull` sits
-// inside), then every access consumes its ring slot and refills it with the access kPipe further on.
+// Software-pipelined form of the vectorised epilogue (p.vec): the whole tile loop of one epilogue warp.
+// The epilogue functor's global reads do not depend on the accumulator and cost ~1000+ cycles under load, so they run
+// R = Epi::kPipe accesses ahead of their use through a ring of registers - across tile boundaries: while the last R
+// accesses of a tile are computed, the first R of the CTA's next tile are already in flight (for the half-height
+// tiles of the node-batched contractions, M64, that is the whole next tile).
 // Positions are cursors (Epi::Cur) computed once per 32-column chunk and bumped by four rows per access - no
-// per-element index arithmetic.  A 32x32 chunk = 8 accesses per lane (lane -> row 4*it + lane/8, columns 4*(lane%8)..+3).
-template <int BN, class Epi>
-__device__ __forceinline__ void tc_epilogue_tile_pipe(const Epi& epi, const TcP& p, uint32_t tmem_acc, uint32_t tfull, uint32_t tfull_parity,
-                                                      int q, int half, float* buf, int lane, int z1, int z2, int m0, int n0) {
+// per-element index arithmetic.  A 32x32 chunk = 8 accesses per lane (lane -> row 4*it + lane/8, columns 4*(lane%8)..+3);
+// half-height tiles keep 16 rows per TMEM lane quadrant, i.e. 4 accesses per chunk.
+template <int BN, bool M64, class Epi, class Dec>
+__device__ __forceinline__ void tc_epilogue_loop_pipe(const Epi& epi, const TcP& p, uint32_t tmem_base, const Dec& decode, uint32_t tfull0,
+                                                      uint32_t tempty0, int q, int half, float* buf, int lane) {
     constexpr int LD = TC_EPI_LD;
-    constexpr int R = Epi::kPipe;           // ring size = prefetch distance in accesses
     constexpr int NCH = (BN / 32 + 1) / 2;  // 32-column chunks per warp (two warps share a TMEM lane quadrant)
-    constexpr int ACC = NCH * 8;            // accesses per lane and tile
-    static_assert(R >= 1 && R <= 8, "kPipe out of range");
+    constexpr int ITS = M64 ? 4 : 8;        // accesses per chunk
+    constexpr int ACC = NCH * ITS;          // accesses per lane and tile
+    constexpr int R = Epi::kPipe < ACC ? Epi::kPipe : ACC;  // ring size = prefetch distance in accesses
+    constexpr int ROWS_Q = M64 ? 16 : 32;
     const int pM = p.M, pN = p.N, pdbg = p.dbg_mode;
-    const int rows_per_q = p.m64 ? 16 : 32;  // see tc_epilogue_tile
-    const int row_base = m0 + q * rows_per_q;
-    const int row_lim = min(pM, row_base + rows_per_q);
     const int rq = lane >> 3, cq = lane & 7;
-    const int col0 = n0 + half * 32 + 4 * cq;  // this lane's first column in chunk 0; chunk ci is 64*ci further
-    const bool any_row = row_base < row_lim;
-    const bool do_loads = !(pdbg & 32);        // debug mode bit 5: no epilogue global reads (A/B measurements)
+    const bool do_loads = !(pdbg & 32);  // debug mode bit 5: no epilogue global reads (A/B measurements)
+    const int total = p.total_tiles, stride = gridDim.x;
 
-    typename Epi::Cur lc = epi.begin4(z1, z2, row_base + rq, col0);  // load cursor (runs R accesses ahead)
-    typename Epi::Cur sc = lc;                                        // store cursor
+    struct Tile { int z1, z2, m0, n0; };
+    auto next_nonempty = [&](int t, Tile& tl) {  // first tile >= t of this CTA with work in its split; total if none
+        for (; t < total; t += stride) {
+            int kt0, kt1;
+            decode(t, tl.z1, tl.z2, tl.m0, tl.n0, kt0, kt1);
+            if (kt0 < kt1) return t;
+        }
+        return total;
+    };
+    Tile cur, nxt;
+    int tile = next_nonempty(blockIdx.x, cur);
+    if (tile >= total) return;
+
+    typename Epi::Cur lc, sc;
     EpiIn4 ring[R];
-    // access a (compile time) = chunk a / 8, row 4 * (a % 8) + rq of the quadrant
-    auto issue = [&](auto A_) {
-        constexpr int a = decltype(A_)::value;
-        if constexpr (a < ACC) {
-            constexpr int ci = a / 8, it = a % 8;
-            const int col = col0 + 64 * ci;
-            if (it == 0 && ci > 0) lc = epi.begin4(z1, z2, row_base + rq, col);
-            if (col < pN && row_base + 4 * it + rq < row_lim && do_loads) ring[a % R] = epi.load4(lc);
-            epi.advance4(lc, 4);
-        }
+    // The accesses of a tile run in NR rounds of R (one ring revolution each): only the R accesses of a round are
+    // unrolled (slot j = compile time), the round index is a run-time loop - this keeps the epilogue code small, which
+    // matters because every launch of these short kernels starts with a cold instruction cache.
+    constexpr int NR = ACC / R;
+    static_assert(ACC % R == 0, "ring size must divide the accesses of a tile");
+    // read access (round rd, slot j) of tile tl into ring[j]
+    auto issue = [&](const Tile& tl, int rd, auto J_) {
+        constexpr int j = decltype(J_)::value;
+        const int a = rd * R + j;
+        const int ci = a / ITS, it = a % ITS;
+        const int row_base = tl.m0 + q * ROWS_Q;
+        const int col = tl.n0 + half * 32 + 4 * cq + 64 * ci;
+        if (it == 0) lc = epi.begin4(tl.z1, tl.z2, row_base + rq, col);
+        if (col < pN && row_base + 4 * it + rq < min(pM, row_base + ROWS_Q) && do_loads) ring[j] = epi.load4(lc);
+        epi.advance4(lc, 4);
     };
-    if (any_row) tc_static_for<0, R>(issue);
-    mbar_wait(tfull, tfull_parity);
-    tc_fence_after();
-    if (!any_row) return;
-    auto step = [&](auto A_) {
-        constexpr int a = decltype(A_)::value;
-        constexpr int ci = a / 8, it = a % 8;
-        const int col = col0 + 64 * ci;
-        const bool chunk_ok = n0 + (half + 2 * ci) * 32 < pN;  // warp-uniform
-        if (it == 0 && chunk_ok) {
-            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((half + 2 * ci) * 32);
-            uint32_t r[32];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ci > 0) __syncwarp();  // every lane is done reading the previous chunk from the staging tile
+    {
+        auto pro = [&](auto J_) { issue(cur, 0, J_); };
+        tc_static_for<0, R>(pro);
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    while (true) {
+        const int ntile = next_nonempty(tile + stride, nxt);
+        const bool has_next = ntile < total;
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / stride) * 8 + 4] = clock64();
+        mbar_wait(tfull0 + 8u * acc, acc_phase);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+        const int row_base = cur.m0 + q * ROWS_Q;
+        const int row_lim = min(pM, row_base + ROWS_Q);
+#pragma unroll 1
+        for (int rd = 0; rd < NR; ++rd) {
+            auto step = [&](auto J_) {
+                constexpr int j = decltype(J_)::value;
+                const int a = rd * R + j;
+                const int ci = a / ITS, it = a % ITS;
+                const int col = cur.n0 + half * 32 + 4 * cq + 64 * ci;
+                const bool chunk_ok = cur.n0 + (half + 2 * ci) * 32 < pN && row_base < row_lim;  // warp-uniform
+                if (it == 0 && chunk_ok) {
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((half + 2 * ci) * 32);
+                    uint32_t r[32];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    __syncwarp();  // every lane is done reading the previous chunk (or tile) from the staging tile
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(buf + lane * LD + 4 * j) =
-                    make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                __uint_as_float(r[4 * j + 3]));
-            __syncwarp();
+                    for (int jj = 0; jj < 8; ++jj)
+                        *reinterpret_cast<float4*>(buf + lane * LD + 4 * jj) =
+                            make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]), __uint_as_float(r[4 * jj + 2]),
+                                        __uint_as_float(r[4 * jj + 3]));
+                    __syncwarp();
+                }
+                if (it == 0) sc = epi.begin4(cur.z1, cur.z2, row_base + rq, col);
+                // arithmetic + writes of this access, then its ring slot is refilled with the access R further on
+                if (chunk_ok) {
+                    const int rl = 4 * it + rq;
+                    const float4 v = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
+                    if (col < pN && row_base + rl < row_lim && !(pdbg & 1)) epi.store4(sc, v, ring[j]);
+                }
+                epi.advance4(sc, 4);
+                if (rd + 1 < NR) issue(cur, rd + 1, J_);
+                else if (has_next) issue(nxt, 0, J_);
+            };
+            tc_static_for<0, R>(step);
         }
-        if (it == 0 && ci > 0) sc = epi.begin4(z1, z2, row_base + rq, col);
-        // arithmetic + writes of this access, then its ring slot is refilled with the access R further on
-        if (chunk_ok) {
-            const int rl = 4 * it + rq;
-            const float4 v = *reinterpret_cast<const float4*>(buf + rl * LD + 4 * cq);
-            if (col < pN && row_base + rl < row_lim && !(pdbg & 1)) epi.store4(sc, v, ring[a % R]);
-        }
-        epi.advance4(sc, 4);
-        issue(IntC<a + R>{});
-    };
-    tc_static_for<0, ACC>(step);
-    __syncwarp();
+        tc_fence_before();
+        __syncwarp();
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / stride) * 8 + 6] = clock64();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (!has_next) break;
+        tile = ntile;
+        cur = nxt;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,7 +439,6 @@ __device__ __forceinline__ void tc_epilogue_tile_candres(const Epi& e, const TcP
     const int row_base = m0 + q * rows_per_q;           // row inside the node's [B, H] block
     const int row_lim = min(p.M, row_base + rows_per_q);
     const bool any_row = row_base < row_lim;            // same for both warps of the quadrant
-    const int fast = e.fast;
     const long long g0 = (long long)z1 * e.rows_per_z;  // first (node, batch) row of this node
 
     // ---------------- phase 1: hc = tanh(acc + GX[2H:3H]); h1 = r*h + (1-r)*hc ----------------
@@ -458,7 +497,7 @@ __device__ __forceinline__ void tc_epilogue_tile_candres(const Epi& e, const TcP
             if (row_base + rl < row_lim) {
                 float* sp = buf + rl * LD + 4 * cq;
                 const float4 acc = *reinterpret_cast<const float4*>(sp);
-                const float4 hc = tanh4(acc + gx[u], fast);
+                const float4 hc = tanh4(acc + gx[u], 1);
                 const float4 h1 = rr[u] * hh[u] + one_minus(rr[u]) * hc;
                 st4(e.HC + i + (long long)(4 * b + u) * 4 * H, hc);
                 st4(e.H1 + i + (long long)(4 * b + u) * 4 * H, h1);
@@ -516,8 +555,8 @@ __device__ __forceinline__ void tc_epilogue_tile_candres(const Epi& e, const TcP
             r2v[nt][2] = cr[nt][2] + xr[nt][1].x; r2v[nt][3] = cr[nt][3] + xr[nt][1].y;
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                z2[x] = fast ? sigmoid_fast(z2[x]) : sigmoidf_(z2[x]);
-                r2v[nt][x] = fast ? sigmoid_fast(r2v[nt][x]) : sigmoidf_(r2v[nt][x]);
+                z2[x] = sigmoid_fast(z2[x]);
+                r2v[nt][x] = sigmoid_fast(r2v[nt][x]);
                 zhv[nt][x] = z2[x] * h1v[nt][x];
             }
             const int c = c0 + 8 * nt;
@@ -561,7 +600,7 @@ __device__ __forceinline__ void tc_epilogue_tile_candres(const Epi& e, const TcP
             hc2[0] = cf[nt][0] + xu[nt][0].x; hc2[1] = cf[nt][1] + xu[nt][0].y; hc2[2] = cf[nt][2] + xu[nt][1].x; hc2[3] = cf[nt][3] + xu[nt][1].y;
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                hc2[x] = fast ? tanh_fast(hc2[x]) : tanhf(hc2[x]);
+                hc2[x] = tanh_fast(hc2[x]);
                 const float res = r2v[nt][x] * h1v[nt][x] + (1.f - r2v[nt][x]) * hc2[x];
                 y[x] = m * h1v[nt][x] + (1.f - m) * res;
             }
@@ -586,7 +625,8 @@ __device__ __forceinline__ void tc_epilogue_tile_candres(const Epi& e, const TcP
 // ---------------------------------------------------------------------------------------------
 // VEC: the vectorised, software-pipelined epilogue (N % 4 == 0 and 16-byte aligned epilogue operands); the scalar
 // epilogue is a separate instantiation because ptxas spills when both live in one kernel.
-template <int BN, bool A_KC, bool B_KC, bool BF16, class Epi, bool VEC>
+// M64 (with VEC): half-height tiles, known at compile time so that the epilogue pipeline enumerates only their rows.
+template <int BN, bool A_KC, bool B_KC, bool BF16, class Epi, bool VEC, bool M64 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcP p, const Epi epi) {
     constexpr bool FUSED = IsFusedRes<Epi>::value;
@@ -780,30 +820,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             asm volatile("bar.sync 5, 256;" ::: "memory");
         }
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            int z1, z2, m0, n0, kt0, kt1;
-            decode(tile, z1, z2, m0, n0, kt0, kt1);
-            if (kt0 >= kt1) continue;
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
-            if constexpr (FUSED) {
-                tc_epilogue_tile_candres(epi, p, tmem_base + (uint32_t)(acc * BN), tfull_bar(acc), acc_phase, q, half, buf,
-                                         epi_buf + ((warp - 4) ^ 4) * (32 * S::EPI_LD), res_w, res_w + 128 * TC_RES_LD, lane, z1, m0);
-            } else if constexpr (VEC) {
-                // the wait on the accumulator is inside: the first global reads of the epilogue are issued before it
-                tc_epilogue_tile_pipe<BN>(epi, p, tmem_base + (uint32_t)(acc * BN), tfull_bar(acc), acc_phase, q, half, buf, lane,
-                                          z1, z2, m0, n0);
-            } else {
-                mbar_wait(tfull_bar(acc), acc_phase);
-                tc_fence_after();
-                tc_epilogue_tile(epi, p, tmem_base + (uint32_t)(acc * BN), BN, q, half, buf, lane, z1, z2, m0, n0);
+        if constexpr (VEC && !FUSED) {
+            tc_epilogue_loop_pipe<BN, M64>(epi, p, tmem_base, decode, tfull_bar(0), tempty_bar(0), q, half, buf, lane);
+        } else {
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int z1, z2, m0, n0, kt0, kt1;
+                decode(tile, z1, z2, m0, n0, kt0, kt1);
+                if (kt0 >= kt1) continue;
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
+                if constexpr (FUSED) {
+                    tc_epilogue_tile_candres(epi, p, tmem_base + (uint32_t)(acc * BN), tfull_bar(acc), acc_phase, q, half, buf,
+                                             epi_buf + ((warp - 4) ^ 4) * (32 * S::EPI_LD), res_w, res_w + 128 * TC_RES_LD, lane, z1, m0);
+                } else {
+                    mbar_wait(tfull_bar(acc), acc_phase);
+                    tc_fence_after();
+                    tc_epilogue_tile(epi, p, tmem_base + (uint32_t)(acc * BN), BN, q, half, buf, lane, z1, z2, m0, n0);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / gridDim.x) * 8 + 6] = clock64();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -952,17 +992,24 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     constexpr bool FUSED = IsFusedRes<Epi>::value;
     using S = TcSmem<BN, FUSED>;
     void (*kern)(const CUtensorMap, const CUtensorMap, const TcP, const Epi);
+    int variant = 0;
     if constexpr (FUSED) {
         if (!t.vec || BN != 64 || p.N != 64 || t.tiles_n != 1) return cudaErrorNotSupported;  // caller launches the three unfused contractions
         kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true>;
+    } else if (!t.vec) {
+        kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, false>;
+    } else if (t.m64) {
+        kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true, true>;
+        variant = 2;
     } else {
-        kern = t.vec ? gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true> : gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, false>;
+        kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true, false>;
+        variant = 1;
     }
-    static bool configured[2] = {false, false};  // per template instantiation and epilogue flavour
-    if (!configured[t.vec]) {
+    static bool configured[3] = {false, false, false};  // per template instantiation and epilogue flavour
+    if (!configured[variant]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
-        configured[t.vec] = true;
+        configured[variant] = true;
     }
     const int grid = total < sm_count() ? (int)total : sm_count();
     cudaLaunchConfig_t cfg;

@@ -25,7 +25,7 @@
 
 namespace matgcn {
 
-enum EpiKind : int { EK_STORE = 0, EK_ATOMIC, EK_GATE, EK_CAND, EK_RESCAND, EK_B1, EK_B2, EK_B4, EK_B6 };
+enum EpiKind : int { EK_STORE = 0, EK_ATOMIC, EK_GATE, EK_CAND, EK_RESCAND, EK_B1, EK_B2, EK_B4, EK_B6, EK_PLAIN };
 enum PhaseKind : int { PK_GEMM = 0, PK_HEAD = 1 };
 
 // elementwise head of the reverse step (B0 of DESIGN.md section 3)
@@ -38,6 +38,7 @@ struct HeadArgs {
 
 template <class E> struct EpiKindOf;
 template <> struct EpiKindOf<EpiStore> { static constexpr int v = EK_STORE; };
+template <> struct EpiKindOf<EpiPlain> { static constexpr int v = EK_PLAIN; };
 template <> struct EpiKindOf<EpiAtomic> { static constexpr int v = EK_ATOMIC; };
 template <> struct EpiKindOf<EpiGate> { static constexpr int v = EK_GATE; };
 template <> struct EpiKindOf<EpiCand> { static constexpr int v = EK_CAND; };
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_multi_kernel(const __gr
                 const int bn = P->bn;
                 switch (P->epi_kind) {
                     case EK_STORE: mp_epilogue_phase<EpiStore>(P, bn, tmem_base, tfull0, tempty0, st, q, half, buf, lane); break;
+                    case EK_PLAIN: mp_epilogue_phase<EpiPlain>(P, bn, tmem_base, tfull0, tempty0, st, q, half, buf, lane); break;
                     case EK_ATOMIC: mp_epilogue_phase<EpiAtomic>(P, bn, tmem_base, tfull0, tempty0, st, q, half, buf, lane); break;
                     case EK_GATE: mp_epilogue_phase<EpiGate>(P, bn, tmem_base, tfull0, tempty0, st, q, half, buf, lane); break;
                     case EK_CAND: mp_epilogue_phase<EpiCand>(P, bn, tmem_base, tfull0, tempty0, st, q, half, buf, lane); break;

@@ -201,6 +201,56 @@ __global__ void view_weight_grad_kernel(const float* __restrict__ dpool, const f
 
 // Column sums of a [T][Z][rows][ld] array over (t, rows) for the first ncol columns; columns < split go to
 // out1[z*ld1 + col], the rest to out2[z*ld2 + col - split].   grid (Z, chunks), partial sums by atomics.
+// Vectorised column sums for the bias gradients: src[t*st + z*sz + r*ncol + c] summed over (t, r) for every block z
+// (rows are dense: ld == ncol, ncol % 4 == 0, 16-byte aligned).  grid (Z, S): block (z, y) takes the 64-row chunks
+// y, y+S, ... of the (t, chunk) space; thread -> (row lane, float4 column); four independent 16-byte loads in flight.
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ src, int T, long long st, long long sz, int rows,
+                                                      int ncol, int split, float* __restrict__ out1, int ld1,
+                                                      float* __restrict__ out2, int ld2) {
+    extern __shared__ float4 cs_red[];  // [lanes][ncol / 4]
+    const int nc4 = ncol >> 2;
+    const int lanes = blockDim.x / nc4;
+    const int c4 = threadIdx.x % nc4, lane = threadIdx.x / nc4;
+    const int z = blockIdx.x;
+    const int chunks_per_t = (rows + 63) >> 6;
+    const int nchunks = T * chunks_per_t;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < lanes) {
+        for (int ch = blockIdx.y; ch < nchunks; ch += gridDim.y) {
+            const int t = ch / chunks_per_t, r0 = (ch - t * chunks_per_t) << 6;
+            const int r1 = min(rows, r0 + 64);
+            const float* base = src + (long long)t * st + (long long)z * sz + 4 * c4;
+            for (int r = r0 + lane; r < r1; r += 4 * lanes) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ru = r + u * lanes;
+                    v[u] = ru < r1 ? *reinterpret_cast<const float4*>(base + (long long)ru * ncol) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+            }
+        }
+        cs_red[lane * nc4 + c4] = s;
+    }
+    __syncthreads();
+    if (lane == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            const float4 o = cs_red[l * nc4 + c4];
+            s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+        }
+        const float vals[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int col = 4 * c4 + u;
+            if (col < split) atomicAdd(out1 + (long long)z * ld1 + col, vals[u]);
+            else atomicAdd(out2 + (long long)z * ld2 + col - split, vals[u]);
+        }
+    }
+}
+static bool colsum4_ok(const float* src, long long st, long long sz, int ncol) {
+    return aligned16(src) && !(st & 3) && !(sz & 3) && !(ncol & 3) && ncol / 4 <= 256;
+}
 __global__ void colsum_kernel(const float* __restrict__ src, int T, long long st, long long sz, int rows, int ld,
                               int ncol, int split, float* __restrict__ out1, int ld1, float* __restrict__ out2, int ld2) {
     const int z = blockIdx.x;
@@ -525,6 +575,21 @@ static cudaError_t to_bf16(const float* src, long long spitch, __nv_bfloat16* ds
     return cudaGetLastError();
 }
 
+// bf16 [N*K, Cin, 3H] concatenation of the input rows of the gate and candidate weights: WX[nk, i, 0:2H] = Wg[nk, i, :],
+// WX[nk, i, 2H:3H] = Wu[nk, i, :] (i < Cin) - lets the time-batched input gradient run as ONE contraction over 3H per support.
+__global__ void pack_wx16_kernel(const float* __restrict__ Wg, const float* __restrict__ Wu, int NK, int Cin, int I, int H,
+                                 __nv_bfloat16* __restrict__ WX) {
+    const long long total = (long long)NK * Cin * 3 * H;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % (3 * H));
+        const long long ri = idx / (3 * H);
+        const int i = (int)(ri % Cin);
+        const long long nk = ri / Cin;
+        const float v = c < 2 * H ? Wg[(nk * I + i) * 2 * H + c] : Wu[(nk * I + i) * H + c - 2 * H];
+        WX[idx] = __float2bfloat16_rn(v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // adaptive adjacency
 // ------------------------------------------------------------------------------------------
@@ -712,7 +777,7 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     return w;
 }
 struct LayerBws {
-    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, total;
+    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, WX16, total;
 };
 static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp) {
     LayerBws w;
@@ -730,7 +795,8 @@ static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp)
     w.MPH = take((sizeof(MPhase) * (size_t)(7 * T + 2) + 256) / 4);
     w.DPT16 = take(((size_t)K * U) / 2 + 64);
     w.DPX16 = take(((size_t)T * K * UX) / 2 + 64);
-    w.DG16 = take(((size_t)3 * U) / 2 + 64);  // bf16 twin of the current step's pre-activation gradients [N*B, 3H]
+    w.DG16 = take(((size_t)T * 3 * U) / 2 + 64);  // bf16 twin of the pre-activation gradients DG [T, N*B, 3H]
+    w.WX16 = take(((size_t)N * K * Cin * 3 * H) / 2 + 64);  // bf16 [N, K, Cin, 3H]: gate | candidate input-row weights
     w.total = o;
     return w;
 }
@@ -919,8 +985,9 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     {
         GemmP pp = prop_params(M, ldm, N, Kp, PX, B * Cin);
         pp.sB1 = K * UX;
-        if (bf) { pp.A16 = M16; pp.B16 = PX16; }
-        CK((gemm_any<CfgBig, true, false>(tc, pp, epi_store(PX + UX, K * UX, 0, B * Cin), T, st)));
+        EpiStore e = epi_store(PX + UX, K * UX, 0, B * Cin);
+        if (bf) { pp.A16 = M16; pp.B16 = PX16; e.C16 = PX16 + UX; }
+        CK((gemm_any<CfgBig, true, false>(tc, pp, e, T, st)));
     }
     TR();
 
@@ -998,7 +1065,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             __nv_bfloat16* PH16t = PH16 + (long long)t * K * U;
             __nv_bfloat16* PZ16t = PZ16 + (long long)t * K * U;
             {
-                EpiStore e = epi_store(PHt + U, 0, 0, B * H);
+                EpiPlain e = epi_plain(PHt + U, 0, 0, B * H);
                 if (bf) { p.A16 = M16; p.B16 = PH16t; e.C16 = PH16t + U; }
                 STEP_GEMM(0, CfgBig, true, false, p, e, 1);
             }
@@ -1012,7 +1079,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             // (c) PZ[t,1..] = M * (z*h)
             {
                 GemmP pp = prop_params(M, ldm, N, Kp, PZt, B * H);
-                EpiStore e = epi_store(PZt + U, 0, 0, B * H);
+                EpiPlain e = epi_plain(PZt + U, 0, 0, B * H);
                 if (bf) { pp.A16 = M16; pp.B16 = PZ16t; e.C16 = PZ16t + U; }
                 STEP_GEMM(2, CfgBig, true, false, pp, e, 1);
             }
@@ -1094,7 +1161,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     const __nv_bfloat16* M16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.M16);  // written by the forward pass
     __nv_bfloat16* DPT16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.DPT16);
     __nv_bfloat16* DPX16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.DPX16);
-    __nv_bfloat16* DG16 = bf ? reinterpret_cast<__nv_bfloat16*>(bws + bw.DG16) : nullptr;
+    __nv_bfloat16* DG16T = bf ? reinterpret_cast<__nv_bfloat16*>(bws + bw.DG16) : nullptr;
     const __nv_bfloat16* WG16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.WG16);  // written by the forward pass
     const __nv_bfloat16* WU16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.WU16);
     CK(cudaMemsetAsync(DHC, 0, sizeof(float) * U, st));
@@ -1111,6 +1178,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             const float* H1t = ws + w.H1 + t * U; const float* Z2t = ws + w.Z2 + t * U; const float* R2t = ws + w.R2 + t * U;
             const float* HC2t = ws + w.HC2 + t * U;
             float* DGt = DG + (long long)t * 3 * U; float* DRt = DR + (long long)t * 3 * U;
+            __nv_bfloat16* DG16 = bf ? DG16T + (long long)t * 3 * U : nullptr;
             // B0
             if (use_multi) {
                 mb.add_head(HeadArgs{dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES, DRt, dmix + t});
@@ -1138,13 +1206,11 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.B = Wu + (long long)Cin * H; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sB2 = (long long)I * H;
             if (bf) { p.A16 = DG16 + 2 * H; p.B16 = WU16 + (long long)Cin * H; p.keepB = 1; }
             {
-                EpiStore e = epi_store(DPT, (long long)B * H, U, H);
+                EpiPlain e = epi_plain(DPT, (long long)B * H, U, H);
                 if (bf) e.C16 = DPT16;
+                // the adaptive slices are also kept per step (operands of dM): second destination instead of a copy
+                if (n_adp && !use_multi) { e.D2 = DPZA + (long long)t * n_adp * U; e.d2_lo = 1; e.d2_hi = 1 + n_adp; }
                 STEP_GEMM(2, CfgMid, true, true, p, e, N * K);
-            }
-            if (n_adp && !use_multi) {
-                CK(cudaMemcpyAsync(DPZA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
-                TR();
             }
             // B4: dzh = DPT[0] + sum_{k>=1} M_k^T DPT[k]
             memset(&p, 0, sizeof(p));
@@ -1161,13 +1227,10 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = (long long)I * 2 * H;
             if (bf) { p.A16 = DG16; p.B16 = WG16 + (long long)Cin * 2 * H; p.keepB = 1; }
             {
-                EpiStore e = epi_store(DPT, (long long)B * H, U, H);
+                EpiPlain e = epi_plain(DPT, (long long)B * H, U, H);
                 if (bf) e.C16 = DPT16;
+                if (n_adp && !use_multi) { e.D2 = DPHA + (long long)t * n_adp * U; e.d2_lo = 1; e.d2_hi = 1 + n_adp; }
                 STEP_GEMM(4, CfgMid, true, true, p, e, N * K);
-            }
-            if (n_adp && !use_multi) {
-                CK(cudaMemcpyAsync(DPHA + (long long)t * n_adp * U, DPT + U, sizeof(float) * n_adp * U, cudaMemcpyDeviceToDevice, st));
-                TR();
             }
             // B6: carry = DHD + DPT[0] + sum M_k^T DPT[k]
             memset(&p, 0, sizeof(p));
@@ -1198,11 +1261,17 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.lda = H; p.sA1 = (long long)B * H; p.sA2 = U; p.sAk = K * U; p.M = H; p.K = B;
     p.ldb = 3 * H; p.sB1 = (long long)B * 3 * H; p.sB2 = 0; p.sBk = 3 * U;
     p.A = PH; p.B = DG; p.N = 2 * H;
+    const __nv_bfloat16* PH16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PH16);  // bf16 twins written by the forward pass
+    const __nv_bfloat16* PZ16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PZ16);
+    const __nv_bfloat16* PX16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PX16);
+    if (bf) { p.A16 = PH16; p.B16 = DG16T; }   // these contractions stream the saved state: half the bytes with the twins
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
     TR();
     p.A = PZ; p.B = DG + 2 * H; p.N = H;
+    if (bf) { p.A16 = PZ16; p.B16 = DG16T + 2 * H; }
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu + (long long)Cin * H, (long long)K * I * H, (long long)I * H, H), N * K, st)));
     TR();
+    p.A16 = nullptr; p.B16 = nullptr;
     // residual-GRU weight gradients accumulate by atomics: clear them first
     CK(cudaMemsetAsync(dRgw, 0, sizeof(float) * (size_t)2 * H * I, st));
     TR();
@@ -1229,36 +1298,73 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         // input rows 0:Cin from PX, and the bias gradients (column sums of DG over (t, b))
         p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
         p.A = PX; p.B = DG; p.N = 2 * H;
+        if (bf) { p.A16 = PX16; p.B16 = DG16T; }
         CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
         TR();
         p.B = DG + 2 * H; p.N = H;
+        if (bf) p.B16 = DG16T + 2 * H;
         CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
         TR();
+        p.A16 = nullptr; p.B16 = nullptr;
         CK(cudaMemsetAsync(dbg, 0, sizeof(float) * (size_t)N * 2 * H, st));
         TR();
         CK(cudaMemsetAsync(dbu, 0, sizeof(float) * (size_t)N * H, st));
         TR();
+        const size_t cs_smem = sizeof(float4) * (256 / (3 * H / 4 > 0 ? 3 * H / 4 : 1)) * (3 * H / 4);
         dim3 g1(N, 8);
-        colsum_kernel<<<g1, cs_threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
+        if (colsum4_ok(DG, 3 * U, (long long)B * 3 * H, 3 * H))
+            colsum4_kernel<<<g1, 256, cs_smem, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
+        else
+            colsum_kernel<<<g1, cs_threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
         count_launch();
         TR();
         dim3 g2(1, 1184);
-        colsum_kernel<<<g2, cs_threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
+        if (colsum4_ok(DR, 3 * U, 0, 3 * H))
+            colsum4_kernel<<<g2, 256, cs_smem, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
+        else
+            colsum_kernel<<<g2, cs_threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
         count_launch();
         TR();
         CK(cudaGetLastError());
         // DPX[t,k,n] = DG[t,n][:,0:2H] * Wg[n,k,0:Cin,:]^T + DG[t,n][:,2H:] * Wu[n,k,0:Cin,:]^T     per k: z = (t, n)
-        for (int k = 0; k < K; ++k) {
+        bool dpx_done = false;
+        if (bf && !(Cin & 7)) {
+            // bf16 mode: one contraction over all 3H pre-activation gradients per support, against the packed input-row weights
+            __nv_bfloat16* WX16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.WX16);
+            pack_wx16_kernel<<<148 * 8, 256, 0, st>>>(Wg, Wu, N * K, Cin, I, H, WX16);
+            count_launch();
+            TR();
+            CK(cudaGetLastError());
+            dpx_done = true;
+            for (int k = 0; k < K && dpx_done; ++k) {
+                memset(&p, 0, sizeof(p));
+                p.splits = 1; p.Z2 = N; p.KB = 1;
+                p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 3 * H;
+                p.A16 = DG16T;
+                p.B16 = WX16 + (long long)k * Cin * 3 * H; p.ldb = 3 * H; p.N = Cin; p.sB1 = 0; p.sB2 = (long long)K * Cin * 3 * H;
+                EpiStore e = epi_store(DPX + (long long)k * UX, K * UX, (long long)B * Cin, Cin);
+                if (k >= 1) e.C16 = DPX16 + (long long)k * UX;
+                const cudaError_t de = Cin <= 64 ? launch_gemm_tc<64, true, true, EpiStore, true>(p, e, T * N, st)
+                                                 : launch_gemm_tc<128, true, true, EpiStore, true>(p, e, T * N, st);
+                if (de == cudaErrorNotSupported && k == 0) { dpx_done = false; break; }  // fall back to the two-pass form below
+                CK(de);
+                g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+                TR();
+            }
+        }
+        for (int k = 0; k < K && !dpx_done; ++k) {
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = N; p.KB = 1;
             p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 2 * H;
             p.B = Wg + (long long)k * I * 2 * H; p.ldb = 2 * H; p.N = Cin; p.sB1 = 0; p.sB2 = (long long)K * I * 2 * H;
             EpiStore e = epi_store(DPX + (long long)k * UX, K * UX, (long long)B * Cin, Cin);
             if (bf && k >= 1) e.C16 = DPX16 + (long long)k * UX;  // (the accumulating second launch writes the final twin)
+            if (bf) { p.A16 = DG16T; p.B16 = WG16 + (long long)k * I * 2 * H; }
             CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
             TR();
             p.A = DG + 2 * H; p.K = H;
             p.B = Wu + (long long)k * I * H; p.ldb = H; p.sB2 = (long long)K * I * H;
+            if (bf) { p.A16 = DG16T + 2 * H; p.B16 = WU16 + (long long)k * I * H; }
             e.accumulate = 1;
             CK((gemm_any<CfgMid, true, true>(tc, p, e, T * N, st)));
             TR();
