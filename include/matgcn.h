@@ -79,6 +79,14 @@ int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_
                            const float* dW, const float* db, int N, int D, int K, int I, int O,
                            float* dE, float* dpool, float* dbias_pool, float* dc, void* stream);
 
+/* The same two operators with the arithmetic of the big products selectable (flags as for the layer entry points):
+ * MATGCN_FLAG_TF32 runs E x pool, dW x pool^T and E^T x dW on the tensor-core engine. */
+int matgcn_nodeweights_fwd_ex(const float* E, const float* pool, const float* bias_pool, const float* c,
+                              int N, int D, int K, int I, int O, float* W, float* b, int flags, void* stream);
+int matgcn_nodeweights_bwd_ex(const float* E, const float* pool, const float* bias_pool, const float* c,
+                              const float* dW, const float* db, int N, int D, int K, int I, int O,
+                              float* dE, float* dpool, float* dbias_pool, float* dc, int flags, void* stream);
+
 /* -------------------------------------------------------------------------------------------
  * Support propagation as a standalone operator (the dominant contraction of the path):
  *   P[k, n, col] = sum_m M[k, n, m] * X[m, col]

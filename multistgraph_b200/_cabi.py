@@ -38,6 +38,9 @@ _SIGNATURES = {
     "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),
     "matgcn_adaptive_adj_bwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, _F, _F, _F, c_void_p]),
     "matgcn_nodeweights_fwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, _F, _F, c_void_p]),
+    "matgcn_nodeweights_fwd_ex": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, _F, _F, c_int, c_void_p]),
+    "matgcn_nodeweights_bwd_ex": (c_int, [_F, _F, _F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, _F, _F, _F, _F, c_int,
+                                          c_void_p]),
     "matgcn_nodeweights_bwd": (c_int, [_F, _F, _F, _F, _F, _F, c_int, c_int, c_int, c_int, c_int,
                                        _F, _F, _F, _F, c_void_p]),
     "matgcn_encoder_layer_fwd_ws_bytes": (c_size_t, [c_int] * 6),

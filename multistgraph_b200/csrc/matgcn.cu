@@ -565,7 +565,21 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, long long spitch, 
         dst[r * dpitch + c] = __float2bfloat16_rn(src[r * spitch + c]);
     }
 }
+// contiguous form: 16-byte loads, 8-byte stores (n % 4 == 0, aligned pointers)
+__global__ void to_bf16_vec_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        st4_bf16(dst + 4 * i, ld4(src + 4 * i));
+}
 static cudaError_t to_bf16(const float* src, long long spitch, __nv_bfloat16* dst, long long dpitch, long long n, int rows, cudaStream_t st) {
+    if (rows == 1 && !(n & 3) && aligned16(src) && !(reinterpret_cast<uintptr_t>(dst) & 7)) {
+        const long long n4 = n >> 2;
+        long long blocks = (n4 + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks < 1) blocks = 1;
+        to_bf16_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n4);
+        count_launch();
+        return cudaGetLastError();
+    }
     const long long total = n * rows;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -629,8 +643,16 @@ extern "C" int matgcn_adaptive_adj_bwd(const float* L, const float* Rt, const fl
 // ------------------------------------------------------------------------------------------
 // per-node weights
 // ------------------------------------------------------------------------------------------
+extern "C" int matgcn_nodeweights_fwd_ex(const float* E, const float* pool, const float* bias_pool, const float* c,
+                                         int N, int D, int K, int I, int O, float* W, float* b, int flags, void* stream);
 extern "C" int matgcn_nodeweights_fwd(const float* E, const float* pool, const float* bias_pool, const float* c,
                                       int N, int D, int K, int I, int O, float* W, float* b, void* stream) {
+    return matgcn_nodeweights_fwd_ex(E, pool, bias_pool, c, N, D, K, I, O, W, b, MATGCN_FLAG_EXACT, stream);
+}
+// flags & MATGCN_FLAG_TF32: the big product (E x pool, a stream of N*K*I*O outputs) runs on the tensor-core engine
+extern "C" int matgcn_nodeweights_fwd_ex(const float* E, const float* pool, const float* bias_pool, const float* c,
+                                         int N, int D, int K, int I, int O, float* W, float* b, int flags, void* stream) {
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     REQUIRE(E && pool && bias_pool && c && W && b, "null pointer");
     REQUIRE(N > 0 && D > 0 && K > 0 && I > 0 && O > 0, "bad dims");
     cudaStream_t st = (cudaStream_t)stream;
@@ -642,15 +664,24 @@ extern "C" int matgcn_nodeweights_fwd(const float* E, const float* pool, const f
     p.A = E; p.lda = D; p.B = pool; p.ldb = (int)KIO; p.M = N; p.N = (int)KIO; p.K = D;
     EpiStore e = epi_store(W, 0, 0, (int)KIO);
     e.scale = c; e.scale_div = I * O;
-    CK((launch_gemm<CfgBig, true, false>(p, e, 1, st)));
+    CK((gemm_any<CfgBig, true, false>(tc, p, e, 1, st)));
     p.B = bias_pool; p.ldb = O; p.N = O;
     CK((launch_gemm<CfgMid, true, false>(p, epi_store(b, 0, 0, O), 1, st)));
     return 0;
 }
 
+extern "C" int matgcn_nodeweights_bwd_ex(const float* E, const float* pool, const float* bias_pool, const float* c,
+                                         const float* dW, const float* db, int N, int D, int K, int I, int O,
+                                         float* dE, float* dpool, float* dbias_pool, float* dc, int flags, void* stream);
 extern "C" int matgcn_nodeweights_bwd(const float* E, const float* pool, const float* bias_pool, const float* c,
                                       const float* dW, const float* db, int N, int D, int K, int I, int O,
                                       float* dE, float* dpool, float* dbias_pool, float* dc, void* stream) {
+    return matgcn_nodeweights_bwd_ex(E, pool, bias_pool, c, dW, db, N, D, K, I, O, dE, dpool, dbias_pool, dc, MATGCN_FLAG_EXACT, stream);
+}
+extern "C" int matgcn_nodeweights_bwd_ex(const float* E, const float* pool, const float* bias_pool, const float* c,
+                                         const float* dW, const float* db, int N, int D, int K, int I, int O,
+                                         float* dE, float* dpool, float* dbias_pool, float* dc, int flags, void* stream) {
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     REQUIRE(E && pool && bias_pool && c && dW && db && dE && dpool && dbias_pool && dc, "null pointer");
     REQUIRE(N > 0 && D > 0 && K > 0 && I > 0 && O > 0, "bad dims");
     cudaStream_t st = (cudaStream_t)stream;
@@ -671,14 +702,22 @@ extern "C" int matgcn_nodeweights_bwd(const float* E, const float* pool, const f
     p.splits = (int)((KIO + 2047) / 2048);
     if (p.splits > 128) p.splits = 128;
     EpiAtomic ea{dE, 0, 0, D};
-    CK((launch_gemm<CfgSkinnyN, true, true>(p, ea, 1, st)));
+    if (tc) {
+        // both big contractions stream dW once each on the tensor-core engine (split-K for the N x D one)
+        GemmP q = p;
+        q.splits = (int)((KIO + 4095) / 4096);
+        if (q.splits > 64) q.splits = 64;
+        CK((gemm_any<CfgSkinnyN, true, true>(true, q, ea, 1, st)));
+    } else {
+        CK((launch_gemm<CfgSkinnyN, true, true>(p, ea, 1, st)));
+    }
     p.A = db; p.lda = O; p.B = bias_pool; p.ldb = O; p.K = O; p.splits = 1;
     CK((launch_gemm<CfgSkinnyN, true, true>(p, ea, 1, st)));
     // G[d,col] = sum_n E[n,d] dW[n,col] ; dpool = c[k] * G
     p.A = E; p.lda = D; p.B = dW; p.ldb = (int)KIO; p.M = D; p.N = (int)KIO; p.K = N; p.splits = 1;
     EpiStore eg = epi_store(dpool, 0, 0, (int)KIO);
     eg.scale = c; eg.scale_div = I * O;
-    CK((launch_gemm<CfgSkinnyM, false, false>(p, eg, 1, st)));
+    CK((gemm_any<CfgSkinnyM, false, false>(tc, p, eg, 1, st)));
     // dc[k] = sum G * pool = sum dpool * pool / c[k]
     {
         dim3 grid(K, 64);
@@ -985,7 +1024,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     {
         GemmP pp = prop_params(M, ldm, N, Kp, PX, B * Cin);
         pp.sB1 = K * UX;
-        EpiStore e = epi_store(PX + UX, K * UX, 0, B * Cin);
+        EpiPlain e = epi_plain(PX + UX, K * UX, 0, B * Cin);
         if (bf) { pp.A16 = M16; pp.B16 = PX16; e.C16 = PX16 + UX; }
         CK((gemm_any<CfgBig, true, false>(tc, pp, e, T, st)));
     }
@@ -1009,11 +1048,13 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     p.M = B; p.K = Cin;
     {
         p.B = Wg; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = 0; p.sBk = (long long)I * 2 * H;
+        if (bf) { p.A16 = PX16; p.B16 = WG16; }
         EpiStore e = epi_store(GX, (long long)B * 3 * H, 3 * U, 3 * H);
         e.bias = bg; e.bias_s1 = 2 * H;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, N * T, st)));
         TR();
         p.B = Wu; p.ldb = H; p.N = H; p.sB1 = (long long)K * I * H; p.sBk = (long long)I * H;
+        if (bf) p.B16 = WU16;
         e = epi_store(GX + 2 * H, (long long)B * 3 * H, 3 * U, 3 * H);
         e.bias = bu; e.bias_s1 = H;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, N * T, st)));

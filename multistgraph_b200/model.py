@@ -292,8 +292,8 @@ class MultiATGCN(nn.Module):
             cell, res = enc.agru_cells[layer], enc.res_cells[layer]
             pool_g, c_g = self._view_weights(cell.gate, k_total)
             pool_u, c_u = self._view_weights(cell.update, k_total)
-            w_g, b_g = ops.node_weights(self.node_emb, pool_g, cell.gate.bias_pool, c_g)
-            w_u, b_u = ops.node_weights(self.node_emb, pool_u, cell.update.bias_pool, c_u)
+            w_g, b_g = ops.node_weights(self.node_emb, pool_g, cell.gate.bias_pool, c_g, self.matgcn_flags)
+            w_u, b_u = ops.node_weights(self.node_emb, pool_u, cell.update.bias_pool, c_u, self.matgcn_flags)
             cur = ops.encoder_layer(cur, None, bases, w_g, b_g, w_u, b_u,
                                     res.gate.weight, res.gate.bias, res.update.weight, res.update.bias,
                                     mix[layer], n_adp, self.matgcn_flags)
@@ -315,7 +315,14 @@ class MultiATGCN(nn.Module):
         # channels, so it is the contraction below.  Written as a matmul so it stays true fp32
         # (cuDNN convolutions default to TF32, which breaks the 1e-4 parity bound).
         w = self.end_conv.weight[:, :, 0, :]                        # [T_out*C, T, H]
-        out = torch.einsum("btnh,oth->bon", out, w) + self.end_conv.bias[None, :, None]
+        if out.shape[1] == y_nm.shape[0] and out.stride() == y_nm.permute(2, 0, 1, 3).stride():
+            # the activations still sit node-major in memory ([T, N, B, H]): contract per time step without first
+            # copying 4*B*T*N*H bytes into [B*N, T*H] order (what einsum would do), then sum the T partial products
+            t_steps, n_nodes, n_batch, hid = y_nm.shape
+            part = torch.bmm(out.permute(1, 2, 0, 3).reshape(t_steps, n_nodes * n_batch, hid), w.permute(1, 2, 0))
+            out = part.sum(0).reshape(n_nodes, n_batch, -1).permute(1, 2, 0) + self.end_conv.bias[None, :, None]
+        else:
+            out = torch.einsum("btnh,oth->bon", out, w) + self.end_conv.bias[None, :, None]
         out = out.reshape(-1, self.output_window, self.output_dim, self.num_nodes).permute(0, 1, 3, 2)
         return out
 

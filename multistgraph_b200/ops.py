@@ -62,16 +62,17 @@ class _AdaptiveAdjFn(torch.autograd.Function):
 
 class _NodeWeightsFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, E, pool, bias_pool, c):
+    def forward(ctx, E, pool, bias_pool, c, flags):
         E, pool, bias_pool, c = _f32c(E, "E"), _f32c(pool, "pool"), _f32c(bias_pool, "bias_pool"), _f32c(c, "c")
+        ctx.flags = int(flags)
         n, d = E.shape
         d2, k, i, o = pool.shape
         if d2 != d or bias_pool.shape != (d, o) or c.shape != (k,):
             raise _cabi.MatgcnError("node_weights: inconsistent shapes")
         W = torch.empty(n, k, i, o, device=E.device, dtype=torch.float32)
         b = torch.empty(n, o, device=E.device, dtype=torch.float32)
-        _cabi.check(_cabi.lib().matgcn_nodeweights_fwd(_ptr(E), _ptr(pool), _ptr(bias_pool), _ptr(c),
-                                                        n, d, k, i, o, _ptr(W), _ptr(b), _stream()),
+        _cabi.check(_cabi.lib().matgcn_nodeweights_fwd_ex(_ptr(E), _ptr(pool), _ptr(bias_pool), _ptr(c),
+                                                           n, d, k, i, o, _ptr(W), _ptr(b), ctx.flags, _stream()),
                     "matgcn_nodeweights_fwd")
         ctx.save_for_backward(E, pool, bias_pool, c)
         return W, b
@@ -86,11 +87,11 @@ class _NodeWeightsFn(torch.autograd.Function):
         dpool = torch.empty_like(pool)
         dbias_pool = torch.empty_like(bias_pool)
         dc = torch.empty_like(c)
-        _cabi.check(_cabi.lib().matgcn_nodeweights_bwd(_ptr(E), _ptr(pool), _ptr(bias_pool), _ptr(c), _ptr(dW),
-                                                        _ptr(db), n, d, k, i, o, _ptr(dE), _ptr(dpool),
-                                                        _ptr(dbias_pool), _ptr(dc), _stream()),
+        _cabi.check(_cabi.lib().matgcn_nodeweights_bwd_ex(_ptr(E), _ptr(pool), _ptr(bias_pool), _ptr(c), _ptr(dW),
+                                                           _ptr(db), n, d, k, i, o, _ptr(dE), _ptr(dpool),
+                                                           _ptr(dbias_pool), _ptr(dc), ctx.flags, _stream()),
                     "matgcn_nodeweights_bwd")
-        return dE, dpool, dbias_pool, dc
+        return dE, dpool, dbias_pool, dc, None
 
 
 class _EncoderLayerFn(torch.autograd.Function):
@@ -249,9 +250,9 @@ def adaptive_adjacency(L, Rt, ldm):
     return _AdaptiveAdjFn.apply(L, Rt, ldm)
 
 
-def node_weights(E, pool, bias_pool, c):
-    """(W [N,K,I,O], b [N,O]) with the view weights c folded into W."""
-    return _NodeWeightsFn.apply(E, pool, bias_pool, c)
+def node_weights(E, pool, bias_pool, c, flags=0):
+    """(W [N,K,I,O], b [N,O]) with the view weights c folded into W.  flags as for ``encoder_layer``."""
+    return _NodeWeightsFn.apply(E, pool, bias_pool, c, flags)
 
 
 def encoder_layer(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags=0):

@@ -246,7 +246,7 @@ def install(ops_module):
     ops_module.matmul = lambda A, B, flags=0: A @ B
     ops_module.encoder_layer = lambda *a: MirrorLayerFn.apply(*a[:13])
     ops_module.adaptive_adjacency = lambda L, Rt, ldm: MirrorAdjFn.apply(L, Rt, ldm)
-    ops_module.node_weights = lambda E, pool, bp, c: MirrorNodeWeightsFn.apply(E, pool, bp, c)
+    ops_module.node_weights = lambda E, pool, bp, c, flags=0: MirrorNodeWeightsFn.apply(E, pool, bp, c)
 
     def restore():
         ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights = saved

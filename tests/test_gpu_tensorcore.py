@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+from multistgraph_b200 import ops  # noqa: E402
 from multistgraph_b200 import _cabi
 from multistgraph_b200.model import MultiATGCN
 from multistgraph_b200.synthetic import make_batch, make_config, make_data_feature
@@ -129,6 +130,32 @@ def test_persistent_recurrence_kernel_matches_per_phase_launches():
     for k in g0:
         assert max_rel_err(g1[k], g0[k]) < 1e-4, k   # split-K atomics reorder sums slightly
     assert n1 < 300, "persistent mode should need far fewer launches (got %d)" % n1
+
+
+@pytest.mark.parametrize("N,D,K,I,O", [(33, 10, 5, 66, 128), (50, 20, 5, 128, 64), (403, 20, 5, 128, 128)])
+def test_node_weights_op_tensor_core(N, D, K, I, O):
+    """Per-node weight generation and its backward with the big products on the tensor-core engine (TF32), against
+    the torch mirror of the operator."""
+    from tests import host_mirror as hm
+    E, pool, bp = _rand(N, D, seed=1), _rand(D, K, I, O, seed=2) * 0.1, _rand(D, O, seed=3)
+    c = torch.softmax(_rand(K, seed=4), 0)
+    dW, db = _rand(N, K, I, O, seed=5), _rand(N, O, seed=6)
+    ref_in = [t.clone().requires_grad_(True) for t in (E, pool, bp, c)]
+    W_ref, b_ref = hm.MirrorNodeWeightsFn.apply(*ref_in)
+    torch.autograd.backward([W_ref, b_ref], [dW, db])
+    gpu_in = [t.to(DEV).requires_grad_(True) for t in (E, pool, bp, c)]
+    n0 = _cabi.lib().matgcn_tc_launch_count()
+    W, b = ops.node_weights(*gpu_in, _cabi.FLAG_TF32)
+    torch.autograd.backward([W, b], [dW.to(DEV), db.to(DEV)])
+    torch.cuda.synchronize()
+    if D % 4 == 0:  # TMA needs 16-byte row pitches: with D % 4 != 0 the products that read E fall back to the FFMA engine
+        assert _cabi.lib().matgcn_tc_launch_count() - n0 >= 3, "the big products did not run on the tensor-core engine"
+    errs = {"W": max_rel_err(W, W_ref), "b": max_rel_err(b, b_ref)}
+    for nm, a, r in zip(["dE", "dpool", "dbias_pool", "dc"], gpu_in, ref_in):
+        errs[nm] = max_rel_err(a.grad, r.grad)
+    print("[tc nodeweights N=%d] " % N + ", ".join("%s=%.2e" % kv for kv in errs.items()))
+    bad = {k: v for k, v in errs.items() if not (v < 2e-3)}
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])
