@@ -233,15 +233,15 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r1_prop_kernel_ncu.json")
-    if flags == _cabi.FLAG_TF32 and os.path.exists(prof):
+    prof = os.path.join(ROOT, "profiles", "r1_prop_kernel_ncu_bf16.json" if bf16 else "r1_prop_kernel_ncu.json")
+    if flags and os.path.exists(prof):
         with open(prof) as f:
             pj = json.load(f)
         if pj["shape"] == {"Kp": kp, "N": n_nodes, "cols": cols}:  # the ncu --set full capture of this very shape
             traffic = pj["dram_bytes_read"] + pj["dram_bytes_write"]
-    kern = ("gemm_tc_kernel<128,A_KC,B_NC,BF16,EpiStore> (support propagation, tcgen05 kind::f16 bf16 + TMA)" if bf16
-            else "gemm_tc_kernel<128,A_KC,B_NC,EpiStore> (support propagation, tcgen05 kind::tf32 + TMA)" if flags
-            else "gemm_kernel<CfgBig,A_KC,B_NC,EpiStore> (support propagation, fp32 FFMA)")
+    kern = ("gemm_tc_kernel<128,A_KC,B_NC,BF16,EpiPlain> (support propagation, tcgen05 kind::f16 bf16 + TMA)" if bf16
+            else "gemm_tc_kernel<128,A_KC,B_NC,TF32,EpiPlain> (support propagation, tcgen05 kind::tf32 + TMA)" if flags
+            else "gemm_kernel<CfgBig,A_KC,B_NC,EpiPlain> (support propagation, fp32 FFMA)")
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "kernel": kern, "launch_ms": ms, "flops_per_launch": flops,
             "algorithmic_bytes_per_launch": (2.0 if bf16 else 4.0) * (kp * n_nodes * ldm + n_nodes * cols) + 4.0 * kp * n_nodes * cols,
@@ -351,8 +351,9 @@ def run_ours(args):
                            "l2": "per-step working set (several GB of saved activations) is far larger than the 126 MB L2",
                            "mode": {0: "exact: fp32 FFMA kernels (1e-4 parity)",
                                     1: "fast: contractions on tcgen05 tensor cores as TF32, fp32 storage and accumulation",
-                                    3: "fast: tcgen05 tensor cores; support propagation on bf16 operand twins, the rest TF32; "
-                                       "fp32 storage of the state and fp32 accumulation"}[model.matgcn_flags]},
+                                    3: "fast: tcgen05 tensor cores; the streamed contractions (support propagation, per-node gate / "
+                                       "candidate products and their reverse-step and weight-gradient counterparts) read bf16 "
+                                       "operand twins, the rest is TF32; fp32 storage of the state, fp32 accumulation"}[model.matgcn_flags]},
                 "clocks": clocks,
                 "e2e": {"value": global_batch / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world},
@@ -377,8 +378,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--mode", default="tf32", choices=["tf32", "bf16", "exact"],
-                    help="tf32: tcgen05 tensor cores (headline); exact: fp32 FFMA kernels")
+    ap.add_argument("--mode", default="bf16", choices=["tf32", "bf16", "exact"],
+                    help="bf16 (headline): tcgen05 tensor cores, bf16 operand twins for the streamed contractions, the rest "
+                         "TF32; tf32: TF32 tensor cores with fp32 operands; exact: fp32 FFMA kernels (1e-4 parity)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work allowed for the baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")

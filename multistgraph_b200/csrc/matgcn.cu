@@ -281,6 +281,33 @@ __global__ void colsum_kernel(const float* __restrict__ src, int T, long long st
 }
 
 // B0: head of the reverse step.  dy = dY[t] + carry ; residual-mix backward up to da3.
+// 16-byte form of the kernel below (H % 4 == 0, n % 4 == 0, aligned pointers): one float4 per thread and stream
+__global__ void __launch_bounds__(256) bwd_head4_kernel(const float* __restrict__ dY, const float* __restrict__ carry,
+                                                        const float* __restrict__ H1, const float* __restrict__ R2,
+                                                        const float* __restrict__ HC2, const float* __restrict__ mix_t, long long n4,
+                                                        int H, float* __restrict__ DH1, float* __restrict__ DRES,
+                                                        float* __restrict__ DR, float* __restrict__ dmix_t) {
+    __shared__ float red[32];
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float part = 0.f;
+    if (i4 < n4) {
+        const long long i = 4 * i4;
+        const float g = __ldg(mix_t);
+        const float4 a = ld4(dY + i), b = ld4(carry + i), h1 = ld4(H1 + i), r2 = ld4(R2 + i), hc2 = ld4(HC2 + i);
+        const float4 dy = a + b;
+        const float4 res = r2 * h1 + one_minus(r2) * hc2;
+        const float4 pr = dy * (h1 - res);
+        part = (pr.x + pr.y) + (pr.z + pr.w);
+        const float4 dres = (1.f - g) * dy;
+        st4(DRES + i, dres);
+        st4(DH1 + i, g * dy + dres * r2);
+        const long long row = i / H;
+        const int c = (int)(i - row * H);
+        st4(DR + row * 3 * H + 2 * H + c, dres * one_minus(r2) * one_minus(hc2 * hc2));
+    }
+    part = block_reduce(part, red, false);
+    if (threadIdx.x == 0) atomicAdd(dmix_t, part);
+}
 __global__ void bwd_head_kernel(const float* __restrict__ dY, const float* __restrict__ carry,
                                 const float* __restrict__ H1, const float* __restrict__ R2,
                                 const float* __restrict__ HC2, const float* __restrict__ mix_t, long long n, int H,
@@ -880,7 +907,7 @@ static cudaError_t propagate(bool tc, const float* M, int ldm, int N, int Kp, co
     p.KB = 1; p.Z2 = 1; p.splits = 1;
     p.A = M; p.lda = ldm; p.M = Kp * N; p.K = N;
     p.B = slot0; p.ldb = cols; p.N = cols; p.sB1 = zstride;
-    return gemm_any<CfgBig, true, false>(tc, p, epi_store(slot1, zstride, 0, cols), Z, st);
+    return gemm_any<CfgBig, true, false>(tc, p, epi_plain(slot1, zstride, 0, cols), Z, st);  // the epilogue the layer entry points use
 }
 
 extern "C" int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P,
@@ -917,7 +944,7 @@ extern "C" int matgcn_propagate_fwd_bf16(const void* M16, int Kp, int N, int ldm
     p.KB = 1; p.Z2 = 1; p.splits = 1;
     p.A16 = (const __nv_bfloat16*)M16; p.lda = ldm; p.M = Kp * N; p.K = N;
     p.B16 = (const __nv_bfloat16*)X16; p.ldb = cols; p.N = cols;
-    cudaError_t e = launch_gemm_tc<128, true, false, EpiStore, true>(p, epi_store(P, 0, 0, cols), 1, (cudaStream_t)stream);
+    cudaError_t e = launch_gemm_tc<128, true, false, EpiPlain, true>(p, epi_plain(P, 0, 0, cols), 1, (cudaStream_t)stream);
     if (e == cudaErrorNotSupported) return fail(__func__, "operands do not meet the TMA alignment rules");
     CK(e);
     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1224,8 +1251,14 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             if (use_multi) {
                 mb.add_head(HeadArgs{dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES, DRt, dmix + t});
             } else {
-                bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t,
-                                                                            mix + t, U, H, DH1, DRES, DRt, dmix + t);
+                const float* dyt = dy + (long long)t * dy_tstride;
+                if (!(H & 3) && !(U & 3) && aligned16(dyt) && aligned16(DHC) && aligned16(H1t) && aligned16(R2t) && aligned16(HC2t) &&
+                    aligned16(DH1) && aligned16(DRES) && aligned16(DRt))
+                    bwd_head4_kernel<<<(unsigned)((U / 4 + 255) / 256), 256, 0, st>>>(dyt, DHC, H1t, R2t, HC2t, mix + t, U / 4, H, DH1,
+                                                                                     DRES, DRt, dmix + t);
+                else
+                    bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dyt, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES,
+                                                                                DRt, dmix + t);
                 count_launch();
                 TR();
                 CK(cudaGetLastError());

@@ -307,22 +307,19 @@ class MultiATGCN(nn.Module):
             raise ValueError("sequence longer than input_window (weights_gru has %d steps)" % self.input_window)
         x_nm = fused.permute(1, 2, 0, 3).contiguous()               # node-major [T, N, B, C0]
         y_nm = self._encode(x_nm)                                   # [T, N, B, H]
-        out = y_nm.permute(2, 0, 1, 3)                              # [B, T, N, H]
         if self.fnn_off:
-            out = out[:, -1:, :, :]
-        out = F.dropout(out, p=0.1, training=self.training)
-        # end_conv = Conv2d(T -> T_out*C, kernel (1, H)) (MA.py:340-344, 417): time steps are the
-        # channels, so it is the contraction below.  Written as a matmul so it stays true fp32
-        # (cuDNN convolutions default to TF32, which breaks the 1e-4 parity bound).
+            y_nm = y_nm[-1:]
+        # Dropout and the output head work on the node-major tensor as it sits in memory: the mask is drawn in that
+        # element order (same distribution; the reference's [B,T,N,H] order would need a 4*B*T*N*H-byte relayout and the
+        # slow strided dropout kernel), and the head contracts per time step instead of first copying into [B*N, T*H] order.
+        y_nm = F.dropout(y_nm, p=0.1, training=self.training)
+        # end_conv = Conv2d(T -> T_out*C, kernel (1, H)) (MA.py:340-344, 417): time steps are the channels, so it is a
+        # contraction over (t, h).  Written as matmuls so it stays true fp32 (cuDNN convolutions default to TF32, which
+        # breaks the 1e-4 parity bound).
         w = self.end_conv.weight[:, :, 0, :]                        # [T_out*C, T, H]
-        if out.shape[1] == y_nm.shape[0] and out.stride() == y_nm.permute(2, 0, 1, 3).stride():
-            # the activations still sit node-major in memory ([T, N, B, H]): contract per time step without first
-            # copying 4*B*T*N*H bytes into [B*N, T*H] order (what einsum would do), then sum the T partial products
-            t_steps, n_nodes, n_batch, hid = y_nm.shape
-            part = torch.bmm(out.permute(1, 2, 0, 3).reshape(t_steps, n_nodes * n_batch, hid), w.permute(1, 2, 0))
-            out = part.sum(0).reshape(n_nodes, n_batch, -1).permute(1, 2, 0) + self.end_conv.bias[None, :, None]
-        else:
-            out = torch.einsum("btnh,oth->bon", out, w) + self.end_conv.bias[None, :, None]
+        t_steps, n_nodes, n_batch, hid = y_nm.shape
+        part = torch.bmm(y_nm.reshape(t_steps, n_nodes * n_batch, hid), w.permute(1, 2, 0))   # [T, N*B, T_out*C]
+        out = part.sum(0).reshape(n_nodes, n_batch, -1).permute(1, 2, 0) + self.end_conv.bias[None, :, None]
         out = out.reshape(-1, self.output_window, self.output_dim, self.num_nodes).permute(0, 1, 3, 2)
         return out
 
