@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from logging import getLogger
 
+from collections import OrderedDict
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -142,14 +144,21 @@ class MultiATGCN(nn.Module):
         # not part of the checkpoint, exactly like the reference's plain python list
         self.register_buffer("static_bases", torch.from_numpy(np.stack(stat, 0)), persistent=False)
         self.static = data_feature.get("static", None)
-        if self.static is not None:
-            raise NotImplementedError(
-                "data_feature['static'] is set (add_static=true): that branch re-runs a randomised "
-                "torch.pca_lowrank on every forward (MA.py:291, 407) and is outside the accelerated path; "
-                "the shipped default add_static=false passes static=None")
 
         # --- parameters, in the reference's registration order (MA.py:286-344) -------------
-        self.node_emb = nn.Parameter(torch.randn(n, self.embed_dim_node), requires_grad=True)
+        if self.static is not None:
+            # add_static=true (MA.py:286-294): node embeddings start from a PCA of the static node features pushed through
+            # a Linear+ReLU (overwritten by _init_parameters like every other parameter, but the module, its parameters
+            # and its RNG consumption are part of the checkpoint / seeded-init contract)
+            feat = torch.as_tensor(np.asarray(self.static), dtype=torch.float32)
+            self.register_buffer("static_feat", feat, persistent=False)
+            self.static_rank = min(n, self.embed_dim_node)
+            self.static_initial_node = nn.Sequential(OrderedDict(
+                [("embd", nn.Linear(self.static_rank, self.embed_dim_node, bias=True)), ("relu1", nn.ReLU())]))
+            _, _, v = torch.pca_lowrank(feat, q=self.static_rank)
+            self.node_emb = nn.Parameter(self.static_initial_node(torch.matmul(feat, v)).detach(), requires_grad=True)
+        else:
+            self.node_emb = nn.Parameter(torch.randn(n, self.embed_dim_node), requires_grad=True)
         adj_t = torch.from_numpy(np.ascontiguousarray(views["adj_mx"]))
         m, p, v = torch.svd(adj_t)
         da = self.embed_dim_adj
@@ -179,6 +188,9 @@ class MultiATGCN(nn.Module):
             [nn.Parameter(torch.empty(1, 24, n, self.output_dim)) for _ in range(self.len_ts)])
         self.weight_tsg = nn.Parameter(torch.empty(self.len_ts))
 
+        if self.static is not None:  # MA.py:335-338: initial hidden state from the static features
+            self.static_initial_gru = nn.Sequential(OrderedDict(
+                [("embd", nn.Linear(self.static_rank, self.hidden_dim, bias=True)), ("relu1", nn.ReLU())]))
         self.encoder = _EncoderParams(config, self.feature_final)
         self.end_conv = nn.Conv2d(self.input_window, self.output_window * self.output_dim,
                                   kernel_size=(1, self.hidden_dim), bias=True)
@@ -273,7 +285,7 @@ class MultiATGCN(nn.Module):
             c = c.expand(k_total)
         return pool, c
 
-    def _encode(self, x_nm):
+    def _encode(self, x_nm, h0=None):
         enc = self.encoder
         mix = torch.sigmoid(enc.weights_gru)
         if self.gcn_off:
@@ -282,7 +294,7 @@ class MultiATGCN(nn.Module):
             cur = x_nm
             for layer in range(self.num_layers):
                 cell = enc.agru_cells[layer]
-                cur = ops.dense_gru_layer(cur, None, cell.gate.weight, cell.gate.bias, cell.update.weight,
+                cur = ops.dense_gru_layer(cur, h0, cell.gate.weight, cell.gate.bias, cell.update.weight,
                                           cell.update.bias, self.matgcn_flags)
             return cur
         bases, n_adp = self._base_matrices()
@@ -294,7 +306,7 @@ class MultiATGCN(nn.Module):
             pool_u, c_u = self._view_weights(cell.update, k_total)
             w_g, b_g = ops.node_weights(self.node_emb, pool_g, cell.gate.bias_pool, c_g, self.matgcn_flags)
             w_u, b_u = ops.node_weights(self.node_emb, pool_u, cell.update.bias_pool, c_u, self.matgcn_flags)
-            cur = ops.encoder_layer(cur, None, bases, w_g, b_g, w_u, b_u,
+            cur = ops.encoder_layer(cur, h0, bases, w_g, b_g, w_u, b_u,
                                     res.gate.weight, res.gate.bias, res.update.weight, res.update.bias,
                                     mix[layer], n_adp, self.matgcn_flags)
         return cur
@@ -306,7 +318,14 @@ class MultiATGCN(nn.Module):
         if fused.shape[1] > self.input_window:
             raise ValueError("sequence longer than input_window (weights_gru has %d steps)" % self.input_window)
         x_nm = fused.permute(1, 2, 0, 3).contiguous()               # node-major [T, N, B, C0]
-        y_nm = self._encode(x_nm)                                   # [T, N, B, H]
+        h0 = None
+        if self.static is not None:
+            # MA.py:405-409: the same static embedding starts every layer and every sample; the reference re-runs the
+            # (randomised) torch.pca_lowrank on every forward, and so does this
+            _, _, v = torch.pca_lowrank(self.static_feat, q=self.static_rank)
+            emb = self.static_initial_gru(torch.matmul(self.static_feat, v))           # [N, H]
+            h0 = emb[:, None, :].expand(-1, x_nm.shape[2], -1).contiguous()            # node-major [N, B, H]
+        y_nm = self._encode(x_nm, h0)                               # [T, N, B, H]
         if self.fnn_off:
             y_nm = y_nm[-1:]
         # Dropout and the output head work on the node-major tensor as it sits in memory: the mask is drawn in that

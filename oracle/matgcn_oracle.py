@@ -252,9 +252,9 @@ class OracleModel:
         self.len_p = data_feature.get("len_period", 0)
         self.len_t = data_feature.get("len_trend", 0)
         self.scaler = data_feature.get("scaler")
-        if data_feature.get("static", None) is not None:
-            raise NotImplementedError("oracle covers static=None (add_static=false, the shipped default); "
-                                      "the static branch re-runs a randomised pca_lowrank per forward (MA.py:407)")
+        # add_static=true (MA.py:286-294, 335-338, 405-409): static node features -> initial hidden state
+        st = data_feature.get("static", None)
+        self.static = None if st is None else torch.as_tensor(np.asarray(st), dtype=torch.float32)
         self.static_sup = [s.to(dtype) for s in build_static_supports(config, data_feature)["supports"]]
         self.training = False
 
@@ -334,6 +334,14 @@ class OracleModel:
         xb = batch["X"].to("cpu", self.dtype)
         fused = self.fuse(xb)
         h0 = torch.zeros(self.layers, xb.shape[0], self.n, self.hid, dtype=self.dtype)
+        if self.static is not None:
+            # MA.py:405-409: pca_lowrank is called on the float32 features exactly like the reference (it is randomised:
+            # parity needs the same RNG state or a patched torch.pca_lowrank), the rest runs in the oracle's dtype
+            q = min(self.n, self.p["node_emb"].shape[1]) if "static_initial_gru.embd.weight" not in self.p else \
+                self.p["static_initial_gru.embd.weight"].shape[1]
+            _, _, v = torch.pca_lowrank(self.static, q=q)
+            emb = torch.relu(self._linear("static_initial_gru.embd", (self.static @ v).to(self.dtype)))
+            h0 = emb.expand(self.layers, xb.shape[0], -1, -1)
         enc = self.encoder(fused, h0)
         if self.fnn_off:
             enc = enc[:, -1:, :, :]

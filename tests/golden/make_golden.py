@@ -43,6 +43,10 @@ CASES = {
                                                   output_window=6, node_specific_off=True)),
     "one_layer": dict(N=7, B=2, cfg=dict(adjtype="multi", adpadj="bidirection", cheb_order=2, output_window=6,
                                           num_layers=1)),
+    # add_static=true: static node features -> similarity view (MA.py:244-250), PCA-initialised node embedding
+    # (MA.py:286-294) and initial hidden state (MA.py:335-338, 405-409); torch.pca_lowrank patched deterministic
+    "add_static": dict(N=9, B=2, static_dim=6, cfg=dict(adjtype="multi", adpadj="bidirection", cheb_order=2,
+                                                        output_window=6)),
 }
 
 
@@ -50,8 +54,13 @@ def build_case(name, spec, seed=1234):
     sys.path.insert(0, "/root/reference")
     from libcity.model.traffic_flow_prediction.MultiATGCN import MultiATGCN as RefModel
 
+    from tests.util import exact_pca_lowrank
+
+    torch.pca_lowrank = exact_pca_lowrank  # the reference's randomised PCA, made deterministic (see tests/util.py)
     cfg = make_config(embed_dim=4, rnn_units=8, batch_size=spec["B"], **spec["cfg"])
     df = make_data_feature(spec["N"], seed=seed)
+    if spec.get("static_dim"):
+        df["static"] = np.random.default_rng(seed + 1).normal(size=(spec["N"], spec["static_dim"])).astype(np.float32)
     batch = make_batch(spec["N"], spec["B"], cfg["output_window"], seed=seed)
     torch.manual_seed(seed)
     model = RefModel(dict(cfg), df)
@@ -64,6 +73,8 @@ def build_case(name, spec, seed=1234):
            "geo_id": np.asarray(df["coordinate"]["geo_id"]),
            "coordinates": np.asarray(list(df["coordinate"]["coordinates"])).astype("U"),
            "forecast": y.detach().numpy(), "loss": np.asarray(loss.item(), dtype=np.float64)}
+    if df.get("static") is not None:
+        out["static"] = df["static"]
     for k, v in sd.items():
         out["param/" + k] = v.numpy()
     for k, p in model.named_parameters():
@@ -79,5 +90,7 @@ def build_case(name, spec, seed=1234):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for nm, sp in CASES.items():
-        build_case(nm, sp)
+        if not only or nm in only:
+            build_case(nm, sp)

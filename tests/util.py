@@ -25,7 +25,8 @@ def load_golden(name):
     lc, lp, lt = (int(v) for v in z["len_windows"])
     coord = pd.DataFrame({"geo_id": z["geo_id"], "coordinates": [str(s) for s in z["coordinates"]]})
     adj = z["adj_mx"]
-    df = {"scaler": StandardScaler(0.0, 1.0), "adj_mx": adj, "static": None, "coordinate": coord,
+    static = z["static"] if "static" in z.files else None   # add_static=true cases carry the node features
+    df = {"scaler": StandardScaler(0.0, 1.0), "adj_mx": adj, "static": static, "coordinate": coord,
           "num_nodes": adj.shape[0], "feature_dim": 2, "output_dim": 1, "ext_dim": 1,
           "len_closeness": lc, "len_period": lp, "len_trend": lt, "num_batches": 1}
     params = {k[len("param/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
@@ -50,3 +51,21 @@ def max_rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 def clone_batch(batch, device=None):
     return {k: (v.clone() if device is None else v.clone().to(device)) for k, v in batch.items()}
+
+
+def exact_pca_lowrank(A, q=None, center=True, niter=2, M=None):
+    """Deterministic stand-in for ``torch.pca_lowrank`` (a randomised algorithm the reference calls on every forward
+    when ``add_static`` is on, MA.py:291, 407): exact SVD of the centred matrix, columns of V sign-normalised so that
+    the result does not depend on device, dtype or RNG state.  The golden ``add_static`` case was generated from the
+    real reference with this patch active (tests/golden/make_golden.py); ``tests/conftest.py`` installs it for the suite."""
+    A = torch.as_tensor(A)
+    q = min(6, A.shape[-2], A.shape[-1]) if q is None else q
+    Ac = (A - A.mean(dim=-2, keepdim=True)) if center else A
+    U, S, Vh = torch.linalg.svd(Ac.double().cpu(), full_matrices=False)
+    V = Vh.transpose(-2, -1)[..., :q]
+    idx = V.abs().argmax(dim=-2, keepdim=True)
+    sign = torch.sign(torch.gather(V, -2, idx))
+    sign[sign == 0] = 1.0
+    V = V * sign
+    U = U[..., :q] * sign
+    return U.to(A.dtype).to(A.device), S[..., :q].to(A.dtype).to(A.device), V.to(A.dtype).to(A.device)
