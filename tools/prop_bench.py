@@ -15,15 +15,22 @@ for kp, n, cols in shapes:
     M = torch.randn(kp, n, ldm, device=dev) * 0.05
     X = torch.randn(n, cols, device=dev)
     P = torch.empty(kp, n, cols, device=dev)
-    for flags in (1, 0):
+    M16, X16 = M.bfloat16(), X.bfloat16()
+    modes = (3,) if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else (1, 0)
+    for flags in modes:
+        def run(flags=flags):
+            if flags == 3:
+                _cabi.check(lib.matgcn_propagate_fwd_bf16(M16.data_ptr(), kp, n, ldm, X16.data_ptr(), cols, P.data_ptr(), st), "p16")
+            else:
+                _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st), "p")
         for _ in range(2):
-            _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st), "p")
+            run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         iters = 10
         e0.record()
         for _ in range(iters):
-            _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st), "p")
+            run()
         e1.record(); e1.synchronize()
         ms = e0.elapsed_time(e1) / iters
         fl = 2.0 * kp * n * n * cols
