@@ -14,6 +14,7 @@
 #include "epilogues.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc_multi.cuh"
+#include "res_bwd.cuh"
 
 using namespace matgcn;
 
@@ -1247,32 +1248,45 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             const float* HC2t = ws + w.HC2 + t * U;
             float* DGt = DG + (long long)t * 3 * U; float* DRt = DR + (long long)t * 3 * U;
             __nv_bfloat16* DG16 = bf ? DG16T + (long long)t * 3 * U : nullptr;
-            // B0
-            if (use_multi) {
-                mb.add_head(HeadArgs{dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES, DRt, dmix + t});
-            } else {
-                const float* dyt = dy + (long long)t * dy_tstride;
-                if (!(H & 3) && !(U & 3) && aligned16(dyt) && aligned16(DHC) && aligned16(H1t) && aligned16(R2t) && aligned16(HC2t) &&
-                    aligned16(DH1) && aligned16(DRES) && aligned16(DRt))
-                    bwd_head4_kernel<<<(unsigned)((U / 4 + 255) / 256), 256, 0, st>>>(dyt, DHC, H1t, R2t, HC2t, mix + t, U / 4, H, DH1,
-                                                                                     DRES, DRt, dmix + t);
-                else
-                    bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dyt, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES,
-                                                                                DRt, dmix + t);
-                count_launch();
-                TR();
-                CK(cudaGetLastError());
+            // B0 + B1 + B2 in one launch when the fused form applies (fast modes, H = 64): see res_bwd.cuh
+            bool rb_fused = false;
+            if (tc && !use_multi && fused_tail_enabled()) {
+                ResBwdArgs ra{dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t, Z2t, PHt, Rt_, HCt, mix + t, ws + w.RUH, ws + w.RGH,
+                              DRt, DGt, DG16, DHD, dmix + t, (long long)NB};
+                if (res_bwd_fused_ok(ra, H)) {
+                    CK(launch_res_bwd_fused(ra, st));
+                    TR();
+                    rb_fused = true;
+                }
             }
-            // B1: dzh2 = da3 [NB,H] * Ruw[:, Cin:]  (B element (k=o, n=j) at o*H + j of the dense copy)
-            memset(&p, 0, sizeof(p));
-            p.splits = 1; p.Z2 = 1; p.KB = 1;
-            p.A = DRt + 2 * H; p.lda = 3 * H; p.M = NB; p.K = H;
-            p.B = ws + w.RUH; p.ldb = H; p.N = H;
-            STEP_GEMM(0, CfgMid, true, false, p, (EpiB1{DH1, DRt, DRES, H1t, Z2t, R2t, HC2t, H}), 1);
-            // B2: dh1 += da2 [NB,2H] * Rgw[:, Cin:]
-            p.A = DRt; p.K = 2 * H;
-            p.B = ws + w.RGH;
-            STEP_GEMM(1, CfgMid, true, false, p, (EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H, DG16}), 1);
+            if (!rb_fused) {
+                // B0
+                if (use_multi) {
+                    mb.add_head(HeadArgs{dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES, DRt, dmix + t});
+                } else {
+                    const float* dyt = dy + (long long)t * dy_tstride;
+                    if (!(H & 3) && !(U & 3) && aligned16(dyt) && aligned16(DHC) && aligned16(H1t) && aligned16(R2t) && aligned16(HC2t) &&
+                        aligned16(DH1) && aligned16(DRES) && aligned16(DRt))
+                        bwd_head4_kernel<<<(unsigned)((U / 4 + 255) / 256), 256, 0, st>>>(dyt, DHC, H1t, R2t, HC2t, mix + t, U / 4, H, DH1,
+                                                                                         DRES, DRt, dmix + t);
+                    else
+                        bwd_head_kernel<<<(unsigned)((U + 255) / 256), 256, 0, st>>>(dyt, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES,
+                                                                                    DRt, dmix + t);
+                    count_launch();
+                    TR();
+                    CK(cudaGetLastError());
+                }
+                // B1: dzh2 = da3 [NB,H] * Ruw[:, Cin:]  (B element (k=o, n=j) at o*H + j of the dense copy)
+                memset(&p, 0, sizeof(p));
+                p.splits = 1; p.Z2 = 1; p.KB = 1;
+                p.A = DRt + 2 * H; p.lda = 3 * H; p.M = NB; p.K = H;
+                p.B = ws + w.RUH; p.ldb = H; p.N = H;
+                STEP_GEMM(0, CfgMid, true, false, p, (EpiB1{DH1, DRt, DRES, H1t, Z2t, R2t, HC2t, H}), 1);
+                // B2: dh1 += da2 [NB,2H] * Rgw[:, Cin:]
+                p.A = DRt; p.K = 2 * H;
+                p.B = ws + w.RGH;
+                STEP_GEMM(1, CfgMid, true, false, p, (EpiB2{DH1, PHt, Rt_, HCt, DHD, DGt, H, DG16}), 1);
+            }
             // B3: DPT[k][n] = dau[n] [B,H] * Wu[n,k,Cin:,:]^T      z = (n, k)
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = K; p.KB = 1;
