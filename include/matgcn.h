@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MATGCN_ABI_VERSION 2
+#define MATGCN_ABI_VERSION 3
 
 /* flags of the contraction-heavy entry points */
 #define MATGCN_FLAG_EXACT 0 /* fp32 FFMA kernels: 1e-4 parity with the reference */
@@ -197,6 +197,59 @@ int matgcn_dense_gru_layer_fwd(int T, int N, int B, int Cin, int H, const float*
 int matgcn_dense_gru_layer_bwd(int T, int N, int B, int Cin, int H, const float* dy, long long dy_tstride, const float* x,
                                long long x_tstride, const float* Gw, const float* Uw, float* ws, float* bws, float* dx,
                                float* dh0, float* dGw, float* dGb, float* dUw, float* dUb, int flags, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Callers either side of the path.
+ *
+ * f1 - optimiser half of TrafficStateExecutor._train_epoch (libcity/executor/traffic_state_executor.py:413-422):
+ *      torch.nn.utils.clip_grad_norm_(parameters, max_norm) (executor:420-421) followed by
+ *      torch.optim.Adam(lr, eps, betas, weight_decay).step() (executor:146-147), fused over ONE flat fp32 bucket
+ *      (parameters, gradients and both Adam moments contiguous, n elements each, 16-byte aligned).
+ *   matgcn_grad_sumsq:    *sumsq = sum_i grad[i]^2   (device double; overwritten)
+ *   matgcn_adam_clip_step: g = grad * grad_scale * min(1, max_norm / (|grad_scale| * sqrt(*sumsq) + 1e-6));
+ *                          then torch.optim.Adam's update (no amsgrad) with bias corrections of `step` (>= 1).
+ *      grad_scale folds the 1/world of the data-parallel mean; max_norm <= 0 disables clipping (sumsq may be NULL);
+ *      write_grad != 0 stores the scaled/clipped gradient back (what clip_grad_norm_ leaves in .grad);
+ *      norm_out (device float, may be NULL) receives the total gradient norm clip_grad_norm_ returns.
+ * ----------------------------------------------------------------------------------------- */
+int matgcn_grad_sumsq(const float* grad, long long n, double* sumsq, void* stream);
+int matgcn_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, const double* sumsq,
+                          float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          long long step, int write_grad, float* norm_out, void* stream);
+
+/* f2 - batch assembly: replaces MTHDataset._get_sample_indices / _generate_input_data
+ *      (libcity/data/dataset/dataset_subclass/mth_dataset.py:31-60, 62-158) plus the per-batch collate and upload
+ *      (libcity/data/utils.py:68-72, libcity/data/batch.py:43-57) with a gather from a series resident in HBM.
+ *   series       [T_total, N, F]   the (already scaled) time series
+ *   seg_offsets  [n_seg] (device int)  time-slice distance of each input segment's start before the label start, in
+ *                the order the reference concatenates them: closeness oldest..newest, period oldest..newest, trend
+ *   label_starts [B] (device int64)  first predicted time slice of each sample
+ *   X            [B, n_seg*in_window, N, F] out;  y [B, out_window, N, F] out
+ *   bad_flag     device int, set to 1 if any sample is not a valid one under the reference's rules (its chunks are
+ *                then left unwritten); the caller zeroes it.
+ * ----------------------------------------------------------------------------------------- */
+int matgcn_assemble_windows(const float* series, long long T_total, int N, int F, const int* seg_offsets, int n_seg,
+                            int in_window, int out_window, const long long* label_starts, int B, float* X, float* y,
+                            int* bad_flag, void* stream);
+
+/* f3 - dropout + output head: replaces MA.py:416-417 (F.dropout(p=0.1, training) on the encoder output, then
+ *      end_conv = Conv2d(T -> T_out*C, kernel (1, H)), MA.py:340-344: the time steps are the channels), on the
+ *      node-major encoder output as it sits in the layer workspace:
+ *        out[r, o] = bias[o] + sum_t sum_h drop(y[t, r, h]) * w[o, t, h]        r = (node, batch) row, rows = N*B
+ *   y     [Tc, rows, H] with time stride y_tstride (floats); H must be 64
+ *   w     [O, Tc, H] (= end_conv.weight[:, :, 0, :]), bias [O], out [rows, O]
+ *   p_drop in [0,1): 0 = eval mode.  The mask is counter-based (Philox4x32-10 keyed by `seed`, 16 bits per element)
+ *   and never stored: the backward regenerates it from the same seed.  The realised drop probability is
+ *   round(p*65536)/65536 and kept values are scaled by matgcn_head_dropout_scale(p) = 1/(1 - that), so E[drop(x)] = x.
+ *   Backward overwrites dy [Tc, rows, H] (contiguous), dw [O, Tc, H], dbias [O].
+ *   matgcn_head_dropout_mask writes the multipliers (0 or scale) of elements 0..n-1 (tests / diagnostics).
+ * All arithmetic is fp32 FFMA (no TF32), so the 1e-4 parity bound of the head holds in every mode. */
+float matgcn_head_dropout_scale(float p_drop);
+int matgcn_head_fwd(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, const float* bias, int O,
+                    float p_drop, unsigned long long seed, float* out, void* stream);
+int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, int O, float p_drop,
+                    unsigned long long seed, const float* dout, float* dy, float* dw, float* dbias, void* stream);
+int matgcn_head_dropout_mask(long long n, float p_drop, unsigned long long seed, float* mult, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,9 +13,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmatgcn.so")
-SOURCES = ["matgcn.cu"]
+# translation unit -> the headers it depends on (None = every .cuh in csrc/); each is compiled to its own object so
+# that touching the small train_step.cu does not rebuild the 3-minute tensor-core unit
+SOURCES = {"matgcn.cu": None, "train_step.cu": []}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
+PUBLIC_HEADER = os.path.join(os.path.dirname(HERE), "include", "matgcn.h")
 
 
 def _nvcc() -> str:
@@ -25,19 +28,39 @@ def _nvcc() -> str:
     return "nvcc"
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def _obj(src: str) -> str:
+    return os.path.join(CSRC, "_obj", os.path.splitext(src)[0] + ".o")
+
+
+def _deps(src: str):
+    hdrs = SOURCES[src]
+    if hdrs is None:
+        hdrs = [f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    return [os.path.join(CSRC, src), PUBLIC_HEADER] + [os.path.join(CSRC, h) for h in hdrs]
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    built = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "matgcn.h"))
+    built = os.path.getmtime(target)
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
+
+
+def needs_build() -> bool:
+    return any(_stale(_obj(s), _deps(s)) for s in SOURCES) or _stale(LIB, [_obj(s) for s in SOURCES])
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(os.path.join(CSRC, "_obj"), exist_ok=True)
+    for src in SOURCES:
+        if force or _stale(_obj(src), _deps(src)):
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-o", _obj(src), os.path.join(CSRC, src)]
+            if verbose:
+                print("[matgcn build]", " ".join(cmd), flush=True)
+            subprocess.run(cmd, check=True)
+    cmd = [_nvcc(), "-shared", "-o", LIB] + [_obj(s) for s in SOURCES]
     if verbose:
         print("[matgcn build]", " ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

@@ -27,6 +27,8 @@ static int fail(const char* where, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, what);
     return -1;
 }
+// error sink of the library's other translation units (train_step.cu); not part of the public header
+extern "C" void matgcn_internal_set_error(const char* where, const char* what) { snprintf(g_err, sizeof(g_err), "%s: %s", where, what); }
 #define CK(call)                                                                       \
     do {                                                                               \
         cudaError_t e_ = (call);                                                       \

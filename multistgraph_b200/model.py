@@ -331,14 +331,22 @@ class MultiATGCN(nn.Module):
         # Dropout and the output head work on the node-major tensor as it sits in memory: the mask is drawn in that
         # element order (same distribution; the reference's [B,T,N,H] order would need a 4*B*T*N*H-byte relayout and the
         # slow strided dropout kernel), and the head contracts per time step instead of first copying into [B*N, T*H] order.
-        y_nm = F.dropout(y_nm, p=0.1, training=self.training)
-        # end_conv = Conv2d(T -> T_out*C, kernel (1, H)) (MA.py:340-344, 417): time steps are the channels, so it is a
-        # contraction over (t, h).  Written as matmuls so it stays true fp32 (cuDNN convolutions default to TF32, which
-        # breaks the 1e-4 parity bound).
         w = self.end_conv.weight[:, :, 0, :]                        # [T_out*C, T, H]
         t_steps, n_nodes, n_batch, hid = y_nm.shape
-        part = torch.bmm(y_nm.reshape(t_steps, n_nodes * n_batch, hid), w.permute(1, 2, 0))   # [T, N*B, T_out*C]
-        out = part.sum(0).reshape(n_nodes, n_batch, -1).permute(1, 2, 0) + self.end_conv.bias[None, :, None]
+        if hid == ops.HEAD_HIDDEN:
+            # one kernel: counter-based dropout mask (never stored) + the (t, h) contraction in true fp32, reading y once where it
+            # sits in the layer workspace; the backward writes dy straight in the layout the layer backward consumes.  The seed is
+            # drawn from torch's CPU generator, so torch.manual_seed reproduces a run.
+            drop = 0.1 if self.training else 0.0
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop > 0 else 0
+            out = ops.output_head(y_nm, w, self.end_conv.bias, drop, seed).reshape(n_nodes, n_batch, -1).permute(1, 2, 0)
+        else:
+            y_nm = F.dropout(y_nm, p=0.1, training=self.training)
+            # end_conv = Conv2d(T -> T_out*C, kernel (1, H)) (MA.py:340-344, 417): time steps are the channels, so it is a
+            # contraction over (t, h).  Written as matmuls so it stays true fp32 (cuDNN convolutions default to TF32, which
+            # breaks the 1e-4 parity bound).
+            part = torch.bmm(y_nm.reshape(t_steps, n_nodes * n_batch, hid), w.permute(1, 2, 0))   # [T, N*B, T_out*C]
+            out = part.sum(0).reshape(n_nodes, n_batch, -1).permute(1, 2, 0) + self.end_conv.bias[None, :, None]
         out = out.reshape(-1, self.output_window, self.output_dim, self.num_nodes).permute(0, 1, 3, 2)
         return out
 

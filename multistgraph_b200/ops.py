@@ -245,6 +245,57 @@ def matmul(A, B, flags=0):
     return _MatmulFn.apply(A, B, flags)
 
 
+class _OutputHeadFn(torch.autograd.Function):
+    """Dropout + end_conv (MA.py:416-417, 340-344) on the node-major encoder output: matgcn_head_fwd / matgcn_head_bwd.
+    The dropout mask is regenerated in the backward from the seed; nothing but (y, w) is saved."""
+
+    @staticmethod
+    def forward(ctx, y, w, bias, p_drop, seed):
+        if not y.is_cuda or y.dtype != torch.float32:
+            raise _cabi.MatgcnError("output_head: y must be a float32 CUDA tensor (no CPU path)")
+        Tc, N, B, H = y.shape
+        if y.stride(3) != 1 or y.stride(2) != H or y.stride(1) != B * H or (y.stride(0) & 3):
+            y = y.contiguous()
+        w, bias = _f32c(w, "w"), _f32c(bias, "bias")
+        O = w.shape[0]
+        if w.shape != (O, Tc, H) or bias.shape != (O,):
+            raise _cabi.MatgcnError("output_head: inconsistent shapes")
+        out = torch.empty(N * B, O, device=y.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_head_fwd(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), _ptr(bias), O, float(p_drop),
+                                                int(seed), _ptr(out), _stream()), "matgcn_head_fwd")
+        ctx.save_for_backward(y, w)
+        ctx.p_drop, ctx.seed = float(p_drop), int(seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, w = ctx.saved_tensors
+        Tc, N, B, H = y.shape
+        O = w.shape[0]
+        dout = _f32c(dout, "dout")
+        dy = torch.empty(Tc, N, B, H, device=y.device, dtype=torch.float32)
+        dw = torch.empty(O, Tc, H, device=y.device, dtype=torch.float32)
+        db = torch.empty(O, device=y.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_head_bwd(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), O, ctx.p_drop, ctx.seed, _ptr(dout),
+                                                _ptr(dy), _ptr(dw), _ptr(db), _stream()), "matgcn_head_bwd")
+        return dy, dw, db, None, None
+
+
+HEAD_HIDDEN = 64  # rnn_units the fused head kernels are written for
+
+
+def output_head(y, w, bias, p_drop=0.0, seed=0):
+    """out[n*B + b, o] = bias[o] + sum_t sum_h dropout(y[t, n, b, h]) * w[o, t, h]   (y node-major [Tc, N, B, H])."""
+    return _OutputHeadFn.apply(y, w, bias, p_drop, seed)
+
+
+def dropout_multipliers(n, p_drop, seed, device):
+    """The 0 / scale multipliers output_head applies to elements 0..n-1 of y in [t, n, b, h] order (tests, diagnostics)."""
+    m = torch.empty((n + 3) // 4 * 4, device=device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().matgcn_head_dropout_mask(m.numel(), float(p_drop), int(seed), _ptr(m), _stream()), "dropout_mask")
+    return m[:n]
+
+
 def adaptive_adjacency(L, Rt, ldm):
     """[N, ldm] row-softmax adaptive adjacency; columns >= N are zero."""
     return _AdaptiveAdjFn.apply(L, Rt, ldm)

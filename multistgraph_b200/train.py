@@ -1,0 +1,187 @@
+"""The callers either side of the Multi-ATGCN path, on the device.
+
+f1  ``FusedClipAdam`` + ``fused_train_step``: the loop body of ``TrafficStateExecutor._train_epoch``
+    (libcity/executor/traffic_state_executor.py:413-422) with the optimiser half -
+    ``clip_grad_norm_(model.parameters(), max_grad_norm)`` (executor:420-421) and ``torch.optim.Adam.step()``
+    (executor:146-147) - as two launches over ONE flat bucket (``matgcn_grad_sumsq`` + ``matgcn_adam_clip_step``)
+    instead of ~60 per-parameter kernels.  Parameters, gradients and both moments are views into four flat fp32
+    buffers (each parameter starts on a 256-byte boundary, which also keeps every weight tensor TMA-aligned).
+f2  ``DeviceWindowBank``: ``MTHDataset._generate_input_data`` (mth_dataset.py:112-158) + the per-batch collate
+    and upload (libcity/data/utils.py:68-72, batch.py:43-57) replaced by a gather from a series resident in HBM
+    (``matgcn_assemble_windows``); the host sends only the B label-start indices of a batch.
+
+No CPU fallback: both need the CUDA library and CUDA tensors and raise ``MatgcnError`` otherwise.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from ._cabi import MatgcnError
+
+_ALIGN = 64  # floats: every parameter's slot starts on a 256-byte boundary
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class FusedClipAdam:
+    """Adam (no amsgrad) with an optional global-norm clip, over flat buffers.  Same arithmetic as
+    ``clip_grad_norm_`` followed by ``torch.optim.Adam(params, lr, betas, eps, weight_decay).step()``.
+
+    After construction ``p.data`` and ``p.grad`` of every trainable parameter are views into ``self.param`` /
+    ``self.grad`` (so autograd accumulates straight into the bucket and a data-parallel all-reduce is one call on
+    ``self.grad``).  ``zero_grad`` is one memset."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_grad_norm: Optional[float] = None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise MatgcnError("FusedClipAdam needs CUDA parameters: there is no CPU fallback")
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise MatgcnError("FusedClipAdam needs float32 parameters on one device")
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.max_grad_norm = max_grad_norm
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = off
+        self.param = torch.zeros(off, device=dev)
+        self.grad = torch.zeros(off, device=dev)
+        self.exp_avg = torch.zeros(off, device=dev)
+        self.exp_avg_sq = torch.zeros(off, device=dev)
+        self._sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.grad_norm = torch.zeros(1, device=dev)      # total norm of the last step (what clip_grad_norm_ returns)
+        self.step_count = 0
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                self.param[o:o + p.numel()].copy_(p.data.reshape(-1))
+                p.data = self.param[o:o + p.numel()].view_as(p)
+        self._pin_grads()
+        self._lib = _cabi.lib()
+
+    # -- gradient bucket -------------------------------------------------------------------------
+    def _pin_grads(self):
+        es = self.grad.element_size()
+        base = self.grad.data_ptr()
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != base + o * es:
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Replaces optimizer.zero_grad() (executor:414): one memset; the views are re-pinned in case a caller
+        dropped them."""
+        self.grad.zero_()
+        self._pin_grads()
+
+    def all_reduce(self, group=None) -> float:
+        """Sums the bucket over the data-parallel ranks and returns the factor (1/world) that ``step`` folds into
+        the update (each rank's loss is a mean over its shard: SURVEY.md 8e)."""
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(group)
+            if world > 1:
+                dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+                return 1.0 / world
+        return 1.0
+
+    # -- update ----------------------------------------------------------------------------------
+    def step(self, grad_scale: float = 1.0):
+        self.step_count += 1
+        st = _stream()
+        clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        _cabi.check(self._lib.matgcn_grad_sumsq(self.grad.data_ptr(), self.total, self._sumsq.data_ptr(), st), "grad_sumsq")
+        _cabi.check(self._lib.matgcn_adam_clip_step(
+            self.param.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.total,
+            self._sumsq.data_ptr(), float(self.max_grad_norm) if clip else 0.0, float(grad_scale), self.lr, self.betas[0],
+            self.betas[1], self.eps, self.weight_decay, self.step_count, 1, self.grad_norm.data_ptr(), st), "adam_clip_step")
+
+    # -- checkpointing (executor:95, 106, 118, 136 save/load optimizer.state_dict()) ---------------
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
+
+
+def fused_train_step(model, batch, opt: FusedClipAdam):
+    """One iteration of ``TrafficStateExecutor._train_epoch`` (executor:413-422): zero_grad -> calculate_loss ->
+    backward -> [data-parallel all-reduce] -> clip_grad_norm_ + Adam (fused).  Returns the device loss tensor."""
+    opt.zero_grad()
+    loss = model.calculate_loss(batch)
+    loss.backward()
+    scale = opt.all_reduce()
+    opt.step(grad_scale=scale)
+    return loss.detach()
+
+
+class DeviceWindowBank:
+    """The series ``[T_total, N, F]`` stays in HBM; ``assemble(label_starts)`` gathers a batch
+    ``X [B, (len_c+len_p+len_t)*input_window, N, F]``, ``y [B, output_window, N, F]`` exactly as
+    ``MTHDataset._generate_input_data`` (mth_dataset.py:112-158) lays samples out: closeness, period, trend
+    segments, each oldest to newest (mth_dataset.py:59, 140-153), target = series[s : s + output_window] (:105).
+
+    The reference scales windows after cutting them (an elementwise affine map with global statistics), so handing
+    this class the already scaled series is equivalent."""
+
+    def __init__(self, series: torch.Tensor, input_window: int, output_window: int, len_closeness: int, len_period: int,
+                 len_trend: int, interval_period: int = 1, interval_trend: int = 7, points_per_hour: int = 1,
+                 hour_each_day: int = 24):
+        if series.device.type != "cuda":
+            raise MatgcnError("DeviceWindowBank needs a CUDA series: there is no CPU fallback")
+        if series.dim() != 3 or series.dtype != torch.float32:
+            raise ValueError("series must be float32 [T_total, N, F]")
+        assert len_closeness + len_period + len_trend > 0        # mth_dataset.py:16
+        self.series = series.contiguous()
+        self.T_total, self.N, self.F = self.series.shape
+        self.input_window, self.output_window = int(input_window), int(output_window)
+        offs = []
+        # the reference's own expressions (mth_dataset.py:50, 82-83, 90-91, 98-99), segments oldest first
+        for i in range(len_closeness, 0, -1):
+            offs.append(int(points_per_hour * (input_window / points_per_hour) * i))
+        for i in range(len_period, 0, -1):
+            offs.append(int(points_per_hour * (interval_period * hour_each_day) * i))
+        for i in range(len_trend, 0, -1):
+            offs.append(int(points_per_hour * (interval_trend * hour_each_day) * i))
+        self.seg_offsets_host = offs
+        self.n_seg = len(offs)
+        self.seg_offsets = torch.tensor(offs, device=series.device, dtype=torch.int32)
+        self._bad = torch.zeros(1, device=series.device, dtype=torch.int32)
+        self._lib = _cabi.lib()
+
+    def valid_label_starts(self) -> torch.Tensor:
+        """Label starts the reference would emit a sample for (mth_dataset.py:45-46, 52-58, 78-79), in order."""
+        lo = max(self.seg_offsets_host)
+        hi = self.T_total - max(self.input_window, self.output_window)
+        return torch.arange(lo, hi + 1, dtype=torch.int64) if hi >= lo else torch.empty(0, dtype=torch.int64)
+
+    def assemble(self, label_starts: torch.Tensor, out_x: Optional[torch.Tensor] = None, out_y: Optional[torch.Tensor] = None,
+                 check: bool = False):
+        """label_starts: int64 [B] (host or device; a host tensor is the only per-batch upload).  Returns {'X','y'}."""
+        dev = self.series.device
+        ls = label_starts.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        B = ls.numel()
+        X = out_x if out_x is not None else torch.empty(B, self.n_seg * self.input_window, self.N, self.F, device=dev)
+        y = out_y if out_y is not None else torch.empty(B, self.output_window, self.N, self.F, device=dev)
+        if check:
+            self._bad.zero_()
+        _cabi.check(self._lib.matgcn_assemble_windows(self.series.data_ptr(), self.T_total, self.N, self.F,
+                                                      self.seg_offsets.data_ptr(), self.n_seg, self.input_window,
+                                                      self.output_window, ls.data_ptr(), B, X.data_ptr(), y.data_ptr(),
+                                                      self._bad.data_ptr(), _stream()), "assemble_windows")
+        if check and int(self._bad.item()):
+            raise MatgcnError("assemble_windows: a label start is not a valid sample under mth_dataset.py:45-58, 78-79")
+        return {"X": X, "y": y}

@@ -237,11 +237,21 @@ def dense_gru_layer_mirror(x, h0, Gw, Gb, Uw, Ub, flags=0):
     return torch.stack(ys, 0)
 
 
+def output_head_mirror(y, w, bias, p_drop=0.0, seed=0):
+    """torch restatement of ops.output_head (MA.py:416-417); the counter-based mask itself is checked on the GPU
+    (tests/test_gpu_train.py), here dropout is torch's."""
+    y = torch.nn.functional.dropout(y, p=p_drop, training=p_drop > 0)
+    tc, n, b, h = y.shape
+    return torch.einsum("trh,oth->ro", y.reshape(tc, n * b, h), w) + bias[None, :]
+
+
 def install(ops_module):
     """Point the three autograd entry points of ``multistgraph_b200.ops`` at the mirror
     (tests only; returns a restore callable)."""
     saved = (ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights)
     saved_dense, saved_mm = ops_module.dense_gru_layer, ops_module.matmul
+    saved_head = ops_module.output_head
+    ops_module.output_head = output_head_mirror
     ops_module.dense_gru_layer = dense_gru_layer_mirror
     ops_module.matmul = lambda A, B, flags=0: A @ B
     ops_module.encoder_layer = lambda *a: MirrorLayerFn.apply(*a[:13])
@@ -251,4 +261,5 @@ def install(ops_module):
     def restore():
         ops_module.encoder_layer, ops_module.adaptive_adjacency, ops_module.node_weights = saved
         ops_module.dense_gru_layer, ops_module.matmul = saved_dense, saved_mm
+        ops_module.output_head = saved_head
     return restore

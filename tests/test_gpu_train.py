@@ -1,0 +1,256 @@
+"""GPU parity of SURVEY.md 8f rows f1 (fused clip + Adam over the flat bucket) and f2 (window gather from a series
+resident in HBM), through the C ABI, against the oracle (oracle/window_oracle.py) and against torch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import window_oracle as wo
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "windows", "windows_small.npz")
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------
+# f2
+# ------------------------------------------------------------------------------------------------
+WCASES = {
+    "shipped_like": (24, 24, 2, 1, 1, 7, 28, 1, 24),
+    "short_out": (24, 3, 2, 1, 0, 7, 7, 1, 24),
+    "closeness_only": (12, 6, 3, 0, 0, 1, 7, 1, 24),
+    "half_hour": (24, 12, 1, 2, 1, 1, 3, 2, 24),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WCASES))
+def test_window_gather_bit_exact_vs_oracle_and_golden(name):
+    from multistgraph_b200.train import DeviceWindowBank
+
+    g = np.load(GOLD)
+    df = g[name + "/series"]            # row sizes N*F = 10, 9, 7, 4 -> the 8-byte, scalar, scalar and 16-byte variants
+    iw, ow, lc, lp, lt, ip, it, pph, hed = WCASES[name]
+    x, y, starts = wo.generate_input_data(df, iw, ow, lc, lp, lt, ip, it, pph, hed)
+    bank = DeviceWindowBank(torch.from_numpy(df).to(_dev()), iw, ow, lc, lp, lt, ip, it, pph, hed)
+    assert torch.equal(bank.valid_label_starts(), torch.from_numpy(starts))
+    out = bank.assemble(torch.from_numpy(starts), check=True)
+    assert np.array_equal(out["X"].cpu().numpy(), x)
+    assert np.array_equal(out["y"].cpu().numpy(), y)
+    pick = g[name + "/pick"]
+    assert np.array_equal(out["X"].cpu().numpy()[pick], g[name + "/x_pick"])   # the real reference's samples
+    # shuffled, repeated and empty batches
+    perm = torch.from_numpy(np.random.default_rng(1).permutation(np.concatenate([starts, starts[:3]])))
+    out2 = bank.assemble(perm, check=True)
+    idx = np.searchsorted(starts, perm.numpy())
+    assert np.array_equal(out2["X"].cpu().numpy(), x[idx]) and np.array_equal(out2["y"].cpu().numpy(), y[idx])
+    out0 = bank.assemble(torch.empty(0, dtype=torch.int64))
+    assert out0["X"].shape[0] == 0
+
+
+def test_window_gather_flags_invalid_label_starts():
+    from multistgraph_b200._cabi import MatgcnError
+    from multistgraph_b200.train import DeviceWindowBank
+
+    bank = DeviceWindowBank(torch.randn(100, 3, 2, device=_dev()), 24, 24, 1, 0, 0)
+    bank.assemble(torch.tensor([24, 76]), check=True)
+    for bad in (23, 77, -1):
+        with pytest.raises(MatgcnError):
+            bank.assemble(torch.tensor([30, bad]), check=True)
+
+
+def test_window_gather_full_size_checksum():
+    """Baltimore shape (N=403, F=2, heads 2/1/1 at 7 d / 28 d, batch 64): every output element is a copy, so per-sample
+    sums must equal sums of the corresponding series slices computed independently with torch indexing."""
+    from multistgraph_b200.train import DeviceWindowBank
+
+    torch.manual_seed(0)
+    series = torch.randn(24 * 40, 403, 2, device=_dev())
+    bank = DeviceWindowBank(series, 24, 24, 2, 1, 1, 7, 28)
+    starts = bank.valid_label_starts()
+    sel = starts[torch.randperm(len(starts))[:64]]
+    out = bank.assemble(sel, check=True)
+    assert out["X"].shape == (64, 96, 403, 2) and out["y"].shape == (64, 24, 403, 2)
+    for b in (0, 17, 63):
+        s = int(sel[b])
+        want = torch.cat([series[s - o: s - o + 24] for o in bank.seg_offsets_host], 0)
+        assert torch.equal(out["X"][b], want)
+        assert torch.equal(out["y"][b], series[s: s + 24])
+
+
+# ------------------------------------------------------------------------------------------------
+# f1
+# ------------------------------------------------------------------------------------------------
+class _Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Parameter(torch.randn(37, 5))
+        self.b = torch.nn.Parameter(torch.randn(129))
+        self.c = torch.nn.Parameter(torch.randn(3, 4, 7))
+        self.frozen = torch.nn.Parameter(torch.randn(4), requires_grad=False)
+
+
+@pytest.mark.parametrize("wd,max_norm", [(0.0, 5.0), (0.0, None), (1e-3, 0.5)])
+def test_fused_clip_adam_matches_torch_and_oracle(wd, max_norm):
+    """Bound: fp32 arithmetic in a different association order than torch's foreach kernels -> 2e-6 relative."""
+    from multistgraph_b200.train import FusedClipAdam
+
+    torch.manual_seed(0)
+    m1 = _Toy().to(_dev())
+    m2 = _Toy().to(_dev())
+    m2.load_state_dict(m1.state_dict())
+    ref = torch.optim.Adam([p for p in m1.parameters() if p.requires_grad], lr=0.01, eps=1e-8, weight_decay=wd)
+    opt = FusedClipAdam(m2.parameters(), lr=0.01, eps=1e-8, weight_decay=wd, max_grad_norm=max_norm)
+    names = [n for n, p in m2.named_parameters() if p.requires_grad]
+    p64 = {n: dict(m1.named_parameters())[n].detach().double().cpu().numpy().ravel() for n in names}
+    flat = np.concatenate([p64[n] for n in names])
+    mo, vo = np.zeros_like(flat), np.zeros_like(flat)
+    for step in range(1, 6):
+        grads = {n: torch.randn_like(dict(m1.named_parameters())[n]) * (4.0 if step % 2 else 0.05) for n in names}
+        opt.zero_grad()
+        for n in names:
+            dict(m1.named_parameters())[n].grad = grads[n].clone()
+            dict(m2.named_parameters())[n].grad.add_(grads[n])       # accumulates into the flat bucket like autograd does
+        if max_norm is not None:
+            total = torch.nn.utils.clip_grad_norm_([p for p in m1.parameters() if p.requires_grad], max_norm)
+        ref.step()
+        opt.step()
+        gflat = np.concatenate([grads[n].double().cpu().numpy().ravel() for n in names])
+        flat, g_after, mo, vo, total_o = wo.adam_clip_reference(flat, gflat, mo, vo, step, 0.01, 0.9, 0.999, 1e-8, wd, max_norm)
+        got = np.concatenate([dict(m2.named_parameters())[n].detach().cpu().numpy().ravel() for n in names])
+        want = np.concatenate([dict(m1.named_parameters())[n].detach().cpu().numpy().ravel() for n in names])
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() / scale < 2e-6
+        assert np.abs(got - flat).max() / scale < 2e-6
+        if max_norm is not None:
+            assert abs(float(opt.grad_norm) - float(total)) / float(total) < 1e-6
+            assert abs(float(opt.grad_norm) - total_o) / total_o < 1e-6
+            gm2 = np.concatenate([dict(m2.named_parameters())[n].grad.cpu().numpy().ravel() for n in names])
+            assert np.abs(gm2 - g_after).max() / np.abs(g_after).max() < 1e-6       # .grad holds the clipped gradient
+    assert torch.equal(m2.frozen, m1.frozen)
+    # padding slots between parameters never move
+    assert float(opt.param.abs().sum()) > 0 and opt.total % 64 == 0
+
+
+def test_fused_train_step_matches_executor_loop_on_the_model():
+    """The drop-in model trained 3 steps by fused_train_step vs the reference executor's loop body
+    (zero_grad / calculate_loss / backward / clip_grad_norm_(5) / Adam.step), same seeds: forecasts stay within 1e-4."""
+    from multistgraph_b200.model import MultiATGCN
+    from multistgraph_b200.synthetic import make_batch, make_config, make_data_feature
+    from multistgraph_b200.train import FusedClipAdam, fused_train_step
+
+    dev = _dev()
+    n, b = 23, 4
+    cfg = make_config(adjtype="multi", adpadj="bidirection", embed_dim=6, output_window=6, batch_size=b, device=dev)
+    df = make_data_feature(n, seed=3)
+    torch.manual_seed(0)
+    ma = MultiATGCN(dict(cfg), df).to(dev).eval()
+    torch.manual_seed(0)
+    mb = MultiATGCN(dict(cfg), df).to(dev).eval()
+    mb.load_state_dict(ma.state_dict())
+    oa = torch.optim.Adam(ma.parameters(), lr=0.003, eps=1e-8)
+    ob = FusedClipAdam(mb.parameters(), lr=0.003, eps=1e-8, max_grad_norm=5.0)
+    for i in range(3):
+        batch = {k: v.to(dev) for k, v in make_batch(n, b, 6, seed=10 + i).items()}
+        oa.zero_grad()
+        la = ma.calculate_loss({k: v.clone() for k, v in batch.items()})
+        la.backward()
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), 5.0)
+        oa.step()
+        lb = fused_train_step(mb, {k: v.clone() for k, v in batch.items()}, ob)
+        assert abs(float(la) - float(lb)) / abs(float(la)) < 1e-4
+    probe = {k: v.to(dev) for k, v in make_batch(n, b, 6, seed=99).items()}
+    with torch.no_grad():
+        ya, yb = ma.predict(probe), mb.predict(probe)
+    assert (ya - yb).abs().max() / ya.abs().max() < 1e-4
+    sa, sb = ma.state_dict(), mb.state_dict()
+    assert list(sa) == list(sb)
+
+
+# ------------------------------------------------------------------------------------------------
+# f3: dropout + output head (MA.py:416-417)
+# ------------------------------------------------------------------------------------------------
+def _head_case(tc, n, b, o, seed=0):
+    torch.manual_seed(seed)
+    dev = _dev()
+    h = 64
+    big = torch.randn(tc, 3, n, b, h, device=dev)            # y lives strided inside a larger buffer, like the layer workspace
+    y = big[:, 1]
+    w = torch.randn(o, tc, h, device=dev) * 0.1
+    bias = torch.randn(o, device=dev)
+    return y, w, bias
+
+
+@pytest.mark.parametrize("tc,n,b,o", [(24, 13, 5, 24), (24, 7, 64, 12), (1, 9, 3, 3), (5, 6, 11, 40), (24, 2, 32, 2)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_output_head_matches_torch_fp64(tc, n, b, o, p):
+    """fp32 FFMA head vs an fp64 torch restatement with the SAME mask (read back through matgcn_head_dropout_mask):
+    bound 2e-6 relative to the largest element (fp32 summation order only)."""
+    from multistgraph_b200 import _cabi, ops
+
+    y, w, bias = _head_case(tc, n, b, o)
+    seed = 1234567
+    yq, wq, bq = y.clone().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    out = ops.output_head(yq, wq, bq, p, seed)
+    assert out.shape == (n * b, o)
+    g = torch.randn_like(out)
+    out.backward(g)
+    mult = ops.dropout_multipliers(y.numel(), p, seed, y.device).reshape(y.shape).double()
+    if p == 0.0:
+        assert torch.all(mult == 1.0)
+    yd, wd, bd = y.double().requires_grad_(True), w.double().requires_grad_(True), bias.double().requires_grad_(True)
+    ref = torch.einsum("trh,oth->ro", (yd * mult).reshape(tc, n * b, 64), wd) + bd[None, :]
+    ref.backward(g.double())
+    rel = lambda a, r: float((a.double() - r).abs().max() / r.abs().max().clamp_min(1e-30))  # noqa: E731
+    assert rel(out, ref) < 2e-6
+    assert rel(yq.grad, yd.grad) < 2e-6
+    assert rel(wq.grad, wd.grad) < 2e-5        # atomically accumulated over row chunks
+    assert rel(bq.grad, bd.grad) < 2e-5
+    assert abs(_cabi.lib().matgcn_head_dropout_scale(0.1) - 65536.0 / (65536 - 6554)) < 1e-6
+
+
+def test_dropout_mask_statistics_and_determinism():
+    from multistgraph_b200 import _cabi, ops
+
+    n = 1 << 22
+    m1 = ops.dropout_multipliers(n, 0.1, 42, _dev())
+    m2 = ops.dropout_multipliers(n, 0.1, 42, _dev())
+    m3 = ops.dropout_multipliers(n, 0.1, 43, _dev())
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    scale = _cabi.lib().matgcn_head_dropout_scale(0.1)
+    vals = torch.unique(m1)
+    assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - scale) < 1e-6
+    frac = float((m1 == 0).float().mean())
+    sigma = (0.1 * 0.9 / n) ** 0.5
+    assert abs(frac - 6554 / 65536) < 5 * sigma
+    assert abs(float(m1.mean()) - 1.0) < 5 * sigma * scale          # E[drop(x)] = x
+    # no visible structure across the 8-element groups or between neighbours
+    keep = (m1 != 0).float().reshape(-1, 8)
+    assert float((keep.mean(0) - 0.9).abs().max()) < 6 * (0.09 / (n / 8)) ** 0.5
+    c = float(((keep[:, :-1] - 0.9) * (keep[:, 1:] - 0.9)).mean())
+    assert abs(c) < 6 * 0.09 / (n * 7 / 8) ** 0.5
+
+
+def test_model_train_mode_is_reproducible_under_manual_seed():
+    from multistgraph_b200.model import MultiATGCN
+    from multistgraph_b200.synthetic import make_batch, make_config, make_data_feature
+
+    dev = _dev()
+    n, b = 17, 4
+    cfg = make_config(adjtype="multi", adpadj="bidirection", embed_dim=6, output_window=6, batch_size=b, device=dev)
+    df = make_data_feature(n, seed=3)
+    torch.manual_seed(0)
+    model = MultiATGCN(dict(cfg), df).to(dev).train()
+    batch = {k: v.to(dev) for k, v in make_batch(n, b, 6, seed=1).items()}
+    losses = []
+    for s in (5, 5, 6):
+        torch.manual_seed(s)
+        losses.append(float(model.calculate_loss({k: v.clone() for k, v in batch.items()})))
+    assert losses[0] == losses[1] and losses[0] != losses[2]
+    model.eval()
+    le = float(model.calculate_loss({k: v.clone() for k, v in batch.items()}))
+    assert abs(le - losses[0]) / abs(le) < 0.2      # dropout perturbs, it does not change the scale
