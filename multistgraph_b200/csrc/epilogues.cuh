@@ -166,30 +166,32 @@ struct EpiPlain {
     __nv_bfloat16* C16;  // may be null
     float* D2;           // may be null: see EpiStore
     int d2_lo, d2_hi;
+    int c_z2_hi;         // the fp32 copy C is written only for blocks z2 < c_z2_hi (bf16 mode: slots that are consumed as
+                         // bf16 twins only skip their fp32 store; 0 = never, INT_MAX = always)
     bool vec_ok() const { return aligned16(C) && (!C16 || aligned16(C16)) && (!D2 || aligned16(D2)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3); }
     __device__ __forceinline__ EpiIn load(int, int, int, int) const { return EpiIn{}; }
     __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn&) const {
         const long long o = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
-        C[o] = acc;
+        if (z2 < c_z2_hi) C[o] = acc;
         if (C16) C16[o] = __float2bfloat16_rn(acc);
         if (D2 && z2 >= d2_lo && z2 < d2_hi) D2[o - (long long)d2_lo * s2] = acc;
     }
     __device__ __forceinline__ EpiIn4 load4(int, int, int, int) const { return EpiIn4{}; }
     __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4&) const {
         const long long o = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
-        st4(C + o, acc);
+        if (z2 < c_z2_hi) st4(C + o, acc);
         if (C16) st4_bf16(C16 + o, acc);
         if (D2 && z2 >= d2_lo && z2 < d2_hi) st4(D2 + o - (long long)d2_lo * s2, acc);
     }
-    struct Cur { long long off; int dup; };
+    struct Cur { long long off; int dup; int main; };
     __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
-        return Cur{z1 * s1 + z2 * s2 + (long long)row * ldc + col, (D2 && z2 >= d2_lo && z2 < d2_hi) ? 1 : 0};
+        return Cur{z1 * s1 + z2 * s2 + (long long)row * ldc + col, (D2 && z2 >= d2_lo && z2 < d2_hi) ? 1 : 0, z2 < c_z2_hi ? 1 : 0};
     }
     __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ldc; }
     __device__ __forceinline__ EpiIn4 load4(const Cur&) const { return EpiIn4{}; }
     __device__ __forceinline__ void prefetch4(const Cur&) const {}
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4&) const {
-        st4(C + c.off, acc);
+        if (c.main) st4(C + c.off, acc);
         if (C16) st4_bf16(C16 + c.off, acc);
         if (c.dup) st4(D2 + c.off - (long long)d2_lo * s2, acc);
     }
@@ -198,7 +200,7 @@ struct EpiPlain {
 inline EpiPlain epi_plain(float* C, long long s1, long long s2, int ldc) {
     EpiPlain e;
     memset(&e, 0, sizeof(e));
-    e.C = C; e.s1 = s1; e.s2 = s2; e.ldc = ldc;
+    e.C = C; e.s1 = s1; e.s2 = s2; e.ldc = ldc; e.c_z2_hi = 0x7fffffff;
     return e;
 }
 

@@ -46,6 +46,7 @@ struct GemmP {
     const __nv_bfloat16* A16;
     const __nv_bfloat16* B16;
     int keepB;    // tensor-core engine: load B with the L2 evict-last policy (an operand re-read by every step of a recurrence)
+    int need16;   // the fp32 operands are NOT valid (their producer skipped the fp32 store): only the bf16 engine may run this
     int M, N, K;  // K: inner reduction length of one k-batch
     int KB;       // number of k-batches
     int lda, ldb;

@@ -51,6 +51,7 @@ static cudaError_t gemm_any(bool tc, const GemmP& p, const Epi& epi, int Z, cuda
         if (e == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
         if (e != cudaErrorNotSupported) return e;
     }
+    if (p.need16) return cudaErrorNotSupported;  // no fallback may read the fp32 operands: fail loudly
     if (tc && p.K >= 8) {
         cudaError_t e = (p.N <= 64) ? launch_gemm_tc<64, A_KC, B_KC, Epi>(p, epi, Z, st)
                                     : launch_gemm_tc<128, A_KC, B_KC, Epi>(p, epi, Z, st);
@@ -1050,12 +1051,18 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         CK(to_bf16(Wg, 0, WG16, 0, (long long)N * K * I * 2 * H, 1, st));
         CK(to_bf16(Wu, 0, WU16, 0, (long long)N * K * I * H, 1, st));
     }
+    // bf16 mode: the propagated slots (k >= 1) of PX / PH / PZ exist only as bf16 twins - their fp32 stores are skipped, and the
+    // contractions that consume them are marked need16 (no fallback engine may touch the unwritten fp32 slots).
+    // Needs shapes for which the bf16 tensor-core launches are always eligible (16-byte pitches) and the per-phase launch path.
+    const bool skip32 = bf && !(tc && multi_enabled()) && !(H & 7) && !(ldm & 7) && B >= 8;  // (B = reduction length of the weight gradients)
+    const bool skip32x = skip32 && !xside_small_ok(Cin, H, K) && !(Cin & 7);
     // PX[t, 1..K) = M * x_t  (all t at once)
     {
         GemmP pp = prop_params(M, ldm, N, Kp, PX, B * Cin);
         pp.sB1 = K * UX;
         EpiPlain e = epi_plain(PX + UX, K * UX, 0, B * Cin);
         if (bf) { pp.A16 = M16; pp.B16 = PX16; e.C16 = PX16 + UX; }
+        if (skip32x) e.c_z2_hi = 0;   // every consumer of PX[t, k >= 1] reads the bf16 twin
         CK((gemm_any<CfgBig, true, false>(tc, pp, e, T, st)));
     }
     TR();
@@ -1079,6 +1086,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     {
         p.B = Wg; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = 0; p.sBk = (long long)I * 2 * H;
         if (bf) { p.A16 = PX16; p.B16 = WG16; }
+        p.need16 = skip32x ? 1 : 0;
         EpiStore e = epi_store(GX, (long long)B * 3 * H, 3 * U, 3 * H);
         e.bias = bg; e.bias_s1 = 2 * H;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, N * T, st)));
@@ -1138,6 +1146,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             {
                 EpiPlain e = epi_plain(PHt + U, 0, 0, B * H);
                 if (bf) { p.A16 = M16; p.B16 = PH16t; e.C16 = PH16t + U; }
+                if (skip32) e.c_z2_hi = 0;
                 STEP_GEMM(0, CfgBig, true, false, p, e, 1);
             }
             // (b) gate: per node [B, K*H] x [K*H, 2H]
@@ -1146,12 +1155,14 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             p.A = PHt; p.lda = H; p.sA1 = (long long)B * H; p.sAk = U; p.M = B; p.K = H;
             p.B = Wg + (long long)Cin * 2 * H; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sBk = (long long)I * 2 * H;
             if (bf) { p.A16 = PH16t; p.B16 = WG16 + (long long)Cin * 2 * H; p.keepB = 1; }
+            p.need16 = skip32 ? 1 : 0;
             STEP_GEMM(1, CfgMid, true, false, p, (EpiGate{GXt, PHt, Zt, Rt_, PZt, B, H, tc ? 1 : 0, bf ? PZ16t : nullptr}), N);
             // (c) PZ[t,1..] = M * (z*h)
             {
                 GemmP pp = prop_params(M, ldm, N, Kp, PZt, B * H);
                 EpiPlain e = epi_plain(PZt + U, 0, 0, B * H);
                 if (bf) { pp.A16 = M16; pp.B16 = PZ16t; e.C16 = PZ16t + U; }
+                if (skip32) e.c_z2_hi = 0;
                 STEP_GEMM(2, CfgBig, true, false, pp, e, 1);
             }
             // (d) candidate
@@ -1164,7 +1175,8 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
                               bf ? PH16t + (long long)K * U : nullptr, RgH, RuH};
                 cudaError_t fe = cudaErrorNotSupported;
                 if (bf) fe = launch_gemm_tc<64, true, false, EpiCandRes, true>(p, ef, N, st);
-                if (fe == cudaErrorNotSupported) fe = launch_gemm_tc<64, true, false, EpiCandRes>(p, ef, N, st);
+                if (fe == cudaErrorNotSupported && !p.need16) fe = launch_gemm_tc<64, true, false, EpiCandRes>(p, ef, N, st);
+                if (fe == cudaErrorNotSupported && p.need16) return fail(__func__, "bf16 engine unavailable for a contraction whose fp32 operand was skipped");
                 if (fe == cudaSuccess) {
                     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
                     TR();
@@ -1241,6 +1253,8 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     TR();
     GemmP p;
     bool use_multi = tc && multi_enabled();
+    // same rule as the forward pass: in bf16 mode the propagated slots k >= 1 (PH / PZ / PX there, DPT here) exist only as bf16 twins
+    const bool skip32 = bf && !use_multi && !(H & 7) && !(ldm & 7) && B >= 8;
     for (int attempt = 0; attempt < 2; ++attempt) {
         MultiBuilder mb;
         for (int t = T - 1; t >= 0; --t) {
@@ -1298,6 +1312,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             {
                 EpiPlain e = epi_plain(DPT, (long long)B * H, U, H);
                 if (bf) e.C16 = DPT16;
+                if (skip32) e.c_z2_hi = 1;   // DPT[k >= 1] is consumed as its bf16 twin only (B4); DPT[0] stays fp32 (EpiB4 reads it)
                 // the adaptive slices are also kept per step (operands of dM): second destination instead of a copy
                 if (n_adp && !use_multi) { e.D2 = DPZA + (long long)t * n_adp * U; e.d2_lo = 1; e.d2_hi = 1 + n_adp; }
                 STEP_GEMM(2, CfgMid, true, true, p, e, N * K);
@@ -1308,6 +1323,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
             if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
+            p.need16 = skip32 ? 1 : 0;
             STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H, DG16}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPZA + (long long)t * n_adp * U, (long long)n_adp * U);
             // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
@@ -1319,6 +1335,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             {
                 EpiPlain e = epi_plain(DPT, (long long)B * H, U, H);
                 if (bf) e.C16 = DPT16;
+                if (skip32) e.c_z2_hi = 1;
                 if (n_adp && !use_multi) { e.D2 = DPHA + (long long)t * n_adp * U; e.d2_lo = 1; e.d2_hi = 1 + n_adp; }
                 STEP_GEMM(4, CfgMid, true, true, p, e, N * K);
             }
@@ -1328,6 +1345,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
             if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
+            p.need16 = skip32 ? 1 : 0;
             STEP_GEMM(5, CfgBig, false, false, p, (EpiB6{DPT, DHD, DHC, B * H}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPHA + (long long)t * n_adp * U, (long long)n_adp * U);
         }
@@ -1355,13 +1373,14 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     const __nv_bfloat16* PZ16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PZ16);
     const __nv_bfloat16* PX16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PX16);
     if (bf) { p.A16 = PH16; p.B16 = DG16T; }   // these contractions stream the saved state: half the bytes with the twins
+    p.need16 = skip32 ? 1 : 0;                 // (and in that case the forward never wrote the fp32 PH / PZ slots k >= 1)
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
     TR();
     p.A = PZ; p.B = DG + 2 * H; p.N = H;
     if (bf) { p.A16 = PZ16; p.B16 = DG16T + 2 * H; }
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu + (long long)Cin * H, (long long)K * I * H, (long long)I * H, H), N * K, st)));
     TR();
-    p.A16 = nullptr; p.B16 = nullptr;
+    p.A16 = nullptr; p.B16 = nullptr; p.need16 = 0;
     // residual-GRU weight gradients accumulate by atomics: clear them first
     CK(cudaMemsetAsync(dRgw, 0, sizeof(float) * (size_t)2 * H * I, st));
     TR();
@@ -1389,13 +1408,14 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
         p.A = PX; p.B = DG; p.N = 2 * H;
         if (bf) { p.A16 = PX16; p.B16 = DG16T; }
+        p.need16 = (skip32 && !(Cin & 7)) ? 1 : 0;
         CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
         TR();
         p.B = DG + 2 * H; p.N = H;
         if (bf) p.B16 = DG16T + 2 * H;
         CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWu, (long long)K * I * H, (long long)I * H, H), N * K, st)));
         TR();
-        p.A16 = nullptr; p.B16 = nullptr;
+        p.A16 = nullptr; p.B16 = nullptr; p.need16 = 0;
         CK(cudaMemsetAsync(dbg, 0, sizeof(float) * (size_t)N * 2 * H, st));
         TR();
         CK(cudaMemsetAsync(dbu, 0, sizeof(float) * (size_t)N * H, st));

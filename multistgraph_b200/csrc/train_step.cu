@@ -207,167 +207,244 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 }
 
 constexpr int HD_H = 64;        // rnn_units the head kernels are written for
-constexpr int HD_RT = 64;       // rows per tile
-constexpr int HD_LDY = 68;      // smem pitch of the y tile / w tile (floats): conflict-free 16-byte row accesses
-constexpr int HD_OMAX = 32;     // output channels per backward pass
-constexpr int HD_OFWD = 24;     // output channels per forward pass (6 per thread)
+constexpr int HD_RT = 32;       // rows per tile: 128 threads, thread (rg = tid/16, hg = tid%16) owns rows 4rg..4rg+3, columns 4hg..4hg+3
+constexpr int HD_THREADS = 128;
+constexpr int HD_LD = 68;       // smem pitch (floats): conflict-free 16-byte row accesses
+constexpr int HD_OMAX = 24;     // output channels per pass (one accumulator set per channel and thread)
 
-// forward: one block per 64-row tile, loop over t; thread (row = tid/4, og = tid%4) owns OPT outputs o = og + 4*j
-template <int OPT>
-__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ y, long long y_tstride, int Tc, long long rows,
-                                                       const float* __restrict__ w, const float* __restrict__ bias, int O, int o0,
-                                                       DropP dp, float* __restrict__ out) {
-    __shared__ __align__(16) float ys[2][HD_RT * HD_LDY];
-    __shared__ __align__(16) float wsm[2][4 * OPT * HD_LDY];
-    const int tid = threadIdx.x, row = tid >> 2, og = tid & 3;
-    const long long r0 = (long long)blockIdx.x * HD_RT;
-    float acc[OPT];
+// the thread's 4x4 block of y (rows 4rg+i, columns 4hg..) -> registers; rows beyond the end read as zero
+__device__ __forceinline__ void head_load_y(const float* __restrict__ y, long long y_tstride, int t, long long rows, long long r0,
+                                            int rg, int hg, float4 (&v)[4]) {
 #pragma unroll
-    for (int j = 0; j < OPT; ++j) acc[j] = 0.f;
-    auto load_tile = [&](int t, int buf) {
-        // y tile: 64 rows x 16 float4; thread -> float4 pairs (one 8-element mask group)
-        for (int idx = tid; idx < HD_RT * 8; idx += 256) {
-            const int r = idx >> 3, h8 = (idx & 7) * 8;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (r0 + r < rows) {
-                const float* src = y + (long long)t * y_tstride + (r0 + r) * HD_H + h8;
-                a = *reinterpret_cast<const float4*>(src); b = *reinterpret_cast<const float4*>(src + 4);
-                const unsigned long long e = ((unsigned long long)t * rows + (r0 + r)) * HD_H + h8;
-                a = mul4(a, drop_mult4(dp, e)); b = mul4(b, drop_mult4(dp, e + 4));
-            }
-            *reinterpret_cast<float4*>(&ys[buf][r * HD_LDY + h8]) = a;
-            *reinterpret_cast<float4*>(&ys[buf][r * HD_LDY + h8 + 4]) = b;
-        }
-        for (int idx = tid; idx < 4 * OPT * 16; idx += 256) {
-            const int oo = idx >> 4, h4 = (idx & 15) * 4, o = o0 + oo;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (o < O && oo < HD_OFWD) v = *reinterpret_cast<const float4*>(w + ((long long)o * Tc + t) * HD_H + h4);
-            *reinterpret_cast<float4*>(&wsm[buf][oo * HD_LDY + h4]) = v;
+    for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + 4 * rg + i;
+        v[i] = r < rows ? *reinterpret_cast<const float4*>(y + (long long)t * y_tstride + r * HD_H + 4 * hg) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+// keep-multipliers of the same 4x4 block.  The two lanes of a pair (hg even / odd) share every 8-element mask group:
+// each computes the Philox block of two of the four rows and they swap halves.
+__device__ __forceinline__ void head_mults(const DropP& dp, int t, long long rows, long long r0, int rg, int hg, float4 (&m)[4]) {
+    if (dp.thr == 0u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        return;
+    }
+    const bool odd = hg & 1;
+    uint32_t oa[2], ob[2], ra[2], rb[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const long long r = r0 + 4 * rg + (odd ? 2 : 0) + j;
+        const unsigned long long grp = (((unsigned long long)t * rows + r) * HD_H + 4 * hg) >> 3;
+        const uint4 rnd = philox4x32_10((uint32_t)grp, (uint32_t)(grp >> 32), (uint32_t)dp.seed, (uint32_t)(dp.seed >> 32));
+        oa[j] = odd ? rnd.z : rnd.x; ob[j] = odd ? rnd.w : rnd.y;
+        ra[j] = __shfl_xor_sync(0xffffffffu, odd ? rnd.x : rnd.z, 1);
+        rb[j] = __shfl_xor_sync(0xffffffffu, odd ? rnd.y : rnd.w, 1);
+    }
+    const uint32_t a[4] = {odd ? ra[0] : oa[0], odd ? ra[1] : oa[1], odd ? oa[0] : ra[0], odd ? oa[1] : ra[1]};
+    const uint32_t b[4] = {odd ? rb[0] : ob[0], odd ? rb[1] : ob[1], odd ? ob[0] : rb[0], odd ? ob[1] : rb[1]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        m[i] = make_float4((a[i] & 0xFFFFu) >= dp.thr ? dp.scale : 0.f, (a[i] >> 16) >= dp.thr ? dp.scale : 0.f,
+                           (b[i] & 0xFFFFu) >= dp.thr ? dp.scale : 0.f, (b[i] >> 16) >= dp.thr ? dp.scale : 0.f);
+}
+
+// forward: one block per 32-row tile, loop over t with the accumulators (OW outputs x 4 rows, partial over the thread's 4
+// columns) in registers; one butterfly over the 16 column groups at the end.  y goes global -> registers, w_t through smem.
+template <int OW>
+__global__ void __launch_bounds__(HD_THREADS) head_fwd_kernel(const float* __restrict__ y, long long y_tstride, int Tc, long long rows,
+                                                              const float* __restrict__ w, const float* __restrict__ bias, int O, int o0,
+                                                              DropP dp, float* __restrict__ out) {
+    __shared__ __align__(16) float wsm[2][OW * HD_LD];
+    const int tid = threadIdx.x, rg = tid >> 4, hg = tid & 15;
+    const long long r0 = (long long)blockIdx.x * HD_RT;
+    const int ow = min(O - o0, OW);
+    float acc[OW][4];
+#pragma unroll
+    for (int oo = 0; oo < OW; ++oo)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[oo][i] = 0.f;
+    // w_t tile: global -> registers (issued a whole step ahead) -> shared memory after the step's arithmetic
+    constexpr int WPT = (OW * 16 + HD_THREADS - 1) / HD_THREADS;
+    float4 wreg[WPT];
+    auto fetch_w = [&](int t) {
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) {
+            const int idx = tid + k * HD_THREADS, oo = idx >> 4, h4 = (idx & 15) * 4;
+            wreg[k] = (idx < OW * 16 && oo < ow) ? *reinterpret_cast<const float4*>(w + ((long long)(o0 + oo) * Tc + t) * HD_H + h4)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    load_tile(0, 0);
+    auto stash_w = [&](int buf) {
+#pragma unroll
+        for (int k = 0; k < WPT; ++k) {
+            const int idx = tid + k * HD_THREADS, oo = idx >> 4, h4 = (idx & 15) * 4;
+            if (idx < OW * 16) *reinterpret_cast<float4*>(&wsm[buf][oo * HD_LD + h4]) = wreg[k];
+        }
+    };
+    float4 yv[4], yn[4];
+    head_load_y(y, y_tstride, 0, rows, r0, rg, hg, yv);
+    fetch_w(0);
+    stash_w(0);
     __syncthreads();
     for (int t = 0; t < Tc; ++t) {
         const int buf = t & 1;
-        if (t + 1 < Tc) load_tile(t + 1, buf ^ 1);
-        const float* yr = &ys[buf][row * HD_LDY];
-#pragma unroll 4
-        for (int h4 = 0; h4 < 16; ++h4) {
-            const float4 yv = *reinterpret_cast<const float4*>(yr + 4 * h4);
+        if (t + 1 < Tc) { head_load_y(y, y_tstride, t + 1, rows, r0, rg, hg, yn); fetch_w(t + 1); }
+        float4 m[4];
+        head_mults(dp, t, rows, r0, rg, hg, m);
 #pragma unroll
-            for (int j = 0; j < OPT; ++j) acc[j] = dot4(yv, *reinterpret_cast<const float4*>(&wsm[buf][(og + 4 * j) * HD_LDY + 4 * h4]), acc[j]);
+        for (int i = 0; i < 4; ++i) yv[i] = mul4(yv[i], m[i]);
+#pragma unroll
+        for (int oo = 0; oo < OW; ++oo) {
+            const float4 wv = *reinterpret_cast<const float4*>(&wsm[buf][oo * HD_LD + 4 * hg]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[oo][i] = dot4(yv[i], wv, acc[oo][i]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yv[i] = yn[i];
+        if (t + 1 < Tc) stash_w(buf ^ 1);   // (buffer buf^1 was last read in step t-1, which every thread has left)
         __syncthreads();
     }
-    if (r0 + row < rows) {
+    // sum over the 16 column groups (lanes hg of a half-warp), then lane hg writes outputs hg and hg+16
 #pragma unroll
-        for (int j = 0; j < OPT; ++j) {
-            const int o = o0 + og + 4 * j;
-            if (o < O && og + 4 * j < HD_OFWD) out[(r0 + row) * O + o] = acc[j] + bias[o];
+    for (int oo = 0; oo < OW; ++oo)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float v = acc[oo][i];
+            v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8);
+            acc[oo][i] = v;
+        }
+#pragma unroll
+    for (int oo = 0; oo < OW; ++oo) {
+        if ((oo & 15) == hg && oo < ow) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long r = r0 + 4 * rg + i;
+                if (r < rows) out[r * O + o0 + oo] = acc[oo][i] + bias[o0 + oo];
+            }
         }
     }
 }
 
-// backward: block (chunk, t) walks its row tiles: dy tile = mask * (dout tile x w_t), dw_t += dout^T x drop(y) (registers,
-// one atomic per element per block at the end), dbias by the t == 0 blocks.
-//   dy mapping: thread (rg = tid/16, hg = tid%16) -> rows 4rg..4rg+3, columns 4hg..4hg+3
-//   dw mapping: thread (os = tid/16, hg = tid%16) -> outputs os, os+16 (of this 32-wide pass), columns 4hg..4hg+3
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ y, long long y_tstride, int Tc, long long rows,
-                                                       const float* __restrict__ w, int O, int o0, DropP dp,
-                                                       const float* __restrict__ dout, float* __restrict__ dy, int dy_accumulate,
-                                                       float* __restrict__ dw, float* __restrict__ dbias) {
-    __shared__ __align__(16) float ys[HD_RT * HD_LDY];          // dropped y tile [row][h]
-    __shared__ __align__(16) float wsm[HD_OMAX * HD_LDY];       // w_t [o][h]
-    __shared__ __align__(16) float ds[HD_OMAX * HD_LDY];        // dout tile transposed [o][row]
-    const int tid = threadIdx.x, t = blockIdx.y;
-    const int rg = tid >> 4, hg = tid & 15, os = tid >> 4;
-    const int ow = min(O - o0, HD_OMAX);
-    for (int idx = tid; idx < HD_OMAX * 16; idx += 256) {
+// backward: block (chunk, t) walks its row tiles.  Per tile and thread: dy block = mask * (dout rows x w_t) and the partial
+// dw_t[o][4hg..] += sum over its 4 rows of dout[r][o] * drop(y)[r][4hg..] - both from the SAME two shared-memory reads per
+// output channel (32 FMA per 2 LDS.128).  The dw partials stay in registers over all tiles of the block and are reduced over
+// the row groups once at the end (shuffle + shared memory), then one atomic per element and block.
+template <int OW>
+__global__ void __launch_bounds__(HD_THREADS) head_bwd_kernel(const float* __restrict__ y, long long y_tstride, int Tc, long long rows,
+                                                              const float* __restrict__ w, int O, int o0, DropP dp,
+                                                              const float* __restrict__ dout, float* __restrict__ dy, int dy_accumulate,
+                                                              float* __restrict__ dw) {
+    __shared__ __align__(16) float wsm[OW * HD_LD];            // w_t [o][h]
+    __shared__ __align__(16) float ds[OW * HD_LD];             // dout tile transposed [o][row] (32 rows used)
+    __shared__ __align__(16) float red[4 * 8 * HD_H];          // end-of-block reduction: [warp][8 outputs][h]
+    const int tid = threadIdx.x, t = blockIdx.y, rg = tid >> 4, hg = tid & 15, warp = tid >> 5, lane = tid & 31;
+    const int ow = min(O - o0, OW);
+    for (int idx = tid; idx < OW * 16; idx += HD_THREADS) {
         const int oo = idx >> 4, h4 = (idx & 15) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (oo < ow) v = *reinterpret_cast<const float4*>(w + ((long long)(o0 + oo) * Tc + t) * HD_H + h4);
-        *reinterpret_cast<float4*>(&wsm[oo * HD_LDY + h4]) = v;
+        *reinterpret_cast<float4*>(&wsm[oo * HD_LD + h4]) = v;
     }
-    float4 dwa = make_float4(0.f, 0.f, 0.f, 0.f), dwb = dwa;
-    float db = 0.f;
+    float4 dwacc[OW];
+#pragma unroll
+    for (int oo = 0; oo < OW; ++oo) dwacc[oo] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long ntiles = (rows + HD_RT - 1) / HD_RT;
+    float4 yv[4];
+    constexpr int DPT_ = HD_RT * OW / HD_THREADS;   // dout elements per thread and tile
+    static_assert(HD_RT * OW % HD_THREADS == 0, "tile must divide evenly");
+    float dreg[DPT_];
+    auto fetch_d = [&](long long r0) {
+#pragma unroll
+        for (int k = 0; k < DPT_; ++k) {
+            const int idx = tid + k * HD_THREADS, r = idx / OW, oo = idx - r * OW;
+            dreg[k] = (oo < ow && r0 + r < rows) ? dout[(r0 + r) * O + o0 + oo] : 0.f;
+        }
+    };
+    if ((long long)blockIdx.x < ntiles) {
+        head_load_y(y, y_tstride, t, rows, (long long)blockIdx.x * HD_RT, rg, hg, yv);
+        fetch_d((long long)blockIdx.x * HD_RT);
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long r0 = tile * HD_RT;
-        __syncthreads();   // previous tile's readers are done (and wsm is visible on the first pass)
-        for (int idx = tid; idx < HD_RT * 8; idx += 256) {
-            const int r = idx >> 3, h8 = (idx & 7) * 8;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (r0 + r < rows) {
-                const float* src = y + (long long)t * y_tstride + (r0 + r) * HD_H + h8;
-                a = *reinterpret_cast<const float4*>(src); b = *reinterpret_cast<const float4*>(src + 4);
-                const unsigned long long e = ((unsigned long long)t * rows + (r0 + r)) * HD_H + h8;
-                a = mul4(a, drop_mult4(dp, e)); b = mul4(b, drop_mult4(dp, e + 4));
-            }
-            *reinterpret_cast<float4*>(&ys[r * HD_LDY + h8]) = a;
-            *reinterpret_cast<float4*>(&ys[r * HD_LDY + h8 + 4]) = b;
+        __syncthreads();   // the previous tile's readers of ds are done (and wsm is visible on the first pass)
+#pragma unroll
+        for (int k = 0; k < DPT_; ++k) {
+            const int idx = tid + k * HD_THREADS, r = idx / OW, oo = idx - r * OW;
+            ds[oo * HD_LD + r] = dreg[k];
         }
-        for (int idx = tid; idx < HD_RT * HD_OMAX; idx += 256) {
-            const int r = idx / HD_OMAX, oo = idx % HD_OMAX;
-            ds[oo * HD_LDY + r] = (oo < ow && r0 + r < rows) ? dout[(r0 + r) * O + o0 + oo] : 0.f;
+        float4 m[4], yn[4];
+        head_mults(dp, t, rows, r0, rg, hg, m);
+        if (tile + gridDim.x < ntiles) {
+            head_load_y(y, y_tstride, t, rows, (tile + gridDim.x) * HD_RT, rg, hg, yn);
+            fetch_d((tile + gridDim.x) * HD_RT);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) yv[i] = mul4(yv[i], m[i]);
         __syncthreads();
-        // ---- dy tile ----
-        float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0, d2 = d0, d3 = d0;
-        for (int oo = 0; oo < ow; ++oo) {
-            const float4 dv = *reinterpret_cast<const float4*>(&ds[oo * HD_LDY + 4 * rg]);
-            const float4 wv = *reinterpret_cast<const float4*>(&wsm[oo * HD_LDY + 4 * hg]);
-            d0.x = fmaf(dv.x, wv.x, d0.x); d0.y = fmaf(dv.x, wv.y, d0.y); d0.z = fmaf(dv.x, wv.z, d0.z); d0.w = fmaf(dv.x, wv.w, d0.w);
-            d1.x = fmaf(dv.y, wv.x, d1.x); d1.y = fmaf(dv.y, wv.y, d1.y); d1.z = fmaf(dv.y, wv.z, d1.z); d1.w = fmaf(dv.y, wv.w, d1.w);
-            d2.x = fmaf(dv.z, wv.x, d2.x); d2.y = fmaf(dv.z, wv.y, d2.y); d2.z = fmaf(dv.z, wv.z, d2.z); d2.w = fmaf(dv.z, wv.w, d2.w);
-            d3.x = fmaf(dv.w, wv.x, d3.x); d3.y = fmaf(dv.w, wv.y, d3.y); d3.z = fmaf(dv.w, wv.z, d3.z); d3.w = fmaf(dv.w, wv.w, d3.w);
-        }
-        {
-            const float4* dd[4] = {&d0, &d1, &d2, &d3};
+        float4 d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int oo = 0; oo < OW; ++oo) {
+            const float4 dv = *reinterpret_cast<const float4*>(&ds[oo * HD_LD + 4 * rg]);
+            const float4 wv = *reinterpret_cast<const float4*>(&wsm[oo * HD_LD + 4 * hg]);
+            const float dvv[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const long long r = r0 + 4 * rg + i;
-                if (r < rows) {
-                    const unsigned long long e = ((unsigned long long)t * rows + r) * HD_H + 4 * hg;
-                    float4 v = mul4(*dd[i], drop_mult4(dp, e));
-                    float4* dst = reinterpret_cast<float4*>(dy + ((long long)t * rows + r) * HD_H + 4 * hg);
-                    if (dy_accumulate) { const float4 old = *dst; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
-                    *dst = v;
-                }
+                d[i].x = fmaf(dvv[i], wv.x, d[i].x); d[i].y = fmaf(dvv[i], wv.y, d[i].y);
+                d[i].z = fmaf(dvv[i], wv.z, d[i].z); d[i].w = fmaf(dvv[i], wv.w, d[i].w);
+                dwacc[oo].x = fmaf(dvv[i], yv[i].x, dwacc[oo].x); dwacc[oo].y = fmaf(dvv[i], yv[i].y, dwacc[oo].y);
+                dwacc[oo].z = fmaf(dvv[i], yv[i].z, dwacc[oo].z); dwacc[oo].w = fmaf(dvv[i], yv[i].w, dwacc[oo].w);
             }
         }
-        // ---- dw_t partial: outputs os and os+16, columns 4hg.. ----
-#pragma unroll 4
-        for (int r4 = 0; r4 < HD_RT / 4; ++r4) {
-            const float4 da = *reinterpret_cast<const float4*>(&ds[os * HD_LDY + 4 * r4]);
-            const float4 dbv = *reinterpret_cast<const float4*>(&ds[(os + 16) * HD_LDY + 4 * r4]);
-            const float4 y0 = *reinterpret_cast<const float4*>(&ys[(4 * r4 + 0) * HD_LDY + 4 * hg]);
-            const float4 y1 = *reinterpret_cast<const float4*>(&ys[(4 * r4 + 1) * HD_LDY + 4 * hg]);
-            const float4 y2 = *reinterpret_cast<const float4*>(&ys[(4 * r4 + 2) * HD_LDY + 4 * hg]);
-            const float4 y3 = *reinterpret_cast<const float4*>(&ys[(4 * r4 + 3) * HD_LDY + 4 * hg]);
-            dwa.x = fmaf(da.x, y0.x, fmaf(da.y, y1.x, fmaf(da.z, y2.x, fmaf(da.w, y3.x, dwa.x))));
-            dwa.y = fmaf(da.x, y0.y, fmaf(da.y, y1.y, fmaf(da.z, y2.y, fmaf(da.w, y3.y, dwa.y))));
-            dwa.z = fmaf(da.x, y0.z, fmaf(da.y, y1.z, fmaf(da.z, y2.z, fmaf(da.w, y3.z, dwa.z))));
-            dwa.w = fmaf(da.x, y0.w, fmaf(da.y, y1.w, fmaf(da.z, y2.w, fmaf(da.w, y3.w, dwa.w))));
-            dwb.x = fmaf(dbv.x, y0.x, fmaf(dbv.y, y1.x, fmaf(dbv.z, y2.x, fmaf(dbv.w, y3.x, dwb.x))));
-            dwb.y = fmaf(dbv.x, y0.y, fmaf(dbv.y, y1.y, fmaf(dbv.z, y2.y, fmaf(dbv.w, y3.y, dwb.y))));
-            dwb.z = fmaf(dbv.x, y0.z, fmaf(dbv.y, y1.z, fmaf(dbv.z, y2.z, fmaf(dbv.w, y3.z, dwb.z))));
-            dwb.w = fmaf(dbv.x, y0.w, fmaf(dbv.y, y1.w, fmaf(dbv.z, y2.w, fmaf(dbv.w, y3.w, dwb.w))));
-            if (t == 0 && hg == 0) db += (da.x + da.y) + (da.z + da.w);
-            if (t == 0 && hg == 1) db += (dbv.x + dbv.y) + (dbv.z + dbv.w);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long r = r0 + 4 * rg + i;
+            if (r < rows) {
+                float4 v = mul4(d[i], m[i]);
+                float4* dst = reinterpret_cast<float4*>(dy + ((long long)t * rows + r) * HD_H + 4 * hg);
+                if (dy_accumulate) { const float4 old = *dst; v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+                *dst = v;
+            }
+            yv[i] = yn[i];
         }
     }
-    if (os < ow) {
-        float* dst = dw + ((long long)(o0 + os) * Tc + t) * HD_H + 4 * hg;
-        atomicAdd(dst, dwa.x); atomicAdd(dst + 1, dwa.y); atomicAdd(dst + 2, dwa.z); atomicAdd(dst + 3, dwa.w);
+    // dw_t: sum the two row groups of a warp by shuffle, the four warps through shared memory, 8 output channels at a time
+#pragma unroll
+    for (int oo = 0; oo < OW; ++oo) {
+        dwacc[oo].x += __shfl_xor_sync(0xffffffffu, dwacc[oo].x, 16); dwacc[oo].y += __shfl_xor_sync(0xffffffffu, dwacc[oo].y, 16);
+        dwacc[oo].z += __shfl_xor_sync(0xffffffffu, dwacc[oo].z, 16); dwacc[oo].w += __shfl_xor_sync(0xffffffffu, dwacc[oo].w, 16);
     }
-    if (os + 16 < ow) {
-        float* dst = dw + ((long long)(o0 + os + 16) * Tc + t) * HD_H + 4 * hg;
-        atomicAdd(dst, dwb.x); atomicAdd(dst + 1, dwb.y); atomicAdd(dst + 2, dwb.z); atomicAdd(dst + 3, dwb.w);
+#pragma unroll
+    for (int c = 0; c < (OW + 7) / 8; ++c) {
+        __syncthreads();
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (8 * c + j < OW) *reinterpret_cast<float4*>(&red[(warp * 8 + j) * HD_H + 4 * hg]) = dwacc[8 * c + j];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 8 * HD_H; idx += HD_THREADS) {
+            const int j = idx >> 6, h = idx & 63, oo = 8 * c + j;
+            if (oo < ow) {
+                const float v = (red[(0 * 8 + j) * HD_H + h] + red[(1 * 8 + j) * HD_H + h]) + (red[(2 * 8 + j) * HD_H + h] + red[(3 * 8 + j) * HD_H + h]);
+                atomicAdd(dw + ((long long)(o0 + oo) * Tc + t) * HD_H + h, v);
+            }
+        }
     }
-    if (t == 0 && dbias) {
-        if (hg == 0 && os < ow) atomicAdd(dbias + o0 + os, db);
-        if (hg == 1 && os + 16 < ow) atomicAdd(dbias + o0 + os + 16, db);
-    }
+}
+
+// dbias[o] = sum_r dout[r, o]
+__global__ void __launch_bounds__(256) head_dbias_kernel(const float* __restrict__ dout, long long rows, int O, float* __restrict__ dbias) {
+    const long long n = rows * O;
+    // thread -> fixed column class: element index i = base + k*stride with stride a multiple of O keeps i % O constant
+    const long long stride = (long long)gridDim.x * blockDim.x / O * O;
+    const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (stride == 0 || base >= stride) return;
+    float s = 0.f;
+    for (long long i = base; i < n; i += stride) s += dout[i];
+    atomicAdd(dbias + base % O, s);
 }
 
 __global__ void __launch_bounds__(256) dropout_mask_kernel(long long n4, DropP dp, float* __restrict__ mult) {
@@ -469,11 +546,11 @@ extern "C" int matgcn_head_fwd(const float* y, long long y_tstride, int Tc, long
     const DropP dp = make_drop(p_drop, seed);
     const unsigned grid = (unsigned)((rows + HD_RT - 1) / HD_RT);
     cudaStream_t st = (cudaStream_t)stream;
-    for (int o0 = 0; o0 < O; o0 += HD_OFWD) {
-        const int ow = O - o0 < HD_OFWD ? O - o0 : HD_OFWD;
-        if (ow <= 4) head_fwd_kernel<1><<<grid, 256, 0, st>>>(y, y_tstride, Tc, rows, w, bias, O, o0, dp, out);
-        else if (ow <= 12) head_fwd_kernel<3><<<grid, 256, 0, st>>>(y, y_tstride, Tc, rows, w, bias, O, o0, dp, out);
-        else head_fwd_kernel<6><<<grid, 256, 0, st>>>(y, y_tstride, Tc, rows, w, bias, O, o0, dp, out);
+    for (int o0 = 0; o0 < O; o0 += HD_OMAX) {
+        const int ow = O - o0 < HD_OMAX ? O - o0 : HD_OMAX;
+        if (ow <= 4) head_fwd_kernel<4><<<grid, HD_THREADS, 0, st>>>(y, y_tstride, Tc, rows, w, bias, O, o0, dp, out);
+        else if (ow <= 12) head_fwd_kernel<12><<<grid, HD_THREADS, 0, st>>>(y, y_tstride, Tc, rows, w, bias, O, o0, dp, out);
+        else head_fwd_kernel<24><<<grid, HD_THREADS, 0, st>>>(y, y_tstride, Tc, rows, w, bias, O, o0, dp, out);
         matgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     TS_CK(cudaGetLastError());
@@ -492,12 +569,23 @@ extern "C" int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long
     if (rows == 0) return 0;
     const DropP dp = make_drop(p_drop, seed);
     const long long ntiles = (rows + HD_RT - 1) / HD_RT;
-    long long chunks = (2LL * sm_count_ts() + Tc - 1) / Tc;      // ~2 blocks per SM in total
+    long long chunks = (3LL * sm_count_ts() + Tc - 1) / Tc;      // ~3 resident blocks per SM in total
     if (chunks > ntiles) chunks = ntiles;
     if (chunks < 1) chunks = 1;
     dim3 grid((unsigned)chunks, (unsigned)Tc);
     for (int o0 = 0; o0 < O; o0 += HD_OMAX) {
-        head_bwd_kernel<<<grid, 256, 0, st>>>(y, y_tstride, Tc, rows, w, O, o0, dp, dout, dy, o0 > 0 ? 1 : 0, dw, dbias);
+        const int ow = O - o0 < HD_OMAX ? O - o0 : HD_OMAX;
+        const int accum = o0 > 0 ? 1 : 0;
+        if (ow <= 4) head_bwd_kernel<4><<<grid, HD_THREADS, 0, st>>>(y, y_tstride, Tc, rows, w, O, o0, dp, dout, dy, accum, dw);
+        else if (ow <= 12) head_bwd_kernel<12><<<grid, HD_THREADS, 0, st>>>(y, y_tstride, Tc, rows, w, O, o0, dp, dout, dy, accum, dw);
+        else head_bwd_kernel<24><<<grid, HD_THREADS, 0, st>>>(y, y_tstride, Tc, rows, w, O, o0, dp, dout, dy, accum, dw);
+        matgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    {
+        long long blocks = (rows * O + 256 * 64 - 1) / (256 * 64);
+        if (blocks > 2LL * sm_count_ts()) blocks = 2LL * sm_count_ts();
+        if (blocks * 256 < O) blocks = (O + 255) / 256;
+        head_dbias_kernel<<<(unsigned)blocks, 256, 0, st>>>(dout, rows, O, dbias);
         matgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     TS_CK(cudaGetLastError());
