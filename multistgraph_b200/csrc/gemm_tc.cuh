@@ -298,11 +298,18 @@ __device__ __forceinline__ void tc_static_for(F& f) {
 // Positions are cursors (Epi::Cur) computed once per 32-column chunk and bumped by four rows per access - no
 // per-element index arithmetic.  A 32x32 chunk = 8 accesses per lane (lane -> row 4*it + lane/8, columns 4*(lane%8)..+3);
 // half-height tiles keep 16 rows per TMEM lane quadrant, i.e. 4 accesses per chunk.
-template <int BN, bool M64, class Epi, class Dec>
+// SPLIT (half-height 64-wide tiles: the node-batched contractions of the reverse step and of the time-batched gradients, whose
+// epilogue is a latency chain of ~2k cycles for 16 rows x 32 columns per warp): the two warps of a TMEM lane quadrant take
+// ALTERNATE TILES instead of alternate column chunks, each with the whole 64-column row block, and the accumulator ring has
+// four buffers - two tiles are in their epilogue at any time.
+template <int BN, bool M64, bool SPLIT, class Epi, class Dec>
 __device__ __forceinline__ void tc_epilogue_loop_pipe(const Epi& epi, const TcP& p, uint32_t tmem_base, const Dec& decode, uint32_t tfull0,
                                                       uint32_t tempty0, int q, int half, float* buf, int lane) {
     constexpr int LD = TC_EPI_LD;
-    constexpr int NCH = (BN / 32 + 1) / 2;  // 32-column chunks per warp (two warps share a TMEM lane quadrant)
+    constexpr int NCH = SPLIT ? BN / 32 : (BN / 32 + 1) / 2;  // 32-column chunks per warp (two warps share a TMEM lane quadrant)
+    constexpr int CSTEP = SPLIT ? 32 : 64;                    // column distance between consecutive chunks of this warp
+    constexpr int NACC = SPLIT ? 4 : 2;                       // accumulator buffers in TMEM
+    const int hoff = SPLIT ? 0 : half * 32;                   // first column of this warp inside the tile
     constexpr int ITS = M64 ? 4 : 8;        // accesses per chunk
     constexpr int ACC = NCH * ITS;          // accesses per lane and tile
     constexpr int R = Epi::kPipe < ACC ? Epi::kPipe : ACC;  // ring size = prefetch distance in accesses
@@ -323,6 +330,7 @@ __device__ __forceinline__ void tc_epilogue_loop_pipe(const Epi& epi, const TcP&
     };
     Tile cur, nxt;
     int tile = next_nonempty(blockIdx.x, cur);
+    if (SPLIT && half == 1 && tile < total) tile = next_nonempty(tile + stride, cur);  // this warp takes the odd tiles of the CTA
     if (tile >= total) return;
 
     typename Epi::Cur lc, sc;
@@ -338,7 +346,7 @@ __device__ __forceinline__ void tc_epilogue_loop_pipe(const Epi& epi, const TcP&
         const int a = rd * R + j;
         const int ci = a / ITS, it = a % ITS;
         const int row_base = tl.m0 + q * ROWS_Q;
-        const int col = tl.n0 + half * 32 + 4 * cq + 64 * ci;
+        const int col = tl.n0 + hoff + 4 * cq + CSTEP * ci;
         if (it == 0) lc = epi.begin4(tl.z1, tl.z2, row_base + rq, col);
         if (col < pN && row_base + 4 * it + rq < min(pM, row_base + ROWS_Q) && do_loads) ring[j] = epi.load4(lc);
         epi.advance4(lc, 4);
@@ -347,12 +355,13 @@ __device__ __forceinline__ void tc_epilogue_loop_pipe(const Epi& epi, const TcP&
         auto pro = [&](auto J_) { issue(cur, 0, J_); };
         tc_static_for<0, R>(pro);
     }
-    int acc = 0;
+    int acc = SPLIT ? half : 0;
     uint32_t acc_phase = 0;
     while (true) {
-        const int ntile = next_nonempty(tile + stride, nxt);
+        int ntile = next_nonempty(tile + stride, nxt);
+        if (SPLIT && ntile < total) ntile = next_nonempty(ntile + stride, nxt);
         const bool has_next = ntile < total;
-        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / stride) * 8 + 4] = clock64();
+        if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || (SPLIT && threadIdx.x == 256))) p.dbg[(tile / stride) * 8 + 4] = clock64();
         mbar_wait(tfull0 + 8u * acc, acc_phase);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
@@ -364,10 +373,10 @@ __device__ __forceinline__ void tc_epilogue_loop_pipe(const Epi& epi, const TcP&
                 constexpr int j = decltype(J_)::value;
                 const int a = rd * R + j;
                 const int ci = a / ITS, it = a % ITS;
-                const int col = cur.n0 + half * 32 + 4 * cq + 64 * ci;
-                const bool chunk_ok = cur.n0 + (half + 2 * ci) * 32 < pN && row_base < row_lim;  // warp-uniform
+                const int col = cur.n0 + hoff + 4 * cq + CSTEP * ci;
+                const bool chunk_ok = cur.n0 + hoff + CSTEP * ci < pN && row_base < row_lim;  // warp-uniform
                 if (it == 0 && chunk_ok) {
-                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((half + 2 * ci) * 32);
+                    const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(hoff + CSTEP * ci);
                     uint32_t r[32];
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -402,9 +411,10 @@ __device__ __forceinline__ void tc_epilogue_loop_pipe(const Epi& epi, const TcP&
         }
         tc_fence_before();
         __syncwarp();
-        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(tile / stride) * 8 + 6] = clock64();
+        if (p.dbg && blockIdx.x == 0 && (threadIdx.x == 128 || (SPLIT && threadIdx.x == 256))) p.dbg[(tile / stride) * 8 + 6] = clock64();
         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        acc += SPLIT ? 2 : 1;
+        if (acc >= NACC) { acc -= NACC; acc_phase ^= 1; }
         if (!has_next) break;
         tile = ntile;
         cur = nxt;
@@ -643,7 +653,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* epi_buf = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES);
     // bars: [0,STAGES) full, [STAGES,2*STAGES) empty, then tmem_full[2], tmem_empty[2]; then the TMEM base slot
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    constexpr bool SPLIT = VEC && M64 && BN == 64 && !FUSED;   // see tc_epilogue_loop_pipe
+    constexpr int NACC = SPLIT ? 4 : 2;                        // accumulator buffers of BN TMEM columns each
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NACC);
     float* res_w = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::EPI_BYTES + S::BAR_BYTES);  // FUSED only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -651,21 +663,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + NACC + a); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < NACC; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), TC_EPI_WARPS);
+            mbar_init(tempty_bar(a), SPLIT ? TC_EPI_WARPS / 2 : TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(NACC * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -784,7 +796,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 umma_commit(tfull_bar(acc));  // accumulator complete
                 if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp == 3) {
@@ -821,7 +833,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("bar.sync 5, 256;" ::: "memory");
         }
         if constexpr (VEC && !FUSED) {
-            tc_epilogue_loop_pipe<BN, M64>(epi, p, tmem_base, decode, tfull_bar(0), tempty_bar(0), q, half, buf, lane);
+            tc_epilogue_loop_pipe<BN, M64, SPLIT>(epi, p, tmem_base, decode, tfull_bar(0), tempty_bar(0), q, half, buf, lane);
         } else {
             int acc = 0;
             uint32_t acc_phase = 0;
@@ -851,7 +863,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NACC * BN));
     }
 }
 

@@ -31,18 +31,23 @@ def run(skip):
         lib.matgcn_debug_set_timeline(buf.data_ptr())
         lib.matgcn_debug_set_timeline_skip(skip)
     _cabi.check(lib.matgcn_encoder_layer_fwd(*dims, ldm, p(x), x.stride(0), None, p(M), p(Wg), p(bg), p(Wu), p(bu), p(Rgw),
-                                             p(Rgb), p(Ruw), p(Rub), p(mix), p(ws), 1, st), "fwd")
+                                             p(Rgb), p(Ruw), p(Rub), p(mix), p(ws), FLAGS, st), "fwd")
     _cabi.check(lib.matgcn_encoder_layer_bwd(*dims, ldm, n_adp, p(dY), dY.stride(0), p(M), p(Wg), p(Wu), p(Rgw), p(Ruw), p(mix),
-                                             p(ws), p(bws), *[p(o) for o in outs], 1, st), "bwd")
+                                             p(ws), p(bws), *[p(o) for o in outs], FLAGS, st), "bwd")
     torch.cuda.synchronize()
     lib.matgcn_debug_set_timeline(None)
     return buf.cpu().view(-1, 8)
 
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+FLAGS = int(sys.argv[2]) if len(sys.argv) > 2 else 3   # 1 = tf32, 3 = bf16
 lib.matgcn_debug_set_mode(mode)
 print('debug mode', mode)
 run(-1)
-for label, skip in [("fwd prop", 5 + 0), ("fwd gate (per-node)", 5 + 1), ("fwd fused tail (cand + residual cell)", 5 + 3), ("bwd B1", 5 + 4 * T + 0), ("bwd B2", 5 + 4 * T + 1), ("bwd B3 (per-node NT)", 5 + 4 * T + 2), ("bwd B4", 5 + 4 * T + 3), ("bwd B5", 5 + 4 * T + 4)]:
+# tensor-core launches in order: 5 input-side ones, 4 per forward step (prop, gate, prop, fused tail), then per reverse step
+# B3, B4, B5, B6 (the fused head of the reverse step is not a tensor-core launch)
+for label, skip in [("fwd prop", 5 + 0), ("fwd gate (per-node)", 5 + 1), ("fwd fused tail (cand + residual cell)", 5 + 3),
+                    ("bwd B3 (per-node NT)", 5 + 4 * T + 0), ("bwd B4", 5 + 4 * T + 1), ("bwd B5 (per-node NT)", 5 + 4 * T + 2),
+                    ("bwd B6", 5 + 4 * T + 3)]:
     b = run(skip)
     t0 = b[0, 0].item()
     print("==", label)
