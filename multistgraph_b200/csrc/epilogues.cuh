@@ -159,7 +159,7 @@ inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
 // short kernels starts with a cold instruction cache.)
 struct EpiPlain {
     static constexpr int kBatch = 8;
-    static constexpr int kPipe = 1;   // no global reads
+    static constexpr int kPipe = 8;   // no global reads; 8 = that many accesses unrolled per round (independent LDS -> STG chains)
     float* C;
     long long s1, s2;
     int ldc;

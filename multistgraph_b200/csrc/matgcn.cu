@@ -15,6 +15,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc_multi.cuh"
 #include "res_bwd.cuh"
+#include "xside_mma.cuh"
 
 using namespace matgcn;
 
@@ -531,15 +532,23 @@ __global__ void __launch_bounds__(256) xside_bwd_dr_small_kernel(
         for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
     }
     const long long rows = (long long)T * NB;
-    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    float drn[XS_J], xvn = 0.f;
+    auto fetch = [&](long long r) {   // loads of the warp's next row, issued before the arithmetic of the current one
         const long long t = r / NB, nb = r - t * NB;
         const float* drp = DR + r * H3;
+#pragma unroll
+        for (int j = 0; j < XS_J; ++j) drn[j] = (lane + 32 * j < H3) ? drp[lane + 32 * j] : 0.f;
+        xvn = lane < Cin ? PX[t * K * UX + nb * Cin + lane] : 0.f;
+    };
+    if ((long long)blockIdx.x * 8 + warp < rows) fetch((long long)blockIdx.x * 8 + warp);
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+        const long long t = r / NB, nb = r - t * NB;
         float dr[XS_J];
 #pragma unroll
-        for (int j = 0; j < XS_J; ++j) dr[j] = (lane + 32 * j < H3) ? drp[lane + 32 * j] : 0.f;
+        for (int j = 0; j < XS_J; ++j) dr[j] = drn[j];
         float* x0 = DPX + t * K * UX + nb * Cin;          // DPX[t,0,n,b,:]
-        const float* xin = PX + t * K * UX + nb * Cin;    // PX[t,0,n,b,:] = x
-        float xv = lane < Cin ? xin[lane] : 0.f;
+        const float xv = xvn;
+        if (r + (long long)gridDim.x * 8 < rows) fetch(r + (long long)gridDim.x * 8);
         float part[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1396,13 +1405,23 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     if (small_x) {
         // tiny channel count (layer 0): one pass over DG (input-row weight gradient, bias gradient, DPX) and one pass
         // over DR (residual input-column gradients, residual bias gradient, residual share of dx into DPX[t,0])
-        xside_bwd_dg_small_kernel<<<N, 256, 0, st>>>(PX, DG, Wg, Wu, T, N, B, Cin, H, K, dWg, dWu, dbg, dbu, DPX);
-        count_launch();
-        TR();
-        xside_bwd_dr_small_kernel<<<592, 256, 0, st>>>(PX, DR, Rgw, Ruw, T, N, B, Cin, H, K, dRgw, dRuw, dRgb, dRub, DPX);
-        count_launch();
-        TR();
-        CK(cudaGetLastError());
+        if (tc && xside_mma_ok(Cin, H, K, DG, PX, DPX) && aligned16(DR)) {
+            // fast modes: the same two passes as warp-level TF32 mma.sync products (xside_mma.cuh)
+            XsMmaArgs xa{DG, PX, DPX, Wg, Wu, dWg, dWu, dbg, dbu, T, N, B, Cin, H, K};
+            CK(launch_xside_bwd_mma<true>(xa, st));
+            TR();
+            XsMmaArgs xr{DR, PX, DPX, Rgw, Ruw, dRgw, dRuw, dRgb, dRub, T, N, B, Cin, H, K};
+            CK(launch_xside_bwd_mma<false>(xr, st));
+            TR();
+        } else {
+            xside_bwd_dg_small_kernel<<<N, 256, 0, st>>>(PX, DG, Wg, Wu, T, N, B, Cin, H, K, dWg, dWu, dbg, dbu, DPX);
+            count_launch();
+            TR();
+            xside_bwd_dr_small_kernel<<<592, 256, 0, st>>>(PX, DR, Rgw, Ruw, T, N, B, Cin, H, K, dRgw, dRuw, dRgb, dRub, DPX);
+            count_launch();
+            TR();
+            CK(cudaGetLastError());
+        }
     } else {
         // input rows 0:Cin from PX, and the bias gradients (column sums of DG over (t, b))
         p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = UX; p.sAk = K * UX; p.M = Cin;
