@@ -208,10 +208,11 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
     bf16 = bool(flags & _cabi.FLAG_BF16)
     if bf16:
         M16, X16 = M.bfloat16(), X.bfloat16()
+        P16 = torch.empty(kp, n_nodes, cols, device=device, dtype=torch.bfloat16)
 
-        def launch():
-            _cabi.check(lib.matgcn_propagate_fwd_bf16(M16.data_ptr(), kp, n_nodes, ldm, X16.data_ptr(), cols, P.data_ptr(), st),
-                        "propagate_bf16")
+        def launch():   # the launch exactly as a bf16-mode step issues it: bf16 operands in, bf16 twin of the result out
+            _cabi.check(lib.matgcn_propagate_fwd_bf16_twin(M16.data_ptr(), kp, n_nodes, ldm, X16.data_ptr(), cols, P16.data_ptr(), st),
+                        "propagate_bf16_twin")
     else:
         def launch():
             _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n_nodes, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st),
@@ -233,7 +234,7 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r1_prop_kernel_ncu_bf16.json" if bf16 else "r1_prop_kernel_ncu.json")
+    prof = os.path.join(ROOT, "profiles", "r1_prop_kernel_ncu_bf16_twin.json" if bf16 else "r1_prop_kernel_ncu.json")
     if flags and os.path.exists(prof):
         with open(prof) as f:
             pj = json.load(f)
@@ -244,7 +245,8 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
             else "gemm_kernel<CfgBig,A_KC,B_NC,EpiPlain> (support propagation, fp32 FFMA)")
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "kernel": kern, "launch_ms": ms, "flops_per_launch": flops,
-            "algorithmic_bytes_per_launch": (2.0 if bf16 else 4.0) * (kp * n_nodes * ldm + n_nodes * cols) + 4.0 * kp * n_nodes * cols,
+            "algorithmic_bytes_per_launch": (2.0 if bf16 else 4.0) * (kp * n_nodes * ldm + n_nodes * cols)
+                                            + (2.0 if bf16 else 4.0) * kp * n_nodes * cols,
             "peak_source": peaks["source"] + " bf16 dense burst",
             "note": "peak is the measured bf16 cuBLAS figure; TF32 tensor-core peak is half of it, the fp32 FFMA "
                     "kernel of exact mode cannot approach either"}

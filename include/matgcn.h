@@ -108,6 +108,8 @@ int matgcn_set_fused_tail(int on);
 /* The same contraction with bf16 twins of M and X (device arrays of __nv_bfloat16), float32 output: the kernel the
  * layer entry points launch for the propagation when MATGCN_FLAG_BF16 is set. */
 int matgcn_propagate_fwd_bf16(const void* M16, int Kp, int N, int ldm, const void* X16, int cols, float* P, void* stream);
+/* The same launch as a bf16-mode step issues it: only the bf16 twin P16 [Kp, N, cols] of the result is stored. */
+int matgcn_propagate_fwd_bf16_twin(const void* M16, int Kp, int N, int ldm, const void* X16, int cols, void* P16, void* stream);
 
 /* Diagnostics: device buffer (int64, >= 8 per tile of CTA 0) that later tensor-core launches fill with clock64()
  * stamps [producer start, mma wait, mma start, mma committed, epilogue wait, epilogue start, epilogue end]; NULL disables. */

@@ -34,6 +34,7 @@ _SIGNATURES = {
                                   c_void_p]),
     "matgcn_set_fused_tail": (c_int, [c_int]),
     "matgcn_propagate_fwd_bf16": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_void_p]),
+    "matgcn_propagate_fwd_bf16_twin": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_void_p]),
     "matgcn_gemm_debug_bf16": (c_int, [c_int, c_int, c_int, c_int, c_int, _F, c_int, _F, c_int, _F, c_int, c_int, c_void_p]),
     "matgcn_adaptive_adj_fwd": (c_int, [_F, _F, c_int, c_int, _F, c_int, c_void_p]),
     "matgcn_adaptive_adj_bwd": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, _F, _F, _F, c_void_p]),

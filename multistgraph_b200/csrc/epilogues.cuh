@@ -166,15 +166,17 @@ struct EpiPlain {
     __nv_bfloat16* C16;  // may be null
     float* D2;           // may be null: see EpiStore
     int d2_lo, d2_hi;
+    __nv_bfloat16* D2h;  // may be null: the same second copy as bf16 (same block range and indexing as D2)
     int c_z2_hi;         // the fp32 copy C is written only for blocks z2 < c_z2_hi (bf16 mode: slots that are consumed as
                          // bf16 twins only skip their fp32 store; 0 = never, INT_MAX = always)
-    bool vec_ok() const { return aligned16(C) && (!C16 || aligned16(C16)) && (!D2 || aligned16(D2)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3); }
+    bool vec_ok() const { return aligned16(C) && (!C16 || aligned16(C16)) && (!D2 || aligned16(D2)) && (!D2h || aligned16(D2h)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3); }
     __device__ __forceinline__ EpiIn load(int, int, int, int) const { return EpiIn{}; }
     __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn&) const {
         const long long o = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
         if (z2 < c_z2_hi) C[o] = acc;
         if (C16) C16[o] = __float2bfloat16_rn(acc);
         if (D2 && z2 >= d2_lo && z2 < d2_hi) D2[o - (long long)d2_lo * s2] = acc;
+        if (D2h && z2 >= d2_lo && z2 < d2_hi) D2h[o - (long long)d2_lo * s2] = __float2bfloat16_rn(acc);
     }
     __device__ __forceinline__ EpiIn4 load4(int, int, int, int) const { return EpiIn4{}; }
     __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4&) const {
@@ -182,10 +184,11 @@ struct EpiPlain {
         if (z2 < c_z2_hi) st4(C + o, acc);
         if (C16) st4_bf16(C16 + o, acc);
         if (D2 && z2 >= d2_lo && z2 < d2_hi) st4(D2 + o - (long long)d2_lo * s2, acc);
+        if (D2h && z2 >= d2_lo && z2 < d2_hi) st4_bf16(D2h + o - (long long)d2_lo * s2, acc);
     }
     struct Cur { long long off; int dup; int main; };
     __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
-        return Cur{z1 * s1 + z2 * s2 + (long long)row * ldc + col, (D2 && z2 >= d2_lo && z2 < d2_hi) ? 1 : 0, z2 < c_z2_hi ? 1 : 0};
+        return Cur{z1 * s1 + z2 * s2 + (long long)row * ldc + col, ((D2 || D2h) && z2 >= d2_lo && z2 < d2_hi) ? 1 : 0, z2 < c_z2_hi ? 1 : 0};
     }
     __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ldc; }
     __device__ __forceinline__ EpiIn4 load4(const Cur&) const { return EpiIn4{}; }
@@ -193,7 +196,10 @@ struct EpiPlain {
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4&) const {
         if (c.main) st4(C + c.off, acc);
         if (C16) st4_bf16(C16 + c.off, acc);
-        if (c.dup) st4(D2 + c.off - (long long)d2_lo * s2, acc);
+        if (c.dup) {
+            if (D2) st4(D2 + c.off - (long long)d2_lo * s2, acc);
+            if (D2h) st4_bf16(D2h + c.off - (long long)d2_lo * s2, acc);
+        }
     }
     EPI_CALL_OPERATOR
 };

@@ -964,6 +964,26 @@ extern "C" int matgcn_propagate_fwd_bf16(const void* M16, int Kp, int N, int ldm
     return 0;
 }
 
+// The propagation launch exactly as a bf16-mode step issues it: bf16 operands, and only the bf16 twin of the result is stored
+// (P16 [Kp, N, cols]; the fp32 copy of the propagated slots is skipped - EpiPlain::c_z2_hi = 0).
+extern "C" int matgcn_propagate_fwd_bf16_twin(const void* M16, int Kp, int N, int ldm, const void* X16, int cols, void* P16, void* stream) {
+    REQUIRE(M16 && X16 && P16, "null pointer");
+    REQUIRE(Kp > 0 && N > 0 && cols > 0 && ldm >= N, "bad dims");
+    GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.KB = 1; p.Z2 = 1; p.splits = 1;
+    p.A16 = (const __nv_bfloat16*)M16; p.lda = ldm; p.M = Kp * N; p.K = N;
+    p.B16 = (const __nv_bfloat16*)X16; p.ldb = cols; p.N = cols;
+    EpiPlain e = epi_plain(reinterpret_cast<float*>(P16), 0, 0, cols);   // C is never dereferenced
+    e.C16 = (__nv_bfloat16*)P16;
+    e.c_z2_hi = 0;
+    cudaError_t err = launch_gemm_tc<128, true, false, EpiPlain, true>(p, e, 1, (cudaStream_t)stream);
+    if (err == cudaErrorNotSupported) return fail(__func__, "operands do not meet the TMA alignment rules");
+    CK(err);
+    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 // Plain C = A*B through either engine, for unit tests of the GEMM kernels (all operand layouts).
 extern "C" int matgcn_gemm_debug(int a_kc, int b_kc, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                                  float* C, int ldc, int splits, int flags, void* stream) {
@@ -1323,7 +1343,12 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                 if (bf) e.C16 = DPT16;
                 if (skip32) e.c_z2_hi = 1;   // DPT[k >= 1] is consumed as its bf16 twin only (B4); DPT[0] stays fp32 (EpiB4 reads it)
                 // the adaptive slices are also kept per step (operands of dM): second destination instead of a copy
-                if (n_adp && !use_multi) { e.D2 = DPZA + (long long)t * n_adp * U; e.d2_lo = 1; e.d2_hi = 1 + n_adp; }
+                if (n_adp && !use_multi) {
+                    // (bf16 mode: kept as bf16 in the same storage - the dM contraction reads it as a bf16 operand)
+                    if (skip32) e.D2h = reinterpret_cast<__nv_bfloat16*>(DPZA) + (long long)t * n_adp * U;
+                    else e.D2 = DPZA + (long long)t * n_adp * U;
+                    e.d2_lo = 1; e.d2_hi = 1 + n_adp;
+                }
                 STEP_GEMM(2, CfgMid, true, true, p, e, N * K);
             }
             // B4: dzh = DPT[0] + sum_{k>=1} M_k^T DPT[k]
@@ -1345,7 +1370,11 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                 EpiPlain e = epi_plain(DPT, (long long)B * H, U, H);
                 if (bf) e.C16 = DPT16;
                 if (skip32) e.c_z2_hi = 1;
-                if (n_adp && !use_multi) { e.D2 = DPHA + (long long)t * n_adp * U; e.d2_lo = 1; e.d2_hi = 1 + n_adp; }
+                if (n_adp && !use_multi) {
+                    if (skip32) e.D2h = reinterpret_cast<__nv_bfloat16*>(DPHA) + (long long)t * n_adp * U;
+                    else e.D2 = DPHA + (long long)t * n_adp * U;
+                    e.d2_lo = 1; e.d2_hi = 1 + n_adp;
+                }
                 STEP_GEMM(4, CfgMid, true, true, p, e, N * K);
             }
             // B6: carry = DHD + DPT[0] + sum M_k^T DPT[k]
@@ -1534,13 +1563,19 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.K = B * H; p.lda = B * H; p.ldb = B * H;
         p.splits = T;
         p.A = DPHA + (long long)a * U; p.sAk = (long long)n_adp * U; p.B = PH; p.sBk = K * U;
+        if (skip32) {   // the per-step adaptive slices were kept as bf16 (D2h above); h_t has its bf16 twin in slot 0 of PH16
+            p.A16 = reinterpret_cast<const __nv_bfloat16*>(DPHA) + (long long)a * U; p.B16 = PH16; p.need16 = 1;
+        }
         CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
         TR();
         p.A = DPZA + (long long)a * U; p.B = PZ;
+        if (skip32) { p.A16 = reinterpret_cast<const __nv_bfloat16*>(DPZA) + (long long)a * U; p.B16 = PZ16; }
         CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
         TR();
         p.K = B * Cin; p.lda = B * Cin; p.ldb = B * Cin;
         p.A = DPX + (long long)(a + 1) * UX; p.sAk = K * UX; p.B = PX; p.sBk = K * UX;
+        p.A16 = nullptr; p.B16 = nullptr; p.need16 = 0;
+        if (bf && !small_x && !(Cin & 7)) { p.A16 = DPX16 + (long long)(a + 1) * UX; p.B16 = PX16; }
         CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
         TR();
     }

@@ -16,10 +16,13 @@ for kp, n, cols in shapes:
     X = torch.randn(n, cols, device=dev)
     P = torch.empty(kp, n, cols, device=dev)
     M16, X16 = M.bfloat16(), X.bfloat16()
-    modes = (3,) if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else (1, 0)
+    P16 = torch.empty(kp, n, cols, device=dev, dtype=torch.bfloat16)
+    modes = (3,) if (len(sys.argv) > 2 and sys.argv[2] == "bf16") else (4,) if (len(sys.argv) > 2 and sys.argv[2] == "twin") else (1, 0)
     for flags in modes:
         def run(flags=flags):
-            if flags == 3:
+            if flags == 4:   # the launch of a bf16-mode step: bf16 in, bf16 twin out
+                _cabi.check(lib.matgcn_propagate_fwd_bf16_twin(M16.data_ptr(), kp, n, ldm, X16.data_ptr(), cols, P16.data_ptr(), st), "twin")
+            elif flags == 3:
                 _cabi.check(lib.matgcn_propagate_fwd_bf16(M16.data_ptr(), kp, n, ldm, X16.data_ptr(), cols, P.data_ptr(), st), "p16")
             else:
                 _cabi.check(lib.matgcn_propagate_fwd(M.data_ptr(), kp, n, ldm, X.data_ptr(), cols, P.data_ptr(), flags, st), "p")
