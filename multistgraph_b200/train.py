@@ -117,15 +117,32 @@ class FusedClipAdam:
         self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
 
 
-def fused_train_step(model, batch, opt: FusedClipAdam):
+def fused_train_step(model, batch, opt: FusedClipAdam, micro_batches: int = 1):
     """One iteration of ``TrafficStateExecutor._train_epoch`` (executor:413-422): zero_grad -> calculate_loss ->
-    backward -> [data-parallel all-reduce] -> clip_grad_norm_ + Adam (fused).  Returns the device loss tensor."""
+    backward -> [data-parallel all-reduce] -> clip_grad_norm_ + Adam (fused).  Returns the device loss tensor.
+
+    ``micro_batches > 1`` runs the forward/backward over that many consecutive slices of the batch, each weighted by its share
+    of the samples, and accumulates their gradients in the flat bucket before the single update: the saved activations of only
+    one slice are alive at a time (the N = 8192 shape at 64 samples per GPU needs it).  The result equals the one-shot step
+    whenever the loss is a mean over samples with equal mask density per slice (the same caveat as batch sharding)."""
     opt.zero_grad()
-    loss = model.calculate_loss(batch)
-    loss.backward()
+    if micro_batches <= 1:
+        loss = model.calculate_loss(batch)
+        loss.backward()
+        loss = loss.detach()
+    else:
+        total = next(iter(batch.values())).shape[0]
+        bounds = [total * i // micro_batches for i in range(micro_batches + 1)]
+        loss = None
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            if hi == lo:
+                continue
+            part = model.calculate_loss({k: v[lo:hi] for k, v in batch.items()}) * ((hi - lo) / total)
+            part.backward()
+            loss = part.detach() if loss is None else loss + part.detach()
     scale = opt.all_reduce()
     opt.step(grad_scale=scale)
-    return loss.detach()
+    return loss
 
 
 class DeviceWindowBank:
