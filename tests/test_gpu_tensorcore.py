@@ -227,3 +227,34 @@ def test_gemm_engine_bf16(a_kc, b_kc, M, N, K, splits):
     print("[bf16 gemm a_kc=%d b_kc=%d %dx%dx%d s=%d] err=%.2e" % (a_kc, b_kc, M, N, K, splits, err))
     assert err < 1e-5
     assert torch.isnan(C[:, N:]).all()
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32", MODEL_TOL), ("bf16", BF16_TOL)])
+def test_full_size_fast_modes_match_exact_mode(mode, tol):
+    """Baltimore shape (N=403, K=5, D=20, 24 -> 24) at batch 16: the fast modes against the exact fp32 engine of the same
+    library (itself pinned to the oracle at 1e-4) - the only place where the full-size tile shapes, the bf16-only slots, the
+    split epilogue and the mma.sync input-side gradients are all exercised together.  Bounds: those of the mode on every
+    parameter gradient, 2e-3 on the forecast."""
+    from multistgraph_b200.synthetic import workload
+
+    cfg, df, batch = workload("baltimore_multi", seed=0, batch=16)
+    outs = {}
+    for m in ("exact", mode):
+        c = dict(cfg)
+        c["matgcn_mode"] = m
+        c["device"] = torch.device(DEV)
+        torch.manual_seed(0)
+        model = MultiATGCN(c, df).to(DEV).eval()
+        y = model.predict(clone_batch(batch, DEV))
+        model.calculate_loss(clone_batch(batch, DEV)).backward()
+        torch.cuda.synchronize()
+        outs[m] = (y.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
+    y0, g0 = outs["exact"]
+    y1, g1 = outs[mode]
+    errs = {"forecast": max_rel_err(y1, y0)}
+    for k in g0:
+        errs["d" + k] = max_rel_err(g1[k], g0[k])
+    print("[full size %s vs exact] " % mode + ", ".join("%s=%.2e" % kv for kv in sorted(errs.items(), key=lambda kv: -kv[1])[:6]))
+    assert errs["forecast"] < 2e-3
+    bad = {k: v for k, v in errs.items() if not (v < tol)}
+    assert not bad, bad

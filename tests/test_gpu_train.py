@@ -281,5 +281,8 @@ def test_micro_batched_step_equals_one_shot_step():
     l3 = fused_train_step(models[1], {k: v.clone() for k, v in batch.items()}, opts[1], micro_batches=3)
     assert abs(float(l1) - float(l3)) / abs(float(l1)) < 1e-5
     assert abs(float(opts[0].grad_norm) - float(opts[1].grad_norm)) / float(opts[0].grad_norm) < 1e-4
+    # (the accumulated, clipped gradients are compared, not the parameters: the first Adam step moves every element by
+    # lr * sign(g), which is ill-conditioned where g is ~0)
     for (k, p), (_, q) in zip(models[0].named_parameters(), models[1].named_parameters()):
-        assert (p - q).abs().max() <= 2e-5 * p.abs().max().clamp_min(1e-3), k
+        if p.grad is not None and float(p.grad.abs().max()) > 0:
+            assert (p.grad - q.grad).abs().max() <= 1e-4 * p.grad.abs().max(), k
