@@ -46,6 +46,9 @@ struct GemmP {
     const __nv_bfloat16* A16;
     const __nv_bfloat16* B16;
     int keepB;    // tensor-core engine: load B with the L2 evict-last policy (an operand re-read by every step of a recurrence)
+    const void* pf_base;  // tensor-core engine: L2 warm-up for the next launch (see TcP::pf_*); null = none
+    long long pf_stride;
+    int pf_chunk, pf_n;
     int need16;   // the fp32 operands are NOT valid (their producer skipped the fp32 store): only the bf16 engine may run this
     int M, N, K;  // K: inner reduction length of one k-batch
     int KB;       // number of k-batches

@@ -43,6 +43,11 @@ extern "C" void matgcn_internal_set_error(const char* where, const char* what) {
 // Engine dispatch: fast mode (flags & MATGCN_FLAG_TF32) sends a contraction to the tcgen05/TMA kernel when
 // its operands meet the TMA alignment rules, otherwise (and always in exact mode) to the fp32 SIMT kernel.
 static std::atomic<unsigned long long> g_tc_launches{0};
+// L2 warm-up of the next launch's weight blocks (TcP::pf_*); MATGCN_L2_WARM=0 switches it off for A/B measurements
+static bool l2_warm_enabled() {
+    static const bool on = []() { const char* e = getenv("MATGCN_L2_WARM"); return !(e && e[0] == '0'); }();
+    return on;
+}
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
 static cudaError_t gemm_any(bool tc, const GemmP& p, const Epi& epi, int Z, cudaStream_t st) {
     if (tc && p.K >= 8 && p.A16 && p.B16) {
@@ -1176,6 +1181,9 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
                 EpiPlain e = epi_plain(PHt + U, 0, 0, B * H);
                 if (bf) { p.A16 = M16; p.B16 = PH16t; e.C16 = PH16t + U; }
                 if (skip32) e.c_z2_hi = 0;
+                if (bf && l2_warm_enabled()) {   // the gate contraction that follows streams Wg16[n, k, Cin:, :] from HBM
+                    p.pf_base = WG16 + (long long)Cin * 2 * H; p.pf_stride = (long long)I * 2 * H * 2; p.pf_chunk = H * 2 * H * 2; p.pf_n = N * K;
+                }
                 STEP_GEMM(0, CfgBig, true, false, p, e, 1);
             }
             // (b) gate: per node [B, K*H] x [K*H, 2H]
@@ -1192,6 +1200,9 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
                 EpiPlain e = epi_plain(PZt + U, 0, 0, B * H);
                 if (bf) { pp.A16 = M16; pp.B16 = PZ16t; e.C16 = PZ16t + U; }
                 if (skip32) e.c_z2_hi = 0;
+                if (bf && l2_warm_enabled()) {   // the candidate contraction that follows streams Wu16[n, k, Cin:, :]
+                    pp.pf_base = WU16 + (long long)Cin * H; pp.pf_stride = (long long)I * H * 2; pp.pf_chunk = H * H * 2; pp.pf_n = N * K;
+                }
                 STEP_GEMM(2, CfgBig, true, false, pp, e, 1);
             }
             // (d) candidate
@@ -1358,6 +1369,9 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
             if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
             p.need16 = skip32 ? 1 : 0;
+            if (bf && l2_warm_enabled()) {   // B5 streams Wg16[n, k, Cin:, :]
+                p.pf_base = WG16 + (long long)Cin * 2 * H; p.pf_stride = (long long)I * 2 * H * 2; p.pf_chunk = H * 2 * H * 2; p.pf_n = N * K;
+            }
             STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H, DG16}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPZA + (long long)t * n_adp * U, (long long)n_adp * U);
             // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
@@ -1384,6 +1398,9 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
             if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
             p.need16 = skip32 ? 1 : 0;
+            if (bf && l2_warm_enabled() && t > 0) {   // B3 of the next reverse step streams Wu16[n, k, Cin:, :]
+                p.pf_base = WU16 + (long long)Cin * H; p.pf_stride = (long long)I * H * 2; p.pf_chunk = H * H * 2; p.pf_n = N * K;
+            }
             STEP_GEMM(5, CfgBig, false, false, p, (EpiB6{DPT, DHD, DHC, B * H}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPHA + (long long)t * n_adp * U, (long long)n_adp * U);
         }
