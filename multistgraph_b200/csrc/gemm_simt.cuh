@@ -39,6 +39,9 @@ __device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const float4& v) {
 }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// a range to pull into L2: n chunks of `chunk` bytes (a multiple of 128), `stride` bytes apart
+struct PfRange { const char* base; long long stride; int chunk, n; };
+
 struct GemmP {
     const float* A;
     const float* B;
@@ -46,9 +49,8 @@ struct GemmP {
     const __nv_bfloat16* A16;
     const __nv_bfloat16* B16;
     int keepB;    // tensor-core engine: load B with the L2 evict-last policy (an operand re-read by every step of a recurrence)
-    const void* pf_base;  // tensor-core engine: L2 warm-up for the next launch (see TcP::pf_*); null = none
-    long long pf_stride;
-    int pf_chunk, pf_n;
+    PfRange pf[8];        // tensor-core engine: L2 warm-up for the next launches (see TcP::pf); npf ranges in use
+    int npf;
     int need16;   // the fp32 operands are NOT valid (their producer skipped the fp32 store): only the bf16 engine may run this
     int M, N, K;  // K: inner reduction length of one k-batch
     int KB;       // number of k-batches

@@ -66,12 +66,10 @@ struct TcP {
     int vec;                // 1: N % 4 == 0 and the epilogue's pointers/pitches allow 16-byte accesses
     int dbg_mode;           // diagnostics only: 1 = skip epilogue stores
     long long* dbg;         // optional per-tile timeline of CTA 0 (tools/tc_timeline.py); null in production
-    // L2 warm-up for the NEXT launch of the stream: pf_n chunks of pf_chunk bytes, pf_stride bytes apart, from pf_base
-    // (the hidden-row weight blocks a following per-node contraction streams from HBM; this launch is L2-bound and leaves
-    // the HBM pipe idle).  pf_n = 0: none.
-    const char* pf_base;
-    long long pf_stride;
-    int pf_chunk, pf_n;
+    // L2 warm-up for the NEXT launches of the stream (weights a following per-node contraction streams from HBM, saved
+    // activations the next elementwise-heavy kernel reads): this launch is L2-bound and leaves the HBM pipe idle.
+    PfRange pf[8];
+    int npf;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -807,13 +805,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 3) {
         // ================================ L2 warm-up for the next launch ================================
-        if (p.pf_n > 0) {
-            const int lines = p.pf_chunk >> 7;                        // 128-byte lines per chunk
-            const long long total = (long long)p.pf_n * lines;
+        for (int r = 0; r < p.npf; ++r) {
+            const PfRange pr = p.pf[r];
+            const int lines = pr.chunk >> 7;                          // 128-byte lines per chunk
+            const long long total = (long long)pr.n * lines;
             for (long long i = (long long)blockIdx.x * 32 + lane; i < total; i += (long long)gridDim.x * 32) {
                 const long long ch = i / lines;
                 const int ln = (int)(i - ch * lines);
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p.pf_base + ch * p.pf_stride + ((long long)ln << 7)));
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pr.base + ch * pr.stride + ((long long)ln << 7)));
             }
         }
         // ================================ epilogue-input prefetch ================================
@@ -1000,7 +999,8 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
     t.d_tn = make_fastdiv((uint32_t)t.tiles_n);
     t.tA_dim = t.tB_dim = t.t = 0;
     t.keepB = p.keepB;
-    t.pf_base = reinterpret_cast<const char*>(p.pf_base); t.pf_stride = p.pf_stride; t.pf_chunk = p.pf_chunk; t.pf_n = p.pf_base ? p.pf_n : 0;
+    t.npf = p.npf < 0 ? 0 : (p.npf > 8 ? 8 : p.npf);
+    for (int r = 0; r < t.npf; ++r) t.pf[r] = p.pf[r];
     t.vec = ((p.N & 3) == 0 && epi.vec_ok()) ? 1 : 0;
     // M <= 64 (every node-batched contraction at batch 64): M=64 MMAs, whose accumulator spreads 16 rows over each
     // TMEM lane quadrant (layout verified on hardware by tools/m64_probe.py), halve the MMA work and keep all

@@ -44,9 +44,41 @@ extern "C" void matgcn_internal_set_error(const char* where, const char* what) {
 // its operands meet the TMA alignment rules, otherwise (and always in exact mode) to the fp32 SIMT kernel.
 static std::atomic<unsigned long long> g_tc_launches{0};
 // L2 warm-up of the next launch's weight blocks (TcP::pf_*); MATGCN_L2_WARM=0 switches it off for A/B measurements
+static int l2_warm_level();
+static void add_pf(GemmP& p, const void* base, long long stride_bytes, long long chunk_bytes, int n) {
+    if (!base || p.npf >= 8 || chunk_bytes < 128 || chunk_bytes > 0x7fffff00LL || n <= 0) return;
+    // budget: what one launch pulls in must sit in L2 next to its own working set (126 MB L2; large shapes simply skip ranges)
+    long long have = chunk_bytes * n;
+    for (int r = 0; r < p.npf; ++r) have += (long long)p.pf[r].chunk * p.pf[r].n;
+    if (have > (64LL << 20)) return;
+    p.pf[p.npf++] = PfRange{reinterpret_cast<const char*>(base), stride_bytes, (int)(chunk_bytes & ~127LL), n};
+}
 static bool l2_warm_enabled() {
-    static const bool on = []() { const char* e = getenv("MATGCN_L2_WARM"); return !(e && e[0] == '0'); }();
-    return on;
+    return l2_warm_level() > 0;
+}
+// Warm-up pays where (a) a step's working set - the bf16 weight twins it streams plus ~20 [N,B,H] fp32 blocks of saved
+// activations, pre-activations and gradients - clearly exceeds L2, so that the next launch would otherwise start on HBM
+// latency (measured at N=403, B=64: -2.4 % step time with both layers warmed; at N=237, where the set is about L2-sized,
+// +2 %), and (b) the largest block to pull in, the gate weights' hidden rows, fits the per-launch budget (N=883: +0.6 % when
+// only parts fit).  MATGCN_L2_WARM=3 forces it on, 0 switches it off, 1 restricts it to the weight blocks.
+static bool l2_warm_layer(int N, int K, int Cin, int H, int B) {
+    if (!l2_warm_enabled()) return false;
+    if (l2_warm_level() >= 3) return true;
+    static const long long l2 = []() {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev);
+        return v > 0 ? (long long)v : (126LL << 20);
+    }();
+    const long long twins = (long long)N * K * (Cin + H) * 3 * H * 2;      // Wg16 + Wu16 bytes
+    const long long acts = 20LL * N * B * H * 4;
+    const long long gate_rows = (long long)N * K * H * 2 * H * 2;          // Wg16[n, k, Cin:, :] bytes
+    return twins + acts > l2 + l2 / 4 && gate_rows <= (64LL << 20);
+}
+// level 1: weight blocks only; level 2 (default): also the saved activations / pre-activations the next launches read
+static int l2_warm_level() {
+    static const int lvl = []() { const char* e = getenv("MATGCN_L2_WARM"); return (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 2; }();
+    return lvl;
 }
 template <class Cfg, bool A_KC, bool B_KC, class Epi>
 static cudaError_t gemm_any(bool tc, const GemmP& p, const Epi& epi, int Z, cudaStream_t st) {
@@ -1090,6 +1122,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     // Needs shapes for which the bf16 tensor-core launches are always eligible (16-byte pitches) and the per-phase launch path.
     const bool skip32 = bf && !(tc && multi_enabled()) && !(H & 7) && !(ldm & 7) && B >= 8;  // (B = reduction length of the weight gradients)
     const bool skip32x = skip32 && !xside_small_ok(Cin, H, K) && !(Cin & 7);
+    const bool warm = l2_warm_layer(N, K, Cin, H, B);
     // PX[t, 1..K) = M * x_t  (all t at once)
     {
         GemmP pp = prop_params(M, ldm, N, Kp, PX, B * Cin);
@@ -1181,8 +1214,9 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
                 EpiPlain e = epi_plain(PHt + U, 0, 0, B * H);
                 if (bf) { p.A16 = M16; p.B16 = PH16t; e.C16 = PH16t + U; }
                 if (skip32) e.c_z2_hi = 0;
-                if (bf && l2_warm_enabled()) {   // the gate contraction that follows streams Wg16[n, k, Cin:, :] from HBM
-                    p.pf_base = WG16 + (long long)Cin * 2 * H; p.pf_stride = (long long)I * 2 * H * 2; p.pf_chunk = H * 2 * H * 2; p.pf_n = N * K;
+                if (bf && warm) {   // the gate contraction that follows streams Wg16[n, k, Cin:, :] from HBM
+                    add_pf(p, WG16 + (long long)Cin * 2 * H, (long long)I * 2 * H * 2, (long long)H * 2 * H * 2, N * K);
+                    if (l2_warm_level() >= 2) add_pf(p, GXt, 0, (long long)3 * U * 4, 1);   // its epilogue reads GX[t] (and the tail after it)
                 }
                 STEP_GEMM(0, CfgBig, true, false, p, e, 1);
             }
@@ -1200,8 +1234,9 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
                 EpiPlain e = epi_plain(PZt + U, 0, 0, B * H);
                 if (bf) { pp.A16 = M16; pp.B16 = PZ16t; e.C16 = PZ16t + U; }
                 if (skip32) e.c_z2_hi = 0;
-                if (bf && l2_warm_enabled()) {   // the candidate contraction that follows streams Wu16[n, k, Cin:, :]
-                    pp.pf_base = WU16 + (long long)Cin * H; pp.pf_stride = (long long)I * H * 2; pp.pf_chunk = H * H * 2; pp.pf_n = N * K;
+                if (bf && warm) {   // the candidate contraction that follows streams Wu16[n, k, Cin:, :]
+                    add_pf(pp, WU16 + (long long)Cin * H, (long long)I * H * 2, (long long)H * H * 2, N * K);
+                    if (l2_warm_level() >= 2) add_pf(pp, RXt, 0, (long long)3 * U * 4, 1);  // the fused tail reads RX[t]
                 }
                 STEP_GEMM(2, CfgBig, true, false, pp, e, 1);
             }
@@ -1295,6 +1330,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     bool use_multi = tc && multi_enabled();
     // same rule as the forward pass: in bf16 mode the propagated slots k >= 1 (PH / PZ / PX there, DPT here) exist only as bf16 twins
     const bool skip32 = bf && !use_multi && !(H & 7) && !(ldm & 7) && B >= 8;
+    const bool warm = l2_warm_layer(N, K, Cin, H, B);
     for (int attempt = 0; attempt < 2; ++attempt) {
         MultiBuilder mb;
         for (int t = T - 1; t >= 0; --t) {
@@ -1369,8 +1405,8 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
             if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
             p.need16 = skip32 ? 1 : 0;
-            if (bf && l2_warm_enabled()) {   // B5 streams Wg16[n, k, Cin:, :]
-                p.pf_base = WG16 + (long long)Cin * 2 * H; p.pf_stride = (long long)I * 2 * H * 2; p.pf_chunk = H * 2 * H * 2; p.pf_n = N * K;
+            if (bf && warm) {   // B5 streams Wg16[n, k, Cin:, :]
+                add_pf(p, WG16 + (long long)Cin * 2 * H, (long long)I * 2 * H * 2, (long long)H * 2 * H * 2, N * K);
             }
             STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H, DG16}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPZA + (long long)t * n_adp * U, (long long)n_adp * U);
@@ -1398,8 +1434,15 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             p.B = DPT + U; p.ldb = B * H; p.N = B * H;
             if (bf) { p.A16 = M16; p.B16 = DPT16 + U; }
             p.need16 = skip32 ? 1 : 0;
-            if (bf && l2_warm_enabled() && t > 0) {   // B3 of the next reverse step streams Wu16[n, k, Cin:, :]
-                p.pf_base = WU16 + (long long)Cin * H; p.pf_stride = (long long)I * H * 2; p.pf_chunk = H * H * 2; p.pf_n = N * K;
+            if (bf && warm && t > 0) {   // B3 of the next reverse step streams Wu16[n, k, Cin:, :]
+                add_pf(p, WU16 + (long long)Cin * H, (long long)I * H * 2, (long long)H * H * 2, N * K);
+                if (l2_warm_level() >= 2) {   // ... and its fused head reads the saved activations of step t-1
+                    const long long ub = (long long)U * 4;
+                    add_pf(p, ws + w.H1 + (t - 1) * U, 0, ub, 1); add_pf(p, ws + w.R2 + (t - 1) * U, 0, ub, 1);
+                    add_pf(p, ws + w.HC2 + (t - 1) * U, 0, ub, 1); add_pf(p, ws + w.Z2 + (t - 1) * U, 0, ub, 1);
+                    add_pf(p, PH + (long long)(t - 1) * K * U, 0, ub, 1); add_pf(p, ws + w.R + (t - 1) * U, 0, ub, 1);
+                    add_pf(p, ws + w.HC + (t - 1) * U, 0, ub, 1);
+                }
             }
             STEP_GEMM(5, CfgBig, false, false, p, (EpiB6{DPT, DHD, DHC, B * H}), 1);
             if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPHA + (long long)t * n_adp * U, (long long)n_adp * U);
