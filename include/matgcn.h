@@ -156,6 +156,9 @@ size_t matgcn_encoder_layer_bwd_ws_bytes(int T, int N, int B, int Cin, int H, in
 size_t matgcn_encoder_layer_y_offset(int T, int N, int B, int Cin, int H, int K);
 size_t matgcn_encoder_layer_y_tstride(int T, int N, int B, int Cin, int H, int K);
 
+/* With MATGCN_FLAG_TF32 | MATGCN_FLAG_BF16 (and H % 8 == 0, ldm % 8 == 0, B >= 8) the propagated slots k >= 1 of PX (wide
+ * layers), PH and PZ exist only as their bf16 twins: their fp32 areas in the workspace are left unwritten.  Slot 0 of each
+ * (x_t, h_t, z*h) and every other saved activation stay float32 in all modes. */
 /* Float offsets of the named workspace slots, for tests/diagnostics.  names: "PX","GX","RX","PH",
  * "PZ","Z","R","HC","H1","Z2","R2","HC2","ZH2".  Returns (size_t)-1 for an unknown name. */
 size_t matgcn_encoder_layer_slot_offset(const char* name, int T, int N, int B, int Cin, int H, int K);
