@@ -1,4 +1,4 @@
-"""The callers either side of the Multi-ATGCN path, on the device.
+"""The callers either side of the Multi-ATGCN path (f3 is ``ops.output_head``), on the device.
 
 f1  ``FusedClipAdam`` + ``fused_train_step``: the loop body of ``TrafficStateExecutor._train_epoch``
     (libcity/executor/traffic_state_executor.py:413-422) with the optimiser half -
@@ -35,7 +35,11 @@ class FusedClipAdam:
 
     After construction ``p.data`` and ``p.grad`` of every trainable parameter are views into ``self.param`` /
     ``self.grad`` (so autograd accumulates straight into the bucket and a data-parallel all-reduce is one call on
-    ``self.grad``).  ``zero_grad`` is one memset."""
+    ``self.grad``).  ``zero_grad`` is one memset.
+
+    One difference from ``torch.optim.Adam``: a parameter that received no gradient in a step keeps a zero-filled slot instead
+    of ``grad is None``, so with ``weight_decay != 0`` it is decayed where torch would skip it (with the executor's default
+    ``weight_decay = 0`` the update of such a slot is exactly zero, as in torch)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, max_grad_norm: Optional[float] = None):
