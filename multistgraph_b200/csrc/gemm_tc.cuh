@@ -726,9 +726,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int z1, z2, m0, n0, kt0, kt1;
                 decode(tile, z1, z2, m0, n0, kt0, kt1);
                 if (p.dbg && blockIdx.x == 0) p.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
-                for (int kt = kt0; kt < kt1; ++kt) {
-                    const int kb = kt / kt_per_kb;
-                    const int k0 = (kt - kb * kt_per_kb) * BK;
+                // (k-batch, offset inside it) advance incrementally: this single thread's instruction latency is on the critical
+                // path of the short launches, a division per k-block is not free
+                int kb = kt0 / kt_per_kb;
+                int k0 = (kt0 - kb * kt_per_kb) * BK;
+                const int k_end = kt_per_kb * BK;
+                for (int kt = kt0; kt < kt1; ++kt, k0 += BK) {
+                    if (k0 == k_end) { k0 = 0; ++kb; }
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_u32(stage_base + stage * S::STAGE_BYTES);
                     const uint32_t sb = sa + S::A_BYTES;
