@@ -6,12 +6,16 @@
 
 One "step" = one pass of ``TrafficStateExecutor._train_epoch``'s loop body over one batch of
 synthetic input of the named shape: zero_grad -> calculate_loss (forward) -> backward ->
-[gradient all-reduce when N > 1] -> clip_grad_norm_(5) -> Adam step.
+[gradient all-reduce when N > 1] -> clip_grad_norm_(5) -> Adam step (the last two fused over one flat
+bucket, ``train.FusedClipAdam``).
 
 * ``value``  : samples/s with the step's inputs already resident in HBM (CUDA-event timed,
                max over ranks).
 * ``e2e``    : the same metric through the public model API with HOST buffers: every step copies
-               its batch from pinned host memory to the device and reads the loss back.
+               its batch from pinned host memory to the device (on a copy stream, overlapping the
+               previous step) and reads the loss back on the host, all inside the timed region.
+* ``e2e_device_windows``: the same step with the batch gathered on the device from a series
+               resident in HBM (``train.DeviceWindowBank``); only label-start indices are uploaded.
 * ``roofline``: the dominant kernel (support-propagation GEMM), timed live with CUDA events on
                the launching stream at the step's exact shape.
 * ``cpu_baseline``: the oracle (a port of the reference's CPU path) timed on this host's cores
@@ -27,7 +31,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -14,7 +14,7 @@ No CPU fallback: both need the CUDA library and CUDA tensors and raise ``MatgcnE
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Sequence
+from typing import Iterable, Optional
 
 import torch
 import torch.distributed as dist
