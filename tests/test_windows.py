@@ -81,3 +81,17 @@ def test_adam_oracle_matches_torch_clip_and_adam(wd, max_norm):
         if max_norm is not None:
             assert abs(total - float(total_t)) < 1e-12 * max(1.0, total)
             assert np.allclose(g_after, np.concatenate([q.grad.numpy().ravel() for q in params]), rtol=1e-12)
+
+
+def test_train_side_helpers_have_no_cpu_fallback():
+    """The product path of the 8f rows fails loudly without CUDA tensors (no silent PyTorch / oracle route)."""
+    from multistgraph_b200 import ops
+    from multistgraph_b200._cabi import MatgcnError
+    from multistgraph_b200.train import DeviceWindowBank, FusedClipAdam
+
+    with pytest.raises(MatgcnError):
+        FusedClipAdam([torch.nn.Parameter(torch.zeros(3))])
+    with pytest.raises(MatgcnError):
+        DeviceWindowBank(torch.zeros(100, 3, 2), 24, 24, 1, 0, 0)
+    with pytest.raises(MatgcnError):
+        ops.output_head(torch.zeros(2, 3, 4, 64), torch.zeros(5, 2, 64), torch.zeros(5))
