@@ -80,16 +80,22 @@ def od_view(adj_mx) -> np.ndarray:
 
 
 def similarity_view(static, n: int) -> np.ndarray:
-    """1 / euclidean distance between static feature rows (0 -> 1), or I (MultiATGCN.py:244-250)."""
+    """1 / euclidean distance between static feature rows (0 -> 1), or I (MultiATGCN.py:244-250).
+    Distances come from explicit differences (scipy ``cdist``, the reference's own call, MA.py:246): a Gram expansion
+    ``|a|^2 + |b|^2 - 2ab`` cancels badly for duplicated or nearly equal rows of unnormalised features, and then the
+    ``== 0 -> 1`` rule does not fire where the reference's does."""
     if static is None:
         return np.eye(n, dtype=np.float32)
+    from scipy.spatial.distance import cdist
+
     s = np.asarray(static, dtype=np.float64)
-    sq = (s * s).sum(1)
-    d2 = np.maximum(sq[:, None] + sq[None, :] - 2.0 * (s @ s.T), 0.0)
-    d = np.sqrt(d2)
-    d[np.arange(n), np.arange(n)] = 0.0
-    d[d == 0] = 1
-    return (1.0 / d).astype(np.float32)
+    out = np.empty((n, n), dtype=np.float32)
+    step = max(1, (1 << 24) // max(1, n))          # row blocks of ~16 M distances
+    for r0 in range(0, n, step):
+        d = cdist(s[r0:r0 + step], s)
+        d[d == 0] = 1
+        out[r0:r0 + step] = (1.0 / d).astype(np.float32)
+    return out
 
 
 def static_views(adjtype: str, data_feature: dict) -> Dict[str, object]:

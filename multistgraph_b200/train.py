@@ -29,13 +29,20 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-class FusedClipAdam:
+class FusedClipAdam(torch.optim.Optimizer):
     """Adam (no amsgrad) with an optional global-norm clip, over flat buffers.  Same arithmetic as
     ``clip_grad_norm_`` followed by ``torch.optim.Adam(params, lr, betas, eps, weight_decay).step()``.
 
+    It IS a ``torch.optim.Optimizer``: ``param_groups[0]`` carries ``lr`` / ``betas`` / ``eps`` / ``weight_decay`` and
+    ``step`` reads them from there, so the executor's ``_build_lr_scheduler`` (``MultiStepLR`` with the shipped
+    ``lr_decay`` recipe, MultiATGCN.json) attaches to it unchanged, and ``state_dict()`` / ``load_state_dict()`` use
+    ``torch.optim.Adam``'s own per-parameter layout (``step``, ``exp_avg``, ``exp_avg_sq``), so the checkpoints the executor
+    writes (executor:95, 106, 118, 136) move both ways between this class and a stock ``torch.optim.Adam``.
+
     After construction ``p.data`` and ``p.grad`` of every trainable parameter are views into ``self.param`` /
     ``self.grad`` (so autograd accumulates straight into the bucket and a data-parallel all-reduce is one call on
-    ``self.grad``).  ``zero_grad`` is one memset.
+    ``self.grad``).  ``zero_grad`` is one memset.  ``step`` verifies that the views are still in place (a later
+    ``model.to(...)`` / ``.float()`` would silently detach the model from the bucket) and raises otherwise.
 
     One difference from ``torch.optim.Adam``: a parameter that received no gradient in a step keeps a zero-filled slot instead
     of ``grad is None``, so with ``weight_decay != 0`` it is decayed where torch would skip it (with the executor's default
@@ -43,16 +50,20 @@ class FusedClipAdam:
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, max_grad_norm: Optional[float] = None):
-        self.params = [p for p in params if p.requires_grad]
-        if not self.params:
+        plist = [p for p in params if p.requires_grad]
+        if not plist:
             raise ValueError("no trainable parameters")
-        dev = self.params[0].device
+        dev = plist[0].device
         if dev.type != "cuda":
             raise MatgcnError("FusedClipAdam needs CUDA parameters: there is no CPU fallback")
-        for p in self.params:
+        for p in plist:
             if p.dtype != torch.float32 or p.device != dev:
                 raise MatgcnError("FusedClipAdam needs float32 parameters on one device")
-        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        super().__init__(plist, dict(lr=float(lr), betas=(float(betas[0]), float(betas[1])), eps=float(eps),
+                                     weight_decay=float(weight_decay)))
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedClipAdam keeps one parameter group (one flat bucket)")
+        self.params = plist
         self.max_grad_norm = max_grad_norm
         self.offsets = []
         off = 0
@@ -74,6 +85,15 @@ class FusedClipAdam:
         self._pin_grads()
         self._lib = _cabi.lib()
 
+    # hyper-parameters live in param_groups[0] (what lr schedulers and checkpoints touch); these are conveniences
+    @property
+    def lr(self) -> float:
+        return float(self.param_groups[0]["lr"])
+
+    @lr.setter
+    def lr(self, v: float):
+        self.param_groups[0]["lr"] = float(v)
+
     # -- gradient bucket -------------------------------------------------------------------------
     def _pin_grads(self):
         es = self.grad.element_size()
@@ -81,6 +101,15 @@ class FusedClipAdam:
         for p, o in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != base + o * es:
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+    def _check_param_views(self):
+        es = self.param.element_size()
+        base = self.param.data_ptr()
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() != base + o * es:
+                raise MatgcnError("FusedClipAdam: a parameter's storage was replaced after the optimiser was built "
+                                  "(model.to(...) / .float() / .half()?): the model no longer reads the flat bucket the "
+                                  "update writes - rebuild the optimiser after moving the model")
 
     def zero_grad(self, set_to_none: bool = False):
         """Replaces optimizer.zero_grad() (executor:414): one memset; the views are re-pinned in case a caller
@@ -99,26 +128,61 @@ class FusedClipAdam:
         return 1.0
 
     # -- update ----------------------------------------------------------------------------------
-    def step(self, grad_scale: float = 1.0):
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self._check_param_views()
+        es, base = self.grad.element_size(), self.grad.data_ptr()
+        for p, o in zip(self.params, self.offsets):   # a gradient that was re-created outside the bucket (zero_grad(set_to_none)
+            if p.grad is not None and p.grad.data_ptr() != base + o * es:   # by a foreign caller) is moved in, not dropped
+                self.grad[o:o + p.numel()].copy_(p.grad.reshape(-1))
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+        g = self.param_groups[0]
         self.step_count += 1
         st = _stream()
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
         _cabi.check(self._lib.matgcn_grad_sumsq(self.grad.data_ptr(), self.total, self._sumsq.data_ptr(), st), "grad_sumsq")
         _cabi.check(self._lib.matgcn_adam_clip_step(
             self.param.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.total,
-            self._sumsq.data_ptr(), float(self.max_grad_norm) if clip else 0.0, float(grad_scale), self.lr, self.betas[0],
-            self.betas[1], self.eps, self.weight_decay, self.step_count, 1, self.grad_norm.data_ptr(), st), "adam_clip_step")
+            self._sumsq.data_ptr(), float(self.max_grad_norm) if clip else 0.0, float(grad_scale), float(g["lr"]),
+            float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.step_count, 1,
+            self.grad_norm.data_ptr(), st), "adam_clip_step")
+        return loss
 
     # -- checkpointing (executor:95, 106, 118, 136 save/load optimizer.state_dict()) ---------------
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+        """``torch.optim.Adam``'s layout: state[i] = {step, exp_avg, exp_avg_sq} per parameter + param_groups."""
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            self.state[p] = {"step": torch.tensor(float(self.step_count)),
+                             "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                             "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+        sd = super().state_dict()
+        self.state.clear()
+        return sd
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.lr, self.betas, self.eps, self.weight_decay = sd["lr"], tuple(sd["betas"]), sd["eps"], sd["weight_decay"]
+        """Accepts a ``torch.optim.Adam`` (or own) state dict; the moments are copied into the flat buffers."""
+        super().load_state_dict(sd)
+        steps = set()
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                st = self.state.get(p)
+                if not st:
+                    continue
+                n = p.numel()
+                self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise MatgcnError("FusedClipAdam.load_state_dict: parameters carry different step counts (%s); one flat bucket "
+                              "has one bias-correction step" % sorted(steps))
+        if steps:
+            self.step_count = steps.pop()
+        self.state.clear()
 
 
 def fused_train_step(model, batch, opt: FusedClipAdam, micro_batches: int = 1):

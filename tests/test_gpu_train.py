@@ -286,3 +286,69 @@ def test_micro_batched_step_equals_one_shot_step():
     for (k, p), (_, q) in zip(models[0].named_parameters(), models[1].named_parameters()):
         if p.grad is not None and float(p.grad.abs().max()) > 0:
             assert (p.grad - q.grad).abs().max() <= 1e-4 * p.grad.abs().max(), k
+
+
+def test_fused_clip_adam_is_a_torch_optimizer_lr_schedule_and_checkpoint_interchange():
+    """ADVICE r1: the executor's default recipe attaches ``MultiStepLR`` (lr_decay, steps [5,10,20,30], ratio 0.75;
+    executor ``_build_lr_scheduler``) and saves / loads ``optimizer.state_dict()``.  Both must work on the fused optimiser,
+    and its checkpoints must move to and from a stock ``torch.optim.Adam``."""
+    from multistgraph_b200.train import FusedClipAdam
+
+    torch.manual_seed(0)
+    m1, m2 = _Toy().to(_dev()), _Toy().to(_dev())
+    m2.load_state_dict(m1.state_dict())
+    ref = torch.optim.Adam([p for p in m1.parameters() if p.requires_grad], lr=0.01, eps=1e-8)
+    opt = FusedClipAdam(m2.parameters(), lr=0.01, eps=1e-8)
+    assert isinstance(opt, torch.optim.Optimizer) and opt.param_groups[0]["lr"] == 0.01
+    s1 = torch.optim.lr_scheduler.MultiStepLR(ref, milestones=[2, 4], gamma=0.75)
+    s2 = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[2, 4], gamma=0.75)
+    names = [n for n, p in m2.named_parameters() if p.requires_grad]
+
+    def one_step(a, b, oa, ob, seed):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        oa.zero_grad()
+        ob.zero_grad()
+        for n in names:
+            gr = torch.randn(dict(a.named_parameters())[n].shape, generator=g).to(_dev())
+            dict(a.named_parameters())[n].grad = gr.clone()
+            pb = dict(b.named_parameters())[n]
+            if pb.grad is None:
+                pb.grad = gr.clone()
+            else:
+                pb.grad.add_(gr)
+        oa.step()
+        ob.step()
+
+    def close(a, b):
+        for n in names:
+            x, y = dict(a.named_parameters())[n], dict(b.named_parameters())[n]
+            assert (x - y).abs().max().item() <= 2e-6 * max(1.0, y.abs().max().item()), n
+
+    for epoch in range(5):
+        one_step(m1, m2, ref, opt, epoch)
+        s1.step()
+        s2.step()
+        assert abs(opt.param_groups[0]["lr"] - ref.param_groups[0]["lr"]) < 1e-12
+    assert abs(opt.lr - 0.01 * 0.75 * 0.75) < 1e-12
+    close(m1, m2)
+    # fused -> torch.optim.Adam and torch.optim.Adam -> fused, then two more steps on both sides
+    m3, m4 = _Toy().to(_dev()), _Toy().to(_dev())
+    m3.load_state_dict(m2.state_dict())
+    m4.load_state_dict(m1.state_dict())
+    adam3 = torch.optim.Adam([p for p in m3.parameters() if p.requires_grad], lr=0.5)
+    adam3.load_state_dict(opt.state_dict())
+    fused4 = FusedClipAdam(m4.parameters(), lr=0.5)
+    fused4.load_state_dict(ref.state_dict())
+    assert fused4.step_count == 5 and abs(fused4.lr - ref.param_groups[0]["lr"]) < 1e-12
+    for k in range(2):
+        one_step(m1, m3, ref, adam3, 100 + k)
+        one_step(m2, m4, opt, fused4, 100 + k)
+    close(m1, m3)
+    close(m1, m4)
+    close(m1, m2)
+    # a parameter whose storage is replaced behind the optimiser's back is an error, not a silent no-op
+    from multistgraph_b200._cabi import MatgcnError
+
+    m2.a.data = m2.a.data.clone()
+    with pytest.raises(MatgcnError):
+        opt.step()

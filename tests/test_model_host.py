@@ -107,3 +107,26 @@ def test_cpu_tensor_raises_without_fallback():
     model.load_state_dict(g["params"])
     with pytest.raises(Exception):
         model.predict(clone_batch(g["batch"]))
+
+
+def test_similarity_view_duplicate_and_near_duplicate_rows():
+    """MA.py:246-248: ``cdist`` distances, exact zeros -> 1.  Duplicated rows of unnormalised features (magnitudes up to 1e5)
+    must hit the ``== 0 -> 1`` rule and rows 1e-3 apart must not lose digits (the Gram expansion did both wrong)."""
+    import numpy as np
+    from scipy.spatial.distance import cdist
+
+    from multistgraph_b200 import graph_prep
+
+    for seed in range(6):
+        rng = np.random.default_rng(seed)
+        n = 97
+        s = rng.random((n, 30)) * 10.0 ** rng.integers(0, 6, size=(1, 30))
+        s[5] = s[40]
+        s[17] = s[40]
+        s[60] = s[61] + 1e-3
+        ref = cdist(s, s, metric="euclidean")
+        ref[ref == 0] = 1
+        ref = (1.0 / ref).astype(np.float32)
+        got = graph_prep.similarity_view(s, n)
+        assert got[5, 40] == 1.0 and got[40, 17] == 1.0 and got[5, 17] == 1.0
+        assert np.array_equal(got, ref)

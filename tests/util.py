@@ -49,6 +49,17 @@ def max_rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a - b).abs().max() / den).item()
 
 
+def elem_rel_err(a: torch.Tensor, b: torch.Tensor, floor_frac: float = 0.05) -> float:
+    """Element-wise relative error with an absolute floor: max |a-b| / max(|b|, floor_frac * max|b|).
+    Stricter than ``max_rel_err`` (small entries are judged against at most 1/floor_frac of their own size)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    den = torch.clamp(b.abs(), min=floor_frac * b.abs().max().item())
+    if den.max().item() == 0.0:
+        return (a - b).abs().max().item()
+    return ((a - b).abs() / den).max().item()
+
+
 def clone_batch(batch, device=None):
     return {k: (v.clone() if device is None else v.clone().to(device)) for k, v in batch.items()}
 
