@@ -100,6 +100,11 @@ int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X,
  * launch per contraction.  Returns the previous setting.  Default off (or MATGCN_MULTI=1 in the environment). */
 int matgcn_set_persistent(int on);
 
+/* Persistent recurrence kernels (bf16 mode, rnn_units = 64): each layer's 24-step recurrence (MA.py:200-211) runs as ONE
+ * cooperative launch whose phases are separated by grid barriers (csrc/rec_fwd.cuh) instead of four launches per time
+ * step.  on = 0 selects one launch per phase.  Returns the previous setting.  Default on (or MATGCN_REC=0 in the environment). */
+int matgcn_set_recurrent_kernel(int on);
+
 /* Fused tail of the forward step (candidate contraction + residual GRU cell + mix in one launch; tensor-core engine,
  * rnn_units = 64).  on = 0 selects the three separate contractions.  Returns the previous setting.  Default on
  * (or MATGCN_FUSED_TAIL=0 in the environment). */

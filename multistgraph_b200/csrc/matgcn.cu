@@ -14,6 +14,7 @@
 #include "epilogues.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc_multi.cuh"
+#include "rec_api.h"
 #include "res_bwd.cuh"
 #include "xside_mma.cuh"
 
@@ -819,6 +820,17 @@ extern "C" int matgcn_set_persistent(int on) {
     multi_flag() = on ? 1 : 0;
     return prev;
 }
+// Persistent recurrence kernels (rec_fwd.cuh: one cooperative launch per layer instead of four launches per time step; bf16 mode,
+// rnn_units = 64).  MATGCN_REC=0 or matgcn_set_recurrent_kernel(0) selects one launch per phase (A/B comparisons, tests).
+static int& rec_flag() {
+    static int f = []() { const char* e = getenv("MATGCN_REC"); return (e && e[0] == '0') ? 0 : 1; }();
+    return f;
+}
+extern "C" int matgcn_set_recurrent_kernel(int on) {
+    const int prev = rec_flag();
+    rec_flag() = on ? 1 : 0;
+    return prev;
+}
 // Fused tail of the forward step (candidate + residual cell + mix in one launch); MATGCN_FUSED_TAIL=0 or
 // matgcn_set_fused_tail(0) selects the three separate contractions (A/B comparisons, tests).
 static int& fused_tail_flag() {
@@ -1197,6 +1209,20 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     }
 
     bool use_multi = tc && multi_enabled();
+    if (skip32 && H == 64 && rec_flag() && fused_tail_enabled()) {
+        // the whole recurrence as one persistent cooperative launch (rec_fwd.cuh)
+        RecFwdArgs ra{T, N, B, Cin, K, ldm, M16, PH16, PZ16, WG16, WU16, GX, RX, PH, PZ,
+                      ws + w.Z, ws + w.R, ws + w.HC, ws + w.H1, ws + w.Z2, ws + w.R2, ws + w.HC2, ws + w.ZH2,
+                      RgH, RuH, mix, reinterpret_cast<unsigned int*>(ws + w.MPH)};
+        const cudaError_t re = launch_rec_fwd(ra, st);
+        if (re == cudaSuccess) {
+            g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+            TR();
+            tr.report("encoder_layer_fwd");
+            return 0;
+        }
+        if (re != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(re));
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         MultiBuilder mb;
         for (int t = 0; t < T; ++t) {

@@ -1,0 +1,50 @@
+"""Persistent recurrence kernels (csrc/rec_fwd.cuh: one cooperative launch per layer, grid barriers between the four
+phases of a time step) against the one-launch-per-phase path of the same library and against the oracle.
+
+Both paths read the same bf16 operand twins and accumulate in fp32 in the same order, so they agree far inside the
+bound of the bf16 mode; the oracle comparison at the Baltimore shape is the parity statement for the mode bench.py quotes."""
+import pytest
+import torch
+
+from multistgraph_b200 import _cabi
+from multistgraph_b200.model import MultiATGCN
+from multistgraph_b200.synthetic import make_batch, make_config, make_data_feature
+from tests.util import clone_batch, max_rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(model, batch, lib, rec):
+    prev = lib.matgcn_set_recurrent_kernel(1 if rec else 0)
+    try:
+        model.zero_grad(set_to_none=True)
+        n0 = lib.matgcn_launch_count()
+        y = model.predict(clone_batch(batch, DEV))
+        n = lib.matgcn_launch_count() - n0
+        model.calculate_loss(clone_batch(batch, DEV)).backward()
+        torch.cuda.synchronize()
+        return y.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}, n
+    finally:
+        lib.matgcn_set_recurrent_kernel(prev)
+
+
+@pytest.mark.parametrize("N,B,adjtype,D,tout", [(70, 8, "multi", 10, 6), (37, 64, "multi", 20, 6), (21, 100, "multi", 10, 6),
+                                                (150, 136, "od", 10, 3), (403, 64, "multi", 20, 24), (237, 64, "od", 10, 3)])
+def test_persistent_forward_matches_per_phase_launches(N, B, adjtype, D, tout):
+    """B = 8 / 64: half-height (M = 64) per-node tiles; B = 100: one full-height tile with a ragged last quadrant; B = 136:
+    two row tiles per node; adjtype 'od' + bidirection: K = 2 supports; (403, 64) and (237, 64): the BASELINE shapes."""
+    cfg = make_config(adjtype=adjtype, adpadj="bidirection", embed_dim=D, output_window=tout, batch_size=B,
+                      device=torch.device(DEV), matgcn_mode="bf16")
+    df = make_data_feature(N, seed=13)
+    batch = make_batch(N, B, tout, seed=13)
+    torch.manual_seed(3)
+    model = MultiATGCN(dict(cfg), df).to(DEV).eval()
+    lib = _cabi.lib()
+    y0, g0, n0 = _run(model, batch, lib, False)
+    y1, g1, n1 = _run(model, batch, lib, True)
+    assert n0 - n1 >= 2 * (4 * 24 - 1), "the persistent kernel should replace four launches per step and layer (%d vs %d)" % (n1, n0)
+    assert torch.isfinite(y1).all()
+    assert max_rel_err(y1, y0) < 1e-5
+    for k in g0:
+        assert max_rel_err(g1[k], g0[k]) < 1e-4, k

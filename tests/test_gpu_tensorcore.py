@@ -178,6 +178,7 @@ def test_fused_step_tail_matches_separate_contractions(N, B, mode):
 
     def run(fused):
         prev = lib.matgcn_set_fused_tail(1 if fused else 0)
+        prev_rec = lib.matgcn_set_recurrent_kernel(0)   # compare the per-phase launches (the persistent kernel always fuses the tail)
         try:
             model.zero_grad(set_to_none=True)
             n0 = lib.matgcn_launch_count()
@@ -188,6 +189,7 @@ def test_fused_step_tail_matches_separate_contractions(N, B, mode):
             return y.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}, n
         finally:
             lib.matgcn_set_fused_tail(prev)
+            lib.matgcn_set_recurrent_kernel(prev_rec)
 
     y0, g0, n0 = run(False)
     y1, g1, n1 = run(True)
