@@ -1,19 +1,29 @@
-// Persistent forward recurrence of one encoder layer (bf16 mode, rnn_units = 64): all T time steps of
+// Persistent forward recurrence of one encoder layer (bf16 mode, rnn_units = 64, at most 64 samples per GPU): all T steps of
 //   PH[t,1..] = M h_{t-1}  ->  gate (per node)  ->  PZ[t,1..] = M (z h)  ->  candidate + residual GRU cell + mix -> h_t
 // (MA.py:120-128, 142-150, 200-211) run as ONE cooperative launch instead of 4 launches per step.
 //
 // Why: one launch of the per-phase path does <= 3 tiles per SM and pays the launch floor, a cold instruction cache and a
-// full pipeline ramp / drain every time (~25 us per phase for ~5 us of work at the Baltimore shape).  Here the four
-// phases of a step are separated by a grid-wide barrier (one L2 atomic + an acquire spin, ~1 us) and the tile ->
-// CTA assignment is static, so that
+// full pipeline ramp / drain every time.  Here the four phases of a step are separated by a grid-wide barrier (one L2 atomic
+// + an acquire spin) and the tile -> CTA assignment is static, so that
 //   * every generic-proxy read of data produced inside the kernel (h_{t-1}, r) is a read of what the SAME CTA wrote;
 //   * the only data that crosses CTAs are the bf16 operand twins, written by epilogue warps (generic proxy) and read by
 //     TMA (async proxy) after the barrier;
-//   * the per-node weight blocks of a CTA's nodes are the same every step (L2-resident, evict-last).
+//   * the per-node weight blocks of a CTA's nodes are the same every step (evict-last in L2).
 //
 // Roles (384 threads, one CTA per SM): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator,
-// warp 3 = L2 prefetch of the next phase's epilogue inputs, warps 4-11 = epilogue.  4-stage ring of 32 KB (A 16 KB | B 16 KB),
-// two 128-column fp32 accumulators in TMEM.
+// warp 3 = L2 prefetch of the next per-node phase's epilogue inputs, warps 4-11 = epilogue.
+// Shared memory: 4-stage operand ring of 32 KB (A 16 KB | B 16 KB), the residual-cell weights as resident TF32 operand
+// tiles (48 KB), two 16 KB operand tiles the epilogue writes (h1, z2*h1), barriers.
+// Tensor memory (512 columns): two 128-column accumulators for the streamed contractions, 128 + 64 columns for the
+// residual-cell products.
+//
+// Epilogues read the accumulator of a 64-row tile (M = 64 MMA: 16 rows per TMEM lane quadrant) with tcgen05.ld.16x256b,
+// whose register layout (thread -> rows lane/4 and lane/4 + 8, column pairs 8j + 2*(lane%4); tools/ubench/ldtm_probe.cu)
+// keeps all 32 lanes busy and gives 32-byte sectors per row quad; everything a tile's epilogue reads from global memory is
+// requested before the accumulator is waited for.
+// The tail (candidate -> residual GRU cell -> mix) keeps its two small products on the tensor cores: the epilogue warps
+// write h1 (then z2*h1) as a 128B-swizzled K-major TF32 operand tile, the MMA warp multiplies it with the resident weights
+// into TMEM and the same warps pick the result up again - three accumulator round trips per tile, no mma.sync.
 #pragma once
 #include "epilogues.cuh"
 #include "gemm_tc.cuh"
@@ -24,10 +34,17 @@ namespace matgcn {
 constexpr int RF_STAGES = 4;
 constexpr int RF_A_BYTES = 16384;
 constexpr int RF_STAGE_BYTES = 32768;
-constexpr int RF_EPI_BYTES = TC_EPI_WARPS * 32 * TC_EPI_LD * 4;
+constexpr int RF_WG_BYTES = 2 * 128 * 128;   // Rg_h [128 outputs][64 inputs] fp32: two 32-wide K slabs of 128 rows x 128 bytes
+constexpr int RF_WU_BYTES = 2 * 64 * 128;    // Ru_h [64][64]
+constexpr int RF_S_BYTES = 2 * 64 * 128;     // h1 / z2*h1 operand tile [64 rows][64] fp32
 constexpr int RF_BAR_BYTES = 256;
-constexpr int RF_RES_BYTES = (3 * 64) * TC_RES_LD * 4;
-constexpr int RF_SMEM_TOTAL = RF_STAGES * RF_STAGE_BYTES + RF_EPI_BYTES + RF_BAR_BYTES + RF_RES_BYTES + 1024;
+constexpr int RF_OFF_WG = RF_STAGES * RF_STAGE_BYTES;
+constexpr int RF_OFF_WU = RF_OFF_WG + RF_WG_BYTES;
+constexpr int RF_OFF_S1 = RF_OFF_WU + RF_WU_BYTES;
+constexpr int RF_OFF_S2 = RF_OFF_S1 + RF_S_BYTES;
+constexpr int RF_OFF_BAR = RF_OFF_S2 + RF_S_BYTES;
+constexpr int RF_SMEM_TOTAL = RF_OFF_BAR + RF_BAR_BYTES + 1024;
+constexpr int RF_TMEM_D2 = 256, RF_TMEM_D3 = 384;
 
 struct RecMaps {
     CUtensorMap M;    // base matrices (A of the propagation): {N, Kp*N}
@@ -41,8 +58,6 @@ struct RecMaps {
 
 struct RecFwdP {
     int T, N, B, K, Cin;
-    int m64;            // B <= 64: M = 64 MMAs for the per-node contractions
-    int node_tiles_m;   // row tiles per node (ceil(B / 128); 1 when m64)
     int prop_tiles_m, prop_tiles_n, prop_kt;
     long long U;        // N * B * 64
     const float* GX; const float* RX;      // [T, N*B, 3H]
@@ -70,27 +85,41 @@ __device__ __forceinline__ void rf_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// 16 TMEM lanes x 32 columns: register 4j + w of a thread = (row lane/4 + 8*(w/2), column 8j + 2*(lane%4) + w%2)
+__device__ __forceinline__ void rf_tmem_ld16x4(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
 __device__ __forceinline__ void rf_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t rf_pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-// 32-byte global accesses (one full sector per lane)
+// 32-byte global store (one full sector per lane)
 __device__ __forceinline__ void rf_st8(void* p, const uint32_t (&v)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
-__device__ __forceinline__ void rf_st8f(float* p, const float* v) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void rf_ld8f(const float* p, float* v) {
-    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
-}
+__device__ __forceinline__ float2 rf_ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ void rf_st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void rf_proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// fine-grained timeline of CTA 0 at the middle time step: slot s of tile i (first four tiles of the CTA) of phase ph
+#define RF_STAMP(ph, i, s)                                                                                                   \
+    do {                                                                                                                     \
+        if (p.dbg && blockIdx.x == 0 && t == (T >> 1) && (i) < 4) p.dbg[T * 16 + (((ph) * 4 + (i)) << 3) + (s)] = clock64(); \
+    } while (0)
+#define RF_STAMP_E(ph, i, s)                        \
+    do {                                            \
+        if (threadIdx.x == 128) RF_STAMP(ph, i, s); \
+    } while (0)
 
 __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_constant__ RecMaps maps, const RecFwdP p) {
     constexpr int H = 64;
@@ -98,17 +127,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
     uint8_t* smem = smem_raw;
     if (smem_u32(smem) & 1023u) __trap();
     uint8_t* stage_base = smem;
-    float* epi_buf = reinterpret_cast<float*>(smem + RF_STAGES * RF_STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RF_STAGES * RF_STAGE_BYTES + RF_EPI_BYTES);
-    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], phase_bar; then the TMEM base slot
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RF_STAGES + 5);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RF_OFF_BAR);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], phase_bar, s1_full, s2_full, r2_full, r3_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RF_STAGES + 9);
     volatile uint32_t* phase_cnt = tmem_slot + 1;   // number of grid barriers this CTA has passed (polled by the prefetch warp)
-    float* res_w = reinterpret_cast<float*>(smem + RF_STAGES * RF_STAGE_BYTES + RF_EPI_BYTES + RF_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t full0 = bar0, empty0 = bar0 + 8u * RF_STAGES, tfull0 = bar0 + 8u * (2 * RF_STAGES);
     const uint32_t tempty0 = tfull0 + 16u, phase_bar = tfull0 + 32u;
+    const uint32_t s1_full = phase_bar + 8u, s2_full = phase_bar + 16u, r2_full = phase_bar + 24u, r3_full = phase_bar + 32u;
+    const uint32_t wg_s = smem_u32(smem + RF_OFF_WG), wu_s = smem_u32(smem + RF_OFF_WU);
+    const uint32_t s1_s = smem_u32(smem + RF_OFF_S1), s2_s = smem_u32(smem + RF_OFF_S2);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < RF_STAGES; ++s) {
@@ -120,12 +150,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
             mbar_init(tempty0 + 8u * a, TC_EPI_WARPS);
         }
         mbar_init(phase_bar, 1);
+        mbar_init(s1_full, TC_EPI_WARPS);
+        mbar_init(s2_full, TC_EPI_WARPS);
+        mbar_init(r2_full, 1);
+        mbar_init(r3_full, 1);
         *phase_cnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (warp >= 4) {
+        // residual-cell weights Rg_h [128][64], Ru_h [64][64] (fp32, row = output) -> K-major 128B-swizzled operand tiles:
+        // element (o, i) -> slab i/32, row o, 16-byte chunk ((i%32)/4) ^ (o%8)
+        const int et = threadIdx.x - 128;
+        for (int idx = et; idx < 3 * 64 * 16; idx += TC_EPI_WARPS * 32) {
+            const int o = idx >> 4, i4 = (idx & 15) * 4;
+            const bool g = o < 128;
+            const int oo = g ? o : o - 128;
+            const float4 v = g ? ld4(p.RgH + oo * 64 + i4) : ld4(p.RuH + oo * 64 + i4);
+            uint8_t* dst = smem + (g ? RF_OFF_WG + (i4 >> 5) * (128 * 128) : RF_OFF_WU + (i4 >> 5) * (64 * 128)) + oo * 128 +
+                           ((((i4 & 31) >> 2) ^ (oo & 7)) << 4);
+            *reinterpret_cast<float4*>(dst) = v;
+        }
+        rf_proxy_fence_smem();   // generic-proxy writes -> tensor-core (async proxy) reads
     }
     tc_fence_before();
     __syncthreads();
@@ -135,8 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
     const int T = p.T, K = p.K;
     const int G = gridDim.x;
     const int prop_tiles = p.prop_tiles_m * p.prop_tiles_n;
-    const int node_tiles = p.N * p.node_tiles_m;
-    const uint32_t a_rows_bytes = p.m64 ? 8192u : 16384u;   // A box of the per-node contractions: 64 or 128 rows of 128 bytes
+    const int node_tiles = p.N;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -156,6 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                         const int slot = t * K;
                         for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
                             const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                            RF_STAMP(ph, tile / G, 0);
                             for (int kt = 0; kt < p.prop_kt; ++kt) {
                                 mbar_wait(empty0 + 8u * stage, phase ^ 1);
                                 const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
@@ -166,24 +215,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                                 tma_load_5d(sb + 8192, tb, fb, tn * 128 + 64, kt * 64, slot, 0, 0);
                                 if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
                             }
+                            RF_STAMP(ph, tile / G, 1);
                         }
                     } else {
                         const bool gate = ph == 1;
                         const CUtensorMap* ta = gate ? &maps.PHa : &maps.PZa;
                         const CUtensorMap* tw = gate ? &maps.WG : &maps.WU;
-                        const uint32_t tx = a_rows_bytes + (gate ? 16384u : 8192u);
-                        for (int tile = blockIdx.x; tile < node_tiles; tile += G) {
-                            const int n = tile / p.node_tiles_m, m0 = (tile - n * p.node_tiles_m) * 128;
+                        const uint32_t tx = 8192u + (gate ? 16384u : 8192u);
+                        for (int n = blockIdx.x; n < node_tiles; n += G) {
+                            RF_STAMP(ph, n / G, 0);
                             for (int k = 0; k < K; ++k) {
                                 mbar_wait(empty0 + 8u * stage, phase ^ 1);
                                 const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
                                 const uint32_t fb = full0 + 8u * stage;
                                 mbar_expect_tx(fb, tx);
-                                tma_load_5d(sa, ta, fb, 0, m0, n, t * K + k, 0);
+                                tma_load_5d(sa, ta, fb, 0, 0, n, t * K + k, 0);
                                 tma_load_5d_hint(sb, tw, fb, 0, p.Cin, k, n, 0, pol);
                                 if (gate) tma_load_5d_hint(sb + 8192, tw, fb, 64, p.Cin, k, n, 0, pol);
                                 if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
                             }
+                            RF_STAMP(ph, n / G, 1);
                         }
                     }
                 }
@@ -192,60 +243,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            // instruction descriptors: D = f32, A = B = bf16, A K-major, B MN-major, N >> 3, M >> 4
-            const uint32_t id_base = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16);
-            const uint32_t id_prop = id_base | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t mnode = p.m64 ? 64u : 128u;
-            const uint32_t id_gate = id_base | ((uint32_t)(128 >> 3) << 17) | ((mnode >> 4) << 24);
-            const uint32_t id_cand = id_base | ((uint32_t)(64 >> 3) << 17) | ((mnode >> 4) << 24);
+            // instruction descriptors: D = f32; bf16 operands, A K-major, B MN-major (streamed contractions);
+            // tf32 operands, both K-major (residual-cell products); N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t id_bf = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16);
+            const uint32_t id_prop = id_bf | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t id_gate = id_bf | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            const uint32_t id_cand = id_bf | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            const uint32_t id_tf = (1u << 4) | (2u << 7) | (2u << 10);
+            const uint32_t id_rg = id_tf | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            const uint32_t id_ru = id_tf | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
             int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int t = 0; t < T; ++t) {
-                for (int ph = 0; ph < 4; ++ph) {
+            uint32_t phase = 0, acc_phase = 0, res_par = 0;
+            int t = 0, ph = 0;
+            auto issue_tile = [&](int nk, uint32_t idesc, int ti) {   // one streamed contraction into the next accumulator buffer
+                mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1);
+                tc_fence_after();
+                RF_STAMP(ph, ti, 2);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 128);
+                for (int kt = 0; kt < nk; ++kt) {
+                    mbar_wait(full0 + 8u * stage, phase);
+                    tc_fence_after();
+                    if (kt == 0) RF_STAMP(ph, ti, 3);
+                    const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t da = umma_desc(sa + kk * 32, 16, 1024, 2);
+                        const uint64_t db = umma_desc(sb + kk * 2048, 8192, 1024, 2);
+                        umma_bf16(tmem_d, da, db, idesc, (kt > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8u * stage);
+                    if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull0 + 8u * acc);
+                RF_STAMP(ph, ti, 4);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            };
+            for (t = 0; t < T; ++t) {
+                for (ph = 0; ph < 3; ++ph) {
                     const bool prop = ph == 0 || ph == 2;
                     const int ntiles = prop ? prop_tiles : node_tiles;
-                    const int nk = prop ? p.prop_kt : K;
-                    const uint32_t idesc = prop ? id_prop : (ph == 1 ? id_gate : id_cand);
-                    for (int tile = blockIdx.x; tile < ntiles; tile += G) {
-                        mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1);
-                        tc_fence_after();
-                        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 128);
-                        for (int kt = 0; kt < nk; ++kt) {
-                            mbar_wait(full0 + 8u * stage, phase);
-                            tc_fence_after();
-                            const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
+                    for (int tile = blockIdx.x; tile < ntiles; tile += G) issue_tile(prop ? p.prop_kt : K, prop ? id_prop : id_gate, tile / G);
+                }
+                // tail: the candidate contraction of the NEXT tile is issued before the residual-cell products of this one
+                ph = 3;
+                if ((int)blockIdx.x < node_tiles) issue_tile(K, id_cand, 0);
+                for (int n = blockIdx.x; n < node_tiles; n += G) {
+                    if (n + G < node_tiles) issue_tile(K, id_cand, n / G + 1);
+                    mbar_wait(s1_full, res_par);   // h1 operand tile written
+                    tc_fence_after();
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const uint64_t da = umma_desc(sa + kk * 32, 16, 1024, 2);
-                                const uint64_t db = umma_desc(sb + kk * 2048, 8192, 1024, 2);
-                                umma_bf16(tmem_d, da, db, idesc, (kt > 0 || kk > 0) ? 1u : 0u);
-                            }
-                            umma_commit(empty0 + 8u * stage);
-                            if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
-                        }
-                        umma_commit(tfull0 + 8u * acc);
-                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                    }
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_tf32(tmem_base + RF_TMEM_D2, umma_desc(s1_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
+                                  umma_desc(wg_s + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 2), id_rg, kk > 0 ? 1u : 0u);
+                    umma_commit(r2_full);
+                    mbar_wait(s2_full, res_par);   // z2*h1 operand tile written
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_tf32(tmem_base + RF_TMEM_D3, umma_desc(s2_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
+                                  umma_desc(wu_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_ru, kk > 0 ? 1u : 0u);
+                    umma_commit(r3_full);
+                    res_par ^= 1;
                 }
             }
         }
     } else if (warp == 3) {
         // ================================ L2 prefetch of epilogue inputs ================================
-        // While a propagation phase runs (L2 -> SM bound, HBM idle) pull the pre-activation rows the NEXT per-node phase of
-        // this CTA reads: GX[t] gate columns before the gate phase, GX[t] candidate columns and RX[t] before the tail.
+        // While a propagation phase runs (L2 -> SM bound, HBM idle) pull the pre-activation rows the per-node phase after it
+        // reads on this CTA: GX[t] during M*h, RX[t] during M*(z*h).
         for (int t = 0; t < T; ++t) {
-            const float* GXt = p.GX + (long long)t * 3 * p.U;
-            const float* RXt = p.RX + (long long)t * 3 * p.U;
-            while (*phase_cnt < (uint32_t)(4 * t)) __nanosleep(256);   // step t has begun
-            for (int tile = blockIdx.x; tile < node_tiles; tile += G) {
-                const int n = tile / p.node_tiles_m, m0 = (tile - n * p.node_tiles_m) * 128;
-                const int rows = min(p.m64 ? 64 : 128, p.B - m0);
-                const long long g0 = (long long)n * p.B + m0;
-                // rows of 3H floats = 6 lines of 128 bytes each: GX whole row (gate: 4 lines, candidate: 2), RX whole row
-                for (int idx = lane; idx < rows * 6; idx += 32) {
-                    const long long off = (g0 + idx / 6) * 3 * H + (idx % 6) * 32;
-                    pf_l2(GXt + off);
-                    pf_l2(RXt + off);
+            for (int part = 0; part < 2; ++part) {
+                const float* X = (part == 0 ? p.GX : p.RX) + (long long)t * 3 * p.U;
+                while (*phase_cnt < (uint32_t)(4 * t + 2 * part)) __nanosleep(256);
+                for (int n = blockIdx.x; n < node_tiles; n += G) {
+                    const float* base = X + (long long)n * p.B * 3 * H;
+                    for (int idx = lane; idx < p.B * 6; idx += 32) pf_l2(base + idx * 32);   // rows of 3H floats = 6 lines
                 }
             }
         }
@@ -253,45 +325,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
         // ================================ epilogue ================================
         const int q = warp & 3;             // TMEM lane quadrant
         const int half = (warp - 4) >> 2;   // which of the two warps of that quadrant
-        float* buf = epi_buf + (warp - 4) * (32 * TC_EPI_LD);
-        float* buf_other = epi_buf + ((warp - 4) ^ 4) * (32 * TC_EPI_LD);
-        {
-            // residual-cell weights Rg_h [128][64] and Ru_h [64][64] -> padded tiles in shared memory, once
-            const int et = threadIdx.x - 128;
-            for (int idx = et; idx < 3 * 64 * 16; idx += TC_EPI_WARPS * 32) {
-                const int n = idx >> 4, k4 = (idx & 15) * 4;
-                const float4 v = n < 128 ? ld4(p.RgH + n * 64 + k4) : ld4(p.RuH + (n - 128) * 64 + k4);
-                *reinterpret_cast<float4*>(res_w + n * TC_RES_LD + k4) = v;
-            }
-            asm volatile("bar.sync 5, 256;" ::: "memory");
-        }
-        TcP tp;   // the fields the fused-tail epilogue reads
-        tp.M = p.B;
-        tp.m64 = p.m64;
         int acc = 0;
-        uint32_t acc_phase = 0, nbar = 0;
-        const int rows_q = p.m64 ? 16 : 32;
+        uint32_t acc_phase = 0, nbar = 0, res_par = 0;
         const int ldc = p.B * H;
         const long long prop_rows = (long long)(K - 1) * p.N;
+        // 16x256b coordinates of this thread inside a 64-row tile: rows b0 and b0 + 8, column pairs 8j + cp (+ 32*half)
+        const int b0 = q * 16 + (lane >> 2);
+        const bool ok0 = b0 < p.B, ok1 = b0 + 8 < p.B;
+        // row offsets (relative to row b0 of the node) used for LOADS: rows past the batch read row 0 of the node instead
+        const long long rd[2] = {ok0 ? 0 : -(long long)b0, ok1 ? 8 : -(long long)b0};
+        const int ch = half * 32 + (lane & 3) * 2;
+        // this thread's 8-byte slots in the operand tiles: slab `half`, rows b0 / b0 + 8 (same swizzle phase: 8 rows apart)
+        const uint32_t s_off = (uint32_t)(half * 8192 + b0 * 128 + ((lane & 1) << 3));
+        const uint32_t s_c0 = (uint32_t)((lane & 2) >> 1), s_x = (uint32_t)(b0 & 7);
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
         for (int t = 0; t < T; ++t) {
-            const long long tU = (long long)t * p.U;
-            const float* GXt = p.GX + 3 * tU;
-            const float* RXt = p.RX + 3 * tU;
-            float* PHt = p.PH + (long long)t * K * p.U;     // h_{t-1} (fp32)
-            float* PZt = p.PZ + (long long)t * K * p.U;     // z*h (fp32)
-            __nv_bfloat16* PH16t = p.PH16 + (long long)t * K * p.U;
-            __nv_bfloat16* PZ16t = p.PZ16 + (long long)t * K * p.U;
             for (int ph = 0; ph < 4; ++ph) {
                 if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(t * 4 + ph) * 4 + 0] = clock64();
                 if (ph == 0 || ph == 2) {
-                    // ---- propagation: bf16 twin of the accumulator -> slots 1.. of PH16 / PZ16 ----
-                    __nv_bfloat16* dst = (ph == 0 ? PH16t : PZ16t) + p.U;
+                    // ---- propagation (128-row tiles, lane = row): bf16 twin of the accumulator -> slots 1.. of PH16 / PZ16 ----
+                    __nv_bfloat16* dst = (ph == 0 ? p.PH16 : p.PZ16) + ((long long)t * K + 1) * p.U;
                     for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
                         const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
                         const long long row = (long long)tm * 128 + q * 32 + lane;
+                        RF_STAMP_E(ph, tile / G, 5);
                         mbar_wait(tfull0 + 8u * acc, acc_phase);
                         tc_fence_after();
-                        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
+                        RF_STAMP_E(ph, tile / G, 6);
+                        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 128) + tlane;
 #pragma unroll
                         for (int cc = 0; cc < 2; ++cc) {
                             const int c = half + 2 * cc;
@@ -313,83 +374,202 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                         }
                         tc_fence_before();
                         __syncwarp();
+                        RF_STAMP_E(ph, tile / G, 7);
                         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
                         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     }
                 } else if (ph == 1) {
                     // ---- gate: z = sigma(acc + GX[:, 0:H]), r = sigma(acc + GX[:, H:2H]); z*h -> slot 0 of PZ / PZ16 ----
-                    float* Zt = p.Z + tU;
-                    float* Rt = p.R + tU;
-                    for (int tile = blockIdx.x; tile < node_tiles; tile += G) {
-                        const int n = tile / p.node_tiles_m, m0 = (tile - n * p.node_tiles_m) * 128;
-                        const int row = m0 + q * rows_q + lane;
-                        const bool ok = lane < rows_q && row < p.B;
-                        const long long g = (long long)n * p.B + row;
-                        const int cz = half * 32;       // this warp's columns of the z half (and, + H, of the r half)
-                        float gz[32], hz[32];
-                        if (ok) {
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        // (every address of the iteration is derived from `tl` below the empty asm: nothing is hoisted out of the
+                        // tile loop, so the per-step pointers of the other phases do not stay live here - see the spill note above)
+                        long long tl = t;
+                        asm volatile("" : "+l"(tl));
+                        const long long tU = tl * p.U;
+                        const float* GXt = p.GX + 3 * tU;
+                        const float* PHt = p.PH + tl * K * p.U;
+                        float* PZt = p.PZ + tl * K * p.U;
+                        __nv_bfloat16* PZ16t = p.PZ16 + tl * K * p.U;
+                        float* Zt = p.Z + tU;
+                        float* Rt = p.R + tU;
+                        const long long g0 = (long long)n * p.B + b0;
+                        const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
+                        float2 gz[8], hz[8], gr[8];   // [2j + row]: this thread's pre-activation inputs and h
+                        // (rows past the batch are redirected to row 0 of the node: every load is unconditional, which keeps these
+                        // arrays in registers; their results are never stored)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                rf_ld8f(GXt + g * 3 * H + cz + 8 * j, gz + 8 * j);
-                                rf_ld8f(PHt + g * H + cz + 8 * j, hz + 8 * j);
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int rw = 0; rw < 2; ++rw) {
+                                const long long o = o0 + rd[rw] * H + 8 * j, x = x0 + rd[rw] * 3 * H + 8 * j;
+                                gz[2 * j + rw] = rf_ld2(GXt + x);
+                                hz[2 * j + rw] = rf_ld2(PHt + o);
+                                gr[2 * j + rw] = rf_ld2(GXt + x + H);
                             }
                         }
+                        RF_STAMP_E(ph, n / G, 5);
                         mbar_wait(tfull0 + 8u * acc, acc_phase);
                         tc_fence_after();
-                        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 128) + ((uint32_t)(q * 32) << 16);
-                        {
-                            uint32_t r[32];
-                            rf_tmem_ld32(tmem_acc + (uint32_t)cz, r);
-                            rf_tmem_wait_ld();
-                            float gr[32];
-                            if (ok) {
+                        RF_STAMP_E(ph, n / G, 6);
+                        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 128) + tlane;
+                        float az[16], ar[16];
+                        rf_tmem_ld16x4(tmem_acc + (uint32_t)(half * 32), az);
+                        rf_tmem_ld16x4(tmem_acc + (uint32_t)(H + half * 32), ar);
+                        rf_tmem_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);   // the accumulator is in registers: release it
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) rf_ld8f(GXt + g * 3 * H + H + cz + 8 * j, gr + 8 * j);
+                        for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float z[8], zh[8];
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int u = 0; u < 8; ++u) {
-                                        z[u] = sigmoid_fast(__uint_as_float(r[8 * j + u]) + gz[8 * j + u]);
-                                        zh[u] = z[u] * hz[8 * j + u];
-                                    }
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) w[u] = rf_pack_bf16(zh[2 * u], zh[2 * u + 1]);
-                                    rf_st8f(Zt + g * H + cz + 8 * j, z);
-                                    rf_st8f(PZt + g * H + cz + 8 * j, zh);
-                                    *reinterpret_cast<uint4*>(PZ16t + g * H + cz + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
-                                }
-                            }
-                            rf_tmem_ld32(tmem_acc + (uint32_t)(H + cz), r);
-                            rf_tmem_wait_ld();
-                            if (ok) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float rr[8];
-#pragma unroll
-                                    for (int u = 0; u < 8; ++u) rr[u] = sigmoid_fast(__uint_as_float(r[8 * j + u]) + gr[8 * j + u]);
-                                    rf_st8f(Rt + g * H + cz + 8 * j, rr);
+                            for (int rw = 0; rw < 2; ++rw) {
+                                if (rw == 0 ? ok0 : ok1) {
+                                    const long long o = o0 + rw * 8 * H + 8 * j;
+                                    const float za = sigmoid_fast(az[4 * j + 2 * rw] + gz[2 * j + rw].x);
+                                    const float zb = sigmoid_fast(az[4 * j + 2 * rw + 1] + gz[2 * j + rw].y);
+                                    const float ha = za * hz[2 * j + rw].x, hb = zb * hz[2 * j + rw].y;
+                                    rf_st2(Zt + o, za, zb);
+                                    rf_st2(PZt + o, ha, hb);
+                                    *reinterpret_cast<uint32_t*>(PZ16t + o) = rf_pack_bf16(ha, hb);
+                                    rf_st2(Rt + o, sigmoid_fast(ar[4 * j + 2 * rw] + gr[2 * j + rw].x),
+                                           sigmoid_fast(ar[4 * j + 2 * rw + 1] + gr[2 * j + rw].y));
                                 }
                             }
                         }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
-                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                        RF_STAMP_E(ph, n / G, 7);
                     }
                 } else {
-                    // ---- candidate + residual GRU cell + mix (gemm_tc.cuh: tc_epilogue_tile_candres) ----
-                    EpiCandRes ef{GXt, PHt, p.R + tU, p.HC + tU, p.H1 + tU, p.B, H, 1, RXt, p.Z2 + tU, p.R2 + tU, p.ZH2 + tU, p.HC2 + tU,
-                                  PHt + (long long)K * p.U, p.mix + t, PH16t + (long long)K * p.U, p.RgH, p.RuH};
-                    for (int tile = blockIdx.x; tile < node_tiles; tile += G) {
-                        const int n = tile / p.node_tiles_m, m0 = (tile - n * p.node_tiles_m) * 128;
-                        tc_epilogue_tile_candres(ef, tp, tmem_base + (uint32_t)(acc * 128), tfull0 + 8u * acc, acc_phase, q, half, buf, buf_other,
-                                                 res_w, res_w + 128 * TC_RES_LD, lane, n, m0);
+                    // ---- tail: candidate, then the residual GRU cell (two TF32 products on the tensor cores) and the mix ----
+                    const float m = __ldg(p.mix + t);
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        long long tl = t;
+                        asm volatile("" : "+l"(tl));
+                        const long long tU = tl * p.U;
+                        const float* GXt = p.GX + 3 * tU;
+                        const float* RXt = p.RX + 3 * tU;
+                        const float* PHt = p.PH + tl * K * p.U;
+                        const float* Rt = p.R + tU;
+                        float* Yt = p.PH + (tl + 1) * K * p.U;
+                        __nv_bfloat16* Y16t = p.PH16 + (tl + 1) * K * p.U;
+                        const long long g0 = (long long)n * p.B + b0;
+                        const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
+                        float2 gc[8], rr[8], hh[8], xz[8], xr[8], xu[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int rw = 0; rw < 2; ++rw) {
+                                const long long o = o0 + rd[rw] * H + 8 * j, x = x0 + rd[rw] * 3 * H + 8 * j;
+                                gc[2 * j + rw] = rf_ld2(GXt + x + 2 * H);
+                                rr[2 * j + rw] = rf_ld2(Rt + o);
+                                hh[2 * j + rw] = rf_ld2(PHt + o);
+                            }
+                        }
+                        RF_STAMP_E(ph, n / G, 5);
+                        mbar_wait(tfull0 + 8u * acc, acc_phase);
+                        tc_fence_after();
+                        RF_STAMP_E(ph, n / G, 6);
+                        float a[16], h1[16], r2[16];
+                        rf_tmem_ld16x4(tmem_base + (uint32_t)(acc * 128) + tlane + (uint32_t)(half * 32), a);
+                        rf_tmem_wait_ld();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
                         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                        // (the residual cell's pre-activation inputs are requested one stage ahead of their use)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int rw = 0; rw < 2; ++rw) {
+                                const long long x = x0 + rd[rw] * 3 * H + 8 * j;
+                                xz[2 * j + rw] = rf_ld2(RXt + x);
+                                xr[2 * j + rw] = rf_ld2(RXt + x + H);
+                            }
+                        }
+                        // stage 1: hc = tanh(acc + GX[:, 2H:]); h1 = r*h + (1-r)*hc -> HC, H1, operand tile S1
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int rw = 0; rw < 2; ++rw) {
+                                const int i = 4 * j + 2 * rw, e = 2 * j + rw;
+                                float ha = 0.f, hb = 0.f;
+                                if (rw == 0 ? ok0 : ok1) {
+                                    const long long o = o0 + rw * 8 * H + 8 * j;
+                                    const float ca = tanh_fast(a[i] + gc[e].x), cb = tanh_fast(a[i + 1] + gc[e].y);
+                                    ha = rr[e].x * hh[e].x + (1.f - rr[e].x) * ca;
+                                    hb = rr[e].y * hh[e].y + (1.f - rr[e].y) * cb;
+                                    rf_st2(p.HC + tU + o, ca, cb);
+                                    rf_st2(p.H1 + tU + o, ha, hb);
+                                }
+                                h1[i] = ha; h1[i + 1] = hb;
+                                const uint32_t sa = s1_s + s_off + (uint32_t)(rw * 1024) + ((((uint32_t)(2 * j) + s_c0) ^ s_x) << 4);
+                                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(ha), "f"(hb) : "memory");
+                            }
+                        }
+                        rf_proxy_fence_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s1_full);
+                        // stage 2: [z2 | r2] = sigma(h1 Rg_h^T + RX[:, 0:2H]); z2*h1 -> Z2, R2, ZH2, operand tile S2
+                        mbar_wait(r2_full, res_par);
+                        tc_fence_after();
+                        float c2[16];
+                        rf_tmem_ld16x4(tmem_base + RF_TMEM_D2 + tlane + (uint32_t)(half * 32), a);
+                        rf_tmem_ld16x4(tmem_base + RF_TMEM_D2 + tlane + (uint32_t)(H + half * 32), c2);
+                        rf_tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int rw = 0; rw < 2; ++rw) xu[2 * j + rw] = rf_ld2(RXt + x0 + rd[rw] * 3 * H + 8 * j + 2 * H);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int rw = 0; rw < 2; ++rw) {
+                                const int i = 4 * j + 2 * rw, e = 2 * j + rw;
+                                float qa = 0.f, qb = 0.f;
+                                r2[i] = 0.f; r2[i + 1] = 0.f;
+                                if (rw == 0 ? ok0 : ok1) {
+                                    const long long o = o0 + rw * 8 * H + 8 * j;
+                                    const float za = sigmoid_fast(a[i] + xz[e].x), zb = sigmoid_fast(a[i + 1] + xz[e].y);
+                                    r2[i] = sigmoid_fast(c2[i] + xr[e].x);
+                                    r2[i + 1] = sigmoid_fast(c2[i + 1] + xr[e].y);
+                                    qa = za * h1[i]; qb = zb * h1[i + 1];
+                                    rf_st2(p.Z2 + tU + o, za, zb);
+                                    rf_st2(p.R2 + tU + o, r2[i], r2[i + 1]);
+                                    rf_st2(p.ZH2 + tU + o, qa, qb);
+                                }
+                                const uint32_t sa = s2_s + s_off + (uint32_t)(rw * 1024) + ((((uint32_t)(2 * j) + s_c0) ^ s_x) << 4);
+                                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(qa), "f"(qb) : "memory");
+                            }
+                        }
+                        tc_fence_before();
+                        rf_proxy_fence_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s2_full);
+                        // stage 3: hc2 = tanh(z2*h1 Ru_h^T + RX[:, 2H:]); residual GRU output, mix -> HC2, h_t (fp32 + bf16 twin)
+                        mbar_wait(r3_full, res_par);
+                        tc_fence_after();
+                        rf_tmem_ld16x4(tmem_base + RF_TMEM_D3 + tlane + (uint32_t)(half * 32), a);
+                        rf_tmem_wait_ld();
+                        tc_fence_before();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int rw = 0; rw < 2; ++rw) {
+                                if (rw == 0 ? ok0 : ok1) {
+                                    const int i = 4 * j + 2 * rw, e = 2 * j + rw;
+                                    const long long o = o0 + rw * 8 * H + 8 * j;
+                                    const float ca = tanh_fast(a[i] + xu[e].x), cb = tanh_fast(a[i + 1] + xu[e].y);
+                                    const float ra = r2[i] * h1[i] + (1.f - r2[i]) * ca, rb = r2[i + 1] * h1[i + 1] + (1.f - r2[i + 1]) * cb;
+                                    const float ya = m * h1[i] + (1.f - m) * ra, yb = m * h1[i + 1] + (1.f - m) * rb;
+                                    rf_st2(p.HC2 + tU + o, ca, cb);
+                                    rf_st2(Yt + o, ya, yb);
+                                    *reinterpret_cast<uint32_t*>(Y16t + o) = rf_pack_bf16(ya, yb);
+                                }
+                            }
+                        }
+                        res_par ^= 1;
+                        RF_STAMP_E(ph, n / G, 7);
                     }
                 }
                 // ---- end of phase: publish this CTA's writes, wait for every CTA ----
@@ -421,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
 }
 
@@ -448,19 +628,15 @@ inline bool rf_make_map(CUtensorMap* map, const void* base, int rank, const unsi
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-
-// cudaErrorNotSupported: the shape does not meet the kernel's requirements (the caller runs one launch per phase instead)
 cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     constexpr int H = 64;
     const int Kp = a.K - 1, I = a.Cin + H;
-    if (a.B < 8 || (a.ldm & 7) || a.K < 2 || a.N < 1 || a.T < 1) return cudaErrorNotSupported;
+    if (a.B < 8 || a.B > 64 || (a.ldm & 7) || a.K < 2 || a.N < 1 || a.T < 1) return cudaErrorNotSupported;
     const unsigned long long U = (unsigned long long)a.N * a.B * H;
     const unsigned long long slots_h = (unsigned long long)a.T * a.K + 1, slots_z = (unsigned long long)a.T * a.K;
     RecFwdP p;
     memset(&p, 0, sizeof(p));
     p.T = a.T; p.N = a.N; p.B = a.B; p.K = a.K; p.Cin = a.Cin;
-    p.m64 = a.B <= 64 ? 1 : 0;
-    p.node_tiles_m = p.m64 ? 1 : (a.B + 127) / 128;
     p.prop_tiles_m = (Kp * a.N + 127) / 128;
     p.prop_tiles_n = (a.B * H + 127) / 128;
     p.prop_kt = (a.N + 63) / 64;
@@ -473,11 +649,10 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     p.dbg = tc_debug_buffer();
     const float* al[] = {a.GX, a.RX, a.PH, a.PZ, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.ZH2, a.RgH, a.RuH};
     for (const float* q : al)
-        if (reinterpret_cast<uintptr_t>(q) & 31) return cudaErrorNotSupported;   // 32-byte accesses
+        if (reinterpret_cast<uintptr_t>(q) & 31) return cudaErrorNotSupported;
     if ((reinterpret_cast<uintptr_t>(a.PH16) & 31) || (reinterpret_cast<uintptr_t>(a.PZ16) & 31)) return cudaErrorNotSupported;
 
     RecMaps maps;
-    const unsigned int arows = p.m64 ? 64u : 128u;
     {
         const unsigned long long d[2] = {(unsigned long long)a.N, (unsigned long long)Kp * a.N}, s[1] = {(unsigned long long)a.ldm * 2};
         const unsigned int b[2] = {64, 128};
@@ -492,7 +667,7 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     }
     {
         const unsigned long long s[3] = {(unsigned long long)H * 2, (unsigned long long)a.B * H * 2, U * 2};
-        const unsigned int b[4] = {64, arows, 1, 1};
+        const unsigned int b[4] = {64, 64, 1, 1};
         const unsigned long long dh[4] = {64, (unsigned long long)a.B, (unsigned long long)a.N, slots_h};
         const unsigned long long dz[4] = {64, (unsigned long long)a.B, (unsigned long long)a.N, slots_z};
         if (!rf_make_map(&maps.PHa, a.PH16, 4, dh, s, b) || !rf_make_map(&maps.PZa, a.PZ16, 4, dz, s, b)) return cudaErrorNotSupported;
@@ -516,7 +691,7 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     }
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int most = max(p.prop_tiles_m * p.prop_tiles_n, a.N * p.node_tiles_m);
+    const int most = max(p.prop_tiles_m * p.prop_tiles_n, a.N);
     const int grid = most < sms ? most : sms;
     cudaError_t e = cudaMemsetAsync(a.gbar, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;

