@@ -74,6 +74,18 @@ __device__ __forceinline__ unsigned int rf_ld_acquire(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// non-blocking test of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void rf_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -96,6 +108,24 @@ __device__ __forceinline__ void rf_tmem_ld16x4(uint32_t taddr, float (&r)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
+// Exchange with the neighbouring lane (lane ^ 1) so that every thread of a 16x256b.x4 fragment holds four float4 instead of
+// eight column pairs: f[2w + m] = row lane/4 + 8w, columns 16m + 4*pc .. + 3 with pc = ((lane & 1) << 1) | ((lane >> 1) & 1).
+// The four lanes of a row then cover 64 contiguous bytes per access: half as many L1 wavefronts as the pair layout.
+__device__ __forceinline__ void rf_quad4(const float (&v)[16], float4 (&f)[4], bool odd) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int je = 8 * m + 2 * w, jo = 8 * m + 4 + 2 * w;   // registers of the column groups 2m and 2m + 1
+            const float s0 = odd ? v[je] : v[jo], s1 = odd ? v[je + 1] : v[jo + 1];
+            const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            f[2 * w + m] = odd ? make_float4(r0, r1, v[jo], v[jo + 1]) : make_float4(v[je], v[je + 1], r0, r1);
+        }
+    }
+}
+__device__ __forceinline__ void rf_sts4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void rf_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t rf_pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -114,7 +144,7 @@ __device__ __forceinline__ void rf_proxy_fence_smem() { asm volatile("fence.prox
 // fine-grained timeline of CTA 0 at the middle time step: slot s of tile i (first four tiles of the CTA) of phase ph
 #define RF_STAMP(ph, i, s)                                                                                                   \
     do {                                                                                                                     \
-        if (p.dbg && blockIdx.x == 0 && t == (T >> 1) && (i) < 4) p.dbg[T * 16 + (((ph) * 4 + (i)) << 3) + (s)] = clock64(); \
+        if (p.dbg && blockIdx.x == 0 && t == (T >> 1) && (i) < 4) p.dbg[T * 16 + (((ph) * 4 + (i)) << 4) + (s)] = clock64(); \
     } while (0)
 #define RF_STAMP_E(ph, i, s)                        \
     do {                                            \
@@ -194,48 +224,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
             const uint64_t pol = l2_policy_evict_last();
             for (int t = 0; t < T; ++t) {
                 for (int ph = 0; ph < 4; ++ph) {
+                    const bool prop = ph == 0 || ph == 2, gate = ph == 1;
+                    const int ntiles = prop ? prop_tiles : node_tiles;
+                    const int nk = prop ? p.prop_kt : K;
+                    const uint32_t tx = prop ? (uint32_t)RF_STAGE_BYTES : 8192u + (gate ? 16384u : 8192u);
+                    const CUtensorMap* ta = gate ? &maps.PHa : &maps.PZa;
+                    const CUtensorMap* tw = gate ? &maps.WG : &maps.WU;
+                    const CUtensorMap* tb = ph == 0 ? &maps.Hs : &maps.Zs;
+                    const int slot = t * K;
+                    // the operand of a k-block that does NOT depend on the previous phase (base matrices / per-node weights)
+                    auto issue_const = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
+                        if (prop) {
+                            const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                            tma_load_5d_hint(sa, &maps.M, fb, kt * 64, tm * 128, 0, 0, 0, pol);
+                        } else {
+                            tma_load_5d_hint(sa + RF_A_BYTES, tw, fb, 0, p.Cin, kt, tile, 0, pol);
+                            if (gate) tma_load_5d_hint(sa + RF_A_BYTES + 8192, tw, fb, 64, p.Cin, kt, tile, 0, pol);
+                        }
+                    };
+                    // ... and the one that does (the state written by the other CTAs in the previous phase)
+                    auto issue_state = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
+                        if (prop) {
+                            const int tn = tile / p.prop_tiles_m;
+                            tma_load_5d(sa + RF_A_BYTES, tb, fb, tn * 128, kt * 64, slot, 0, 0);
+                            tma_load_5d(sa + RF_A_BYTES + 8192, tb, fb, tn * 128 + 64, kt * 64, slot, 0, 0);
+                        } else {
+                            tma_load_5d(sa, ta, fb, 0, 0, tile, slot + kt, 0);
+                        }
+                    };
+                    // before the grid barrier: arm the first stages of this CTA's first tile and request their constant operands
+                    int pre = 0;
+                    if ((t | ph) && (int)blockIdx.x < ntiles) {
+                        int s2 = stage;
+                        uint32_t p2 = phase;
+                        for (; pre < nk && pre < RF_STAGES; ++pre) {
+                            mbar_wait(empty0 + 8u * s2, p2 ^ 1);
+                            const uint32_t fb = full0 + 8u * s2;
+                            mbar_expect_tx(fb, tx);
+                            issue_const(blockIdx.x, pre, smem_u32(stage_base + s2 * RF_STAGE_BYTES), fb);
+                            if (++s2 == RF_STAGES) { s2 = 0; p2 ^= 1; }
+                        }
+                    }
                     if (t | ph) {
                         mbar_wait(phase_bar, nbar & 1u);  // the previous phase is complete on every CTA
                         ++nbar;
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
-                    if (ph == 0 || ph == 2) {
-                        const CUtensorMap* tb = ph == 0 ? &maps.Hs : &maps.Zs;
-                        const int slot = t * K;
-                        for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
-                            const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
-                            RF_STAMP(ph, tile / G, 0);
-                            for (int kt = 0; kt < p.prop_kt; ++kt) {
+                    for (int tile = blockIdx.x; tile < ntiles; tile += G) {
+                        RF_STAMP(ph, tile / G, 0);
+                        for (int kt = 0; kt < nk; ++kt) {
+                            const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES);
+                            const uint32_t fb = full0 + 8u * stage;
+                            if (pre > 0) {
+                                --pre;   // armed above, constant operand already in flight
+                            } else {
                                 mbar_wait(empty0 + 8u * stage, phase ^ 1);
-                                const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
-                                const uint32_t fb = full0 + 8u * stage;
-                                mbar_expect_tx(fb, RF_STAGE_BYTES);
-                                tma_load_5d_hint(sa, &maps.M, fb, kt * 64, tm * 128, 0, 0, 0, pol);
-                                tma_load_5d(sb, tb, fb, tn * 128, kt * 64, slot, 0, 0);
-                                tma_load_5d(sb + 8192, tb, fb, tn * 128 + 64, kt * 64, slot, 0, 0);
-                                if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
-                            }
-                            RF_STAMP(ph, tile / G, 1);
-                        }
-                    } else {
-                        const bool gate = ph == 1;
-                        const CUtensorMap* ta = gate ? &maps.PHa : &maps.PZa;
-                        const CUtensorMap* tw = gate ? &maps.WG : &maps.WU;
-                        const uint32_t tx = 8192u + (gate ? 16384u : 8192u);
-                        for (int n = blockIdx.x; n < node_tiles; n += G) {
-                            RF_STAMP(ph, n / G, 0);
-                            for (int k = 0; k < K; ++k) {
-                                mbar_wait(empty0 + 8u * stage, phase ^ 1);
-                                const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
-                                const uint32_t fb = full0 + 8u * stage;
                                 mbar_expect_tx(fb, tx);
-                                tma_load_5d(sa, ta, fb, 0, 0, n, t * K + k, 0);
-                                tma_load_5d_hint(sb, tw, fb, 0, p.Cin, k, n, 0, pol);
-                                if (gate) tma_load_5d_hint(sb + 8192, tw, fb, 64, p.Cin, k, n, 0, pol);
-                                if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
+                                issue_const(tile, kt, sa, fb);
                             }
-                            RF_STAMP(ph, n / G, 1);
+                            issue_state(tile, kt, sa, fb);
+                            if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
                         }
+                        RF_STAMP(ph, tile / G, 1);
                     }
                 }
             }
@@ -284,26 +334,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     const int ntiles = prop ? prop_tiles : node_tiles;
                     for (int tile = blockIdx.x; tile < ntiles; tile += G) issue_tile(prop ? p.prop_kt : K, prop ? id_prop : id_gate, tile / G);
                 }
-                // tail: the candidate contraction of the NEXT tile is issued before the residual-cell products of this one
+                // tail: the candidate contractions of this CTA's tiles and the residual-cell products the epilogue warps ask for
+                // are interleaved by readiness (non-blocking barrier tests): a residual product is eight MMAs on the critical
+                // path of a tile's epilogue and must not queue behind the operand stream of the next tile
                 ph = 3;
-                if ((int)blockIdx.x < node_tiles) issue_tile(K, id_cand, 0);
-                for (int n = blockIdx.x; n < node_tiles; n += G) {
-                    if (n + G < node_tiles) issue_tile(K, id_cand, n / G + 1);
-                    mbar_wait(s1_full, res_par);   // h1 operand tile written
-                    tc_fence_after();
+                int mt = blockIdx.x, rt = blockIdx.x, mk = 0, rstage = 0;
+                bool open = false;
+                long long spin0 = 0;
+                for (uint32_t it = 0; rt < node_tiles; ++it) {
+                    bool progress = false;
+                    if (rstage == 0 ? mbar_test(s1_full, res_par) : mbar_test(s2_full, res_par)) {
+                        tc_fence_after();
+                        if (rstage == 0) {   // h1 operand tile written: [z2 | r2] pre-activations
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_tf32(tmem_base + RF_TMEM_D2, umma_desc(s1_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
-                                  umma_desc(wg_s + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 2), id_rg, kk > 0 ? 1u : 0u);
-                    umma_commit(r2_full);
-                    mbar_wait(s2_full, res_par);   // z2*h1 operand tile written
-                    tc_fence_after();
+                            for (int kk = 0; kk < 8; ++kk)
+                                umma_tf32(tmem_base + RF_TMEM_D2, umma_desc(s1_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
+                                          umma_desc(wg_s + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, 2), id_rg, kk > 0 ? 1u : 0u);
+                            umma_commit(r2_full);
+                            rstage = 1;
+                        } else {             // z2*h1 operand tile written: candidate pre-activation of the residual cell
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_tf32(tmem_base + RF_TMEM_D3, umma_desc(s2_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
-                                  umma_desc(wu_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_ru, kk > 0 ? 1u : 0u);
-                    umma_commit(r3_full);
-                    res_par ^= 1;
+                            for (int kk = 0; kk < 8; ++kk)
+                                umma_tf32(tmem_base + RF_TMEM_D3, umma_desc(s2_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
+                                          umma_desc(wu_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_ru, kk > 0 ? 1u : 0u);
+                            umma_commit(r3_full);
+                            rstage = 0;
+                            res_par ^= 1;
+                            rt += G;
+                        }
+                        progress = true;
+                    }
+                    if (mt < node_tiles) {
+                        if (!open && mbar_test(tempty0 + 8u * acc, acc_phase ^ 1)) {
+                            tc_fence_after();
+                            RF_STAMP(ph, mt / G, 2);
+                            open = true;
+                            mk = 0;
+                        }
+                        if (open && mbar_test(full0 + 8u * stage, phase)) {
+                            tc_fence_after();
+                            if (mk == 0) RF_STAMP(ph, mt / G, 3);
+                            const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
+                            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 128);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_bf16(tmem_d, umma_desc(sa + kk * 32, 16, 1024, 2), umma_desc(sb + kk * 2048, 8192, 1024, 2), id_cand,
+                                          (mk > 0 || kk > 0) ? 1u : 0u);
+                            umma_commit(empty0 + 8u * stage);
+                            if (++stage == RF_STAGES) { stage = 0; phase ^= 1; }
+                            if (++mk == K) {
+                                umma_commit(tfull0 + 8u * acc);
+                                RF_STAMP(ph, mt / G, 4);
+                                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                                open = false;
+                                mt += G;
+                            }
+                            progress = true;
+                        }
+                    }
+                    if (progress) {
+                        it = 0;
+                    } else {
+                        if (it == 256) spin0 = clock64();
+                        if (it > 256 && (it & 1023) == 0 && clock64() - spin0 > 4000000000LL) __trap();
+                    }
                 }
             }
         }
@@ -329,15 +423,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
         uint32_t acc_phase = 0, nbar = 0, res_par = 0;
         const int ldc = p.B * H;
         const long long prop_rows = (long long)(K - 1) * p.N;
-        // 16x256b coordinates of this thread inside a 64-row tile: rows b0 and b0 + 8, column pairs 8j + cp (+ 32*half)
+        // coordinates of this thread inside a 64-row tile after rf_quad4: rows b0 and b0 + 8, columns ch + 16m .. + 3 (m = 0, 1)
         const int b0 = q * 16 + (lane >> 2);
-        const bool ok0 = b0 < p.B, ok1 = b0 + 8 < p.B;
+        const bool odd = lane & 1;
+        const int pc = ((lane & 1) << 1) | ((lane >> 1) & 1);
+        const bool ok[2] = {b0 < p.B, b0 + 8 < p.B};
+        const int ch = half * 32 + 4 * pc;
         // row offsets (relative to row b0 of the node) used for LOADS: rows past the batch read row 0 of the node instead
-        const long long rd[2] = {ok0 ? 0 : -(long long)b0, ok1 ? 8 : -(long long)b0};
-        const int ch = half * 32 + (lane & 3) * 2;
-        // this thread's 8-byte slots in the operand tiles: slab `half`, rows b0 / b0 + 8 (same swizzle phase: 8 rows apart)
-        const uint32_t s_off = (uint32_t)(half * 8192 + b0 * 128 + ((lane & 1) << 3));
-        const uint32_t s_c0 = (uint32_t)((lane & 2) >> 1), s_x = (uint32_t)(b0 & 7);
+        const long long rd[2] = {ok[0] ? 0 : -(long long)b0, ok[1] ? 8 : -(long long)b0};
+        // this thread's 16-byte slots in the operand tiles: slab `half`, rows b0 / b0 + 8 (same swizzle phase: 8 rows apart),
+        // chunk (4m + pc) ^ (b0 % 8)
+        const uint32_t s_off = (uint32_t)(half * 8192 + b0 * 128);
+        const uint32_t s_x = (uint32_t)(b0 & 7);
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         for (int t = 0; t < T; ++t) {
             for (int ph = 0; ph < 4; ++ph) {
@@ -380,33 +477,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     }
                 } else if (ph == 1) {
                     // ---- gate: z = sigma(acc + GX[:, 0:H]), r = sigma(acc + GX[:, H:2H]); z*h -> slot 0 of PZ / PZ16 ----
-                    for (int n = blockIdx.x; n < node_tiles; n += G) {
-                        // (every address of the iteration is derived from `tl` below the empty asm: nothing is hoisted out of the
-                        // tile loop, so the per-step pointers of the other phases do not stay live here - see the spill note above)
-                        long long tl = t;
-                        asm volatile("" : "+l"(tl));
-                        const long long tU = tl * p.U;
-                        const float* GXt = p.GX + 3 * tU;
-                        const float* PHt = p.PH + tl * K * p.U;
-                        float* PZt = p.PZ + tl * K * p.U;
-                        __nv_bfloat16* PZ16t = p.PZ16 + tl * K * p.U;
-                        float* Zt = p.Z + tU;
-                        float* Rt = p.R + tU;
+                    // per-step bases (derived below an empty asm so that nothing of it is hoisted above the phase: the per-step
+                    // pointers of the other phases then do not stay live here)
+                    long long tl = t;
+                    asm volatile("" : "+l"(tl));
+                    const long long tU = tl * p.U;
+                    const float* GXt = p.GX + 3 * tU;
+                    const float* PHt = p.PH + tl * K * p.U;
+                    float* PZt = p.PZ + tl * K * p.U;
+                    __nv_bfloat16* PZ16t = p.PZ16 + tl * K * p.U;
+                    float* Zt = p.Z + tU;
+                    float* Rt = p.R + tU;
+                    float4 gz[4], hz[4], gr[4];   // [2w + m]: this thread's pre-activation inputs and h
+                    // (rows past the batch are redirected to row 0 of the node: every load is unconditional, which keeps these
+                    // arrays in registers; their results are never stored)
+                    auto load_inputs = [&](int n) {
                         const long long g0 = (long long)n * p.B + b0;
                         const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
-                        float2 gz[8], hz[8], gr[8];   // [2j + row]: this thread's pre-activation inputs and h
-                        // (rows past the batch are redirected to row 0 of the node: every load is unconditional, which keeps these
-                        // arrays in registers; their results are never stored)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) {
-                                const long long o = o0 + rd[rw] * H + 8 * j, x = x0 + rd[rw] * 3 * H + 8 * j;
-                                gz[2 * j + rw] = rf_ld2(GXt + x);
-                                hz[2 * j + rw] = rf_ld2(PHt + o);
-                                gr[2 * j + rw] = rf_ld2(GXt + x + H);
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const long long o = o0 + rd[w] * H + 16 * m2, x = x0 + rd[w] * 3 * H + 16 * m2;
+                                gz[2 * w + m2] = ld4(GXt + x);
+                                hz[2 * w + m2] = ld4(PHt + o);
+                                gr[2 * w + m2] = ld4(GXt + x + H);
                             }
                         }
+                    };
+                    if ((int)blockIdx.x < node_tiles) load_inputs(blockIdx.x);
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const long long o0 = ((long long)n * p.B + b0) * H + ch;
                         RF_STAMP_E(ph, n / G, 5);
                         mbar_wait(tfull0 + 8u * acc, acc_phase);
                         tc_fence_after();
@@ -420,20 +521,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty0 + 8u * acc);   // the accumulator is in registers: release it
                         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                        float4 fz[4], fr[4];
+                        rf_quad4(az, fz, odd);
+                        rf_quad4(ar, fr, odd);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int e = 0; e < 4; ++e) {
+                            fz[e] = sigmoid4(fz[e] + gz[e], 1);
+                            fr[e] = sigmoid4(fr[e] + gr[e], 1);
+                            hz[e] = fz[e] * hz[e];
+                        }
+                        // the next tile's inputs are requested BEFORE this tile's stores enter the memory pipeline
+                        float4 zh[4];
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) {
-                                if (rw == 0 ? ok0 : ok1) {
-                                    const long long o = o0 + rw * 8 * H + 8 * j;
-                                    const float za = sigmoid_fast(az[4 * j + 2 * rw] + gz[2 * j + rw].x);
-                                    const float zb = sigmoid_fast(az[4 * j + 2 * rw + 1] + gz[2 * j + rw].y);
-                                    const float ha = za * hz[2 * j + rw].x, hb = zb * hz[2 * j + rw].y;
-                                    rf_st2(Zt + o, za, zb);
-                                    rf_st2(PZt + o, ha, hb);
-                                    *reinterpret_cast<uint32_t*>(PZ16t + o) = rf_pack_bf16(ha, hb);
-                                    rf_st2(Rt + o, sigmoid_fast(ar[4 * j + 2 * rw] + gr[2 * j + rw].x),
-                                           sigmoid_fast(ar[4 * j + 2 * rw + 1] + gr[2 * j + rw].y));
+                        for (int e = 0; e < 4; ++e) zh[e] = hz[e];
+                        if (n + G < node_tiles) load_inputs(n + G);
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                if (ok[w]) {
+                                    const int e = 2 * w + m2;
+                                    const long long o = o0 + w * 8 * H + 16 * m2;
+                                    st4(Zt + o, fz[e]);
+                                    st4(PZt + o, zh[e]);
+                                    st4_bf16(PZ16t + o, zh[e]);
+                                    st4(Rt + o, fr[e]);
                                 }
                             }
                         }
@@ -442,34 +554,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                 } else {
                     // ---- tail: candidate, then the residual GRU cell (two TF32 products on the tensor cores) and the mix ----
                     const float m = __ldg(p.mix + t);
-                    for (int n = blockIdx.x; n < node_tiles; n += G) {
-                        long long tl = t;
-                        asm volatile("" : "+l"(tl));
-                        const long long tU = tl * p.U;
-                        const float* GXt = p.GX + 3 * tU;
-                        const float* RXt = p.RX + 3 * tU;
-                        const float* PHt = p.PH + tl * K * p.U;
-                        const float* Rt = p.R + tU;
-                        float* Yt = p.PH + (tl + 1) * K * p.U;
-                        __nv_bfloat16* Y16t = p.PH16 + (tl + 1) * K * p.U;
+                    long long tl = t;
+                    asm volatile("" : "+l"(tl));
+                    const long long tU = tl * p.U;
+                    const float* GXt = p.GX + 3 * tU;
+                    const float* RXt = p.RX + 3 * tU;
+                    const float* PHt = p.PH + tl * K * p.U;
+                    const float* Rt = p.R + tU;
+                    float* Yt = p.PH + (tl + 1) * K * p.U;
+                    __nv_bfloat16* Y16t = p.PH16 + (tl + 1) * K * p.U;
+                    float4 gc[4], rr[4], hh[4], xz[4], xr[4], xu[4];
+                    auto load_stage1 = [&](int n) {   // candidate pre-activation input, r and h_{t-1} of a tile
                         const long long g0 = (long long)n * p.B + b0;
                         const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
-                        float2 gc[8], rr[8], hh[8], xz[8], xr[8], xu[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) {
-                                const long long o = o0 + rd[rw] * H + 8 * j, x = x0 + rd[rw] * 3 * H + 8 * j;
-                                gc[2 * j + rw] = rf_ld2(GXt + x + 2 * H);
-                                rr[2 * j + rw] = rf_ld2(Rt + o);
-                                hh[2 * j + rw] = rf_ld2(PHt + o);
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const long long o = o0 + rd[w] * H + 16 * m2, x = x0 + rd[w] * 3 * H + 16 * m2;
+                                gc[2 * w + m2] = ld4(GXt + x + 2 * H);
+                                rr[2 * w + m2] = ld4(Rt + o);
+                                hh[2 * w + m2] = ld4(PHt + o);
                             }
                         }
+                    };
+                    if ((int)blockIdx.x < node_tiles) load_stage1(blockIdx.x);
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const long long g0 = (long long)n * p.B + b0;
+                        const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
                         RF_STAMP_E(ph, n / G, 5);
                         mbar_wait(tfull0 + 8u * acc, acc_phase);
                         tc_fence_after();
                         RF_STAMP_E(ph, n / G, 6);
-                        float a[16], h1[16], r2[16];
+                        float a[16], c2[16];
+                        float4 fa[4], fc[4], h1[4], r2[4];
                         rf_tmem_ld16x4(tmem_base + (uint32_t)(acc * 128) + tlane + (uint32_t)(half * 32), a);
                         rf_tmem_wait_ld();
                         tc_fence_before();
@@ -478,93 +596,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         // (the residual cell's pre-activation inputs are requested one stage ahead of their use)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) {
-                                const long long x = x0 + rd[rw] * 3 * H + 8 * j;
-                                xz[2 * j + rw] = rf_ld2(RXt + x);
-                                xr[2 * j + rw] = rf_ld2(RXt + x + H);
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const long long x = x0 + rd[w] * 3 * H + 16 * m2;
+                                xz[2 * w + m2] = ld4(RXt + x);
+                                xr[2 * w + m2] = ld4(RXt + x + H);
                             }
                         }
                         // stage 1: hc = tanh(acc + GX[:, 2H:]); h1 = r*h + (1-r)*hc -> HC, H1, operand tile S1
+                        rf_quad4(a, fa, odd);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) {
-                                const int i = 4 * j + 2 * rw, e = 2 * j + rw;
-                                float ha = 0.f, hb = 0.f;
-                                if (rw == 0 ? ok0 : ok1) {
-                                    const long long o = o0 + rw * 8 * H + 8 * j;
-                                    const float ca = tanh_fast(a[i] + gc[e].x), cb = tanh_fast(a[i + 1] + gc[e].y);
-                                    ha = rr[e].x * hh[e].x + (1.f - rr[e].x) * ca;
-                                    hb = rr[e].y * hh[e].y + (1.f - rr[e].y) * cb;
-                                    rf_st2(p.HC + tU + o, ca, cb);
-                                    rf_st2(p.H1 + tU + o, ha, hb);
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const int e = 2 * w + m2;
+                                const float4 hc = tanh4(fa[e] + gc[e], 1);
+                                h1[e] = rr[e] * hh[e] + one_minus(rr[e]) * hc;
+                                if (ok[w]) {
+                                    const long long o = o0 + w * 8 * H + 16 * m2;
+                                    st4(p.HC + tU + o, hc);
+                                    st4(p.H1 + tU + o, h1[e]);
                                 }
-                                h1[i] = ha; h1[i + 1] = hb;
-                                const uint32_t sa = s1_s + s_off + (uint32_t)(rw * 1024) + ((((uint32_t)(2 * j) + s_c0) ^ s_x) << 4);
-                                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(ha), "f"(hb) : "memory");
+                                rf_sts4(s1_s + s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4), h1[e]);
                             }
                         }
                         rf_proxy_fence_smem();
                         __syncwarp();
+                        RF_STAMP_E(ph, n / G, 8);
                         if (lane == 0) mbar_arrive(s1_full);
+                        if (n + G < node_tiles) load_stage1(n + G);   // (gc / rr / hh are dead from here on: the next tile's go in flight)
                         // stage 2: [z2 | r2] = sigma(h1 Rg_h^T + RX[:, 0:2H]); z2*h1 -> Z2, R2, ZH2, operand tile S2
                         mbar_wait(r2_full, res_par);
                         tc_fence_after();
-                        float c2[16];
+                        RF_STAMP_E(ph, n / G, 9);
                         rf_tmem_ld16x4(tmem_base + RF_TMEM_D2 + tlane + (uint32_t)(half * 32), a);
                         rf_tmem_ld16x4(tmem_base + RF_TMEM_D2 + tlane + (uint32_t)(H + half * 32), c2);
                         rf_tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) xu[2 * j + rw] = rf_ld2(RXt + x0 + rd[rw] * 3 * H + 8 * j + 2 * H);
+                            for (int m2 = 0; m2 < 2; ++m2) xu[2 * w + m2] = ld4(RXt + x0 + rd[w] * 3 * H + 16 * m2 + 2 * H);
                         }
+                        rf_quad4(a, fa, odd);
+                        rf_quad4(c2, fc, odd);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) {
-                                const int i = 4 * j + 2 * rw, e = 2 * j + rw;
-                                float qa = 0.f, qb = 0.f;
-                                r2[i] = 0.f; r2[i + 1] = 0.f;
-                                if (rw == 0 ? ok0 : ok1) {
-                                    const long long o = o0 + rw * 8 * H + 8 * j;
-                                    const float za = sigmoid_fast(a[i] + xz[e].x), zb = sigmoid_fast(a[i + 1] + xz[e].y);
-                                    r2[i] = sigmoid_fast(c2[i] + xr[e].x);
-                                    r2[i + 1] = sigmoid_fast(c2[i + 1] + xr[e].y);
-                                    qa = za * h1[i]; qb = zb * h1[i + 1];
-                                    rf_st2(p.Z2 + tU + o, za, zb);
-                                    rf_st2(p.R2 + tU + o, r2[i], r2[i + 1]);
-                                    rf_st2(p.ZH2 + tU + o, qa, qb);
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const int e = 2 * w + m2;
+                                const float4 z2 = sigmoid4(fa[e] + xz[e], 1);
+                                r2[e] = sigmoid4(fc[e] + xr[e], 1);
+                                const float4 zh2 = z2 * h1[e];
+                                if (ok[w]) {
+                                    const long long o = o0 + w * 8 * H + 16 * m2;
+                                    st4(p.Z2 + tU + o, z2);
+                                    st4(p.R2 + tU + o, r2[e]);
+                                    st4(p.ZH2 + tU + o, zh2);
                                 }
-                                const uint32_t sa = s2_s + s_off + (uint32_t)(rw * 1024) + ((((uint32_t)(2 * j) + s_c0) ^ s_x) << 4);
-                                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa), "f"(qa), "f"(qb) : "memory");
+                                rf_sts4(s2_s + s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4), zh2);
                             }
                         }
                         tc_fence_before();
                         rf_proxy_fence_smem();
                         __syncwarp();
+                        RF_STAMP_E(ph, n / G, 10);
                         if (lane == 0) mbar_arrive(s2_full);
                         // stage 3: hc2 = tanh(z2*h1 Ru_h^T + RX[:, 2H:]); residual GRU output, mix -> HC2, h_t (fp32 + bf16 twin)
                         mbar_wait(r3_full, res_par);
                         tc_fence_after();
+                        RF_STAMP_E(ph, n / G, 11);
                         rf_tmem_ld16x4(tmem_base + RF_TMEM_D3 + tlane + (uint32_t)(half * 32), a);
                         rf_tmem_wait_ld();
                         tc_fence_before();
+                        rf_quad4(a, fa, odd);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int rw = 0; rw < 2; ++rw) {
-                                if (rw == 0 ? ok0 : ok1) {
-                                    const int i = 4 * j + 2 * rw, e = 2 * j + rw;
-                                    const long long o = o0 + rw * 8 * H + 8 * j;
-                                    const float ca = tanh_fast(a[i] + xu[e].x), cb = tanh_fast(a[i + 1] + xu[e].y);
-                                    const float ra = r2[i] * h1[i] + (1.f - r2[i]) * ca, rb = r2[i + 1] * h1[i + 1] + (1.f - r2[i + 1]) * cb;
-                                    const float ya = m * h1[i] + (1.f - m) * ra, yb = m * h1[i + 1] + (1.f - m) * rb;
-                                    rf_st2(p.HC2 + tU + o, ca, cb);
-                                    rf_st2(Yt + o, ya, yb);
-                                    *reinterpret_cast<uint32_t*>(Y16t + o) = rf_pack_bf16(ya, yb);
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                if (ok[w]) {
+                                    const int e = 2 * w + m2;
+                                    const long long o = o0 + w * 8 * H + 16 * m2;
+                                    const float4 hc2 = tanh4(fa[e] + xu[e], 1);
+                                    const float4 res = r2[e] * h1[e] + one_minus(r2[e]) * hc2;
+                                    const float4 y = m * h1[e] + (1.f - m) * res;
+                                    st4(p.HC2 + tU + o, hc2);
+                                    st4(Yt + o, y);
+                                    st4_bf16(Y16t + o, y);
                                 }
                             }
                         }
@@ -578,16 +696,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                 asm volatile("bar.sync 6, 256;" ::: "memory");
                 if (threadIdx.x == 128) {
                     if (p.dbg && blockIdx.x == 0) p.dbg[(t * 4 + ph) * 4 + 2] = clock64();
-                    __threadfence();
+                    // release: the writes of every epilogue thread (ordered before this point by the CTA barrier) become visible at
+                    // gpu scope before the arrival is; the other CTAs' TMA reads them through the async proxy
                     asm volatile("fence.proxy.async;" ::: "memory");
-                    atomicAdd(p.gbar, 1u);
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
                     const unsigned int target = (nbar + 1u) * (unsigned int)G;
                     long long t0 = 0;
                     for (uint32_t it = 0; rf_ld_acquire(p.gbar) < target; ++it) {
                         if (it == 1024) t0 = clock64();
                         if (it > 1024 && (it & 255) == 0 && clock64() - t0 > 4000000000LL) __trap();
                     }
-                    __threadfence();
                     if (p.dbg && blockIdx.x == 0) p.dbg[(t * 4 + ph) * 4 + 3] = clock64();
                     *phase_cnt = nbar + 1u;
                     mbar_arrive(phase_bar);

@@ -40,7 +40,7 @@ for rec in (0, 1):
     e1.record()
     torch.cuda.synchronize()
     print("layer forward, persistent=%d: %.3f ms" % (rec, e0.elapsed_time(e1) / 5))
-buf = torch.zeros(T * 16 + 256, dtype=torch.int64, device=dev)
+buf = torch.zeros(T * 16 + 512, dtype=torch.int64, device=dev)
 lib.matgcn_debug_set_timeline(buf.data_ptr())
 fwd()
 torch.cuda.synchronize()
@@ -55,14 +55,16 @@ for t in (0, 1, T // 2, T - 1):
         print(" t=%2d %-8s tiles %6d | cta-bar %5d | grid-bar %6d | total %6d" % (t, names[ph], d - s, c - d, (gb - c) if gb else 0, (nxt - s) if nxt else 0))
 tot = int(b[T - 1, 3, 0]) - int(b[0, 0, 0])
 print("recurrence up to the start of the last tail: %d cycles" % tot)
-f = buf.cpu()[T * 16: T * 16 + 128].view(4, 4, 8)
+f = buf.cpu()[T * 16: T * 16 + 256].view(4, 4, 16)
 t0 = int(b[T // 2, 0, 0])
 print("per-tile stamps at t=%d relative to the step start: producer first/last issue | mma acc-free, first operands, committed | epilogue pre-wait, acc ready, done" % (T // 2))
 for ph in range(4):
-    for i in range(4):
+    for i in range(3):
         if int(f[ph, i, 0]) == 0:
             continue
-        print(" %-8s tile %d: prod %6d %6d | mma %6d %6d %6d | epi %6d %6d %6d" % ((names[ph], i) + tuple((int(v) - t0) if int(v) else -1 for v in f[ph, i])))
+        v = [(int(x) - t0) if int(x) else -1 for x in f[ph, i]]
+        print(" %-8s tile %d: prod %6d %6d | mma %6d %6d %6d | epi %6d %6d %6d" % ((names[ph], i) + tuple(v[:8]))
+              + ("  [tail stages: h1 written %d, r2 ready %d, zh2 written %d, r3 ready %d]" % tuple(v[8:12]) if ph == 3 else ""))
 for ph in range(4):
     d = sum(int(b[t, ph, 1]) - int(b[t, ph, 0]) for t in range(T - (ph == 3))) / (T - (ph == 3))
     w = sum(int(b[t, ph, 3]) - int(b[t, ph, 1]) for t in range(T) if int(b[t, ph, 3])) / T
