@@ -20,7 +20,10 @@ bucket, ``train.FusedClipAdam``).
                the launching stream at the step's exact shape.
 * ``cpu_baseline``: the oracle (a port of the reference's CPU path) timed on this host's cores
                on a bounded sample of the same workload.
-Multi-GPU: launched by torchrun, one rank per GPU, weak scaling (fixed per-GPU batch).
+* ``strong_scaling``: BASELINE config 4 (N=883, GLOBAL batch 256 sharded over the ranks): the one scaling target the
+               north star states (>= 7x at 8 GPUs); a few steps after the main measurement, at every --gpus N.
+* ``step_roofline``: SURVEY 8d's work model of the whole step against the measured peaks.
+Multi-GPU: launched by torchrun, one rank per GPU, weak scaling (fixed per-GPU batch) for ``value``.
 """
 from __future__ import annotations
 
@@ -394,6 +397,11 @@ def run_ours(args):
     barrier()
     ms_win = e4.elapsed_time(e5) / args.steps
     clocks = sampler.stop() if rank == 0 else {}
+    strong = None
+    if not args.no_strong_leg and args.workload == DEFAULT_WORKLOAD:
+        del bank
+        torch.cuda.empty_cache()
+        strong = strong_scaling_leg(world, rank, dev, args.mode)
 
     # max over ranks
     if world > 1:
@@ -428,6 +436,13 @@ def run_ours(args):
                                        "note": "SURVEY 8f f2: [T_total,N,F] series resident in HBM, matgcn_assemble_windows gathers "
                                                "each batch; the host uploads only the label-start indices"},
                 "gpu_launches": int(launches), "tc_launches": int(tc_launches), "loss": last_loss, "roofline": roof}
+        if args.workload == DEFAULT_WORKLOAD and per_gpu_batch == w["B"]:
+            # SURVEY 8d, cfg 3: 2.77 TFLOP and 4.51 GB (bf16 storage) / 9.00 GB (fp32) x 3 per train step
+            t_roof = max(2.77e12 / (peaks["bf16_tflops_sustained"] * 1e12), 3 * (4.51e9 if model.matgcn_flags == 3 else 9.00e9) / (peaks["hbm_gbs"] * 1e9))
+            line["step_roofline"] = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms_dev,
+                                     "model": "SURVEY.md 8d: max(algorithmic FLOPs / sustained bf16 peak, algorithmic bytes / HBM peak) per step"}
+        if strong is not None:
+            line["strong_scaling"] = strong
         if world == 1 and model.matgcn_flags != 0 and not args.no_exact_leg:
             # the 1e-4-parity engine (fp32 FFMA kernels) on the same workload, same weights, a few steps: driver-run number
             # for the mode whose parity bound is the north star's fp32 one
@@ -443,6 +458,51 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def strong_scaling_leg(world, rank, dev, mode, steps=3, warmup=2):
+    """BASELINE config 4 - the one scaling target the north star states: N = 883, 24 -> 12, GLOBAL batch 256 sharded over the
+    ranks (256 / world samples per GPU), one flat-bucket all-reduce per step.  Returns (ms per step, max over ranks), per rank batch."""
+    from multistgraph_b200.dp import broadcast_parameters
+    from multistgraph_b200.model import MultiATGCN
+    from multistgraph_b200.synthetic import WORKLOADS, make_batch, workload
+    from multistgraph_b200.train import FusedClipAdam, fused_train_step
+
+    w = WORKLOADS["pems07_scale"]
+    per_rank = w["B"] // world
+    cfg, df, _ = workload("pems07_scale", seed=0, batch=per_rank, device=dev)
+    cfg["matgcn_mode"] = mode
+    torch.manual_seed(0)
+    model = MultiATGCN(dict(cfg), df).to(dev).train()
+    broadcast_parameters(model)
+    opt = FusedClipAdam(model.parameters(), lr=0.003, eps=1e-8, max_grad_norm=5.0)
+    batches = [make_batch(w["N"], per_rank, w["T_out"], seed=300 + rank * 8 + i, device=dev) for i in range(2)]
+    for i in range(warmup):
+        fused_train_step(model, batches[i % 2], opt)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = fused_train_step(model, batches[i % 2], opt)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    last = float(loss.item())
+    del opt, model, batches
+    torch.cuda.empty_cache()
+    return {"workload": "pems07_scale: N=883 nodes, GLOBAL batch 256 (%d per GPU), 24 steps in -> 12 out, K=5 supports" % per_rank,
+            "value": w["B"] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "global_batch": w["B"],
+            "per_gpu_batch": per_rank, "steps": steps, "warmup": warmup, "scaling": "strong", "loss": last,
+            "roofline_samples_per_s": {"1_gpu_flop_bound": 8100.0, "8_gpu_bf16_weight_stream_bound_per_gpu": 7800.0,
+                                       "source": "SURVEY.md section 8d work model"}}
 
 
 def exact_mode_leg(cfg, df, fast_model, resident, dev, steps=3, warmup=1):
@@ -488,6 +548,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work allowed for the baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact-leg", action="store_true", help="skip the few exact-mode steps reported as exact_mode")
+    ap.add_argument("--no-strong-leg", action="store_true",
+                    help="skip the strong-scaling leg (BASELINE config 4: N=883, global batch 256 sharded over the ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

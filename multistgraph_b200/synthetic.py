@@ -93,3 +93,28 @@ def workload(name: str, seed: int = 0, batch=None, device="cpu") -> Tuple[dict, 
                       output_window=w["T_out"], batch_size=b, device=device)
     df = make_data_feature(w["N"], seed=seed)
     return cfg, df, make_batch(w["N"], b, w["T_out"], seed=seed, device=device)
+
+
+def make_series(num_nodes: int, hours: int, seed: int = 0) -> torch.Tensor:
+    """A DC-shaped synthetic hourly series ``[hours, N, 2]`` (channel 0 = visits-like non-negative counts, channel 1 = time of
+    day in [0, 1)): node-specific scales (heavy-tailed, as README.md:44-53 reports mean 30 / std 84 for DC), a daily and a
+    weekly cycle with node-specific phase, a slow spatial coupling through a random sparse graph, and multiplicative noise.
+    The real SafeGraph series is not redistributable, so this stands in for it wherever a trained model
+    has to be evaluated."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(hours, dtype=torch.float32)
+    scale = torch.exp(torch.randn(num_nodes, generator=g) * 1.0 + 2.5)            # median ~12, long right tail
+    phase = torch.rand(num_nodes, generator=g) * 4.0 - 2.0                       # hours
+    daily = 1.0 + 0.8 * torch.sin(2 * torch.pi * (t[:, None] - 14.0 - phase[None, :]) / 24.0)
+    weekly = 1.0 + 0.25 * torch.sin(2 * torch.pi * t[:, None] / (24.0 * 7) + phase[None, :])
+    base = scale[None, :] * daily.clamp_min(0.05) * weekly
+    # spatial coupling: every node also follows the lagged mean of a few random neighbours
+    nbr = torch.randint(num_nodes, (num_nodes, 4), generator=g)
+    coupled = base.clone()
+    coupled[1:] = 0.7 * base[1:] + 0.3 * base[:-1][:, nbr].mean(-1) * (scale / scale[nbr].mean(-1))[None, :]
+    noise = torch.exp(0.15 * torch.randn(hours, num_nodes, generator=g))
+    visits = (coupled * noise).clamp_min(0.0)
+    out = torch.empty(hours, num_nodes, 2)
+    out[..., 0] = visits
+    out[..., 1] = ((t % 24) / 24.0)[:, None]
+    return out
