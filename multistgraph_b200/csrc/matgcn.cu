@@ -1357,7 +1357,26 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     // same rule as the forward pass: in bf16 mode the propagated slots k >= 1 (PH / PZ / PX there, DPT here) exist only as bf16 twins
     const bool skip32 = bf && !use_multi && !(H & 7) && !(ldm & 7) && B >= 8;
     const bool warm = l2_warm_layer(N, K, Cin, H, B);
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    bool rec_done = false;
+    if (skip32 && H == 64 && rec_flag() && fused_tail_enabled()) {
+        // the whole reverse-time recurrence as one persistent cooperative launch (rec_bwd.cuh)
+        CK(cudaMemsetAsync(DH1, 0, sizeof(float) * U, st));    // DHD2: DHD + DPT[0] of the step after (none yet)
+        CK(cudaMemsetAsync(DRES, 0, sizeof(float) * U, st));   // DZ / DC: the dense phases' output (no carry yet)
+        RecBwdArgs ra{T, N, B, Cin, K, ldm, n_adp, dy, dy_tstride, M16, WG16, WU16,
+                      PH, ws + w.Z, ws + w.R, ws + w.HC, ws + w.H1, ws + w.Z2, ws + w.R2, ws + w.HC2,
+                      ws + w.RGH, ws + w.RUH, mix, DG, DR, DG16T, DPT, DPT16, DHD, DH1, DRES,
+                      reinterpret_cast<__nv_bfloat16*>(DPZA), reinterpret_cast<__nv_bfloat16*>(DPHA), DHC, dmix,
+                      reinterpret_cast<unsigned int*>(bws + bw.MPH)};
+        const cudaError_t re = launch_rec_bwd(ra, st);
+        if (re == cudaSuccess) {
+            g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+            TR();
+            rec_done = true;
+        } else if (re != cudaErrorNotSupported) {
+            return fail(__func__, cudaGetErrorString(re));
+        }
+    }
+    for (int attempt = 0; attempt < 2 && !rec_done; ++attempt) {
         MultiBuilder mb;
         for (int t = T - 1; t >= 0; --t) {
             const float* PHt = PH + (long long)t * K * U;

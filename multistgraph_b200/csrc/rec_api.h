@@ -18,4 +18,24 @@ struct RecFwdArgs {
 // cudaErrorNotSupported: the shape does not meet the kernel's requirements (the caller runs one launch per phase instead)
 cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st);
 
+// Reverse-time recurrence of one layer (rec_bwd.cuh): data gradients and pre-activation gradients of all T steps.
+struct RecBwdArgs {
+    int T, N, B, Cin, K, ldm, n_adp;
+    const float* dy; long long dy_tstride;
+    const __nv_bfloat16* M16; const __nv_bfloat16* WG16; const __nv_bfloat16* WU16;
+    // saved by the forward pass: PH (slot 0 of step t = h_{t-1}), Z, R, HC, H1, Z2, R2, HC2  [T, N*B, H]
+    const float* PH; const float* Z; const float* R; const float* HC; const float* H1; const float* Z2; const float* R2; const float* HC2;
+    const float* RgH; const float* RuH; const float* mix;
+    float* DG; float* DR;            // [T, N*B, 3H] out (in place of GX / RX)
+    __nv_bfloat16* DG16;             // [T, N*B, 3H] out: bf16 twin of DG
+    float* DPT0;                     // [N*B*H] scratch: slot 0 of the per-node products
+    __nv_bfloat16* DPT16;            // [K, N*B*H] scratch: slots 1.. of the per-node products (bf16)
+    float* DHD; float* DHD2; float* DZC;   // [N*B*H] scratch (DHD2 and DZC zero-filled by the caller)
+    __nv_bfloat16* DPZA; __nv_bfloat16* DPHA;   // [T, n_adp, N*B*H] out: per-step copies of the adaptive slices (bf16)
+    float* DHC;                      // [N*B*H] out: gradient w.r.t. the initial state
+    float* dmix;                     // [T] out (zero-filled by the caller)
+    unsigned int* gbar;
+};
+cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st);
+
 }  // namespace matgcn

@@ -1,0 +1,686 @@
+// Persistent reverse-time recurrence of one encoder layer (bf16 mode, rnn_units = 64, at most 64 samples per GPU): the
+// backward of MA.py:120-128, 142-150, 200-211 for all T steps as ONE cooperative launch - the counterpart of rec_fwd.cuh.
+// Per step (t = T-1 .. 0), four phases separated by grid barriers:
+//
+//   A  per node   head of the reverse step: dy = dY_t + carry, chain rule of the sigma-mix and of the residual GRU cell (its two
+//                 small products dzh2 = da3 Ru_h and dh1 += [daz2 | dar2] Rg_h as TF32 tcgen05 MMAs on operand tiles the epilogue
+//                 warps write), main-cell gate algebra -> DR[t], DG[t][:, H:3H], DHD; then, for the same rows, the per-node
+//                 products DPT[k] = gu Wu[n,k]^T (five 64x64x64 bf16 MMAs against TMA-streamed weights)
+//   B  dense      DZ = sum_k M_k^T DPT[k]                 (128 x 128 tiles, K = (K-1) N: TMA-fed tcgen05, plain fp32 store)
+//   C  per node   dzh = DZ + DPT[0]; DHD += dzh z; gz = dzh h z (1-z) -> DG[t][:, 0:H]; DPT[k] = [gz | gr] Wg[n,k]^T;
+//                 DHD2 = DHD + DPT[0]
+//   D  dense      DC = sum_k M_k^T DPT[k]                 (the carry of step t-1 is DC + DHD2, formed by its phase A)
+//
+// The elementwise parts of the two dense phases of the per-phase path (EpiB4 / EpiB6) are moved into the per-node phases
+// that follow them: there every access is a row of a node's [B, H] block (coalesced), the dense phases keep a plain store,
+// and DHD / DPT[0] / DHD2 are produced and consumed by the same CTA (static node -> CTA assignment).  Data that crosses CTAs:
+// the bf16 DPT twins (generic-proxy writes -> TMA reads after the barrier) and DZ / DC (read with ld.global.cg: the
+// addresses are reused every step, a stale L1 line must not be hit).
+#pragma once
+#include "rec_fwd.cuh"
+
+namespace matgcn {
+
+constexpr int RB2_STAGES = 3;
+constexpr int RB2_OFF_WUT = RB2_STAGES * RF_STAGE_BYTES;   // Ru_h^T [64 inputs][64 outputs] fp32 K-major: 2 slabs of 64 rows x 128 B
+constexpr int RB2_OFF_WGT = RB2_OFF_WUT + 16384;           // Rg_h^T [64 inputs][128 outputs]: 4 slabs
+constexpr int RB2_OFF_A1 = RB2_OFF_WGT + 32768;            // da3 [64 rows][64] fp32: 2 slabs
+constexpr int RB2_OFF_A2 = RB2_OFF_A1 + 16384;             // [daz2 | dar2] [64 rows][128] fp32: 4 slabs
+constexpr int RB2_OFF_A3 = RB2_OFF_A2 + 32768;             // bf16 operand of the per-node products: gu [64][64] or [gz | gr] [64][128]
+constexpr int RB2_OFF_BAR = RB2_OFF_A3 + 16384;
+constexpr int RB2_SMEM_TOTAL = RB2_OFF_BAR + 256 + 1024;
+constexpr int RB2_TMEM_D1 = 320, RB2_TMEM_D2 = 384;        // D3[k] at columns 64 k (k < 5); dense accumulators at 0 and 128
+
+struct RecBwdMaps {
+    CUtensorMap MT;   // base matrices as the M-contiguous A operand of the transposed propagation: {N, Kp*N}, box 64 x 64
+    CUtensorMap DP;   // DPT16 slots 1.. as its B operand: {B*64, Kp*N}, box 64 x 64
+    CUtensorMap WG;   // per-node gate weights, K-major B operand of DPT = [gz | gr] Wg^T: WG16 {128, I, K, N}
+    CUtensorMap WU;   // per-node candidate weights: WU16 {64, I, K, N}
+};
+
+struct RecBwdP {
+    int T, N, B, K, Cin, n_adp;
+    int prop_tiles_m, prop_tiles_n, prop_kt;
+    long long U, dy_tstride;
+    const float* dy;
+    const float* PH; const float* Z; const float* R; const float* HC; const float* H1; const float* Z2; const float* R2; const float* HC2;
+    const float* RgH; const float* RuH; const float* mix;
+    float* DG; float* DR; __nv_bfloat16* DG16;
+    float* DPT0; __nv_bfloat16* DPT16;
+    float* DHD; float* DHD2; float* DZC;
+    __nv_bfloat16* DPZA; __nv_bfloat16* DPHA;
+    float* DHC; float* dmix;
+    unsigned int* gbar;
+};
+
+__device__ __forceinline__ float4 rb2_ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void rf_st8f(float* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void rb2_sts_bf16x4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(rf_pack_bf16(v.x, v.y)), "r"(rf_pack_bf16(v.z, v.w)) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_constant__ RecBwdMaps maps, const RecBwdP p) {
+    constexpr int H = 64;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (smem_u32(smem) & 1023u) __trap();
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RB2_OFF_BAR);
+    // bars: full[S], empty[S], tmem_full[2], tmem_empty[2], phase_bar, a1_full, a2_full, a3_full, d1_full, d2_full, d3_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RB2_STAGES + 11);
+    volatile uint32_t* phase_cnt = tmem_slot + 1;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t full0 = bar0, empty0 = bar0 + 8u * RB2_STAGES, tfull0 = bar0 + 8u * (2 * RB2_STAGES);
+    const uint32_t tempty0 = tfull0 + 16u, phase_bar = tfull0 + 32u;
+    const uint32_t a1_full = phase_bar + 8u, a2_full = phase_bar + 16u, a3_full = phase_bar + 24u;
+    const uint32_t d1_full = phase_bar + 32u, d2_full = phase_bar + 40u, d3_full = phase_bar + 48u;
+    const uint32_t wut_s = smem_u32(smem + RB2_OFF_WUT), wgt_s = smem_u32(smem + RB2_OFF_WGT);
+    const uint32_t a1_s = smem_u32(smem + RB2_OFF_A1), a2_s = smem_u32(smem + RB2_OFF_A2), a3_s = smem_u32(smem + RB2_OFF_A3);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RB2_STAGES; ++s) {
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8u * a, 1);
+            mbar_init(tempty0 + 8u * a, TC_EPI_WARPS);
+        }
+        mbar_init(phase_bar, 1);
+        mbar_init(a1_full, TC_EPI_WARPS);
+        mbar_init(a2_full, TC_EPI_WARPS);
+        mbar_init(a3_full, TC_EPI_WARPS);
+        mbar_init(d1_full, 1);
+        mbar_init(d2_full, 1);
+        mbar_init(d3_full, 1);
+        *phase_cnt = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (warp >= 4) {
+        // residual-cell weights, TRANSPOSED (the reverse products contract over the output index o):
+        //   Ru_h [64 o][64 i], Rg_h [128 o][64 i]  ->  K-major operand tiles with row = i, K = o:
+        //   element (i, o) -> slab o/32, row i, 16-byte chunk ((o%32)/4) ^ (i%8), word o%4
+        const int et = threadIdx.x - 128;
+        for (int idx = et; idx < 3 * 64 * 16; idx += TC_EPI_WARPS * 32) {
+            const int o = idx >> 4, i4 = (idx & 15) * 4;
+            const bool g = o >= 64;
+            const int oo = g ? o - 64 : o;
+            const float4 v = g ? ld4(p.RgH + oo * 64 + i4) : ld4(p.RuH + oo * 64 + i4);
+            uint8_t* base = smem + (g ? RB2_OFF_WGT : RB2_OFF_WUT) + (oo >> 5) * 8192 + (oo & 3) * 4;
+            const int ch = (oo & 31) >> 2;
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i4 + u;
+                *reinterpret_cast<float*>(base + i * 128 + ((ch ^ (i & 7)) << 4)) = vv[u];
+            }
+        }
+        rf_proxy_fence_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int T = p.T, K = p.K;
+    const int G = gridDim.x;
+    const int prop_tiles = p.prop_tiles_m * p.prop_tiles_n;
+    const int node_tiles = p.N;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, nbar = 0;
+            const uint64_t pol = l2_policy_evict_last();
+            for (int t = T - 1; t >= 0; --t) {
+                for (int ph = 0; ph < 4; ++ph) {
+                    const bool prop = ph == 1 || ph == 3;
+                    const int ntiles = prop ? prop_tiles : node_tiles;
+                    const int nk = prop ? p.prop_kt : K;
+                    const uint32_t tx = prop ? (uint32_t)RF_STAGE_BYTES : (ph == 0 ? 8192u : 16384u);
+                    // per-node phases stream only the weights, which do not depend on the previous phase: they are requested
+                    // before the grid barrier; the dense phases read the base matrices (constant) and the DPT twins (not)
+                    auto issue_const = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
+                        if (prop) {
+                            const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                            tma_load_5d_hint(sa, &maps.MT, fb, tm * 128, kt * 64, 0, 0, 0, pol);
+                            tma_load_5d_hint(sa + 8192, &maps.MT, fb, tm * 128 + 64, kt * 64, 0, 0, 0, pol);
+                        } else if (ph == 0) {
+                            tma_load_5d_hint(sa, &maps.WU, fb, 0, p.Cin, kt, tile, 0, pol);
+                        } else {
+                            tma_load_5d_hint(sa, &maps.WG, fb, 0, p.Cin, kt, tile, 0, pol);
+                            tma_load_5d_hint(sa + 8192, &maps.WG, fb, 64, p.Cin, kt, tile, 0, pol);
+                        }
+                    };
+                    auto issue_state = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
+                        if (prop) {
+                            const int tn = tile / p.prop_tiles_m;
+                            tma_load_5d(sa + RF_A_BYTES, &maps.DP, fb, tn * 128, kt * 64, 0, 0, 0);
+                            tma_load_5d(sa + RF_A_BYTES + 8192, &maps.DP, fb, tn * 128 + 64, kt * 64, 0, 0, 0);
+                        }
+                    };
+                    const bool first = (t == T - 1) && ph == 0;
+                    int pre = 0;
+                    if (!first && (int)blockIdx.x < ntiles) {
+                        int s2 = stage;
+                        uint32_t p2 = phase;
+                        for (; pre < nk && pre < RB2_STAGES; ++pre) {
+                            mbar_wait(empty0 + 8u * s2, p2 ^ 1);
+                            const uint32_t fb = full0 + 8u * s2;
+                            mbar_expect_tx(fb, tx);
+                            issue_const(blockIdx.x, pre, smem_u32(stage_base + s2 * RF_STAGE_BYTES), fb);
+                            if (++s2 == RB2_STAGES) { s2 = 0; p2 ^= 1; }
+                        }
+                    }
+                    if (!first) {
+                        mbar_wait(phase_bar, nbar & 1u);
+                        ++nbar;
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    for (int tile = blockIdx.x; tile < ntiles; tile += G) {
+                        for (int kt = 0; kt < nk; ++kt) {
+                            const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES);
+                            const uint32_t fb = full0 + 8u * stage;
+                            if (pre > 0) {
+                                --pre;
+                            } else {
+                                mbar_wait(empty0 + 8u * stage, phase ^ 1);
+                                mbar_expect_tx(fb, tx);
+                                issue_const(tile, kt, sa, fb);
+                            }
+                            issue_state(tile, kt, sa, fb);
+                            if (++stage == RB2_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            // D = f32.  dense phases: bf16, A and B both MN-major (bits 15, 16), 128 x 128.  per-node products: bf16, both K-major,
+            // 64 x 64.  residual-cell products: tf32, both K-major, 64 x 64.
+            const uint32_t id_prop = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t id_node = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            const uint32_t id_res = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, par12 = 0, par3 = 0;
+            for (int t = T - 1; t >= 0; --t) {
+                for (int ph = 0; ph < 4; ++ph) {
+                    if (ph == 1 || ph == 3) {
+                        for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
+                            mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1);
+                            tc_fence_after();
+                            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 128);
+                            for (int kt = 0; kt < p.prop_kt; ++kt) {
+                                mbar_wait(full0 + 8u * stage, phase);
+                                tc_fence_after();
+                                const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES), sb = sa + RF_A_BYTES;
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_bf16(tmem_d, umma_desc(sa + kk * 2048, 8192, 1024, 2), umma_desc(sb + kk * 2048, 8192, 1024, 2), id_prop,
+                                              (kt > 0 || kk > 0) ? 1u : 0u);
+                                umma_commit(empty0 + 8u * stage);
+                                if (++stage == RB2_STAGES) { stage = 0; phase ^= 1; }
+                            }
+                            umma_commit(tfull0 + 8u * acc);
+                            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                        }
+                    } else {
+                        for (int n = blockIdx.x; n < node_tiles; n += G) {
+                            if (ph == 0) {
+                                mbar_wait(a1_full, par12);   // da3 tile written: dzh2 = da3 Ru_h
+                                tc_fence_after();
+#pragma unroll
+                                for (int kk = 0; kk < 8; ++kk)
+                                    umma_tf32(tmem_base + RB2_TMEM_D1, umma_desc(a1_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
+                                              umma_desc(wut_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_res, kk > 0 ? 1u : 0u);
+                                umma_commit(d1_full);
+                                mbar_wait(a2_full, par12);   // [daz2 | dar2] tile written: dh1 += . Rg_h
+                                tc_fence_after();
+#pragma unroll
+                                for (int kk = 0; kk < 16; ++kk)
+                                    umma_tf32(tmem_base + RB2_TMEM_D2, umma_desc(a2_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
+                                              umma_desc(wgt_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_res, kk > 0 ? 1u : 0u);
+                                umma_commit(d2_full);
+                                par12 ^= 1;
+                            }
+                            mbar_wait(a3_full, par3);        // bf16 operand tile of the per-node products written
+                            tc_fence_after();
+                            const int slabs = ph == 0 ? 1 : 2;
+                            for (int k = 0; k < K; ++k) {
+                                mbar_wait(full0 + 8u * stage, phase);
+                                tc_fence_after();
+                                const uint32_t sb = smem_u32(stage_base + stage * RF_STAGE_BYTES);
+                                for (int s = 0; s < slabs; ++s) {
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        umma_bf16(tmem_base + (uint32_t)(64 * k), umma_desc(a3_s + s * 8192 + kk * 32, 16, 1024, 2),
+                                                  umma_desc(sb + s * 8192 + kk * 32, 16, 1024, 2), id_node, (s > 0 || kk > 0) ? 1u : 0u);
+                                }
+                                umma_commit(empty0 + 8u * stage);
+                                if (++stage == RB2_STAGES) { stage = 0; phase ^= 1; }
+                            }
+                            umma_commit(d3_full);
+                            par3 ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ L2 prefetch ================================
+        // the saved activations the head of the NEXT reverse step (t - 1) reads on this CTA, requested while the dense phase B
+        // of step t runs
+        uint32_t nb = 1;   // barriers passed when phase B of the first step begins
+        for (int t = T - 1; t >= 1; --t, nb += 4) {
+            while (*phase_cnt < nb) __nanosleep(256);
+            const long long tU = (long long)(t - 1) * p.U;
+            const float* arr[9] = {p.H1 + tU, p.R2 + tU, p.HC2 + tU, p.Z2 + tU, p.R + tU, p.HC + tU, p.Z + tU,
+                                   p.PH + (long long)(t - 1) * K * p.U, p.dy + (long long)(t - 1) * p.dy_tstride};
+            for (int n = blockIdx.x; n < node_tiles; n += G) {
+                const long long base = (long long)n * p.B * H;
+                for (int a = 0; a < 9; ++a)
+                    for (int idx = lane; idx < p.B * 2; idx += 32) pf_l2(arr[a] + base + idx * 32);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0, nbar = 0, par12 = 0, par3 = 0;
+        const int ldc = p.B * H;
+        // per-node tiles (64 rows): the thread's coordinates after rf_quad4 (see rec_fwd.cuh)
+        const int b0 = q * 16 + (lane >> 2);
+        const bool odd = lane & 1;
+        const int pc = ((lane & 1) << 1) | ((lane >> 1) & 1);
+        const bool ok[2] = {b0 < p.B, b0 + 8 < p.B};
+        const int ch = half * 32 + 4 * pc;
+        const long long rd[2] = {ok[0] ? 0 : -(long long)b0, ok[1] ? 8 : -(long long)b0};
+        const uint32_t s_off = (uint32_t)(half * 8192 + b0 * 128);   // tf32 tiles: slab `half` (+ 2 for the dar2 columns)
+        const uint32_t s_x = (uint32_t)(b0 & 7);
+        const uint32_t s16_off = (uint32_t)(b0 * 128 + ((pc & 1) << 3));   // bf16 tiles: 64 columns per 128-byte row
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        for (int t = T - 1; t >= 0; --t) {
+            for (int ph = 0; ph < 4; ++ph) {
+                long long tl = t;
+                asm volatile("" : "+l"(tl));   // (nothing below is hoisted above the phase: see rec_fwd.cuh)
+                const long long tU = tl * p.U;
+                // this phase reads what OTHER CTAs wrote in the previous one (DZ / DC): every epilogue thread waits for the grid
+                // barrier, not only the TMA producer
+                if (nbar > 0) mbar_wait(phase_bar, (nbar - 1u) & 1u);
+                if (ph == 1 || ph == 3) {
+                    // ---- dense phases: plain fp32 store of the 128 x 128 tile (lane = node row) ----
+                    for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
+                        const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                        const long long row = (long long)tm * 128 + q * 32 + lane;
+                        mbar_wait(tfull0 + 8u * acc, acc_phase);
+                        tc_fence_after();
+                        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * 128) + tlane;
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc) {
+                            const int c = half + 2 * cc;
+                            const int col = tn * 128 + c * 32;
+                            uint32_t r[32];
+                            rf_tmem_ld32(tmem_acc + (uint32_t)(c * 32), r);
+                            rf_tmem_wait_ld();
+                            if (row < p.N && col < ldc) {
+                                float* o = p.DZC + row * ldc + col;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) rf_st8f(o + 8 * j, r + 8 * j);
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
+                } else if (ph == 0) {
+                    // ---- phase A: head of the reverse step, then DPT[k] = gu Wu[n,k]^T ----
+                    const float* dYt = p.dy + tl * p.dy_tstride;
+                    const float* Hp = p.PH + tl * K * p.U;
+                    const float gmix = __ldg(p.mix + t);
+                    float dmix_part = 0.f;
+                    float4 dyv[4], cv[4], dv[4], h1[4], r2v[4], hc2[4];
+                    auto load_s0 = [&](int n) {
+                        const long long o0 = ((long long)n * p.B + b0) * H + ch;
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const long long o = o0 + rd[w] * H + 16 * m2;
+                                const int e = 2 * w + m2;
+                                dyv[e] = ld4(dYt + o);
+                                cv[e] = rb2_ldcg4(p.DZC + o);
+                                dv[e] = ld4(p.DHD2 + o);
+                                h1[e] = ld4(p.H1 + tU + o);
+                                r2v[e] = ld4(p.R2 + tU + o);
+                                hc2[e] = ld4(p.HC2 + tU + o);
+                            }
+                        }
+                    };
+                    load_s0(min((int)blockIdx.x, node_tiles - 1));   // (unconditional: keeps the arrays in registers)
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const long long g0 = (long long)n * p.B + b0;
+                        const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
+                        float4 z2[4], dh1[4];
+                        // S0: dy, sigma-mix and the elementwise half of the residual cell's chain rule
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const int e = 2 * w + m2;
+                                const float4 dy = dyv[e] + cv[e] + dv[e];
+                                const float4 res = r2v[e] * h1[e] + one_minus(r2v[e]) * hc2[e];
+                                const float4 pr = dy * (h1[e] - res);
+                                const float4 dres = (1.f - gmix) * dy;
+                                const float4 da3 = dres * one_minus(r2v[e]) * one_minus(hc2[e] * hc2[e]);
+                                const float4 dar = dres * (h1[e] - hc2[e]) * r2v[e] * one_minus(r2v[e]);
+                                dh1[e] = gmix * dy + dres * r2v[e];
+                                if (ok[w]) {
+                                    dmix_part += (pr.x + pr.y) + (pr.z + pr.w);
+                                    const long long x = x0 + w * 8 * 3 * H + 16 * m2;
+                                    st4(p.DR + 3 * tU + x + 2 * H, da3);
+                                    st4(p.DR + 3 * tU + x + H, dar);
+                                }
+                                const uint32_t so = s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4);
+                                rf_sts4(a1_s + so, da3);
+                                rf_sts4(a2_s + 16384 + so, dar);
+                            }
+                        }
+                        rf_proxy_fence_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a1_full);
+                        // (inputs of S1 and S2, requested ahead of their use)
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) z2[2 * w + m2] = ld4(p.Z2 + tU + o0 + rd[w] * H + 16 * m2);
+                        }
+                        float4 rr[4], hc[4], hp[4];
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const long long o = o0 + rd[w] * H + 16 * m2;
+                                rr[2 * w + m2] = ld4(p.R + tU + o);
+                                hc[2 * w + m2] = ld4(p.HC + tU + o);
+                                hp[2 * w + m2] = ld4(Hp + o);
+                            }
+                        }
+                        // S1: dzh2 -> daz2, dh1
+                        float a[16];
+                        float4 fa[4];
+                        mbar_wait(d1_full, par12);
+                        tc_fence_after();
+                        rf_tmem_ld16x4(tmem_base + RB2_TMEM_D1 + tlane + (uint32_t)(half * 32), a);
+                        rf_tmem_wait_ld();
+                        rf_quad4(a, fa, odd);
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const int e = 2 * w + m2;
+                                const float4 daz = fa[e] * h1[e] * z2[e] * one_minus(z2[e]);
+                                dh1[e] = dh1[e] + fa[e] * z2[e];
+                                if (ok[w]) st4(p.DR + 3 * tU + x0 + w * 8 * 3 * H + 16 * m2, daz);
+                                rf_sts4(a2_s + s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4), daz);
+                            }
+                        }
+                        tc_fence_before();
+                        rf_proxy_fence_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a2_full);
+                        // S2: dh1 complete -> DHD, candidate / r-gate pre-activation gradients, bf16 operand tile of DPT = gu Wu^T
+                        mbar_wait(d2_full, par12);
+                        tc_fence_after();
+                        rf_tmem_ld16x4(tmem_base + RB2_TMEM_D2 + tlane + (uint32_t)(half * 32), a);
+                        rf_tmem_wait_ld();
+                        rf_quad4(a, fa, odd);
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const int e = 2 * w + m2;
+                                const float4 d = dh1[e] + fa[e];
+                                const float4 gu = d * one_minus(rr[e]) * one_minus(hc[e] * hc[e]);
+                                const float4 gr = d * (hp[e] - hc[e]) * rr[e] * one_minus(rr[e]);
+                                if (ok[w]) {
+                                    const long long o = o0 + w * 8 * H + 16 * m2, x = x0 + w * 8 * 3 * H + 16 * m2;
+                                    st4(p.DHD + o, d * rr[e]);
+                                    st4(p.DG + 3 * tU + x + 2 * H, gu);
+                                    st4(p.DG + 3 * tU + x + H, gr);
+                                    st4_bf16(p.DG16 + 3 * tU + x + 2 * H, gu);
+                                    st4_bf16(p.DG16 + 3 * tU + x + H, gr);
+                                }
+                                rb2_sts_bf16x4(a3_s + s16_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * half + 2 * m2 + (pc >> 1))) ^ s_x) << 4), gu);
+                            }
+                        }
+                        tc_fence_before();
+                        rf_proxy_fence_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a3_full);
+                        load_s0(min(n + G, node_tiles - 1));   // (dyv .. hc2 are dead: the next tile's S0 inputs go in flight)
+                        // S3: the five per-node products -> DPT[0] (fp32), DPT[k >= 1] (bf16 twins only), adaptive slices per step
+                        mbar_wait(d3_full, par3);
+                        tc_fence_after();
+                        for (int k = 0; k < K; ++k) {
+                            rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), a);
+                            rf_tmem_wait_ld();
+                            rf_quad4(a, fa, odd);
+#pragma unroll
+                            for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                                for (int m2 = 0; m2 < 2; ++m2) {
+                                    if (ok[w]) {
+                                        const long long o = o0 + w * 8 * H + 16 * m2;
+                                        if (k == 0) {
+                                            st4(p.DPT0 + o, fa[2 * w + m2]);
+                                        } else {
+                                            st4_bf16(p.DPT16 + (long long)k * p.U + o, fa[2 * w + m2]);
+                                            if (k <= p.n_adp) st4_bf16(p.DPZA + (tl * p.n_adp + (k - 1)) * p.U + o, fa[2 * w + m2]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                        par12 ^= 1;
+                        par3 ^= 1;
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) dmix_part += __shfl_xor_sync(0xffffffffu, dmix_part, off);
+                    if (lane == 0 && dmix_part != 0.f) atomicAdd(p.dmix + t, dmix_part);
+                } else {
+                    // ---- phase C: z-gate algebra on dzh = DZ + DPT[0], then DPT[k] = [gz | gr] Wg[n,k]^T, DHD2 = DHD + dzh z + DPT[0] ----
+                    const float* Hp = p.PH + tl * K * p.U;
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const long long g0 = (long long)n * p.B + b0;
+                        const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
+                        float4 dz[4], d0[4], zz[4], hp[4], dd[4];
+                        uint2 grv[4];
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const long long o = o0 + rd[w] * H + 16 * m2;
+                                const int e = 2 * w + m2;
+                                dz[e] = rb2_ldcg4(p.DZC + o);
+                                d0[e] = ld4(p.DPT0 + o);
+                                zz[e] = ld4(p.Z + tU + o);
+                                hp[e] = ld4(Hp + o);
+                                dd[e] = ld4(p.DHD + o);
+                                grv[e] = *reinterpret_cast<const uint2*>(p.DG16 + 3 * tU + x0 + rd[w] * 3 * H + 16 * m2 + H);
+                            }
+                        }
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) {
+                                const int e = 2 * w + m2;
+                                const float4 dzh = dz[e] + d0[e];
+                                dd[e] = dd[e] + dzh * zz[e];
+                                const float4 gz = dzh * hp[e] * zz[e] * one_minus(zz[e]);
+                                if (ok[w]) {
+                                    const long long x = x0 + w * 8 * 3 * H + 16 * m2;
+                                    st4(p.DG + 3 * tU + x, gz);
+                                    st4_bf16(p.DG16 + 3 * tU + x, gz);
+                                }
+                                const uint32_t so = s16_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * half + 2 * m2 + (pc >> 1))) ^ s_x) << 4);
+                                rb2_sts_bf16x4(a3_s + so, gz);
+                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a3_s + 8192 + so), "r"(grv[e].x), "r"(grv[e].y) : "memory");
+                            }
+                        }
+                        rf_proxy_fence_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a3_full);
+                        float a[16];
+                        float4 fa[4];
+                        mbar_wait(d3_full, par3);
+                        tc_fence_after();
+                        for (int k = 0; k < K; ++k) {
+                            rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), a);
+                            rf_tmem_wait_ld();
+                            rf_quad4(a, fa, odd);
+#pragma unroll
+                            for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                                for (int m2 = 0; m2 < 2; ++m2) {
+                                    if (ok[w]) {
+                                        const long long o = o0 + w * 8 * H + 16 * m2;
+                                        if (k == 0) {
+                                            st4(p.DHD2 + o, dd[2 * w + m2] + fa[2 * w + m2]);
+                                        } else {
+                                            st4_bf16(p.DPT16 + (long long)k * p.U + o, fa[2 * w + m2]);
+                                            if (k <= p.n_adp) st4_bf16(p.DPHA + (tl * p.n_adp + (k - 1)) * p.U + o, fa[2 * w + m2]);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                        par3 ^= 1;
+                    }
+                }
+                // ---- end of phase: publish this CTA's writes, wait for every CTA ----
+                asm volatile("bar.sync 6, 256;" ::: "memory");
+                if (threadIdx.x == 128) {
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
+                    const unsigned int target = (nbar + 1u) * (unsigned int)G;
+                    long long t0 = 0;
+                    for (uint32_t it = 0; rf_ld_acquire(p.gbar) < target; ++it) {
+                        if (it == 1024) t0 = clock64();
+                        if (it > 1024 && (it & 255) == 0 && clock64() - t0 > 4000000000LL) __trap();
+                    }
+                    *phase_cnt = nbar + 1u;
+                    mbar_arrive(phase_bar);
+                }
+                ++nbar;
+            }
+        }
+        // gradient w.r.t. the initial state: the carry the (non-existent) step -1 would read
+        asm volatile("bar.sync 6, 256;" ::: "memory");   // (thread 128 has passed the last grid barrier)
+        for (int n = blockIdx.x; n < node_tiles; n += G) {
+            const long long o0 = ((long long)n * p.B + b0) * H + ch;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                for (int m2 = 0; m2 < 2; ++m2) {
+                    if (ok[w]) {
+                        const long long o = o0 + w * 8 * H + 16 * m2;
+                        st4(p.DHC + o, rb2_ldcg4(p.DZC + o) + ld4(p.DHD2 + o));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
+    constexpr int H = 64;
+    const int Kp = a.K - 1, I = a.Cin + H;
+    if (a.B < 8 || a.B > 64 || (a.ldm & 7) || a.K < 2 || a.K > 5 || a.N < 1 || a.T < 1 || a.n_adp < 0 || a.n_adp > Kp) return cudaErrorNotSupported;
+    const unsigned long long U = (unsigned long long)a.N * a.B * H;
+    RecBwdP p;
+    memset(&p, 0, sizeof(p));
+    p.T = a.T; p.N = a.N; p.B = a.B; p.K = a.K; p.Cin = a.Cin; p.n_adp = a.n_adp;
+    p.prop_tiles_m = (a.N + 127) / 128;
+    p.prop_tiles_n = (a.B * H + 127) / 128;
+    p.prop_kt = (Kp * a.N + 63) / 64;
+    p.U = (long long)U; p.dy_tstride = a.dy_tstride;
+    p.dy = a.dy;
+    p.PH = a.PH; p.Z = a.Z; p.R = a.R; p.HC = a.HC; p.H1 = a.H1; p.Z2 = a.Z2; p.R2 = a.R2; p.HC2 = a.HC2;
+    p.RgH = a.RgH; p.RuH = a.RuH; p.mix = a.mix;
+    p.DG = a.DG; p.DR = a.DR; p.DG16 = a.DG16;
+    p.DPT0 = a.DPT0; p.DPT16 = a.DPT16;
+    p.DHD = a.DHD; p.DHD2 = a.DHD2; p.DZC = a.DZC;
+    p.DPZA = a.DPZA; p.DPHA = a.DPHA;
+    p.DHC = a.DHC; p.dmix = a.dmix;
+    p.gbar = a.gbar;
+    const void* al[] = {a.dy, a.PH, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.RgH, a.RuH, a.DG, a.DR, a.DG16, a.DPT0, a.DPT16, a.DHD,
+                        a.DHD2, a.DZC, a.DHC};
+    for (const void* q : al)
+        if (!q || (reinterpret_cast<uintptr_t>(q) & 31)) return cudaErrorNotSupported;
+    if ((a.dy_tstride & 7) || (a.n_adp > 0 && (!a.DPZA || !a.DPHA || (reinterpret_cast<uintptr_t>(a.DPZA) & 15) || (reinterpret_cast<uintptr_t>(a.DPHA) & 15))))
+        return cudaErrorNotSupported;
+
+    RecBwdMaps maps;
+    {
+        const unsigned long long d[2] = {(unsigned long long)a.N, (unsigned long long)Kp * a.N}, s[1] = {(unsigned long long)a.ldm * 2};
+        const unsigned int b[2] = {64, 64};
+        if (!rf_make_map(&maps.MT, a.M16, 2, d, s, b)) return cudaErrorNotSupported;
+    }
+    {
+        const unsigned long long d[2] = {(unsigned long long)a.B * H, (unsigned long long)Kp * a.N}, s[1] = {(unsigned long long)a.B * H * 2};
+        const unsigned int b[2] = {64, 64};
+        if (!rf_make_map(&maps.DP, a.DPT16 + U, 2, d, s, b)) return cudaErrorNotSupported;
+    }
+    {
+        const unsigned int b[4] = {64, 64, 1, 1};
+        const unsigned long long dg[4] = {128, (unsigned long long)I, (unsigned long long)a.K, (unsigned long long)a.N};
+        const unsigned long long sg[3] = {256, (unsigned long long)I * 256, (unsigned long long)a.K * I * 256};
+        const unsigned long long du[4] = {64, (unsigned long long)I, (unsigned long long)a.K, (unsigned long long)a.N};
+        const unsigned long long su[3] = {128, (unsigned long long)I * 128, (unsigned long long)a.K * I * 128};
+        if (!rf_make_map(&maps.WG, a.WG16, 4, dg, sg, b) || !rf_make_map(&maps.WU, a.WU16, 4, du, su, b)) return cudaErrorNotSupported;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool configured[64] = {};
+    if (dev < 0 || dev >= 64) return cudaErrorNotSupported;
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB2_SMEM_TOTAL);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int most = max(p.prop_tiles_m * p.prop_tiles_n, a.N);
+    const int grid = most < sms ? most : sms;
+    cudaError_t e = cudaMemsetAsync(a.gbar, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)&maps, (void*)&p};
+    e = cudaLaunchCooperativeKernel((void*)rec_bwd_kernel, dim3((unsigned)grid), dim3(TC_THREADS), args, RB2_SMEM_TOTAL, st);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+}  // namespace matgcn

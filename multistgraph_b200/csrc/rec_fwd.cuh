@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                             }
                         }
                     };
-                    if ((int)blockIdx.x < node_tiles) load_inputs(blockIdx.x);
+                    load_inputs(min((int)blockIdx.x, node_tiles - 1));   // (unconditional: keeps the arrays in registers)
                     for (int n = blockIdx.x; n < node_tiles; n += G) {
                         const long long o0 = ((long long)n * p.B + b0) * H + ch;
                         RF_STAMP_E(ph, n / G, 5);
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                         float4 zh[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) zh[e] = hz[e];
-                        if (n + G < node_tiles) load_inputs(n + G);
+                        load_inputs(min(n + G, node_tiles - 1));
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
 #pragma unroll
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                             }
                         }
                     };
-                    if ((int)blockIdx.x < node_tiles) load_stage1(blockIdx.x);
+                    load_stage1(min((int)blockIdx.x, node_tiles - 1));   // (unconditional: keeps the arrays in registers)
                     for (int n = blockIdx.x; n < node_tiles; n += G) {
                         const long long g0 = (long long)n * p.B + b0;
                         const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                         __syncwarp();
                         RF_STAMP_E(ph, n / G, 8);
                         if (lane == 0) mbar_arrive(s1_full);
-                        if (n + G < node_tiles) load_stage1(n + G);   // (gc / rr / hh are dead from here on: the next tile's go in flight)
+                        load_stage1(min(n + G, node_tiles - 1));   // (gc / rr / hh are dead from here on: the next tile's go in flight)
                         // stage 2: [z2 | r2] = sigma(h1 Rg_h^T + RX[:, 0:2H]); z2*h1 -> Z2, R2, ZH2, operand tile S2
                         mbar_wait(r2_full, res_par);
                         tc_fence_after();
