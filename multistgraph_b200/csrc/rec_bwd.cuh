@@ -22,6 +22,8 @@
 namespace matgcn {
 
 constexpr int RB2_STAGES = 3;
+constexpr int RB2_NSTAGES = 2;       // per-node phases: whole-tile weight buffers over the same memory (see the producer)
+constexpr int RB2_WBUF = 49152;      // phase A: two buffers of K x 8 KB; phase C: one buffer of 2 x K x 8 KB over both
 constexpr int RB2_OFF_WUT = RB2_STAGES * RF_STAGE_BYTES;   // Ru_h^T [64 inputs][64 outputs] fp32 K-major: 2 slabs of 64 rows x 128 B
 constexpr int RB2_OFF_WGT = RB2_OFF_WUT + 16384;           // Rg_h^T [64 inputs][128 outputs]: 4 slabs
 constexpr int RB2_OFF_A1 = RB2_OFF_WGT + 32768;            // da3 [64 rows][64] fp32: 2 slabs
@@ -51,6 +53,8 @@ struct RecBwdP {
     __nv_bfloat16* DPZA; __nv_bfloat16* DPHA;
     float* DHC; float* dmix;
     unsigned int* gbar;
+    long long* dbg;      // optional phase timeline of CTA 0 (tools/rec_timeline.py)
+    int prefetch;        // warp 3 pulls the next step's saved activations into L2 during the dense phase B
 };
 
 __device__ __forceinline__ float4 rb2_ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -63,6 +67,11 @@ __device__ __forceinline__ void rb2_sts_bf16x4(uint32_t addr, const float4& v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(rf_pack_bf16(v.x, v.y)), "r"(rf_pack_bf16(v.z, v.w)) : "memory");
 }
 
+#define RB2_STAMP(i, s)                                                                                                     \
+    do {                                                                                                                    \
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128 && t == (T >> 1) && (i) < 4) p.dbg[T * 16 + ((i) << 4) + (s)] = clock64(); \
+    } while (0)
+
 __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_constant__ RecBwdMaps maps, const RecBwdP p) {
     constexpr int H = 64;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -70,8 +79,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
     if (smem_u32(smem) & 1023u) __trap();
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RB2_OFF_BAR);
-    // bars: full[S], empty[S], tmem_full[2], tmem_empty[2], phase_bar, a1_full, a2_full, a3_full, d1_full, d2_full, d3_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RB2_STAGES + 11);
+    // bars: full[S], empty[S], tmem_full[2], tmem_empty[2], phase_bar, a1_full, a2_full, a3_full, d1_full, d2_full, d3_full,
+    //       nfull[2], nempty[2]: the per-node phases use the same ring memory as whole-tile weight buffers - the K weight blocks of
+    //       a node are laid side by side as ONE K-major operand with 64 K rows, so that the K products of a tile are one
+    //       [64 x 64K] MMA per k-step instead of K small ones (an MMA of this size costs ~150 cycles whatever its N);
+    //       the two uses of the memory are never active at the same time
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RB2_STAGES + 11 + 2 * RB2_NSTAGES);
     volatile uint32_t* phase_cnt = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,6 +93,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
     const uint32_t tempty0 = tfull0 + 16u, phase_bar = tfull0 + 32u;
     const uint32_t a1_full = phase_bar + 8u, a2_full = phase_bar + 16u, a3_full = phase_bar + 24u;
     const uint32_t d1_full = phase_bar + 32u, d2_full = phase_bar + 40u, d3_full = phase_bar + 48u;
+    const uint32_t nfull0 = phase_bar + 56u, nempty0 = nfull0 + 8u * RB2_NSTAGES;
     const uint32_t wut_s = smem_u32(smem + RB2_OFF_WUT), wgt_s = smem_u32(smem + RB2_OFF_WGT);
     const uint32_t a1_s = smem_u32(smem + RB2_OFF_A1), a2_s = smem_u32(smem + RB2_OFF_A2), a3_s = smem_u32(smem + RB2_OFF_A3);
 
@@ -99,6 +113,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
         mbar_init(d3_full, 1);
+        for (int s = 0; s < RB2_NSTAGES; ++s) {
+            mbar_init(nfull0 + 8u * s, 1);
+            mbar_init(nempty0 + 8u * s, 1);
+        }
         *phase_cnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -141,66 +159,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, nbar = 0;
+            uint32_t phase = 0, nbar = 0, wuse0 = 0, wuse1 = 0;
             const uint64_t pol = l2_policy_evict_last();
             for (int t = T - 1; t >= 0; --t) {
                 for (int ph = 0; ph < 4; ++ph) {
-                    const bool prop = ph == 1 || ph == 3;
-                    const int ntiles = prop ? prop_tiles : node_tiles;
-                    const int nk = prop ? p.prop_kt : K;
-                    const uint32_t tx = prop ? (uint32_t)RF_STAGE_BYTES : (ph == 0 ? 8192u : 16384u);
-                    // per-node phases stream only the weights, which do not depend on the previous phase: they are requested
-                    // before the grid barrier; the dense phases read the base matrices (constant) and the DPT twins (not)
-                    auto issue_const = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
-                        if (prop) {
-                            const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
-                            tma_load_5d_hint(sa, &maps.MT, fb, tm * 128, kt * 64, 0, 0, 0, pol);
-                            tma_load_5d_hint(sa + 8192, &maps.MT, fb, tm * 128 + 64, kt * 64, 0, 0, 0, pol);
-                        } else if (ph == 0) {
-                            tma_load_5d_hint(sa, &maps.WU, fb, 0, p.Cin, kt, tile, 0, pol);
-                        } else {
-                            tma_load_5d_hint(sa, &maps.WG, fb, 0, p.Cin, kt, tile, 0, pol);
-                            tma_load_5d_hint(sa + 8192, &maps.WG, fb, 64, p.Cin, kt, tile, 0, pol);
-                        }
-                    };
-                    auto issue_state = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
-                        if (prop) {
-                            const int tn = tile / p.prop_tiles_m;
-                            tma_load_5d(sa + RF_A_BYTES, &maps.DP, fb, tn * 128, kt * 64, 0, 0, 0);
-                            tma_load_5d(sa + RF_A_BYTES + 8192, &maps.DP, fb, tn * 128 + 64, kt * 64, 0, 0, 0);
-                        }
-                    };
                     const bool first = (t == T - 1) && ph == 0;
-                    int pre = 0;
-                    if (!first && (int)blockIdx.x < ntiles) {
-                        int s2 = stage;
-                        uint32_t p2 = phase;
-                        for (; pre < nk && pre < RB2_STAGES; ++pre) {
-                            mbar_wait(empty0 + 8u * s2, p2 ^ 1);
-                            const uint32_t fb = full0 + 8u * s2;
-                            mbar_expect_tx(fb, tx);
-                            issue_const(blockIdx.x, pre, smem_u32(stage_base + s2 * RF_STAGE_BYTES), fb);
-                            if (++s2 == RB2_STAGES) { s2 = 0; p2 ^= 1; }
+                    if (ph == 1 || ph == 3) {
+                        // dense phases: base matrices (constant: requested before the grid barrier) and the DPT twins
+                        int pre = 0;
+                        // the ring memory is shared with the per-node weight buffers: both must have been consumed
+                        mbar_wait(nempty0, (wuse0 & 1u) ^ 1u);
+                        mbar_wait(nempty0 + 8u, (wuse1 & 1u) ^ 1u);
+                        if ((int)blockIdx.x < prop_tiles) {
+                            const int tn = blockIdx.x / p.prop_tiles_m, tm = blockIdx.x - tn * p.prop_tiles_m;
+                            int s2 = stage;
+                            uint32_t p2 = phase;
+                            for (; pre < p.prop_kt && pre < RB2_STAGES; ++pre) {
+                                mbar_wait(empty0 + 8u * s2, p2 ^ 1);
+                                const uint32_t fb = full0 + 8u * s2, sa = smem_u32(stage_base + s2 * RF_STAGE_BYTES);
+                                mbar_expect_tx(fb, RF_STAGE_BYTES);
+                                tma_load_5d_hint(sa, &maps.MT, fb, tm * 128, pre * 64, 0, 0, 0, pol);
+                                tma_load_5d_hint(sa + 8192, &maps.MT, fb, tm * 128 + 64, pre * 64, 0, 0, 0, pol);
+                                if (++s2 == RB2_STAGES) { s2 = 0; p2 ^= 1; }
+                            }
                         }
-                    }
-                    if (!first) {
+                        // (this thread skips the barriers that precede the per-node phases: the counter makes sure the parity test below
+                        // is not answered by an older completion)
+                        while (*phase_cnt < nbar + 1u) __nanosleep(32);
                         mbar_wait(phase_bar, nbar & 1u);
                         ++nbar;
                         asm volatile("fence.proxy.async;" ::: "memory");
-                    }
-                    for (int tile = blockIdx.x; tile < ntiles; tile += G) {
-                        for (int kt = 0; kt < nk; ++kt) {
-                            const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES);
-                            const uint32_t fb = full0 + 8u * stage;
-                            if (pre > 0) {
-                                --pre;
-                            } else {
-                                mbar_wait(empty0 + 8u * stage, phase ^ 1);
-                                mbar_expect_tx(fb, tx);
-                                issue_const(tile, kt, sa, fb);
+                        for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
+                            const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                            for (int kt = 0; kt < p.prop_kt; ++kt) {
+                                const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES);
+                                const uint32_t fb = full0 + 8u * stage;
+                                if (pre > 0) {
+                                    --pre;
+                                } else {
+                                    mbar_wait(empty0 + 8u * stage, phase ^ 1);
+                                    mbar_expect_tx(fb, RF_STAGE_BYTES);
+                                    tma_load_5d_hint(sa, &maps.MT, fb, tm * 128, kt * 64, 0, 0, 0, pol);
+                                    tma_load_5d_hint(sa + 8192, &maps.MT, fb, tm * 128 + 64, kt * 64, 0, 0, 0, pol);
+                                }
+                                tma_load_5d(sa + RF_A_BYTES, &maps.DP, fb, tn * 128, kt * 64, 0, 0, 0);
+                                tma_load_5d(sa + RF_A_BYTES + 8192, &maps.DP, fb, tn * 128 + 64, kt * 64, 0, 0, 0);
+                                if (++stage == RB2_STAGES) { stage = 0; phase ^= 1; }
                             }
-                            issue_state(tile, kt, sa, fb);
-                            if (++stage == RB2_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    } else {
+                        // per-node phases stream only the weights, which never depend on the previous phase: they are requested as soon
+                        // as the dense ring (same memory) has been consumed, without waiting for the grid barrier
+                        {
+                            int s2 = stage;
+                            uint32_t p2 = phase;
+                            for (int i = 0; i < RB2_STAGES; ++i) {
+                                mbar_wait(empty0 + 8u * s2, p2 ^ 1);
+                                if (++s2 == RB2_STAGES) { s2 = 0; p2 ^= 1; }
+                            }
+                        }
+                        if (!first) ++nbar;   // (the grid barrier before this phase is not waited for here)
+                        if (ph == 2) mbar_wait(nempty0 + 8u, (wuse1 & 1u) ^ 1u);   // phase C's single buffer spans both of phase A's
+                        int cnt = 0;
+                        for (int n = blockIdx.x; n < node_tiles; n += G, ++cnt) {
+                            const int b = ph == 0 ? (cnt & 1) : 0;
+                            uint32_t& use = b ? wuse1 : wuse0;
+                            mbar_wait(nempty0 + 8u * b, (use & 1u) ^ 1u);
+                            const uint32_t fb = nfull0 + 8u * b;
+                            const uint32_t dst = smem_u32(stage_base + b * RB2_WBUF);
+                            mbar_expect_tx(fb, (uint32_t)K * (ph == 0 ? 8192u : 16384u));
+                            for (int k = 0; k < K; ++k) {
+                                if (ph == 0) {
+                                    tma_load_5d_hint(dst + k * 8192, &maps.WU, fb, 0, p.Cin, k, n, 0, pol);
+                                } else {
+                                    tma_load_5d_hint(dst + k * 8192, &maps.WG, fb, 0, p.Cin, k, n, 0, pol);
+                                    tma_load_5d_hint(dst + (K + k) * 8192, &maps.WG, fb, 64, p.Cin, k, n, 0, pol);
+                                }
+                            }
+                            ++use;
                         }
                     }
                 }
@@ -212,10 +248,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
             // D = f32.  dense phases: bf16, A and B both MN-major (bits 15, 16), 128 x 128.  per-node products: bf16, both K-major,
             // 64 x 64.  residual-cell products: tf32, both K-major, 64 x 64.
             const uint32_t id_prop = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t id_node = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+            const uint32_t id_node0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 4) << 24);   // (N is set per instruction)
             const uint32_t id_res = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
             int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0, par12 = 0, par3 = 0;
+            uint32_t phase = 0, acc_phase = 0, par12 = 0, par3 = 0, wuse0 = 0, wuse1 = 0;
             for (int t = T - 1; t >= 0; --t) {
                 for (int ph = 0; ph < 4; ++ph) {
                     if (ph == 1 || ph == 3) {
@@ -238,7 +274,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         }
                     } else {
-                        for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        int cnt = 0;
+                        for (int n = blockIdx.x; n < node_tiles; n += G, ++cnt) {
                             if (ph == 0) {
                                 mbar_wait(a1_full, par12);   // da3 tile written: dzh2 = da3 Ru_h
                                 tc_fence_after();
@@ -247,31 +284,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                     umma_tf32(tmem_base + RB2_TMEM_D1, umma_desc(a1_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
                                               umma_desc(wut_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_res, kk > 0 ? 1u : 0u);
                                 umma_commit(d1_full);
-                                mbar_wait(a2_full, par12);   // [daz2 | dar2] tile written: dh1 += . Rg_h
+                                // dh1 += [daz2 | dar2] Rg_h: the dar2 half (written together with da3) runs while the epilogue warps turn
+                                // dzh2 into daz2; only the daz2 half is on the critical path
+#pragma unroll
+                                for (int kk = 8; kk < 16; ++kk)
+                                    umma_tf32(tmem_base + RB2_TMEM_D2, umma_desc(a2_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
+                                              umma_desc(wgt_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_res, kk > 8 ? 1u : 0u);
+                                mbar_wait(a2_full, par12);   // daz2 written
                                 tc_fence_after();
 #pragma unroll
-                                for (int kk = 0; kk < 16; ++kk)
+                                for (int kk = 0; kk < 8; ++kk)
                                     umma_tf32(tmem_base + RB2_TMEM_D2, umma_desc(a2_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2),
-                                              umma_desc(wgt_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_res, kk > 0 ? 1u : 0u);
+                                              umma_desc(wgt_s + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024, 2), id_res, 1u);
                                 umma_commit(d2_full);
                                 par12 ^= 1;
                             }
                             mbar_wait(a3_full, par3);        // bf16 operand tile of the per-node products written
                             tc_fence_after();
+                            // D3 [64 x 64K] = operand tile x [W_0^T | .. | W_{K-1}^T]: per k-step one MMA of up to 256 columns (+ the rest)
+                            const int b = ph == 0 ? (cnt & 1) : 0;
+                            uint32_t& use = b ? wuse1 : wuse0;
+                            mbar_wait(nfull0 + 8u * b, use & 1u);
+                            tc_fence_after();
+                            const uint32_t wb = smem_u32(stage_base + b * RB2_WBUF);
                             const int slabs = ph == 0 ? 1 : 2;
-                            for (int k = 0; k < K; ++k) {
-                                mbar_wait(full0 + 8u * stage, phase);
-                                tc_fence_after();
-                                const uint32_t sb = smem_u32(stage_base + stage * RF_STAGE_BYTES);
-                                for (int s = 0; s < slabs; ++s) {
+                            for (int s = 0; s < slabs; ++s) {
 #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk)
-                                        umma_bf16(tmem_base + (uint32_t)(64 * k), umma_desc(a3_s + s * 8192 + kk * 32, 16, 1024, 2),
-                                                  umma_desc(sb + s * 8192 + kk * 32, 16, 1024, 2), id_node, (s > 0 || kk > 0) ? 1u : 0u);
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    const uint64_t da = umma_desc(a3_s + s * 8192 + kk * 32, 16, 1024, 2);
+                                    const uint32_t acc_in = (s > 0 || kk > 0) ? 1u : 0u;
+                                    for (int k0 = 0; k0 < K; k0 += 4) {
+                                        const uint32_t nn = (uint32_t)min(4, K - k0) * 64u;
+                                        umma_bf16(tmem_base + (uint32_t)(64 * k0), da, umma_desc(wb + (s * K + k0) * 8192 + kk * 32, 16, 1024, 2),
+                                                  id_node0 | ((nn >> 3) << 17), acc_in);
+                                    }
                                 }
-                                umma_commit(empty0 + 8u * stage);
-                                if (++stage == RB2_STAGES) { stage = 0; phase ^= 1; }
                             }
+                            umma_commit(nempty0 + 8u * b);
+                            ++use;
                             umma_commit(d3_full);
                             par3 ^= 1;
                         }
@@ -284,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         // the saved activations the head of the NEXT reverse step (t - 1) reads on this CTA, requested while the dense phase B
         // of step t runs
         uint32_t nb = 1;   // barriers passed when phase B of the first step begins
-        for (int t = T - 1; t >= 1; --t, nb += 4) {
+        for (int t = T - 1; t >= 1 && p.prefetch; --t, nb += 4) {
             while (*phase_cnt < nb) __nanosleep(256);
             const long long tU = (long long)(t - 1) * p.U;
             const float* arr[9] = {p.H1 + tU, p.R2 + tU, p.HC2 + tU, p.Z2 + tU, p.R + tU, p.HC + tU, p.Z + tU,
@@ -320,6 +370,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                 // this phase reads what OTHER CTAs wrote in the previous one (DZ / DC): every epilogue thread waits for the grid
                 // barrier, not only the TMA producer
                 if (nbar > 0) mbar_wait(phase_bar, (nbar - 1u) & 1u);
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[((T - 1 - t) * 4 + ph) * 4 + 0] = clock64();
                 if (ph == 1 || ph == 3) {
                     // ---- dense phases: plain fp32 store of the 128 x 128 tile (lane = node row) ----
                     for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
@@ -375,6 +426,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         const long long g0 = (long long)n * p.B + b0;
                         const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
                         float4 z2[4], dh1[4];
+                        RB2_STAMP(n / G, 0);
                         // S0: dy, sigma-mix and the elementwise half of the residual cell's chain rule
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
@@ -401,6 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         }
                         rf_proxy_fence_smem();
                         __syncwarp();
+                        RB2_STAMP(n / G, 1);
                         if (lane == 0) mbar_arrive(a1_full);
                         // (inputs of S1 and S2, requested ahead of their use)
 #pragma unroll
@@ -424,6 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         float4 fa[4];
                         mbar_wait(d1_full, par12);
                         tc_fence_after();
+                        RB2_STAMP(n / G, 2);
                         rf_tmem_ld16x4(tmem_base + RB2_TMEM_D1 + tlane + (uint32_t)(half * 32), a);
                         rf_tmem_wait_ld();
                         rf_quad4(a, fa, odd);
@@ -441,10 +495,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         tc_fence_before();
                         rf_proxy_fence_smem();
                         __syncwarp();
+                        RB2_STAMP(n / G, 3);
                         if (lane == 0) mbar_arrive(a2_full);
                         // S2: dh1 complete -> DHD, candidate / r-gate pre-activation gradients, bf16 operand tile of DPT = gu Wu^T
                         mbar_wait(d2_full, par12);
                         tc_fence_after();
+                        RB2_STAMP(n / G, 4);
                         rf_tmem_ld16x4(tmem_base + RB2_TMEM_D2 + tlane + (uint32_t)(half * 32), a);
                         rf_tmem_wait_ld();
                         rf_quad4(a, fa, odd);
@@ -470,11 +526,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         tc_fence_before();
                         rf_proxy_fence_smem();
                         __syncwarp();
+                        RB2_STAMP(n / G, 5);
                         if (lane == 0) mbar_arrive(a3_full);
                         load_s0(min(n + G, node_tiles - 1));   // (dyv .. hc2 are dead: the next tile's S0 inputs go in flight)
                         // S3: the five per-node products -> DPT[0] (fp32), DPT[k >= 1] (bf16 twins only), adaptive slices per step
                         mbar_wait(d3_full, par3);
                         tc_fence_after();
+                        RB2_STAMP(n / G, 6);
                         for (int k = 0; k < K; ++k) {
                             rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), a);
                             rf_tmem_wait_ld();
@@ -496,6 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                             }
                         }
                         tc_fence_before();
+                        RB2_STAMP(n / G, 7);
                         par12 ^= 1;
                         par3 ^= 1;
                     }
@@ -505,11 +564,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                 } else {
                     // ---- phase C: z-gate algebra on dzh = DZ + DPT[0], then DPT[k] = [gz | gr] Wg[n,k]^T, DHD2 = DHD + dzh z + DPT[0] ----
                     const float* Hp = p.PH + tl * K * p.U;
-                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                    float4 dz[4], d0[4], zz[4], hp[4], dd[4];
+                    uint2 grv[4];
+                    auto load_c = [&](int n) {
                         const long long g0 = (long long)n * p.B + b0;
                         const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
-                        float4 dz[4], d0[4], zz[4], hp[4], dd[4];
-                        uint2 grv[4];
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
 #pragma unroll
@@ -524,13 +583,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 grv[e] = *reinterpret_cast<const uint2*>(p.DG16 + 3 * tU + x0 + rd[w] * 3 * H + 16 * m2 + H);
                             }
                         }
+                    };
+                    load_c(min((int)blockIdx.x, node_tiles - 1));   // (unconditional: keeps the arrays in registers)
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const long long g0 = (long long)n * p.B + b0;
+                        const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
+                        float4 dk[4];
+                        RB2_STAMP(n / G, 8);
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
 #pragma unroll
                             for (int m2 = 0; m2 < 2; ++m2) {
                                 const int e = 2 * w + m2;
                                 const float4 dzh = dz[e] + d0[e];
-                                dd[e] = dd[e] + dzh * zz[e];
+                                dk[e] = dd[e] + dzh * zz[e];
                                 const float4 gz = dzh * hp[e] * zz[e] * one_minus(zz[e]);
                                 if (ok[w]) {
                                     const long long x = x0 + w * 8 * 3 * H + 16 * m2;
@@ -544,11 +610,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         }
                         rf_proxy_fence_smem();
                         __syncwarp();
+                        RB2_STAMP(n / G, 9);
                         if (lane == 0) mbar_arrive(a3_full);
+                        load_c(min(n + G, node_tiles - 1));   // (the next tile's inputs go in flight during the products)
                         float a[16];
                         float4 fa[4];
                         mbar_wait(d3_full, par3);
                         tc_fence_after();
+                        RB2_STAMP(n / G, 10);
                         for (int k = 0; k < K; ++k) {
                             rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), a);
                             rf_tmem_wait_ld();
@@ -560,7 +629,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                     if (ok[w]) {
                                         const long long o = o0 + w * 8 * H + 16 * m2;
                                         if (k == 0) {
-                                            st4(p.DHD2 + o, dd[2 * w + m2] + fa[2 * w + m2]);
+                                            st4(p.DHD2 + o, dk[2 * w + m2] + fa[2 * w + m2]);
                                         } else {
                                             st4_bf16(p.DPT16 + (long long)k * p.U + o, fa[2 * w + m2]);
                                             if (k <= p.n_adp) st4_bf16(p.DPHA + (tl * p.n_adp + (k - 1)) * p.U + o, fa[2 * w + m2]);
@@ -570,12 +639,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                             }
                         }
                         tc_fence_before();
+                        RB2_STAMP(n / G, 11);
                         par3 ^= 1;
                     }
                 }
                 // ---- end of phase: publish this CTA's writes, wait for every CTA ----
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[((T - 1 - t) * 4 + ph) * 4 + 1] = clock64();
                 asm volatile("bar.sync 6, 256;" ::: "memory");
                 if (threadIdx.x == 128) {
+                    if (p.dbg && blockIdx.x == 0) p.dbg[((T - 1 - t) * 4 + ph) * 4 + 2] = clock64();
                     asm volatile("fence.proxy.async;" ::: "memory");
                     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.gbar) : "memory");
                     const unsigned int target = (nbar + 1u) * (unsigned int)G;
@@ -584,6 +656,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         if (it == 1024) t0 = clock64();
                         if (it > 1024 && (it & 255) == 0 && clock64() - t0 > 4000000000LL) __trap();
                     }
+                    if (p.dbg && blockIdx.x == 0) p.dbg[((T - 1 - t) * 4 + ph) * 4 + 3] = clock64();
                     *phase_cnt = nbar + 1u;
                     mbar_arrive(phase_bar);
                 }
@@ -636,6 +709,11 @@ cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
     p.DPZA = a.DPZA; p.DPHA = a.DPHA;
     p.DHC = a.DHC; p.dmix = a.dmix;
     p.gbar = a.gbar;
+    p.dbg = tc_debug_buffer();
+    {
+        const char* e = getenv("MATGCN_REC_PF");
+        p.prefetch = (e && e[0] == '1');   // off by default: the fill traffic costs the dense phase more than the head gains
+    }
     const void* al[] = {a.dy, a.PH, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.RgH, a.RuH, a.DG, a.DR, a.DG16, a.DPT0, a.DPT16, a.DHD,
                         a.DHD2, a.DZC, a.DHC};
     for (const void* q : al)

@@ -87,7 +87,7 @@ def test_model_fast_mode_matches_oracle(N, B, adjtype, adpadj, D, tout, mode):
     loss = model.calculate_loss(clone_batch(batch, DEV))
     loss.backward()
     torch.cuda.synchronize()
-    assert lib.matgcn_tc_launch_count() > before + 100, "fast mode did not use the tensor-core kernels"
+    assert lib.matgcn_tc_launch_count() > before + 20, "fast mode did not use the tensor-core kernels"
     errs = {"forecast": max_rel_err(y, y_ref), "loss": abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())}
     grads = ora.grads()
     for k, p in model.named_parameters():
