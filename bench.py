@@ -16,8 +16,9 @@ bucket, ``train.FusedClipAdam``).
                previous step) and reads the loss back on the host, all inside the timed region.
 * ``e2e_device_windows``: the same step with the batch gathered on the device from a series
                resident in HBM (``train.DeviceWindowBank``); only label-start indices are uploaded.
-* ``roofline``: the dominant kernel (support-propagation GEMM), timed live with CUDA events on
-               the launching stream at the step's exact shape.
+* ``roofline``: the dominant kernel - the persistent reverse-time recurrence kernel in the default bf16 mode (the forward
+               one beside it), the support-propagation GEMM in the other modes - timed live with CUDA events on the
+               launching stream.
 * ``cpu_baseline``: the oracle (a port of the reference's CPU path) timed on this host's cores
                on a bounded sample of the same workload.
 * ``strong_scaling``: BASELINE config 4 (N=883, GLOBAL batch 256 sharded over the ranks): the one scaling target the
@@ -258,6 +259,55 @@ def propagation_roofline(n_nodes, batch, hidden, kp, ldm, device, peaks, flags, 
                     "kernel of exact mode cannot approach either"}
 
 
+def recurrence_roofline(model, batches, opt, train_step, lib, n_nodes, batch, k_supports, n_adp, t_steps, peaks, steps=3):
+    """The dominant kernels of the bf16 path are the two persistent recurrence kernels (csrc/rec_fwd.cuh, rec_bwd.cuh: one
+    cooperative launch per layer and direction).  Their launches are timed with CUDA events on the launching stream inside
+    real train steps (matgcn_rec_timing); the roofline is stated for the larger one, the reverse-time kernel.
+    Algorithmic work per launch (DESIGN.md section 4, H = 64): FLOPs = T [2 * 2 Kp N^2 B H + 2 N B K H 3H + 2 N B H 3H];
+    HBM bytes = T [saved activations read + pre-activation gradients written (as stored: fp32, bf16 twins) + the per-node
+    weight blocks once (bf16)].  By SURVEY 8d's rule the bound is the larger of the two times: HBM."""
+    import ctypes
+
+    H, kp = 64, k_supports - 1
+    u = n_nodes * batch * H
+    flops = t_steps * (2 * 2.0 * kp * n_nodes * n_nodes * batch * H + 2.0 * n_nodes * batch * k_supports * H * 3 * H + 2.0 * n_nodes * batch * H * 3 * H)
+    w_bytes = 2.0 * n_nodes * k_supports * H * 3 * H
+    bytes_bwd = t_steps * (9 * u * 4.0 + (3 * u * 4.0) * 2 + 3 * u * 2.0 + 2 * n_adp * u * 2.0 + w_bytes)
+    bytes_fwd = t_steps * (7 * u * 4.0 + 10 * u * 4.0 + 2 * k_supports * u * 2.0 + w_bytes)
+    lib.matgcn_rec_timing(1)
+    for i in range(steps):
+        train_step(model, batches[i % len(batches)], opt)
+    torch.cuda.synchronize()
+    f_ms, b_ms = ctypes.c_double(), ctypes.c_double()
+    f_n, b_n = ctypes.c_int(), ctypes.c_int()
+    lib.matgcn_rec_timing_read(ctypes.byref(f_ms), ctypes.byref(f_n), ctypes.byref(b_ms), ctypes.byref(b_n))
+    lib.matgcn_rec_timing(0)
+    if f_n.value == 0 or b_n.value == 0:
+        return None
+    fwd_ms, bwd_ms = f_ms.value / f_n.value, b_ms.value / b_n.value
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r2_rec_bwd_ncu.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            pj = json.load(f)
+        if pj.get("shape") == {"N": n_nodes, "B": batch, "K": k_supports, "T": t_steps}:
+            traffic = pj["dram_bytes_read"] + pj["dram_bytes_write"]
+    achieved = bytes_bwd / (bwd_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": traffic,
+            "kernel": "rec_bwd_kernel (persistent reverse-time recurrence of one layer: %d steps x 4 phases, TMA + tcgen05 + TMEM, "
+                      "grid barriers)" % t_steps,
+            "launch_ms": bwd_ms, "launches_timed": b_n.value, "algorithmic_bytes_per_launch": bytes_bwd, "flops_per_launch": flops,
+            "tensor": {"achieved": flops / (bwd_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                       "frac": flops / (bwd_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]},
+            "rec_fwd_kernel": {"launch_ms": fwd_ms, "launches_timed": f_n.value, "algorithmic_bytes_per_launch": bytes_fwd,
+                               "flops_per_launch": flops, "hbm_frac": bytes_fwd / (fwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                               "tensor_frac": flops / (fwd_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]},
+            "peak_source": peaks["source"] + " HBM copy bandwidth; bf16 dense sustained for the tensor view",
+            "note": "timed inside real train steps with CUDA events on the launching stream (both layers' launches averaged); "
+                    "t_hbm > t_flop for this kernel, so the HBM roofline bounds it (SURVEY 8d: take the larger time)"}
+
+
 # ------------------------------------------------------------------------------------------------
 # this repository's arm
 # ------------------------------------------------------------------------------------------------
@@ -413,7 +463,11 @@ def run_ours(args):
 
     if rank == 0:
         peaks = _peaks()
-        roof = propagation_roofline(w["N"], per_gpu_batch, 64, 4, model.ldm, dev, peaks, model.matgcn_flags)
+        roof = None
+        if model.matgcn_flags == 3 and per_gpu_batch <= 64:
+            roof = recurrence_roofline(model, resident, opt, train_step, lib, w["N"], per_gpu_batch, 5, 1, 24, peaks)
+        if roof is None:   # modes / shapes that run one launch per phase: the support-propagation GEMM is the dominant kernel
+            roof = propagation_roofline(w["N"], per_gpu_batch, 64, 4, model.ldm, dev, peaks, model.matgcn_flags)
         line = {"metric": METRIC, "value": global_batch / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "tf32", 3: "bf16+tf32"}.get(model.matgcn_flags, "tf32"), "data": "synthetic",

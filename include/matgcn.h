@@ -105,6 +105,11 @@ int matgcn_set_persistent(int on);
  * step.  on = 0 selects one launch per phase.  Returns the previous setting.  Default on (or MATGCN_REC=0 in the environment). */
 int matgcn_set_recurrent_kernel(int on);
 
+/* Device timing of the persistent recurrence kernels (measurement only): while on, each of their launches is bracketed by CUDA
+ * events on its stream; the read call waits for them and returns the summed milliseconds and launch counts since it was turned on. */
+int matgcn_rec_timing(int on);
+int matgcn_rec_timing_read(double* fwd_ms, int* fwd_launches, double* bwd_ms, int* bwd_launches);
+
 /* Fused tail of the forward step (candidate contraction + residual GRU cell + mix in one launch; tensor-core engine,
  * rnn_units = 64).  on = 0 selects the three separate contractions.  Returns the previous setting.  Default on
  * (or MATGCN_FUSED_TAIL=0 in the environment). */

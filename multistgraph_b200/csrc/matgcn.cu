@@ -831,6 +831,15 @@ extern "C" int matgcn_set_recurrent_kernel(int on) {
     rec_flag() = on ? 1 : 0;
     return prev;
 }
+extern "C" int matgcn_rec_timing(int on) {
+    rec_timing_enable(on != 0);
+    return 0;
+}
+extern "C" int matgcn_rec_timing_read(double* fwd_ms, int* fwd_launches, double* bwd_ms, int* bwd_launches) {
+    REQUIRE(fwd_ms && fwd_launches && bwd_ms && bwd_launches, "null pointer");
+    rec_timing_read(fwd_ms, fwd_launches, bwd_ms, bwd_launches);
+    return 0;
+}
 // Fused tail of the forward step (candidate + residual cell + mix in one launch); MATGCN_FUSED_TAIL=0 or
 // matgcn_set_fused_tail(0) selects the three separate contractions (A/B comparisons, tests).
 static int& fused_tail_flag() {

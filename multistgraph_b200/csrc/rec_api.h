@@ -38,4 +38,9 @@ struct RecBwdArgs {
 };
 cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st);
 
+// Optional device timing of the two persistent kernels (bench.py's roofline): while enabled, every launch is bracketed by CUDA
+// events on its stream; rec_timing_read() waits for them and returns the summed durations and launch counts since enabling.
+void rec_timing_enable(bool on);
+void rec_timing_read(double* fwd_ms, int* fwd_n, double* bwd_ms, int* bwd_n);
+
 }  // namespace matgcn

@@ -756,9 +756,7 @@ cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(a.gbar, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&maps, (void*)&p};
-    e = cudaLaunchCooperativeKernel((void*)rec_bwd_kernel, dim3((unsigned)grid), dim3(TC_THREADS), args, RB2_SMEM_TOTAL, st);
-    count_launch();
-    return e != cudaSuccess ? e : cudaGetLastError();
+    return rec_launch((const void*)rec_bwd_kernel, grid, args, RB2_SMEM_TOTAL, st, 1);
 }
 
 }  // namespace matgcn

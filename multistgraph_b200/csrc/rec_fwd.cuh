@@ -29,6 +29,9 @@
 #include "gemm_tc.cuh"
 #include "rec_api.h"
 
+#include <utility>
+#include <vector>
+
 namespace matgcn {
 
 constexpr int RF_STAGES = 4;
@@ -67,6 +70,7 @@ struct RecFwdP {
     __nv_bfloat16* PH16; __nv_bfloat16* PZ16;
     unsigned int* gbar;  // zeroed grid-barrier counter
     long long* dbg;      // optional timeline of CTA 0 (tools/rec_timeline.py)
+    int prefetch;        // warp 3 pulls GX[t] / RX[t] into L2 during the propagation phases (MATGCN_REC_PF=1 turns it on)
 };
 
 __device__ __forceinline__ unsigned int rf_ld_acquire(const unsigned int* p) {
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
         // ================================ L2 prefetch of epilogue inputs ================================
         // While a propagation phase runs (L2 -> SM bound, HBM idle) pull the pre-activation rows the per-node phase after it
         // reads on this CTA: GX[t] during M*h, RX[t] during M*(z*h).
-        for (int t = 0; t < T; ++t) {
+        for (int t = 0; t < T && p.prefetch; ++t) {
             for (int part = 0; part < 2; ++part) {
                 const float* X = (part == 0 ? p.GX : p.RX) + (long long)t * 3 * p.U;
                 while (*phase_cnt < (uint32_t)(4 * t + 2 * part)) __nanosleep(256);
@@ -746,6 +750,52 @@ inline bool rf_make_map(CUtensorMap* map, const void* base, int rank, const unsi
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+struct RecTiming {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[2];   // [0] forward, [1] backward
+};
+inline RecTiming& rec_timing() {
+    static RecTiming t;
+    return t;
+}
+void rec_timing_enable(bool on) {
+    RecTiming& t = rec_timing();
+    for (auto& v : t.ev) {
+        for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        v.clear();
+    }
+    t.on = on;
+}
+void rec_timing_read(double* fwd_ms, int* fwd_n, double* bwd_ms, int* bwd_n) {
+    RecTiming& t = rec_timing();
+    double ms[2] = {0.0, 0.0};
+    for (int i = 0; i < 2; ++i)
+        for (auto& e : t.ev[i]) {
+            cudaEventSynchronize(e.second);
+            float f = 0.f;
+            if (cudaEventElapsedTime(&f, e.first, e.second) == cudaSuccess) ms[i] += f;
+        }
+    *fwd_ms = ms[0]; *fwd_n = (int)t.ev[0].size();
+    *bwd_ms = ms[1]; *bwd_n = (int)t.ev[1].size();
+}
+// cooperative launch, bracketed by events when the timing hook is on
+inline cudaError_t rec_launch(const void* kern, int grid, void** args, int smem, cudaStream_t st, int which) {
+    RecTiming& t = rec_timing();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (t.on) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+    }
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(TC_THREADS), args, smem, st);
+    if (t.on) {
+        cudaEventRecord(e1, st);
+        t.ev[which].emplace_back(e0, e1);
+    }
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     constexpr int H = 64;
     const int Kp = a.K - 1, I = a.Cin + H;
@@ -765,6 +815,10 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     p.PH16 = a.PH16; p.PZ16 = a.PZ16;
     p.gbar = a.gbar;
     p.dbg = tc_debug_buffer();
+    {
+        const char* e = getenv("MATGCN_REC_PF");
+        p.prefetch = (e && e[0] == '1');   // off by default: measured within noise (the fill traffic costs the propagation what the epilogues gain)
+    }
     const float* al[] = {a.GX, a.RX, a.PH, a.PZ, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.ZH2, a.RgH, a.RuH};
     for (const float* q : al)
         if (reinterpret_cast<uintptr_t>(q) & 31) return cudaErrorNotSupported;
@@ -814,9 +868,7 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(a.gbar, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&maps, (void*)&p};
-    e = cudaLaunchCooperativeKernel((void*)rec_fwd_kernel, dim3((unsigned)grid), dim3(TC_THREADS), args, RF_SMEM_TOTAL, st);
-    count_launch();
-    return e != cudaSuccess ? e : cudaGetLastError();
+    return rec_launch((const void*)rec_fwd_kernel, grid, args, RF_SMEM_TOTAL, st, 0);
 }
 
 }  // namespace matgcn
