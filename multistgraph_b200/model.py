@@ -100,7 +100,7 @@ class _EncoderParams(nn.Module):
 
 class MultiATGCN(nn.Module):
     def __init__(self, config, data_feature):
-        super().__init__()
+        nn.Module.__init__(self)   # (not super(): libcity_plugin.py mixes LibCity's AbstractTrafficStateModel in after this class)
         self.data_feature = data_feature
         g = config.get
         self.num_nodes = data_feature.get("num_nodes", 1)
