@@ -96,10 +96,6 @@ int matgcn_nodeweights_bwd_ex(const float* E, const float* pool, const float* bi
 int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X, int cols, float* P, int flags,
                          void* stream);
 
-/* Experimental: run each layer's recurrence as one persistent cooperative kernel (fast mode only) instead of one
- * launch per contraction.  Returns the previous setting.  Default off (or MATGCN_MULTI=1 in the environment). */
-int matgcn_set_persistent(int on);
-
 /* Persistent recurrence kernels (bf16 mode, rnn_units = 64): each layer's 24-step recurrence (MA.py:200-211) runs as ONE
  * cooperative launch whose phases are separated by grid barriers (csrc/rec_fwd.cuh) instead of four launches per time
  * step.  on = 0 selects one launch per phase.  Returns the previous setting.  Default on (or MATGCN_REC=0 in the environment). */

@@ -26,7 +26,6 @@ _SIGNATURES = {
     "matgcn_launch_count": (ctypes.c_ulonglong, []),
     "matgcn_tc_launch_count": (ctypes.c_ulonglong, []),
     "matgcn_propagate_fwd": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_int, c_void_p]),
-    "matgcn_set_persistent": (c_int, [c_int]),
     "matgcn_debug_set_timeline": (c_int, [c_void_p]),
     "matgcn_debug_set_mode": (c_int, [c_int]),
     "matgcn_debug_set_timeline_skip": (c_int, [c_int]),

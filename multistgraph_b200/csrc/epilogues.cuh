@@ -210,6 +210,54 @@ inline EpiPlain epi_plain(float* C, long long s1, long long s2, int ldc) {
     return e;
 }
 
+// Plain store whose columns are BLOCKS of `blk` columns living `sblk` floats apart (block j = col / blk):
+//   C[j*sblk + z1*s1 + z2*s2 + row*ld + col % blk] = acc,   bf16 twin for the blocks j >= c16_lo.
+// One launch with N = (number of blocks) * blk then replaces one launch per block when the blocks share the A operand
+// (the per-support input gradients DPX[t, k, n] = DG[t, n] WX[n, k]^T: DG is streamed once instead of K times).
+// blk % 32 == 0: a 32-column chunk of the tensor-core epilogue never straddles two blocks.
+struct EpiBlocks {
+    static constexpr int kBatch = 8;
+    static constexpr int kPipe = 8;
+    float* C;
+    long long s1, s2, sblk;
+    int ld, blk;
+    __nv_bfloat16* C16;  // may be null
+    int c16_lo;
+    bool vec_ok() const { return aligned16(C) && (!C16 || aligned16(C16)) && !(s1 & 3) && !(s2 & 3) && !(sblk & 3) && !(ld & 3) && !(blk & 31); }
+    __device__ __forceinline__ long long off(int z1, int z2, int row, int col, int& j) const {
+        j = col / blk;
+        return j * sblk + z1 * s1 + z2 * s2 + (long long)row * ld + (col - j * blk);
+    }
+    __device__ __forceinline__ EpiIn load(int, int, int, int) const { return EpiIn{}; }
+    __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn&) const {
+        int j;
+        const long long o = off(z1, z2, row, col, j);
+        C[o] = acc;
+        if (C16 && j >= c16_lo) C16[o] = __float2bfloat16_rn(acc);
+    }
+    __device__ __forceinline__ EpiIn4 load4(int, int, int, int) const { return EpiIn4{}; }
+    __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4&) const {
+        int j;
+        const long long o = off(z1, z2, row, col, j);
+        st4(C + o, acc);
+        if (C16 && j >= c16_lo) st4_bf16(C16 + o, acc);
+    }
+    struct Cur { long long off; int twin; };
+    __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
+        int j;
+        const long long o = off(z1, z2, row, col, j);
+        return Cur{o, (C16 && j >= c16_lo) ? 1 : 0};
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ld; }
+    __device__ __forceinline__ EpiIn4 load4(const Cur&) const { return EpiIn4{}; }
+    __device__ __forceinline__ void prefetch4(const Cur&) const {}
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4&) const {
+        st4(C + c.off, acc);
+        if (c.twin) st4_bf16(C16 + c.off, acc);
+    }
+    EPI_CALL_OPERATOR
+};
+
 struct EpiAtomic {  // split-K partial sums into a zeroed C
     static constexpr int kBatch = 8;  // float4 rows whose global loads the tensor-core epilogue keeps in flight per lane
     static constexpr int kPipe = 1;   // tensor-core epilogue: how many accesses (float4 rows per lane) its global reads run ahead

@@ -929,14 +929,17 @@ inline bool tc_use_pdl() {
     return on;
 }
 
-inline int sm_count() {
-    static int n = []() {
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
+inline int sm_count() {   // of the current device (cached per device: one process may drive several)
+    static int n[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (n[dev] == 0) {
+        int v = 0;
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v > 0 ? v : 148;
-    }();
-    return n;
+        n[dev] = v > 0 ? v : 148;
+    }
+    return n[dev];
 }
 
 // Operand as a rank-5 tensor map {inner, outer, KB, Z2, Z1}.  `kc`: K is the contiguous (inner) dimension.
@@ -1038,11 +1041,13 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
         kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true, false>;
         variant = 1;
     }
-    static bool configured[3] = {false, false, false};  // per template instantiation and epilogue flavour
-    if (!configured[variant]) {
+    static bool configured[64][3] = {};  // per device (the attribute is per device), template instantiation and epilogue flavour
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev][variant]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
-        configured[variant] = true;
+        if (dev >= 0 && dev < 64) configured[dev][variant] = true;
     }
     const int grid = total < sm_count() ? (int)total : sm_count();
     cudaLaunchConfig_t cfg;

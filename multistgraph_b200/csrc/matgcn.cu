@@ -13,7 +13,6 @@
 #include "gemm_simt.cuh"
 #include "epilogues.cuh"
 #include "gemm_tc.cuh"
-#include "gemm_tc_multi.cuh"
 #include "rec_api.h"
 #include "res_bwd.cuh"
 #include "xside_mma.cuh"
@@ -809,17 +808,6 @@ extern "C" int matgcn_nodeweights_bwd_ex(const float* E, const float* pool, cons
     return 0;
 }
 
-// Persistent multi-phase execution of the recurrences (fast mode only; experimental, off unless enabled).
-static int& multi_flag() {
-    static int on = []() { const char* e = getenv("MATGCN_MULTI"); return (e && e[0] == '1') ? 1 : 0; }();
-    return on;
-}
-static bool multi_enabled() { return multi_flag() != 0; }
-extern "C" int matgcn_set_persistent(int on) {
-    const int prev = multi_flag();
-    multi_flag() = on ? 1 : 0;
-    return prev;
-}
 // Persistent recurrence kernels (rec_fwd.cuh: one cooperative launch per layer instead of four launches per time step; bf16 mode,
 // rnn_units = 64).  MATGCN_REC=0 or matgcn_set_recurrent_kernel(0) selects one launch per phase (A/B comparisons, tests).
 static int& rec_flag() {
@@ -852,15 +840,12 @@ extern "C" int matgcn_set_fused_tail(int on) {
     fused_tail_flag() = on ? 1 : 0;
     return prev;
 }
-// One contraction of a recurrence step: queued as a phase of the persistent kernel, or launched on its own.
+// One contraction of a recurrence step on the one-launch-per-phase path (the modes and shapes the persistent kernels of rec.cu
+// do not cover).
 #define STEP_GEMM(SLOT, Cfg, AKC, BKC, P, EPI, Z)                            \
     do {                                                                     \
-        if (use_multi) {                                                     \
-            mb.add_gemm<AKC, BKC>(SLOT, t, P, EPI, Z);                       \
-        } else {                                                             \
-            CK((gemm_any<Cfg, AKC, BKC>(tc, P, EPI, Z, st)));                \
-            TR();                                                            \
-        }                                                                    \
+        CK((gemm_any<Cfg, AKC, BKC>(tc, P, EPI, Z, st)));                    \
+        TR();                                                                \
     } while (0)
 // Support propagation of one step as GemmP: dst[1..K) = M * src   (slot stride U, cols = B*C)
 static GemmP prop_params(const float* M, int ldm, int N, int Kp, const float* slot0, int cols) {
@@ -901,7 +886,7 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.ZH2 = take((size_t)T * w.U);
     w.RGH = take((size_t)2 * H * H);  // Rgw[:, Cin:] and Ruw[:, Cin:] repacked densely (16-byte aligned rows for TMA)
     w.RUH = take((size_t)H * H);
-    w.MPH = take((sizeof(MPhase) * (size_t)(6 * T + 2) + 256) / 4);  // phase list + grid-barrier counter of the persistent kernel
+    w.MPH = take(256);  // grid-barrier counter of the persistent kernel
     // bf16 twins (sizes in floats = elements / 2): base matrices, PH / PZ / PX (same layouts as the fp32 arrays: slot 0 =
     // the state itself, slots 1.. = its propagated copies) and the per-node weights
     w.M16 = take(((size_t)(K - 1) * N * 8 * ((N + 7) / 8 + 1)) / 2 + 64);
@@ -929,7 +914,7 @@ static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp)
     w.DHD = take(U);
     w.DHC = take(U);
     w.DRES = take(U);
-    w.MPH = take((sizeof(MPhase) * (size_t)(7 * T + 2) + 256) / 4);
+    w.MPH = take(256);
     w.DPT16 = take(((size_t)K * U) / 2 + 64);
     w.DPX16 = take(((size_t)T * K * UX) / 2 + 64);
     w.DG16 = take(((size_t)T * 3 * U) / 2 + 64);  // bf16 twin of the pre-activation gradients DG [T, N*B, 3H]
@@ -1141,7 +1126,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     // bf16 mode: the propagated slots (k >= 1) of PX / PH / PZ exist only as bf16 twins - their fp32 stores are skipped, and the
     // contractions that consume them are marked need16 (no fallback engine may touch the unwritten fp32 slots).
     // Needs shapes for which the bf16 tensor-core launches are always eligible (16-byte pitches) and the per-phase launch path.
-    const bool skip32 = bf && !(tc && multi_enabled()) && !(H & 7) && !(ldm & 7) && B >= 8;  // (B = reduction length of the weight gradients)
+    const bool skip32 = bf && !(H & 7) && !(ldm & 7) && B >= 8;  // (B = reduction length of the weight gradients)
     const bool skip32x = skip32 && !xside_small_ok(Cin, H, K) && !(Cin & 7);
     const bool warm = l2_warm_layer(N, K, Cin, H, B);
     // PX[t, 1..K) = M * x_t  (all t at once)
@@ -1217,7 +1202,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         else CK(cudaMemsetAsync(PH16, 0, sizeof(__nv_bfloat16) * U, st));
     }
 
-    bool use_multi = tc && multi_enabled();
+    constexpr bool use_multi = false;   // (the cooperative multi-phase kernel of round 1 is gone: rec_fwd.cuh replaces it)
     if (skip32 && H == 64 && rec_flag() && fused_tail_enabled()) {
         // the whole recurrence as one persistent cooperative launch (rec_fwd.cuh)
         RecFwdArgs ra{T, N, B, Cin, K, ldm, M16, PH16, PZ16, WG16, WU16, GX, RX, PH, PZ,
@@ -1232,8 +1217,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         }
         if (re != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(re));
     }
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        MultiBuilder mb;
+    {
         for (int t = 0; t < T; ++t) {
             float* PHt = PH + (long long)t * K * U;
             float* PZt = PZ + (long long)t * K * U;
@@ -1307,16 +1291,6 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
             STEP_GEMM(5, CfgMid, true, true, p,
                       (EpiResCand{RXt, H1t, R2t, HC2t, PHt + (long long)K * U, mix + t, H, tc ? 1 : 0, bf ? PH16t + (long long)K * U : nullptr}), 1);
         }
-        if (!use_multi) break;
-        float* mph = ws + w.MPH;
-        const cudaError_t me = mb.launch(mph + 64, reinterpret_cast<unsigned int*>(mph), st);
-        if (me == cudaSuccess) {
-            g_tc_launches.fetch_add(mb.ph.size(), std::memory_order_relaxed);
-            TR();
-            break;
-        }
-        if (me != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(me));
-        use_multi = false;  // some phase is not TMA-eligible at this shape: one launch per phase instead
     }
     tr.report("encoder_layer_fwd");
     return 0;
@@ -1362,7 +1336,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     CK(cudaMemsetAsync(dmix, 0, sizeof(float) * T, st));
     TR();
     GemmP p;
-    bool use_multi = tc && multi_enabled();
+    constexpr bool use_multi = false;
     // same rule as the forward pass: in bf16 mode the propagated slots k >= 1 (PH / PZ / PX there, DPT here) exist only as bf16 twins
     const bool skip32 = bf && !use_multi && !(H & 7) && !(ldm & 7) && B >= 8;
     const bool warm = l2_warm_layer(N, K, Cin, H, B);
@@ -1385,8 +1359,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             return fail(__func__, cudaGetErrorString(re));
         }
     }
-    for (int attempt = 0; attempt < 2 && !rec_done; ++attempt) {
-        MultiBuilder mb;
+    if (!rec_done) {
         for (int t = T - 1; t >= 0; --t) {
             const float* PHt = PH + (long long)t * K * U;
             const float* Zt = ws + w.Z + t * U; const float* Rt_ = ws + w.R + t * U; const float* HCt = ws + w.HC + t * U;
@@ -1407,9 +1380,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             }
             if (!rb_fused) {
                 // B0
-                if (use_multi) {
-                    mb.add_head(HeadArgs{dy + (long long)t * dy_tstride, DHC, H1t, R2t, HC2t, mix + t, U, H, DH1, DRES, DRt, dmix + t});
-                } else {
+                {
                     const float* dyt = dy + (long long)t * dy_tstride;
                     if (!(H & 3) && !(U & 3) && aligned16(dyt) && aligned16(DHC) && aligned16(H1t) && aligned16(R2t) && aligned16(HC2t) &&
                         aligned16(DH1) && aligned16(DRES) && aligned16(DRt))
@@ -1463,7 +1434,6 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                 add_pf(p, WG16 + (long long)Cin * 2 * H, (long long)I * 2 * H * 2, (long long)H * 2 * H * 2, N * K);
             }
             STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H, DG16}), 1);
-            if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPZA + (long long)t * n_adp * U, (long long)n_adp * U);
             // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = K; p.KB = 1;
@@ -1499,18 +1469,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                 }
             }
             STEP_GEMM(5, CfgBig, false, false, p, (EpiB6{DPT, DHD, DHC, B * H}), 1);
-            if (n_adp && use_multi) mb.copy_on_last(DPT + U, DPHA + (long long)t * n_adp * U, (long long)n_adp * U);
         }
-        if (!use_multi) break;
-        float* mph = bws + bw.MPH;
-        const cudaError_t me = mb.launch(mph + 64, reinterpret_cast<unsigned int*>(mph), st);
-        if (me == cudaSuccess) {
-            g_tc_launches.fetch_add(mb.ph.size(), std::memory_order_relaxed);
-            TR();
-            break;
-        }
-        if (me != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(me));
-        use_multi = false;
     }
     if (dh0) CK(cudaMemcpyAsync(dh0, DHC, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
 
@@ -1607,8 +1566,27 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
             count_launch();
             TR();
             CK(cudaGetLastError());
+            dpx_done = false;
+            if (!(Cin & 31)) {
+                // all K supports in ONE launch: the output columns are K blocks of Cin (EpiBlocks), DG is streamed once
+                memset(&p, 0, sizeof(p));
+                p.splits = 1; p.Z2 = N; p.KB = 1;
+                p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 3 * H;
+                p.A16 = DG16T;
+                p.B16 = WX16; p.ldb = 3 * H; p.N = K * Cin; p.sB1 = 0; p.sB2 = (long long)K * Cin * 3 * H;
+                EpiBlocks e{DPX, K * UX, (long long)B * Cin, UX, Cin, Cin, DPX16, 1};
+                const cudaError_t de = launch_gemm_tc<128, true, true, EpiBlocks, true>(p, e, T * N, st);
+                if (de == cudaSuccess) {
+                    g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+                    TR();
+                    dpx_done = true;
+                } else if (de != cudaErrorNotSupported) {
+                    CK(de);
+                }
+            }
+            const bool fused = dpx_done;
             dpx_done = true;
-            for (int k = 0; k < K && dpx_done; ++k) {
+            for (int k = 0; k < K && dpx_done && !fused; ++k) {
                 memset(&p, 0, sizeof(p));
                 p.splits = 1; p.Z2 = N; p.KB = 1;
                 p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 3 * H;
@@ -1659,11 +1637,15 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.A = DR; p.lda = 3 * H; p.sA1 = 3 * U; p.M = NB; p.K = 2 * H;
     p.B = Rgw; p.ldb = I; p.N = Cin;
     if (!small_x) {
+        // one pass over DR (475 MB per layer at the Baltimore shape) instead of two: [Rgw[:, 0:Cin]; Ruw[:, 0:Cin]] packed into
+        // one [3H, Cin] operand (DRES is free once the recurrence is done)
+        float* R3 = DRES;
+        CK(cudaMemcpy2DAsync(R3, sizeof(float) * Cin, Rgw, sizeof(float) * I, sizeof(float) * Cin, 2 * H, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpy2DAsync(R3 + (size_t)2 * H * Cin, sizeof(float) * Cin, Ruw, sizeof(float) * I, sizeof(float) * Cin, H,
+                             cudaMemcpyDeviceToDevice, st));
+        p.K = 3 * H; p.B = R3; p.ldb = Cin;
         EpiStore e = epi_store(dx, UX, 0, Cin);
         e.accumulate = 1;
-        CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
-        TR();
-        p.A = DR + 2 * H; p.K = H; p.B = Ruw;
         CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
         TR();
     }

@@ -191,12 +191,14 @@ inline bool res_bwd_fused_ok(const ResBwdArgs& a, int H) {
 }
 
 inline cudaError_t launch_res_bwd_fused(const ResBwdArgs& a, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured[64] = {};   // per device
     const size_t smem = sizeof(float) * RB_SMEM_FLOATS;
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(res_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const long long ntiles = (a.rows + 15) / 16;
     long long blocks = (ntiles + RB_WARPS - 1) / RB_WARPS;

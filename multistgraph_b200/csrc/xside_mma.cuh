@@ -208,12 +208,14 @@ inline bool xside_mma_ok(int Cin, int H, int K, const void* G, const void* PX, c
 
 template <bool NODE>
 inline cudaError_t launch_xside_bwd_mma(const XsMmaArgs& a, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured[64] = {};   // per device
     const size_t smem = sizeof(float) * XM_SMEM_FLOATS;
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(xside_bwd_mma_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const unsigned grid = NODE ? (unsigned)a.N : (unsigned)sm_count();
     xside_bwd_mma_kernel<NODE><<<grid, XM_WARPS * 32, smem, st>>>(a);
