@@ -368,8 +368,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    h0 = time.perf_counter()
     for i in range(args.steps):
         loss = train_step(model, resident[i % n_host], opt, bucket)
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # host time to ENQUEUE a step (no synchronisation inside the loop)
     e1.record()
     barrier()
     launches = lib.matgcn_launch_count() - l0
@@ -489,7 +491,8 @@ def run_ours(args):
                                        "h2d_bytes_per_step": 8 * per_gpu_batch * world,
                                        "note": "SURVEY 8f f2: [T_total,N,F] series resident in HBM, matgcn_assemble_windows gathers "
                                                "each batch; the host uploads only the label-start indices"},
-                "gpu_launches": int(launches), "tc_launches": int(tc_launches), "loss": last_loss, "roofline": roof}
+                "gpu_launches": int(launches), "tc_launches": int(tc_launches), "loss": last_loss, "roofline": roof,
+                "host_enqueue_ms_per_step": host_ms}
         if args.workload == DEFAULT_WORKLOAD and per_gpu_batch == w["B"]:
             # SURVEY 8d, cfg 3: 2.77 TFLOP and 4.51 GB (bf16 storage) / 9.00 GB (fp32) x 3 per train step
             t_roof = max(2.77e12 / (peaks["bf16_tflops_sustained"] * 1e12), 3 * (4.51e9 if model.matgcn_flags == 3 else 9.00e9) / (peaks["hbm_gbs"] * 1e9))

@@ -262,6 +262,17 @@ int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long long rows,
                     unsigned long long seed, const float* dout, float* dy, float* dw, float* dbias, void* stream);
 int matgcn_head_dropout_mask(long long n, float p_drop, unsigned long long seed, float* mult, void* stream);
 
+/* f3, second half - calculate_loss (MultiATGCN.py:422-427): StandardScaler.inverse_transform (libcity/utils/normalization.py:62-76)
+ *      of forecast and target, then masked_mae_torch(pred, true, 0) (libcity/model/loss.py:17-29), as one streaming pass.
+ *      pred and y are 4-d float32 device tensors [B, T_out, N, C] described by `sizes` and their element strides (the forecast
+ *      is a permuted view of the head's output, the target a channel slice of batch['y']); acc is a 3-double device scratch
+ *      kept for the backward; loss receives the scalar.  bwd: dpred (contiguous [B, T_out, N, C]) = grad_loss * dloss/dpred. */
+int matgcn_masked_mae_fwd(const float* pred, const float* y, const long long* sizes, const long long* pred_strides,
+                          const long long* y_strides, float mean, float std, float min_s, double* acc, float* loss, void* stream);
+int matgcn_masked_mae_bwd(const float* pred, const float* y, const long long* sizes, const long long* pred_strides,
+                          const long long* y_strides, float mean, float std, float min_s, const double* acc, const float* grad_loss,
+                          float* dpred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,10 @@ _SIGNATURES = {
     "matgcn_head_bwd": (c_int, [_F, c_longlong, c_int, c_longlong, c_int, _F, c_int, ctypes.c_float, ctypes.c_ulonglong, _F, _F, _F,
                                 _F, c_void_p]),
     "matgcn_head_dropout_mask": (c_int, [c_longlong, ctypes.c_float, ctypes.c_ulonglong, _F, c_void_p]),
+    "matgcn_masked_mae_fwd": (c_int, [_F, _F, c_void_p, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p,
+                                      _F, c_void_p]),
+    "matgcn_masked_mae_bwd": (c_int, [_F, _F, c_void_p, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p,
+                                      _F, _F, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

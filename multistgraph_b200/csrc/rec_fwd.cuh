@@ -488,7 +488,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     const long long tU = tl * p.U;
                     const float* GXt = p.GX + 3 * tU;
                     const float* PHt = p.PH + tl * K * p.U;
-                    float* PZt = p.PZ + tl * K * p.U;
                     __nv_bfloat16* PZ16t = p.PZ16 + tl * K * p.U;
                     float* Zt = p.Z + tU;
                     float* Rt = p.R + tU;
@@ -547,8 +546,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                                     const int e = 2 * w + m2;
                                     const long long o = o0 + w * 8 * H + 16 * m2;
                                     st4(Zt + o, fz[e]);
-                                    st4(PZt + o, zh[e]);
-                                    st4_bf16(PZ16t + o, zh[e]);
+                                    st4_bf16(PZ16t + o, zh[e]);   // (every consumer of z*h reads the bf16 twin: no fp32 copy)
                                     st4(Rt + o, fr[e]);
                                 }
                             }

@@ -602,3 +602,123 @@ extern "C" int matgcn_head_dropout_mask(long long n, float p_drop, unsigned long
     TS_CK(cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+//  f3 (second half)  calculate_loss (MA.py:422-427): StandardScaler.inverse_transform of forecast and target
+//  (normalization.py:62-76) followed by masked_mae_torch(pred, true, null_val = 0) (loss.py:17-29):
+//      labels[|labels| < min_s] = 0 ; mask = labels != 0 ; mask /= mean(mask) ; loss = mean(|pred - labels| * mask), NaN -> 0
+//  = sum(|pred - labels| over the unmasked elements) / count(unmasked).  One streaming pass over the two [B, T_out, N, C]
+//  tensors (given with their element strides: the forecast is a permuted view of the head's output, the target a channel
+//  slice of the batch) accumulates both sums in fp64; the last block to finish divides them.  The backward is one more pass:
+//      d pred = g * std * sign(pred - labels) * [unmasked] / count.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace {
+struct Loss4 {
+    int d1, d2, d3;                 // sizes of dimensions 1..3 (dimension 0 follows from n)
+    long long ps[4], ys[4];         // element strides of the forecast and of the target
+};
+__device__ __forceinline__ void loss_offsets(const Loss4& g, long long i, long long& po, long long& yo) {
+    const long long i3 = i % g.d3, r2 = i / g.d3;
+    const long long i2 = r2 % g.d2, r1 = r2 / g.d2;
+    const long long i1 = r1 % g.d1, i0 = r1 / g.d1;
+    po = i0 * g.ps[0] + i1 * g.ps[1] + i2 * g.ps[2] + i3 * g.ps[3];
+    yo = i0 * g.ys[0] + i1 * g.ys[1] + i2 * g.ys[2] + i3 * g.ys[3];
+}
+// acc: [0] sum of |pred - label| over unmasked elements, [1] their count, [2] (as unsigned) blocks done
+__global__ void masked_mae_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ y, Loss4 g, long long n, float mean, float sd,
+                                      float min_s, double* __restrict__ acc, float* __restrict__ loss) {
+    double s = 0.0, c = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long po, yo;
+        loss_offsets(g, i, po, yo);
+        float l = y[yo] * sd + mean;
+        const float p = pred[po] * sd + mean;
+        if (fabsf(l) < min_s) l = 0.f;
+        if (l != 0.f) {   // (a NaN label compares unequal to 0: it counts, and its NaN difference becomes 0 below, as in loss.py:26-28)
+            c += 1.0;
+            const float d = fabsf(p - l);
+            if (d == d) s += (double)d;
+        }
+    }
+    __shared__ double ss[32], sc[32];
+    __shared__ bool last;
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sc[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bs = 0.0, bc = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { bs += ss[w]; bc += sc[w]; }
+        atomicAdd(acc, bs);
+        atomicAdd(acc + 1, bc);
+        __threadfence();
+        const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(acc + 2), 1u);
+        last = done + 1 == gridDim.x;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const double ts = *reinterpret_cast<volatile double*>(acc), tc = *reinterpret_cast<volatile double*>(acc + 1);
+        *loss = tc > 0.0 ? (float)(ts / tc) : 0.f;   // no unmasked element: mask / mean(mask) is NaN -> 0 (loss.py:25)
+    }
+}
+__global__ void masked_mae_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ y, Loss4 g, long long n, float mean, float sd,
+                                      float min_s, const double* __restrict__ acc, const float* __restrict__ gout, float* __restrict__ dpred) {
+    const double cnt = acc[1];
+    const float k = cnt > 0.0 ? (float)((double)(*gout) * (double)sd / cnt) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long po, yo;
+        loss_offsets(g, i, po, yo);
+        float l = y[yo] * sd + mean;
+        const float p = pred[po] * sd + mean;
+        if (fabsf(l) < min_s) l = 0.f;
+        const float d = p - l;
+        dpred[i] = (l != 0.f && d == d) ? (d > 0.f ? k : (d < 0.f ? -k : 0.f)) : 0.f;
+    }
+}
+}  // namespace
+
+static bool loss_geometry(const long long* sizes, const long long* pstr, const long long* ystr, Loss4& g, long long& n) {
+    for (int i = 0; i < 4; ++i)
+        if (sizes[i] <= 0 || sizes[i] > 2147483647LL) return false;
+    g.d1 = (int)sizes[1]; g.d2 = (int)sizes[2]; g.d3 = (int)sizes[3];
+    for (int i = 0; i < 4; ++i) { g.ps[i] = pstr[i]; g.ys[i] = ystr[i]; }
+    n = sizes[0] * sizes[1] * sizes[2] * sizes[3];
+    return true;
+}
+
+extern "C" int matgcn_masked_mae_fwd(const float* pred, const float* y, const long long* sizes, const long long* pred_strides,
+                                     const long long* y_strides, float mean, float std, float min_s, double* acc, float* loss,
+                                     void* stream) {
+    TS_REQUIRE(pred && y && sizes && pred_strides && y_strides && acc && loss, "null pointer");
+    Loss4 g;
+    long long n;
+    TS_REQUIRE(loss_geometry(sizes, pred_strides, y_strides, g, n), "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    TS_CK(cudaMemsetAsync(acc, 0, 3 * sizeof(double), st));
+    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 4LL * sm_count_ts()) blocks = 4LL * sm_count_ts();
+    if (blocks < 1) blocks = 1;
+    masked_mae_fwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(pred, y, g, n, mean, std, min_s, acc, loss);
+    matgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
+    TS_CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int matgcn_masked_mae_bwd(const float* pred, const float* y, const long long* sizes, const long long* pred_strides,
+                                     const long long* y_strides, float mean, float std, float min_s, const double* acc,
+                                     const float* grad_loss, float* dpred, void* stream) {
+    TS_REQUIRE(pred && y && sizes && pred_strides && y_strides && acc && grad_loss && dpred, "null pointer");
+    Loss4 g;
+    long long n;
+    TS_REQUIRE(loss_geometry(sizes, pred_strides, y_strides, g, n), "bad sizes");
+    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 4LL * sm_count_ts()) blocks = 4LL * sm_count_ts();
+    if (blocks < 1) blocks = 1;
+    masked_mae_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pred, y, g, n, mean, std, min_s, acc, grad_loss, dpred);
+    matgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
+    TS_CK(cudaGetLastError());
+    return 0;
+}

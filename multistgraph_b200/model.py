@@ -359,8 +359,13 @@ class MultiATGCN(nn.Module):
     def calculate_loss(self, batch):
         y_true = batch["y"]
         y_pred = self.predict(batch)
-        y_true = self._scaler.inverse_transform(y_true[..., self.start_dim:self.end_dim])
-        y_pred = self._scaler.inverse_transform(y_pred)
+        sc = self._scaler
+        if (y_pred.is_cuda and type(sc).__name__ == "StandardScaler" and isinstance(getattr(sc, "mean", None), (int, float))
+                and isinstance(getattr(sc, "std", None), (int, float)) and y_pred.dtype == torch.float32 and y_true.dtype == torch.float32):
+            # inverse scaling of both tensors + masked MAE as one streaming pass (and one for the gradient)
+            return ops.masked_mae_loss(y_pred, y_true[..., self.start_dim:self.end_dim], float(sc.mean), float(sc.std))
+        y_true = sc.inverse_transform(y_true[..., self.start_dim:self.end_dim])
+        y_pred = sc.inverse_transform(y_pred)
         return masked_mae_torch(y_pred, y_true, 0)
 
 

@@ -281,6 +281,46 @@ class _OutputHeadFn(torch.autograd.Function):
         return dy, dw, db, None, None
 
 
+class _MaskedMaeFn(torch.autograd.Function):
+    """calculate_loss (MA.py:422-427) in two launches: StandardScaler.inverse_transform of forecast and target
+    (normalization.py:62-76) + masked_mae_torch(pred, true, 0) (loss.py:17-29): matgcn_masked_mae_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, pred, y, mean, std, min_s):
+        if not pred.is_cuda or pred.dtype != torch.float32 or not y.is_cuda or y.dtype != torch.float32:
+            raise _cabi.MatgcnError("masked_mae_loss: float32 CUDA tensors only (no CPU path)")
+        if pred.dim() != 4 or pred.shape != y.shape:
+            raise _cabi.MatgcnError("masked_mae_loss: forecast and target must be 4-d tensors of one shape")
+        import ctypes
+        arr = ctypes.c_longlong * 4
+        sizes, ps, ys = arr(*pred.shape), arr(*pred.stride()), arr(*y.stride())
+        acc = torch.empty(3, device=pred.device, dtype=torch.float64)
+        loss = torch.empty((), device=pred.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_masked_mae_fwd(_ptr(pred), _ptr(y), sizes, ps, ys, float(mean), float(std), float(min_s),
+                                                      acc.data_ptr(), _ptr(loss), _stream()), "matgcn_masked_mae_fwd")
+        ctx.save_for_backward(pred, y, acc)
+        ctx.consts = (float(mean), float(std), float(min_s))
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        import ctypes
+        pred, y, acc = ctx.saved_tensors
+        mean, std, min_s = ctx.consts
+        arr = ctypes.c_longlong * 4
+        sizes, ps, ys = arr(*pred.shape), arr(*pred.stride()), arr(*y.stride())
+        g = _f32c(gloss.reshape(1), "grad_loss")
+        dpred = torch.empty(pred.shape, device=pred.device, dtype=torch.float32)
+        _cabi.check(_cabi.lib().matgcn_masked_mae_bwd(_ptr(pred), _ptr(y), sizes, ps, ys, mean, std, min_s, acc.data_ptr(), _ptr(g),
+                                                      _ptr(dpred), _stream()), "matgcn_masked_mae_bwd")
+        return dpred, None, None, None, None
+
+
+def masked_mae_loss(pred, y, mean, std, min_s=1e-4):
+    """Scalar loss of ``calculate_loss`` for a ``StandardScaler`` with scalar statistics (forecast and target still scaled)."""
+    return _MaskedMaeFn.apply(pred, y, mean, std, min_s)
+
+
 HEAD_HIDDEN = 64  # rnn_units the fused head kernels are written for
 
 

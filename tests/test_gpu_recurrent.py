@@ -1,5 +1,5 @@
-"""Persistent recurrence kernels (csrc/rec_fwd.cuh: one cooperative launch per layer, grid barriers between the four
-phases of a time step) against the one-launch-per-phase path of the same library and against the oracle.
+"""Persistent recurrence kernels (csrc/rec_fwd.cuh, rec_bwd.cuh: one cooperative launch per layer and direction, grid barriers
+between the four phases of a time step) against the one-launch-per-phase path of the same library.
 
 Both paths read the same bf16 operand twins and accumulate in fp32 in the same order, so they agree far inside the
 bound of the bf16 mode (tests/test_gpu_fullsize_oracle.py holds the oracle comparison at the BASELINE shapes)."""
@@ -30,10 +30,12 @@ def _run(model, batch, lib, rec):
 
 
 @pytest.mark.parametrize("N,B,adjtype,D,tout", [(70, 8, "multi", 10, 6), (37, 64, "multi", 20, 6), (21, 100, "multi", 10, 6),
-                                                (150, 136, "od", 10, 3), (403, 64, "multi", 20, 24), (237, 64, "od", 10, 3)])
+                                                (150, 136, "od", 10, 3), (403, 64, "multi", 20, 24), (237, 64, "od", 10, 3),
+                                                (883, 32, "multi", 20, 12)])
 def test_persistent_forward_matches_per_phase_launches(N, B, adjtype, D, tout):
     """B = 8 / 64: half-height (M = 64) per-node tiles; B = 100: one full-height tile with a ragged last quadrant; B = 136:
-    two row tiles per node; adjtype 'od' + bidirection: K = 2 supports; (403, 64) and (237, 64): the BASELINE shapes."""
+    two row tiles per node; adjtype 'od' + bidirection: K = 2 supports; (403, 64), (237, 64): BASELINE configs 3 and 2, (883, 32):
+    config 4 sharded over eight GPUs (256 / 8 samples per rank; six node tiles and four dense tiles per CTA)."""
     cfg = make_config(adjtype=adjtype, adpadj="bidirection", embed_dim=D, output_window=tout, batch_size=B,
                       device=torch.device(DEV), matgcn_mode="bf16")
     df = make_data_feature(N, seed=13)

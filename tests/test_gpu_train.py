@@ -352,3 +352,43 @@ def test_fused_clip_adam_is_a_torch_optimizer_lr_schedule_and_checkpoint_interch
     m2.a.data = m2.a.data.clone()
     with pytest.raises(MatgcnError):
         opt.step()
+
+
+@pytest.mark.parametrize("mean,std", [(0.0, 1.0), (17.1, 24.1)])
+def test_fused_loss_matches_masked_mae_of_the_reference(mean, std):
+    """SURVEY 8f f3, second half: inverse scaling + masked_mae_torch(pred, true, 0) (MA.py:422-427, loss.py:17-29) as one pass
+    (ops.masked_mae_loss) against the torch restatement of loss.py the CPU tests pin on the reference's golden losses:
+    strided forecast (the permuted view the head returns) and target (a channel slice), labels with exact zeros and with
+    |value| < min_s after inverse scaling, value and gradient; and the all-masked batch, whose loss is 0 (NaN -> 0)."""
+    from multistgraph_b200 import _cabi, ops
+    from multistgraph_b200.model import masked_mae_torch
+    from tests.util import max_rel_err
+
+    g = torch.Generator().manual_seed(3)
+    B, T, N, C = 5, 7, 33, 1
+    pred_store = torch.randn(B, T, C, N, generator=g).to("cuda:0").requires_grad_(True)
+    y_full = torch.randn(B, T, N, 2, generator=g)
+    y_full[0, :, :5, 0] = (0.0 - mean) / std                 # inverse-scaled to exactly 0: masked
+    y_full[1, 2, 7, 0] = (3e-5 - mean) / std                 # |label| < min_s after inverse scaling: masked
+    y_full = y_full.to("cuda:0")
+    pred = pred_store.permute(0, 1, 3, 2)                    # [B, T, N, C], not contiguous
+    y = y_full[..., 0:1]
+    loss = ops.masked_mae_loss(pred, y, mean, std)
+    loss.backward()
+    g_fused = pred_store.grad.clone()
+    pred_store.grad = None
+    ref = masked_mae_torch(pred * std + mean, y * std + mean, 0)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert max_rel_err(g_fused, pred_store.grad) < 2e-6
+    # forward + backward are two launches of this library
+    lib = _cabi.lib()
+    n0 = lib.matgcn_launch_count()
+    ops.masked_mae_loss(pred.detach().requires_grad_(True), y, mean, std).backward()
+    assert lib.matgcn_launch_count() - n0 == 2
+    # every label masked: mask / mean(mask) is NaN everywhere -> replaced by 0 -> loss 0 (loss.py:25-28)
+    y0 = torch.full_like(y, (0.0 - mean) / std)
+    p0 = pred.detach().clone().requires_grad_(True)
+    l0 = ops.masked_mae_loss(p0, y0, mean, std)
+    l0.backward()
+    assert l0.item() == 0.0 and p0.grad.abs().max().item() == 0.0
