@@ -2,13 +2,14 @@
 // backward of MA.py:120-128, 142-150, 200-211 for all T steps as ONE cooperative launch - the counterpart of rec_fwd.cuh.
 // Per step (t = T-1 .. 0), four phases separated by grid barriers:
 //
-//   A  per node   head of the reverse step: dy = dY_t + carry, chain rule of the sigma-mix and of the residual GRU cell (its two
-//                 small products dzh2 = da3 Ru_h and dh1 += [daz2 | dar2] Rg_h as TF32 tcgen05 MMAs on operand tiles the epilogue
-//                 warps write), main-cell gate algebra -> DR[t], DG[t][:, H:3H], DHD; then, for the same rows, the per-node
-//                 products DPT[k] = gu Wu[n,k]^T (five 64x64x64 bf16 MMAs against TMA-streamed weights)
+//   A  per node   first half: head of the reverse step for each of the CTA's nodes: dy = dY_t + carry, chain rule of the sigma-mix
+//                 and of the residual GRU cell (its two small products dzh2 = da3 Ru_h and dh1 += [daz2 | dar2] Rg_h as TF32
+//                 tcgen05 MMAs on operand tiles the epilogue warps write), main-cell gate algebra -> DR[t], DG[t][:, H:3H], DHD.
+//                 second half (after a CTA-local barrier): the per-node products DPT[k] = gu Wu[n,k]^T as an ordinary pipelined
+//                 GEMM - gu rows back through TMA from DG16[t], the K weight blocks side by side as one [64 x 64K] operand
 //   B  dense      DZ = sum_k M_k^T DPT[k]                 (128 x 128 tiles, K = (K-1) N: TMA-fed tcgen05, plain fp32 store)
-//   C  per node   dzh = DZ + DPT[0]; DHD += dzh z; gz = dzh h z (1-z) -> DG[t][:, 0:H]; DPT[k] = [gz | gr] Wg[n,k]^T;
-//                 DHD2 = DHD + DPT[0]
+//   C  per node   first half: dzh = DZ + DPT[0]; DHD += dzh z; gz = dzh h z (1-z) -> DG[t][:, 0:H]; second half:
+//                 DPT[k] = [gz | gr] Wg[n,k]^T (same pipelined form); DHD2 = DHD + DPT[0]
 //   D  dense      DC = sum_k M_k^T DPT[k]                 (the carry of step t-1 is DC + DHD2, formed by its phase A)
 //
 // The elementwise parts of the two dense phases of the per-phase path (EpiB4 / EpiB6) are moved into the per-node phases
@@ -23,13 +24,12 @@ namespace matgcn {
 
 constexpr int RB2_STAGES = 3;
 constexpr int RB2_NSTAGES = 2;       // per-node phases: whole-tile weight buffers over the same memory (see the producer)
-constexpr int RB2_WBUF = 49152;      // phase A: two buffers of K x 8 KB; phase C: one buffer of 2 x K x 8 KB over both
+constexpr int RB2_WBUF = 49152;      // two stages [K x 8 KB weight blocks of one K slab | 8 KB operand columns at +40 KB]
 constexpr int RB2_OFF_WUT = RB2_STAGES * RF_STAGE_BYTES;   // Ru_h^T [64 inputs][64 outputs] fp32 K-major: 2 slabs of 64 rows x 128 B
 constexpr int RB2_OFF_WGT = RB2_OFF_WUT + 16384;           // Rg_h^T [64 inputs][128 outputs]: 4 slabs
 constexpr int RB2_OFF_A1 = RB2_OFF_WGT + 32768;            // da3 [64 rows][64] fp32: 2 slabs
 constexpr int RB2_OFF_A2 = RB2_OFF_A1 + 16384;             // [daz2 | dar2] [64 rows][128] fp32: 4 slabs
-constexpr int RB2_OFF_A3 = RB2_OFF_A2 + 32768;             // bf16 operand of the per-node products: gu [64][64] or [gz | gr] [64][128]
-constexpr int RB2_OFF_BAR = RB2_OFF_A3 + 16384;
+constexpr int RB2_OFF_BAR = RB2_OFF_A2 + 32768;
 constexpr int RB2_SMEM_TOTAL = RB2_OFF_BAR + 256 + 1024;
 constexpr int RB2_TMEM_D1 = 320, RB2_TMEM_D2 = 384;        // D3[k] at columns 64 k (k < 5); dense accumulators at 0 and 128
 
@@ -38,6 +38,7 @@ struct RecBwdMaps {
     CUtensorMap DP;   // DPT16 slots 1.. as its B operand: {B*64, Kp*N}, box 64 x 64
     CUtensorMap WG;   // per-node gate weights, K-major B operand of DPT = [gz | gr] Wg^T: WG16 {128, I, K, N}
     CUtensorMap WU;   // per-node candidate weights: WU16 {64, I, K, N}
+    CUtensorMap DG;   // bf16 pre-activation gradients as the A operand of the per-node products: DG16 {192, B, N, T}, box 64 x 64
 };
 
 struct RecBwdP {
@@ -79,23 +80,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
     if (smem_u32(smem) & 1023u) __trap();
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RB2_OFF_BAR);
-    // bars: full[S], empty[S], tmem_full[2], tmem_empty[2], phase_bar, a1_full, a2_full, a3_full, d1_full, d2_full, d3_full,
+    // bars: full[S], empty[S], tmem_full[2], tmem_empty[2], phase_bar, a1_full, a2_full, d3_empty, d1_full, d2_full, d3_full,
     //       nfull[2], nempty[2]: the per-node phases use the same ring memory as whole-tile weight buffers - the K weight blocks of
     //       a node are laid side by side as ONE K-major operand with 64 K rows, so that the K products of a tile are one
     //       [64 x 64K] MMA per k-step instead of K small ones (an MMA of this size costs ~150 cycles whatever its N);
     //       the two uses of the memory are never active at the same time
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RB2_STAGES + 11 + 2 * RB2_NSTAGES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RB2_STAGES + 12 + 2 * RB2_NSTAGES);
     volatile uint32_t* phase_cnt = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t full0 = bar0, empty0 = bar0 + 8u * RB2_STAGES, tfull0 = bar0 + 8u * (2 * RB2_STAGES);
     const uint32_t tempty0 = tfull0 + 16u, phase_bar = tfull0 + 32u;
-    const uint32_t a1_full = phase_bar + 8u, a2_full = phase_bar + 16u, a3_full = phase_bar + 24u;
+    const uint32_t a1_full = phase_bar + 8u, a2_full = phase_bar + 16u, d3_empty = phase_bar + 24u;
     const uint32_t d1_full = phase_bar + 32u, d2_full = phase_bar + 40u, d3_full = phase_bar + 48u;
-    const uint32_t nfull0 = phase_bar + 56u, nempty0 = nfull0 + 8u * RB2_NSTAGES;
+    const uint32_t nfull0 = phase_bar + 56u, nempty0 = nfull0 + 8u * RB2_NSTAGES, sub_bar = nempty0 + 8u * RB2_NSTAGES;
     const uint32_t wut_s = smem_u32(smem + RB2_OFF_WUT), wgt_s = smem_u32(smem + RB2_OFF_WGT);
-    const uint32_t a1_s = smem_u32(smem + RB2_OFF_A1), a2_s = smem_u32(smem + RB2_OFF_A2), a3_s = smem_u32(smem + RB2_OFF_A3);
+    const uint32_t a1_s = smem_u32(smem + RB2_OFF_A1), a2_s = smem_u32(smem + RB2_OFF_A2);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < RB2_STAGES; ++s) {
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         mbar_init(phase_bar, 1);
         mbar_init(a1_full, TC_EPI_WARPS);
         mbar_init(a2_full, TC_EPI_WARPS);
-        mbar_init(a3_full, TC_EPI_WARPS);
+        mbar_init(d3_empty, TC_EPI_WARPS);
+        mbar_init(sub_bar, TC_EPI_WARPS);
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
         mbar_init(d3_full, 1);
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0, nbar = 0, wuse0 = 0, wuse1 = 0;
+            uint32_t phase = 0, nbar = 0, wuse0 = 0, wuse1 = 0, subpar = 0;
             const uint64_t pol = l2_policy_evict_last();
             for (int t = T - 1; t >= 0; --t) {
                 for (int ph = 0; ph < 4; ++ph) {
@@ -219,24 +221,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                             }
                         }
                         if (!first) ++nbar;   // (the grid barrier before this phase is not waited for here)
-                        if (ph == 2) mbar_wait(nempty0 + 8u, (wuse1 & 1u) ^ 1u);   // phase C's single buffer spans both of phase A's
-                        int cnt = 0;
-                        for (int n = blockIdx.x; n < node_tiles; n += G, ++cnt) {
-                            const int b = ph == 0 ? (cnt & 1) : 0;
-                            uint32_t& use = b ? wuse1 : wuse0;
-                            mbar_wait(nempty0 + 8u * b, (use & 1u) ^ 1u);
-                            const uint32_t fb = nfull0 + 8u * b;
-                            const uint32_t dst = smem_u32(stage_base + b * RB2_WBUF);
-                            mbar_expect_tx(fb, (uint32_t)K * (ph == 0 ? 8192u : 16384u));
+                        // second half of a per-node phase: work items (tile, K slab) - one per tile in phase A (K = 64: gu), two in
+                        // phase C (K = 128: gz | gr) - each with its own 48 KB stage: the K weight blocks of that slab side by side
+                        // (constant: requested right away for the first two items) and the 64 operand columns of DG16[t] (written by
+                        // this CTA's epilogue warps in the first half: requested after the sub-phase barrier)
+                        const int halves = ph == 0 ? 1 : 2;
+                        const uint32_t tx = (uint32_t)K * 8192u + 8192u;
+                        auto issue_w = [&](int n, int h, uint32_t dst, uint32_t fb) {
                             for (int k = 0; k < K; ++k) {
-                                if (ph == 0) {
-                                    tma_load_5d_hint(dst + k * 8192, &maps.WU, fb, 0, p.Cin, k, n, 0, pol);
-                                } else {
-                                    tma_load_5d_hint(dst + k * 8192, &maps.WG, fb, 0, p.Cin, k, n, 0, pol);
-                                    tma_load_5d_hint(dst + (K + k) * 8192, &maps.WG, fb, 64, p.Cin, k, n, 0, pol);
+                                if (ph == 0) tma_load_5d_hint(dst + k * 8192, &maps.WU, fb, 0, p.Cin, k, n, 0, pol);
+                                else tma_load_5d_hint(dst + k * 8192, &maps.WG, fb, 64 * h, p.Cin, k, n, 0, pol);
+                            }
+                        };
+                        int early = 0;
+                        {
+                            uint32_t u0 = wuse0, u1 = wuse1;
+                            for (int n = blockIdx.x; n < node_tiles && early < 2; n += G) {
+                                for (int h = 0; h < halves && early < 2; ++h, ++early) {
+                                    const int bb = early & 1;
+                                    uint32_t& use = bb ? u1 : u0;
+                                    mbar_wait(nempty0 + 8u * bb, (use & 1u) ^ 1u);
+                                    mbar_expect_tx(nfull0 + 8u * bb, tx);
+                                    issue_w(n, h, smem_u32(stage_base + bb * RB2_WBUF), nfull0 + 8u * bb);
+                                    ++use;
                                 }
                             }
-                            ++use;
+                        }
+                        mbar_wait(sub_bar, subpar);   // DG16[t] rows of this CTA's nodes written (generic proxy, fenced at gpu scope) ...
+                        subpar ^= 1u;
+                        asm volatile("fence.proxy.async;" ::: "memory");   // ... and ordered before the TMA reads below
+                        int item = 0;
+                        for (int n = blockIdx.x; n < node_tiles; n += G) {
+                            for (int h = 0; h < halves; ++h, ++item) {
+                                const int bb = item & 1;
+                                uint32_t& use = bb ? wuse1 : wuse0;
+                                const uint32_t fb = nfull0 + 8u * bb;
+                                const uint32_t dst = smem_u32(stage_base + bb * RB2_WBUF);
+                                if (item >= early) {
+                                    mbar_wait(nempty0 + 8u * bb, (use & 1u) ^ 1u);
+                                    mbar_expect_tx(fb, tx);
+                                    issue_w(n, h, dst, fb);
+                                }
+                                tma_load_5d(dst + 40960, &maps.DG, fb, ph == 0 ? 128 : 64 * h, 0, n, t, 0);
+                                ++use;
+                            }
                         }
                     }
                 }
@@ -274,9 +302,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         }
                     } else {
-                        int cnt = 0;
-                        for (int n = blockIdx.x; n < node_tiles; n += G, ++cnt) {
-                            if (ph == 0) {
+                        if (ph == 0) {
+                            for (int n = blockIdx.x; n < node_tiles; n += G) {
                                 mbar_wait(a1_full, par12);   // da3 tile written: dzh2 = da3 Ru_h
                                 tc_fence_after();
 #pragma unroll
@@ -299,29 +326,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 umma_commit(d2_full);
                                 par12 ^= 1;
                             }
-                            mbar_wait(a3_full, par3);        // bf16 operand tile of the per-node products written
-                            tc_fence_after();
-                            // D3 [64 x 64K] = operand tile x [W_0^T | .. | W_{K-1}^T]: per k-step one MMA of up to 256 columns (+ the rest)
-                            const int b = ph == 0 ? (cnt & 1) : 0;
-                            uint32_t& use = b ? wuse1 : wuse0;
-                            mbar_wait(nfull0 + 8u * b, use & 1u);
-                            tc_fence_after();
-                            const uint32_t wb = smem_u32(stage_base + b * RB2_WBUF);
-                            const int slabs = ph == 0 ? 1 : 2;
-                            for (int s = 0; s < slabs; ++s) {
+                        }
+                        // second half of the phase: D3 [64 x 64K] (+)= operand columns (TMA) x [W_0^T | .. | W_{K-1}^T] per work item
+                        // (tile, K slab), an ordinary pipelined GEMM - per k-step one MMA of up to 256 columns (+ the rest)
+                        const int halves = ph == 0 ? 1 : 2;
+                        int item = 0;
+                        for (int n = blockIdx.x; n < node_tiles; n += G) {
+                            for (int h = 0; h < halves; ++h, ++item) {
+                                const int bb = item & 1;
+                                uint32_t& use = bb ? wuse1 : wuse0;
+                                mbar_wait(nfull0 + 8u * bb, use & 1u);                  // weights and operand columns landed
+                                if (h == 0) mbar_wait(d3_empty, par3 ^ 1u);             // the previous tile's products are in registers
+                                tc_fence_after();
+                                const uint32_t wb = smem_u32(stage_base + bb * RB2_WBUF);
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {
-                                    const uint64_t da = umma_desc(a3_s + s * 8192 + kk * 32, 16, 1024, 2);
-                                    const uint32_t acc_in = (s > 0 || kk > 0) ? 1u : 0u;
+                                    const uint64_t da = umma_desc(wb + 40960 + kk * 32, 16, 1024, 2);
+                                    const uint32_t acc_in = (h > 0 || kk > 0) ? 1u : 0u;
                                     for (int k0 = 0; k0 < K; k0 += 4) {
                                         const uint32_t nn = (uint32_t)min(4, K - k0) * 64u;
-                                        umma_bf16(tmem_base + (uint32_t)(64 * k0), da, umma_desc(wb + (s * K + k0) * 8192 + kk * 32, 16, 1024, 2),
+                                        umma_bf16(tmem_base + (uint32_t)(64 * k0), da, umma_desc(wb + k0 * 8192 + kk * 32, 16, 1024, 2),
                                                   id_node0 | ((nn >> 3) << 17), acc_in);
                                     }
                                 }
+                                umma_commit(nempty0 + 8u * bb);
+                                ++use;
                             }
-                            umma_commit(nempty0 + 8u * b);
-                            ++use;
                             umma_commit(d3_full);
                             par3 ^= 1;
                         }
@@ -360,7 +390,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         const long long rd[2] = {ok[0] ? 0 : -(long long)b0, ok[1] ? 8 : -(long long)b0};
         const uint32_t s_off = (uint32_t)(half * 8192 + b0 * 128);   // tf32 tiles: slab `half` (+ 2 for the dar2 columns)
         const uint32_t s_x = (uint32_t)(b0 & 7);
-        const uint32_t s16_off = (uint32_t)(b0 * 128 + ((pc & 1) << 3));   // bf16 tiles: 64 columns per 128-byte row
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         for (int t = T - 1; t >= 0; --t) {
             for (int ph = 0; ph < 4; ++ph) {
@@ -520,43 +549,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                     st4_bf16(p.DG16 + 3 * tU + x + 2 * H, gu);
                                     st4_bf16(p.DG16 + 3 * tU + x + H, gr);
                                 }
-                                rb2_sts_bf16x4(a3_s + s16_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * half + 2 * m2 + (pc >> 1))) ^ s_x) << 4), gu);
                             }
                         }
                         tc_fence_before();
-                        rf_proxy_fence_smem();
-                        __syncwarp();
                         RB2_STAMP(n / G, 5);
-                        if (lane == 0) mbar_arrive(a3_full);
                         load_s0(min(n + G, node_tiles - 1));   // (dyv .. hc2 are dead: the next tile's S0 inputs go in flight)
-                        // S3: the five per-node products -> DPT[0] (fp32), DPT[k >= 1] (bf16 twins only), adaptive slices per step
+                        par12 ^= 1;
+                    }
+                    // the bf16 gu rows of this CTA's nodes are in DG16[t]: hand them to the TMA producer (second half of the phase)
+                    __threadfence();   // the rows must have reached L2, where TMA reads them, before the producer is told
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sub_bar);
+                    // DPT[k] = gu Wu[n,k]^T for all k: products -> registers (accumulator released at once) -> DPT[0] (fp32),
+                    // DPT[k >= 1] (bf16 twins only), adaptive slices per step
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const long long o0 = ((long long)n * p.B + b0) * H + ch;
+                        float fr[5][16];
                         mbar_wait(d3_full, par3);
                         tc_fence_after();
                         RB2_STAMP(n / G, 6);
-                        for (int k = 0; k < K; ++k) {
-                            rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), a);
-                            rf_tmem_wait_ld();
-                            rf_quad4(a, fa, odd);
 #pragma unroll
-                            for (int w = 0; w < 2; ++w) {
+                        for (int k = 0; k < 5; ++k)
+                            rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), fr[k]);   // (k >= K: unused columns)
+                        rf_tmem_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d3_empty);
+                        par3 ^= 1;
 #pragma unroll
-                                for (int m2 = 0; m2 < 2; ++m2) {
-                                    if (ok[w]) {
-                                        const long long o = o0 + w * 8 * H + 16 * m2;
-                                        if (k == 0) {
-                                            st4(p.DPT0 + o, fa[2 * w + m2]);
-                                        } else {
-                                            st4_bf16(p.DPT16 + (long long)k * p.U + o, fa[2 * w + m2]);
-                                            if (k <= p.n_adp) st4_bf16(p.DPZA + (tl * p.n_adp + (k - 1)) * p.U + o, fa[2 * w + m2]);
+                        for (int k = 0; k < 5; ++k) {
+                            if (k < K) {
+                                float4 fa[4];
+                                rf_quad4(fr[k], fa, odd);
+#pragma unroll
+                                for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                                    for (int m2 = 0; m2 < 2; ++m2) {
+                                        if (ok[w]) {
+                                            const long long o = o0 + w * 8 * H + 16 * m2;
+                                            if (k == 0) {
+                                                st4(p.DPT0 + o, fa[2 * w + m2]);
+                                            } else {
+                                                st4_bf16(p.DPT16 + (long long)k * p.U + o, fa[2 * w + m2]);
+                                                if (k <= p.n_adp) st4_bf16(p.DPZA + (tl * p.n_adp + (k - 1)) * p.U + o, fa[2 * w + m2]);
+                                            }
                                         }
                                     }
                                 }
                             }
                         }
-                        tc_fence_before();
                         RB2_STAMP(n / G, 7);
-                        par12 ^= 1;
-                        par3 ^= 1;
                     }
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) dmix_part += __shfl_xor_sync(0xffffffffu, dmix_part, off);
@@ -565,10 +608,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                     // ---- phase C: z-gate algebra on dzh = DZ + DPT[0], then DPT[k] = [gz | gr] Wg[n,k]^T, DHD2 = DHD + dzh z + DPT[0] ----
                     const float* Hp = p.PH + tl * K * p.U;
                     float4 dz[4], d0[4], zz[4], hp[4], dd[4];
-                    uint2 grv[4];
                     auto load_c = [&](int n) {
-                        const long long g0 = (long long)n * p.B + b0;
-                        const long long o0 = g0 * H + ch, x0 = g0 * 3 * H + ch;
+                        const long long o0 = ((long long)n * p.B + b0) * H + ch;
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
 #pragma unroll
@@ -580,7 +621,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 zz[e] = ld4(p.Z + tU + o);
                                 hp[e] = ld4(Hp + o);
                                 dd[e] = ld4(p.DHD + o);
-                                grv[e] = *reinterpret_cast<const uint2*>(p.DG16 + 3 * tU + x0 + rd[w] * 3 * H + 16 * m2 + H);
                             }
                         }
                     };
@@ -603,44 +643,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                     st4(p.DG + 3 * tU + x, gz);
                                     st4_bf16(p.DG16 + 3 * tU + x, gz);
                                 }
-                                const uint32_t so = s16_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * half + 2 * m2 + (pc >> 1))) ^ s_x) << 4);
-                                rb2_sts_bf16x4(a3_s + so, gz);
-                                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a3_s + 8192 + so), "r"(grv[e].x), "r"(grv[e].y) : "memory");
+                                if (ok[w]) st4(p.DHD + o0 + w * 8 * H + 16 * m2, dk[e]);   // DHD += dzh z (read back after the products)
                             }
                         }
-                        rf_proxy_fence_smem();
-                        __syncwarp();
                         RB2_STAMP(n / G, 9);
-                        if (lane == 0) mbar_arrive(a3_full);
-                        load_c(min(n + G, node_tiles - 1));   // (the next tile's inputs go in flight during the products)
-                        float a[16];
-                        float4 fa[4];
+                        load_c(min(n + G, node_tiles - 1));   // (the next tile's inputs go in flight)
+                    }
+                    __threadfence();   // the rows must have reached L2, where TMA reads them, before the producer is told
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sub_bar);
+                    // DPT[k] = [gz | gr] Wg[n,k]^T: DHD2 = DHD + DPT[0]; DPT[k >= 1] as bf16 twins, adaptive slices per step
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const long long o0 = ((long long)n * p.B + b0) * H + ch;
+                        float4 dk2[4];
+#pragma unroll
+                        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                            for (int m2 = 0; m2 < 2; ++m2) dk2[2 * w + m2] = ld4(p.DHD + o0 + rd[w] * H + 16 * m2);
+                        }
+                        float fr[5][16];
                         mbar_wait(d3_full, par3);
                         tc_fence_after();
                         RB2_STAMP(n / G, 10);
-                        for (int k = 0; k < K; ++k) {
-                            rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), a);
-                            rf_tmem_wait_ld();
-                            rf_quad4(a, fa, odd);
 #pragma unroll
-                            for (int w = 0; w < 2; ++w) {
+                        for (int k = 0; k < 5; ++k)
+                            rf_tmem_ld16x4(tmem_base + (uint32_t)(64 * k) + tlane + (uint32_t)(half * 32), fr[k]);   // (k >= K: unused columns)
+                        rf_tmem_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(d3_empty);
+                        par3 ^= 1;
 #pragma unroll
-                                for (int m2 = 0; m2 < 2; ++m2) {
-                                    if (ok[w]) {
-                                        const long long o = o0 + w * 8 * H + 16 * m2;
-                                        if (k == 0) {
-                                            st4(p.DHD2 + o, dk[2 * w + m2] + fa[2 * w + m2]);
-                                        } else {
-                                            st4_bf16(p.DPT16 + (long long)k * p.U + o, fa[2 * w + m2]);
-                                            if (k <= p.n_adp) st4_bf16(p.DPHA + (tl * p.n_adp + (k - 1)) * p.U + o, fa[2 * w + m2]);
+                        for (int k = 0; k < 5; ++k) {
+                            if (k < K) {
+                                float4 fa[4];
+                                rf_quad4(fr[k], fa, odd);
+#pragma unroll
+                                for (int w = 0; w < 2; ++w) {
+#pragma unroll
+                                    for (int m2 = 0; m2 < 2; ++m2) {
+                                        if (ok[w]) {
+                                            const long long o = o0 + w * 8 * H + 16 * m2;
+                                            if (k == 0) {
+                                                st4(p.DHD2 + o, dk2[2 * w + m2] + fa[2 * w + m2]);
+                                            } else {
+                                                st4_bf16(p.DPT16 + (long long)k * p.U + o, fa[2 * w + m2]);
+                                                if (k <= p.n_adp) st4_bf16(p.DPHA + (tl * p.n_adp + (k - 1)) * p.U + o, fa[2 * w + m2]);
+                                            }
                                         }
                                     }
                                 }
                             }
                         }
-                        tc_fence_before();
                         RB2_STAMP(n / G, 11);
-                        par3 ^= 1;
                     }
                 }
                 // ---- end of phase: publish this CTA's writes, wait for every CTA ----
@@ -739,6 +795,9 @@ cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
         const unsigned long long du[4] = {64, (unsigned long long)I, (unsigned long long)a.K, (unsigned long long)a.N};
         const unsigned long long su[3] = {128, (unsigned long long)I * 128, (unsigned long long)a.K * I * 128};
         if (!rf_make_map(&maps.WG, a.WG16, 4, dg, sg, b) || !rf_make_map(&maps.WU, a.WU16, 4, du, su, b)) return cudaErrorNotSupported;
+        const unsigned long long dd[4] = {192, (unsigned long long)a.B, (unsigned long long)a.N, (unsigned long long)a.T};
+        const unsigned long long sd[3] = {384, (unsigned long long)a.B * 384, U * 3 * 2};
+        if (!rf_make_map(&maps.DG, a.DG16, 4, dd, sd, b)) return cudaErrorNotSupported;
     }
     int dev = 0;
     cudaGetDevice(&dev);
