@@ -469,11 +469,12 @@ def run_ours(args):
     global_batch = per_gpu_batch * world
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
+    # the roofline leg runs real train steps (with their all-reduce): EVERY rank takes part, rank 0 reports its own kernels' times
+    peaks = _peaks()
+    roof = None
+    if model.matgcn_flags == 3 and per_gpu_batch <= 64:
+        roof = recurrence_roofline(model, resident, opt, train_step, lib, w["N"], per_gpu_batch, 5, 1, 24, peaks)
     if rank == 0:
-        peaks = _peaks()
-        roof = None
-        if model.matgcn_flags == 3 and per_gpu_batch <= 64:
-            roof = recurrence_roofline(model, resident, opt, train_step, lib, w["N"], per_gpu_batch, 5, 1, 24, peaks)
         if roof is None:   # modes / shapes that run one launch per phase: the support-propagation GEMM is the dominant kernel
             roof = propagation_roofline(w["N"], per_gpu_batch, 64, 4, model.ldm, dev, peaks, model.matgcn_flags)
         line = {"metric": METRIC, "value": global_batch / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
