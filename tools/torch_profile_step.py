@@ -1,5 +1,5 @@
 """Kernel-level summary of one warm train step with torch.profiler (CUPTI): where the non-library time goes.
-usage: python tools/torch_profile_step.py [mode]"""
+usage: python tools/torch_profile_step.py [mode] [workload] [batch]"""
 import os
 import sys
 
@@ -12,7 +12,8 @@ from multistgraph_b200.synthetic import workload
 from multistgraph_b200.train import FusedClipAdam, fused_train_step
 
 dev = torch.device("cuda:0")
-cfg, df, batch = workload("baltimore_multi", seed=0, device=dev)
+wl = sys.argv[2] if len(sys.argv) > 2 else "baltimore_multi"
+cfg, df, batch = workload(wl, seed=0, device=dev, batch=int(sys.argv[3]) if len(sys.argv) > 3 else None)
 cfg["matgcn_mode"] = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 torch.manual_seed(0)
 model = MultiATGCN(dict(cfg), df).to(dev).train()
