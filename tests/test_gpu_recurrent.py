@@ -59,3 +59,28 @@ def test_persistent_forward_matches_per_phase_launches(N, B, adjtype, D, tout):
     assert errs["forecast"] < 2e-3
     bad = {k: v for k, v in errs.items() if not (v < 5e-3)}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("adjtype,adpadj,cheb", [("multi", "bidirection", 3), ("multi", "none", 2), ("od", "unidirection", 2)])
+def test_persistent_kernels_other_support_sets(adjtype, adpadj, cheb):
+    """cheb_order = 3: K = 9 supports - the forward kernel streams any K, the reverse kernel (five per-node accumulators in TMEM)
+    declines and the one-launch-per-phase backward consumes what the persistent forward saved; adpadj = none: no adaptive slices
+    (n_adp = 0, no per-step copies); unidirection: the adaptive view from node_vec1 / node_vec2."""
+    N, B, tout = 45, 16, 6
+    cfg = make_config(adjtype=adjtype, adpadj=adpadj, embed_dim=10, cheb_order=cheb, output_window=tout, batch_size=B,
+                      device=torch.device(DEV), matgcn_mode="bf16")
+    df = make_data_feature(N, seed=21)
+    batch = make_batch(N, B, tout, seed=21)
+    torch.manual_seed(4)
+    model = MultiATGCN(dict(cfg), df).to(DEV).eval()
+    lib = _cabi.lib()
+    y0, g0, n0 = _run(model, batch, lib, False)
+    y1, g1, n1 = _run(model, batch, lib, True)
+    assert n0 - n1 >= 2 * (4 * 24 - 1)
+    errs = {"forecast": max_rel_err(y1, y0)}
+    for k in g0:
+        errs[k] = max_rel_err(g1[k], g0[k])
+    print("[persistent vs per-phase %s/%s cheb %d] worst %.2e (%s)" % (adjtype, adpadj, cheb, max(errs.values()), max(errs, key=errs.get)))
+    assert errs["forecast"] < 2e-3
+    bad = {k: v for k, v in errs.items() if not (v < 5e-3)}
+    assert not bad, bad
