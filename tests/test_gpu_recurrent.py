@@ -84,3 +84,43 @@ def test_persistent_kernels_other_support_sets(adjtype, adpadj, cheb):
     assert errs["forecast"] < 2e-3
     bad = {k: v for k, v in errs.items() if not (v < 5e-3)}
     assert not bad, bad
+
+
+def test_persistent_kernels_stay_inside_their_workspaces():
+    """compute-sanitizer is not available on the GPU pool: the forward and reverse workspaces (everything the two persistent kernels
+    write) are embedded in larger buffers whose guard bands must come back untouched - ragged shape (N not a multiple of any tile,
+    batch below the 64-row tile: TMA clipping, masked rows, the last dense tile's partial rows)."""
+    lib = _cabi.lib()
+    T, N, B, Cin, H, Kp, n_adp = 5, 77, 24, 64, 64, 4, 1
+    K, I = Kp + 1, Cin + H
+    ldm = (N + 7) // 8 * 8
+    g = torch.Generator().manual_seed(0)
+    R = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(DEV)
+    x, M = R(T, N, B, Cin), R(Kp, N, ldm, sc=0.05)
+    Wg, Wu = R(N, K, I, 2 * H, sc=0.05), R(N, K, I, H, sc=0.05)
+    bg, bu, Rgw, Ruw, Rgb, Rub = R(N, 2 * H), R(N, H), R(2 * H, I, sc=0.1), R(H, I, sc=0.1), R(2 * H), R(H)
+    mix, dY = torch.sigmoid(R(T)), R(T, N, B, H)
+    dims = (T, N, B, Cin, H, K)
+    p = lambda t: None if t is None else t.data_ptr()
+    st = torch.cuda.current_stream().cuda_stream
+    guard, sentinel = 1 << 16, 12345.678
+    nws = lib.matgcn_encoder_layer_fwd_ws_bytes(*dims) // 4
+    nbws = lib.matgcn_encoder_layer_bwd_ws_bytes(*dims, n_adp) // 4
+    big_ws = torch.full((nws + 2 * guard,), sentinel, device=DEV)
+    big_bws = torch.full((nbws + 2 * guard,), sentinel, device=DEV)
+    ws, bws = big_ws[guard:guard + nws], big_bws[guard:guard + nbws]
+    ws.zero_()
+    bws.zero_()
+    new = lambda *s: torch.zeros(*s, device=DEV)
+    outs = [new(T, N, B, Cin), None, new(Kp, N, ldm), new(N, K, I, 2 * H), new(N, 2 * H), new(N, K, I, H), new(N, H),
+            new(2 * H, I), new(2 * H), new(H, I), new(H), new(T)]
+    n0 = lib.matgcn_launch_count()
+    _cabi.check(lib.matgcn_encoder_layer_fwd(*dims, ldm, p(x), x.stride(0), None, p(M), p(Wg), p(bg), p(Wu), p(bu), p(Rgw),
+                                             p(Rgb), p(Ruw), p(Rub), p(mix), p(ws), 3, st), "fwd")
+    _cabi.check(lib.matgcn_encoder_layer_bwd(*dims, ldm, n_adp, p(dY), dY.stride(0), p(M), p(Wg), p(Wu), p(Rgw), p(Ruw), p(mix),
+                                             p(ws), p(bws), *[p(o) for o in outs], 3, st), "bwd")
+    torch.cuda.synchronize()
+    assert lib.matgcn_launch_count() - n0 < 60, "the persistent kernels did not run"
+    for name, big, n in (("forward", big_ws, nws), ("reverse", big_bws, nbws)):
+        assert (big[:guard] == sentinel).all() and (big[guard + n:] == sentinel).all(), "%s workspace overrun" % name
+    assert torch.isfinite(ws).all() and all(torch.isfinite(o).all() for o in outs if o is not None)
