@@ -222,7 +222,8 @@ struct EpiBlocks {
     long long s1, s2, sblk;
     int ld, blk;
     __nv_bfloat16* C16;  // may be null
-    int c16_lo;
+    int c16_lo;          // column blocks >= c16_lo get the bf16 twin ...
+    int c32_hi;          // ... and only blocks < c32_hi the fp32 store (blocks whose consumers all read the twin skip it)
     bool vec_ok() const { return aligned16(C) && (!C16 || aligned16(C16)) && !(s1 & 3) && !(s2 & 3) && !(sblk & 3) && !(ld & 3) && !(blk & 31); }
     __device__ __forceinline__ long long off(int z1, int z2, int row, int col, int& j) const {
         j = col / blk;
@@ -232,28 +233,28 @@ struct EpiBlocks {
     __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn&) const {
         int j;
         const long long o = off(z1, z2, row, col, j);
-        C[o] = acc;
+        if (j < c32_hi) C[o] = acc;
         if (C16 && j >= c16_lo) C16[o] = __float2bfloat16_rn(acc);
     }
     __device__ __forceinline__ EpiIn4 load4(int, int, int, int) const { return EpiIn4{}; }
     __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4&) const {
         int j;
         const long long o = off(z1, z2, row, col, j);
-        st4(C + o, acc);
+        if (j < c32_hi) st4(C + o, acc);
         if (C16 && j >= c16_lo) st4_bf16(C16 + o, acc);
     }
     struct Cur { long long off; int twin; };
     __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
         int j;
         const long long o = off(z1, z2, row, col, j);
-        return Cur{o, (C16 && j >= c16_lo) ? 1 : 0};
+        return Cur{o, ((C16 && j >= c16_lo) ? 1 : 0) | (j < c32_hi ? 2 : 0)};
     }
     __device__ __forceinline__ void advance4(Cur& c, int rows) const { c.off += (long long)rows * ld; }
     __device__ __forceinline__ EpiIn4 load4(const Cur&) const { return EpiIn4{}; }
     __device__ __forceinline__ void prefetch4(const Cur&) const {}
     __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4&) const {
-        st4(C + c.off, acc);
-        if (c.twin) st4_bf16(C16 + c.off, acc);
+        if (c.twin & 2) st4(C + c.off, acc);
+        if (c.twin & 1) st4_bf16(C16 + c.off, acc);
     }
     EPI_CALL_OPERATOR
 };

@@ -1502,6 +1502,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     CK(cudaMemsetAsync(dRub, 0, sizeof(float) * H, st));
     TR();
     const bool small_x = xside_small_ok(Cin, H, K);
+    bool dpx16_only = false;   // the fused DPX launch keeps slots k >= 1 as bf16 only: their consumers must read the twins
     const int cs_threads = 3 * H <= 256 ? 256 : 3 * H;
     REQUIRE(3 * H <= 1024, "hidden size too large for the column-sum kernels");
     if (small_x) {
@@ -1574,7 +1575,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                 p.A = DG; p.lda = 3 * H; p.sA1 = 3 * U; p.sA2 = (long long)B * 3 * H; p.M = B; p.K = 3 * H;
                 p.A16 = DG16T;
                 p.B16 = WX16; p.ldb = 3 * H; p.N = K * Cin; p.sB1 = 0; p.sB2 = (long long)K * Cin * 3 * H;
-                EpiBlocks e{DPX, K * UX, (long long)B * Cin, UX, Cin, Cin, DPX16, 1};
+                EpiBlocks e{DPX, K * UX, (long long)B * Cin, UX, Cin, Cin, DPX16, 1, (ldm & 7) ? K : 1};  // (slots k >= 1: bf16 only, see dpx16_only)
                 const cudaError_t de = launch_gemm_tc<128, true, true, EpiBlocks, true>(p, e, T * N, st);
                 if (de == cudaSuccess) {
                     g_tc_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1585,6 +1586,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                 }
             }
             const bool fused = dpx_done;
+            dpx16_only = fused && !(ldm & 7);
             dpx_done = true;
             for (int k = 0; k < K && dpx_done && !fused; ++k) {
                 memset(&p, 0, sizeof(p));
@@ -1626,6 +1628,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.A = M; p.lda = ldm; p.M = N; p.K = Kp * N;
     p.B = DPX + UX; p.ldb = B * Cin; p.N = B * Cin; p.sB1 = K * UX;
     if (bf && !small_x) { p.A16 = M16; p.B16 = DPX16 + UX; }
+    p.need16 = dpx16_only ? 1 : 0;
     {
         EpiStore e = epi_store(dx, UX, 0, B * Cin);
         e.add = DPX; e.add_s1 = K * UX; e.add_ld = B * Cin;
@@ -1672,6 +1675,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         p.A = DPX + (long long)(a + 1) * UX; p.sAk = K * UX; p.B = PX; p.sBk = K * UX;
         p.A16 = nullptr; p.B16 = nullptr; p.need16 = 0;
         if (bf && !small_x && !(Cin & 7)) { p.A16 = DPX16 + (long long)(a + 1) * UX; p.B16 = PX16; }
+        p.need16 = dpx16_only ? 1 : 0;
         CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
         TR();
     }

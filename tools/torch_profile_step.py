@@ -35,3 +35,10 @@ tot = sum(r[0] for r in rows)
 print("device time per step: %.1f us over %d kernel kinds" % (tot, len(rows)))
 for t, c, k in rows[:45]:
     print("%9.1f us  %6.1f x %8.1f us  %5.1f%%  %s" % (t, c, t / max(c, 1e-9), 100 * t / tot, k))
+if os.environ.get("DETAIL"):
+    # individual copies / stock elementwise kernels of the profiled steps, largest first (what the Python side still launches)
+    ev = [e for e in prof.events() if e.device_type.name == "CUDA" and ("Memcpy" in e.name or "at::native" in e.name or "Memset" in e.name)]
+    ev.sort(key=lambda e: -(getattr(e, "device_time", 0) or 0))
+    print("largest stock copies / elementwise kernels (3 steps):")
+    for e in ev[:40]:
+        print("%9.1f us  %s" % (getattr(e, "device_time", 0) or 0, e.name[:120]))
