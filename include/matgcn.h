@@ -101,6 +101,11 @@ int matgcn_propagate_fwd(const float* M, int Kp, int N, int ldm, const float* X,
  * step.  on = 0 selects one launch per phase.  Returns the previous setting.  Default on (or MATGCN_REC=0 in the environment). */
 int matgcn_set_recurrent_kernel(int on);
 
+/* Time-batched residual-cell weight / bias gradients of the layer backward (MA.py:142-150): in the fast modes with rnn_units = 64
+ * one pass over the pre-activation gradients (csrc/dr_pass.cuh) replaces four split-K contractions and a column sum.
+ * on = 0 keeps the separate launches.  Returns the previous setting.  Default on (or MATGCN_DR_PASS=0 in the environment). */
+int matgcn_set_dr_pass(int on);
+
 /* Device timing of the persistent recurrence kernels (measurement only): while on, each of their launches is bracketed by CUDA
  * events on its stream; the read call waits for them and returns the summed milliseconds and launch counts since it was turned on. */
 int matgcn_rec_timing(int on);

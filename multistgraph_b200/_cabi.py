@@ -33,6 +33,7 @@ _SIGNATURES = {
                                   c_void_p]),
     "matgcn_set_fused_tail": (c_int, [c_int]),
     "matgcn_set_recurrent_kernel": (c_int, [c_int]),
+    "matgcn_set_dr_pass": (c_int, [c_int]),
     "matgcn_rec_timing": (c_int, [c_int]),
     "matgcn_rec_timing_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "matgcn_propagate_fwd_bf16": (c_int, [_F, c_int, c_int, c_int, _F, c_int, _F, c_void_p]),

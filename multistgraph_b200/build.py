@@ -16,7 +16,7 @@ LIB = os.path.join(CSRC, "libmatgcn.so")
 # translation unit -> the headers it depends on (None = every .cuh in csrc/); each is compiled to its own object so
 # that touching the small train_step.cu does not rebuild the 3-minute tensor-core unit
 _MAIN_HDRS = ["gemm_simt.cuh", "epilogues.cuh", "gemm_tc.cuh", "res_bwd.cuh", "xside_mma.cuh", "rec_api.h"]
-_REC_HDRS = ["gemm_simt.cuh", "epilogues.cuh", "gemm_tc.cuh", "rec_api.h", "rec_fwd.cuh", "rec_bwd.cuh"]
+_REC_HDRS = ["gemm_simt.cuh", "epilogues.cuh", "gemm_tc.cuh", "rec_api.h", "rec_fwd.cuh", "rec_bwd.cuh", "dr_pass.cuh"]
 SOURCES = {"matgcn.cu": _MAIN_HDRS, "rec.cu": _REC_HDRS, "train_step.cu": []}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

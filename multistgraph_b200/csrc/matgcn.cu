@@ -61,6 +61,17 @@ static bool l2_warm_enabled() {
 // latency (measured at N=403, B=64: -2.4 % step time with both layers warmed; at N=237, where the set is about L2-sized,
 // +2 %), and (b) the largest block to pull in, the gate weights' hidden rows, fits the per-launch budget (N=883: +0.6 % when
 // only parts fit).  MATGCN_L2_WARM=3 forces it on, 0 switches it off, 1 restricts it to the weight blocks.
+// Fused reduction pass over DR (dr_pass.cuh).  MATGCN_DR_PASS=0 or matgcn_set_dr_pass(0) keeps the separate split-K contractions.
+static int& dr_pass_flag() {
+    static int f = []() { const char* e = getenv("MATGCN_DR_PASS"); return (e && e[0] == '0') ? 0 : 1; }();
+    return f;
+}
+static bool dr_pass_enabled() { return dr_pass_flag() != 0; }
+extern "C" int matgcn_set_dr_pass(int on) {
+    const int prev = dr_pass_flag();
+    dr_pass_flag() = on ? 1 : 0;
+    return prev;
+}
 static bool l2_warm_layer(int N, int K, int Cin, int H, int B) {
     if (!l2_warm_enabled()) return false;
     if (l2_warm_level() >= 3) return true;
@@ -1502,6 +1513,23 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     CK(cudaMemsetAsync(dRub, 0, sizeof(float) * H, st));
     TR();
     const bool small_x = xside_small_ok(Cin, H, K);
+    // fast modes, H = 64: ONE pass over DR for the residual-cell weight / bias gradients (dr_pass.cuh) instead of four split-K
+    // contractions and a column-sum kernel (MATGCN_DR_PASS=0 keeps those)
+    bool dr_hidden_done = false, dr_x_done = false, dr_bias_done = false;
+    if (tc && H == 64 && dr_pass_enabled()) {
+        const bool with_x = !small_x && Cin == 64;
+        DrPassArgs da{T, (int)NB, Cin, H, DR, ws + w.H1, ws + w.ZH2, with_x ? PX : nullptr, K * UX,
+                      dRgw, dRuw, small_x ? nullptr : dRgb, small_x ? nullptr : dRub};
+        const cudaError_t de = launch_dr_pass(da, st);
+        if (de == cudaSuccess) {
+            count_launch();
+            g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+            TR();
+            dr_hidden_done = true; dr_x_done = with_x; dr_bias_done = !small_x;
+        } else if (de != cudaErrorNotSupported) {
+            CK(de);
+        }
+    }
     bool dpx16_only = false;   // the fused DPX launch keeps slots k >= 1 as bf16 only: their consumers must read the twins
     const int cs_threads = 3 * H <= 256 ? 256 : 3 * H;
     REQUIRE(3 * H <= 1024, "hidden size too large for the column-sum kernels");
@@ -1551,12 +1579,14 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         count_launch();
         TR();
         dim3 g2(1, 1184);
-        if (colsum4_ok(DR, 3 * U, 0, 3 * H))
-            colsum4_kernel<<<g2, 256, cs_smem, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
-        else
-            colsum_kernel<<<g2, cs_threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
-        count_launch();
-        TR();
+        if (!dr_bias_done) {
+            if (colsum4_ok(DR, 3 * U, 0, 3 * H))
+                colsum4_kernel<<<g2, 256, cs_smem, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
+            else
+                colsum_kernel<<<g2, cs_threads, 0, st>>>(DR, T, 3 * U, 0, NB, 3 * H, 3 * H, 2 * H, dRgb, 2 * H, dRub, H);
+            count_launch();
+            TR();
+        }
         CK(cudaGetLastError());
         // DPX[t,k,n] = DG[t,n][:,0:2H] * Wg[n,k,0:Cin,:]^T + DG[t,n][:,2H:] * Wu[n,k,0:Cin,:]^T     per k: z = (t, n)
         bool dpx_done = false;
@@ -1687,16 +1717,19 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         if (splits > 592) splits = 592;
         if (splits < 1) splits = 1;
         p.splits = splits;
-        // gate, hidden columns
-        p.A = DR; p.M = 2 * H; p.B = ws + w.H1; p.ldb = H; p.sBk = U; p.N = H;
-        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRgw + Cin, 0, 0, I}, 1, st)));
-        TR();
-        // candidate, hidden columns
-        p.A = DR + 2 * H; p.M = H; p.B = ws + w.ZH2;
-        CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw + Cin, 0, 0, I}, 1, st)));
-        TR();
+        if (!dr_hidden_done) {
+            // gate, hidden columns
+            p.A = DR; p.M = 2 * H; p.B = ws + w.H1; p.ldb = H; p.sBk = U; p.N = H;
+            CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRgw + Cin, 0, 0, I}, 1, st)));
+            TR();
+            // candidate, hidden columns
+            p.A = DR + 2 * H; p.M = H; p.B = ws + w.ZH2;
+            CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw + Cin, 0, 0, I}, 1, st)));
+            TR();
+        }
         // input columns
-        if (!small_x) {
+        p.A = DR + 2 * H; p.M = H;
+        if (!small_x && !dr_x_done) {
             p.B = PX; p.ldb = Cin; p.sBk = K * UX; p.N = Cin;
             CK((gemm_any<CfgMid, false, false>(tc, p, EpiAtomic{dRuw, 0, 0, I}, 1, st)));
             TR();

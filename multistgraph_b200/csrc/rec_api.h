@@ -38,6 +38,16 @@ struct RecBwdArgs {
 };
 cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st);
 
+// One pass over DR for all its reductions over (t, n, b): residual-cell weight and bias gradients (dr_pass.cuh).  X (the layer
+// input, [T][NB, 64] with x_tstride floats between steps) may be null: the input columns are then left to the caller; dRgb /
+// dRub may be null (no bias sums).  All outputs are ACCUMULATED into (atomics): the caller zero-fills them.
+struct DrPassArgs {
+    int T, NB, Cin, H;
+    const float* DR; const float* H1; const float* ZH2; const float* X; long long x_tstride;
+    float* dRgw; float* dRuw; float* dRgb; float* dRub;
+};
+cudaError_t launch_dr_pass(const DrPassArgs& a, cudaStream_t st);
+
 // Optional device timing of the two persistent kernels (bench.py's roofline): while enabled, every launch is bracketed by CUDA
 // events on its stream; rec_timing_read() waits for them and returns the summed durations and launch counts since enabling.
 void rec_timing_enable(bool on);
