@@ -153,6 +153,99 @@ inline EpiStore epi_store(float* C, long long s1, long long s2, int ldc) {
     return e;
 }
 
+// EpiStore with its feature set fixed at compile time (F = OR of the ES_* bits in use) for the tensor-core engine's vectorised
+// epilogue: the run-time tests of the generic functor (is there a bias / scale / addend / twin / second copy, reloaded from the
+// constant bank around every 16-byte access) made that epilogue ~130 instructions per access and the time-batched launches
+// with large outputs instruction-bound (profiles/r2g_rx_epilogue_ncu.txt); with the unused paths compiled out it is ~25.
+enum { ES_BIAS = 1, ES_ADD = 2, ES_ACC = 4, ES_C16 = 8, ES_SCALE = 16 };
+template <int F>
+struct EpiStoreT {
+    static constexpr int kBatch = 4;
+    static constexpr int kPipe = 8;
+    static constexpr bool kVecOnly = true;   // no scalar-epilogue kernel is built for it (the caller falls back to EpiStore)
+    float* C;
+    long long s1, s2;
+    int ldc;
+    const float* bias; long long bias_s1;
+    const float* scale; int scale_div;
+    const float* add; long long add_s1, add_s2; int add_ld;
+    __nv_bfloat16* C16;
+    EpiStoreT() = default;
+    explicit EpiStoreT(const EpiStore& e)
+        : C(e.C), s1(e.s1), s2(e.s2), ldc(e.ldc), bias(e.bias), bias_s1(e.bias_s1), scale(e.scale), scale_div(e.scale_div), add(e.add),
+          add_s1(e.add_s1), add_s2(e.add_s2), add_ld(e.add_ld), C16(e.C16) {}
+    static bool matches(const EpiStore& e) {
+        return !e.D2 && !!e.bias == !!(F & ES_BIAS) && !!e.add == !!(F & ES_ADD) && !!e.accumulate == !!(F & ES_ACC) &&
+               !!e.C16 == !!(F & ES_C16) && !!e.scale == !!(F & ES_SCALE);
+    }
+    bool vec_ok() const {
+        return aligned16(C) && (!(F & ES_C16) || aligned16(C16)) && !(s1 & 3) && !(s2 & 3) && !(ldc & 3) &&
+               (!(F & ES_BIAS) || (aligned16(bias) && !(bias_s1 & 3))) && (!(F & ES_SCALE) || !(scale_div & 3)) &&
+               (!(F & ES_ADD) || (aligned16(add) && !(add_s1 & 3) && !(add_s2 & 3) && !(add_ld & 3)));
+    }
+    __device__ __forceinline__ EpiIn load(int z1, int z2, int row, int col) const {
+        EpiIn in;
+        in.a = (F & ES_SCALE) ? __ldg(scale + col / scale_div) : 1.f;
+        in.b = (F & ES_BIAS) ? __ldg(bias + z1 * bias_s1 + col) : 0.f;
+        in.c = (F & ES_ADD) ? add[z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col] : 0.f;
+        in.d = (F & ES_ACC) ? C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] : 0.f;
+        return in;
+    }
+    __device__ __forceinline__ void store(int z1, int z2, int row, int col, float acc, const EpiIn& in) const {
+        const float v = acc * in.a + in.b + in.c + in.d;
+        C[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = v;
+        if (F & ES_C16) C16[z1 * s1 + z2 * s2 + (long long)row * ldc + col] = __float2bfloat16_rn(v);
+    }
+    __device__ __forceinline__ EpiIn4 load4(int z1, int z2, int row, int col) const {
+        EpiIn4 in;
+        in.a = f4((F & ES_SCALE) ? __ldg(scale + col / scale_div) : 1.f);
+        in.b = (F & ES_BIAS) ? ld4(bias + z1 * bias_s1 + col) : f4(0.f);
+        in.c = (F & ES_ADD) ? ld4(add + z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col) : f4(0.f);
+        in.d = (F & ES_ACC) ? ld4(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col) : f4(0.f);
+        return in;
+    }
+    __device__ __forceinline__ void store4(int z1, int z2, int row, int col, const float4& acc, const EpiIn4& in) const {
+        const float4 v = in.a * acc + in.b + in.c + in.d;
+        st4(C + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
+        if (F & ES_C16) st4_bf16(C16 + z1 * s1 + z2 * s2 + (long long)row * ldc + col, v);
+    }
+    struct Cur { long long off, aoff; float4 bias; float scale; };
+    __device__ __forceinline__ Cur begin4(int z1, int z2, int row, int col) const {
+        Cur c;
+        c.off = z1 * s1 + z2 * s2 + (long long)row * ldc + col;
+        c.aoff = (F & ES_ADD) ? z1 * add_s1 + z2 * add_s2 + (long long)row * add_ld + col : 0;
+        c.bias = (F & ES_BIAS) ? ld4(bias + z1 * bias_s1 + col) : f4(0.f);
+        c.scale = (F & ES_SCALE) ? __ldg(scale + col / scale_div) : 1.f;
+        return c;
+    }
+    __device__ __forceinline__ void advance4(Cur& c, int rows) const {
+        c.off += (long long)rows * ldc;
+        if (F & ES_ADD) c.aoff += (long long)rows * add_ld;
+    }
+    __device__ __forceinline__ EpiIn4 load4(const Cur& c) const {
+        EpiIn4 in;
+        if (F & ES_ADD) in.c = ld4(add + c.aoff);
+        if (F & ES_ACC) in.d = ld4(C + c.off);
+        return in;
+    }
+    __device__ __forceinline__ void prefetch4(const Cur& c) const {
+        if (F & ES_ADD) pf_l2(add + c.aoff);
+        if (F & ES_ACC) pf_l2(C + c.off);
+    }
+    __device__ __forceinline__ void store4(const Cur& c, const float4& acc, const EpiIn4& in) const {
+        float4 v = acc;
+        if (F & ES_SCALE) v = c.scale * v;
+        if (F & ES_BIAS) v = v + c.bias;
+        if (F & ES_ADD) v = v + in.c;
+        if (F & ES_ACC) v = v + in.d;
+        st4(C + c.off, v);
+        if (F & ES_C16) st4_bf16(C16 + c.off, v);
+    }
+    EPI_CALL_OPERATOR
+};
+template <class E, class = void> struct EpiVecOnly { static constexpr bool value = false; };
+template <class E> struct EpiVecOnly<E, decltype((void)E::kVecOnly)> { static constexpr bool value = E::kVecOnly; };
+
 // Lean form of EpiStore for the contractions of the recurrence (support propagation, the per-node products of the
 // reverse step): C = acc, optionally with a bf16 twin and a second copy of the blocks z2 in [d2_lo, d2_hi).
 // (EpiStore's optional bias / scale / addend / accumulate paths cost code even when unused, and every launch of these

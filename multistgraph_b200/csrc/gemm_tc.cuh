@@ -1033,7 +1033,8 @@ inline cudaError_t launch_gemm_tc(const GemmP& p, const Epi& epi, int Z, cudaStr
         if (!t.vec || BN != 64 || p.N != 64 || t.tiles_n != 1) return cudaErrorNotSupported;  // caller launches the three unfused contractions
         kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true>;
     } else if (!t.vec) {
-        kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, false>;
+        if constexpr (EpiVecOnly<Epi>::value) return cudaErrorNotSupported;
+        else kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, false>;
     } else if (t.m64) {
         kern = gemm_tc_kernel<BN, A_KC, B_KC, BF16, Epi, true, true>;
         variant = 2;

@@ -109,6 +109,21 @@ static cudaError_t gemm_any(bool tc, const GemmP& p, const Epi& epi, int Z, cuda
     }
     return launch_gemm<Cfg, A_KC, B_KC, Epi>(p, epi, Z, st);
 }
+// Tensor-core launch with EpiStore's feature set fixed at compile time (EpiStoreT<F>, epilogues.cuh) for the time-batched
+// launches whose run time is their epilogue.  cudaErrorNotSupported: the functor uses other features than F, or the shape does
+// not qualify - the caller takes the generic route.  MATGCN_LEAN_EPI=0 switches it off (A/B measurements).
+static bool lean_epi_enabled() {
+    static const bool on = []() { const char* e = getenv("MATGCN_LEAN_EPI"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <int F, int BN, bool A_KC, bool B_KC, bool BF16>
+static cudaError_t launch_store_lean(const GemmP& p, const EpiStore& e, int Z, cudaStream_t st) {
+    if (!lean_epi_enabled() || !EpiStoreT<F>::matches(e) || p.K < 8) return cudaErrorNotSupported;
+    if (BF16 ? !(p.A16 && p.B16) : !(p.A && p.B)) return cudaErrorNotSupported;
+    const cudaError_t le = launch_gemm_tc<BN, A_KC, B_KC, EpiStoreT<F>, BF16>(p, EpiStoreT<F>(e), Z, st);
+    if (le == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    return le;
+}
 extern "C" unsigned long long matgcn_tc_launch_count(void) { return g_tc_launches.load(); }
 
 // Optional per-launch tracing (MATGCN_TRACE=1): a CUDA event after every enqueued operation of the encoder
@@ -679,16 +694,29 @@ static cudaError_t to_bf16(const float* src, long long spitch, __nv_bfloat16* ds
 
 // bf16 [N*K, Cin, 3H] concatenation of the input rows of the gate and candidate weights: WX[nk, i, 0:2H] = Wg[nk, i, :],
 // WX[nk, i, 2H:3H] = Wu[nk, i, :] (i < Cin) - lets the time-batched input gradient run as ONE contraction over 3H per support.
+// (H % 4 == 0: four columns per thread, 16-byte loads and 8-byte stores)
 __global__ void pack_wx16_kernel(const float* __restrict__ Wg, const float* __restrict__ Wu, int NK, int Cin, int I, int H,
                                  __nv_bfloat16* __restrict__ WX) {
-    const long long total = (long long)NK * Cin * 3 * H;
+    const int q = 3 * H / 4;   // column quads per row
+    const long long total = (long long)NK * Cin * q;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % (3 * H));
-        const long long ri = idx / (3 * H);
+        const int c = (int)(idx % q) * 4;
+        const long long ri = idx / q;
         const int i = (int)(ri % Cin);
         const long long nk = ri / Cin;
-        const float v = c < 2 * H ? Wg[(nk * I + i) * 2 * H + c] : Wu[(nk * I + i) * H + c - 2 * H];
-        WX[idx] = __float2bfloat16_rn(v);
+        const float4 v = c < 2 * H ? ld4(Wg + (nk * I + i) * 2 * H + c) : ld4(Wu + (nk * I + i) * H + c - 2 * H);
+        st4_bf16(WX + ri * 3 * H + c, v);
+    }
+}
+// rows of n floats: fp32 copy and bf16 twin in one pass (n % 4 == 0, 16-byte aligned rows)
+__global__ void copy_twin_kernel(const float* __restrict__ src, long long spitch, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst16,
+                                 long long dpitch, long long n4, int rows) {
+    const long long total = n4 * rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n4, c = (i - r * n4) * 4;
+        const float4 v = ld4(src + r * spitch + c);
+        st4(dst + r * dpitch + c, v);
+        st4_bf16(dst16 + r * dpitch + c, v);
     }
 }
 
@@ -752,7 +780,11 @@ extern "C" int matgcn_nodeweights_fwd_ex(const float* E, const float* pool, cons
     p.A = E; p.lda = D; p.B = pool; p.ldb = (int)KIO; p.M = N; p.N = (int)KIO; p.K = D;
     EpiStore e = epi_store(W, 0, 0, (int)KIO);
     e.scale = c; e.scale_div = I * O;
-    CK((gemm_any<CfgBig, true, false>(tc, p, e, 1, st)));
+    {
+        const cudaError_t le = (tc && D >= 8) ? launch_store_lean<ES_SCALE, 128, true, false, false>(p, e, 1, st) : cudaErrorNotSupported;
+        if (le == cudaErrorNotSupported) CK((gemm_any<CfgBig, true, false>(tc, p, e, 1, st)));
+        else CK(le);
+    }
     p.B = bias_pool; p.ldb = O; p.N = O;
     CK((launch_gemm<CfgMid, true, false>(p, epi_store(b, 0, 0, O), 1, st)));
     return 0;
@@ -805,7 +837,11 @@ extern "C" int matgcn_nodeweights_bwd_ex(const float* E, const float* pool, cons
     p.A = E; p.lda = D; p.B = dW; p.ldb = (int)KIO; p.M = D; p.N = (int)KIO; p.K = N; p.splits = 1;
     EpiStore eg = epi_store(dpool, 0, 0, (int)KIO);
     eg.scale = c; eg.scale_div = I * O;
-    CK((gemm_any<CfgSkinnyM, false, false>(tc, p, eg, 1, st)));
+    {
+        const cudaError_t le = (tc && N >= 8) ? launch_store_lean<ES_SCALE, 128, false, false, false>(p, eg, 1, st) : cudaErrorNotSupported;
+        if (le == cudaErrorNotSupported) CK((gemm_any<CfgSkinnyM, false, false>(tc, p, eg, 1, st)));
+        else CK(le);
+    }
     // dc[k] = sum G * pool = sum dpool * pool / c[k]
     {
         dim3 grid(K, 64);
@@ -872,7 +908,7 @@ static GemmP prop_params(const float* M, int ldm, int N, int Kp, const float* sl
 // encoder layer: workspace layout
 // ------------------------------------------------------------------------------------------
 struct LayerWs {
-    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, MPH, M16, PH16, PZ16, PX16, WG16, WU16, total;
+    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, R3X, RB3, BX3, MPH, M16, PH16, PZ16, PX16, WG16, WU16, WX16, total;
     size_t U, UX;  // floats of one [N,B,H] / [N,B,Cin] block
 };
 static size_t align64(size_t v) { return (v + 63) / 64 * 64; }
@@ -897,6 +933,9 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.ZH2 = take((size_t)T * w.U);
     w.RGH = take((size_t)2 * H * H);  // Rgw[:, Cin:] and Ruw[:, Cin:] repacked densely (16-byte aligned rows for TMA)
     w.RUH = take((size_t)H * H);
+    w.R3X = take((size_t)3 * H * Cin);  // [Rgw[:, 0:Cin]; Ruw[:, 0:Cin]] packed [3H, Cin]: the residual cell's input side as ONE operand
+    w.RB3 = take((size_t)3 * H);        // [Rgb; Rub]
+    w.BX3 = take((size_t)N * 3 * H);    // [bg | bu] per node
     w.MPH = take(256);  // grid-barrier counter of the persistent kernel
     // bf16 twins (sizes in floats = elements / 2): base matrices, PH / PZ / PX (same layouts as the fp32 arrays: slot 0 =
     // the state itself, slots 1.. = its propagated copies) and the per-node weights
@@ -906,11 +945,12 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.PX16 = take(((size_t)T * K * w.UX) / 2 + 64);
     w.WG16 = take(((size_t)N * K * (Cin + H) * 2 * H) / 2 + 64);
     w.WU16 = take(((size_t)N * K * (Cin + H) * H) / 2 + 64);
+    w.WX16 = take(((size_t)N * K * Cin * 3 * H) / 2 + 64);  // bf16 [N, K, Cin, 3H]: gate | candidate input-row weights (forward GX, backward DPX)
     w.total = o;
     return w;
 }
 struct LayerBws {
-    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, WX16, total;
+    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, total;
 };
 static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp) {
     LayerBws w;
@@ -929,7 +969,6 @@ static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp)
     w.DPT16 = take(((size_t)K * U) / 2 + 64);
     w.DPX16 = take(((size_t)T * K * UX) / 2 + 64);
     w.DG16 = take(((size_t)T * 3 * U) / 2 + 64);  // bf16 twin of the pre-activation gradients DG [T, N*B, 3H]
-    w.WX16 = take(((size_t)N * K * Cin * 3 * H) / 2 + 64);  // bf16 [N, K, Cin, 3H]: gate | candidate input-row weights
     w.total = o;
     return w;
 }
@@ -1123,12 +1162,19 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     __nv_bfloat16* PX16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PX16);
     __nv_bfloat16* WG16 = reinterpret_cast<__nv_bfloat16*>(ws + w.WG16);
     __nv_bfloat16* WU16 = reinterpret_cast<__nv_bfloat16*>(ws + w.WU16);
-    // x -> slot 0 of PX[t]
-    CK(cudaMemcpy2DAsync(PX, sizeof(float) * K * UX, x, sizeof(float) * x_tstride, sizeof(float) * UX, T,
-                         cudaMemcpyDeviceToDevice, st));
+    // x -> slot 0 of PX[t] (and of its bf16 twin: one pass over x when the rows allow 16-byte accesses)
+    const bool twin_copy = bf && !(UX & 3) && !(x_tstride & 3) && aligned16(x) && aligned16(PX) && aligned16(PX16);
+    if (twin_copy) {
+        copy_twin_kernel<<<148 * 16, 256, 0, st>>>(x, x_tstride, PX, PX16, K * UX, UX >> 2, T);
+        count_launch();
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpy2DAsync(PX, sizeof(float) * K * UX, x, sizeof(float) * x_tstride, sizeof(float) * UX, T,
+                             cudaMemcpyDeviceToDevice, st));
+    }
     if (bf) {
         CK(to_bf16(M, 0, M16, 0, (long long)Kp * N * ldm, 1, st));
-        CK(to_bf16(x, x_tstride, PX16, K * UX, UX, T, st));
+        if (!twin_copy) CK(to_bf16(x, x_tstride, PX16, K * UX, UX, T, st));
         // per-node weights: 2-byte twins are what the step contractions stream (and, marked evict-last, what stays in L2
         // across the 24 steps: 49 MB per layer at the Baltimore size instead of 99 MB of fp32 from HBM every step)
         CK(to_bf16(Wg, 0, WG16, 0, (long long)N * K * I * 2 * H, 1, st));
@@ -1162,12 +1208,46 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         TR();
         CK(cudaGetLastError());
     } else {
+    // the residual cell's input-side weights and biases packed as ONE [3H, Cin] operand (also read by the layer backward)
+    float* R3X = ws + w.R3X; float* RB3 = ws + w.RB3;
+    CK(cudaMemcpy2DAsync(R3X, sizeof(float) * Cin, Rgw, sizeof(float) * I, sizeof(float) * Cin, 2 * H, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpy2DAsync(R3X + (size_t)2 * H * Cin, sizeof(float) * Cin, Ruw, sizeof(float) * I, sizeof(float) * Cin, H,
+                         cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(RB3, Rgb, sizeof(float) * 2 * H, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(RB3 + 2 * H, Rub, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
     // GX[t, n, :, 0:2H] = bg[n] + sum_k PX[t,k,n] * Wg[n,k,0:Cin,:]   z = (n, t), k-batches = k
     memset(&p, 0, sizeof(p));
     p.splits = 1; p.Z2 = T; p.KB = K;
     p.A = PX; p.lda = Cin; p.sA1 = (long long)B * Cin; p.sA2 = K * UX; p.sAk = UX;
     p.M = B; p.K = Cin;
-    {
+    bool gx_done = false;
+    if (bf && !(Cin & 7) && !(H & 3)) {
+        // bf16 mode: gate and candidate columns in ONE contraction against the packed input-row weights WX16 [N, K, Cin, 3H]
+        // (PX16 is streamed once; the layer backward reuses the pack for the input gradients)
+        __nv_bfloat16* WX16 = reinterpret_cast<__nv_bfloat16*>(ws + w.WX16);
+        float* BX3 = ws + w.BX3;
+        pack_wx16_kernel<<<148 * 8, 256, 0, st>>>(Wg, Wu, N * K, Cin, I, H, WX16);
+        count_launch();
+        CK(cudaGetLastError());
+        CK(cudaMemcpy2DAsync(BX3, sizeof(float) * 3 * H, bg, sizeof(float) * 2 * H, sizeof(float) * 2 * H, N, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpy2DAsync(BX3 + 2 * H, sizeof(float) * 3 * H, bu, sizeof(float) * H, sizeof(float) * H, N, cudaMemcpyDeviceToDevice, st));
+        GemmP q = p;
+        q.A16 = PX16; q.B16 = WX16; q.ldb = 3 * H; q.N = 3 * H; q.sB1 = (long long)K * Cin * 3 * H; q.sB2 = 0; q.sBk = (long long)Cin * 3 * H;
+        EpiStore e = epi_store(GX, (long long)B * 3 * H, 3 * U, 3 * H);
+        e.bias = BX3; e.bias_s1 = 3 * H;
+        cudaError_t ge = launch_store_lean<ES_BIAS, 128, true, false, true>(q, e, N * T, st);
+        if (ge == cudaErrorNotSupported) {
+            ge = launch_gemm_tc<128, true, false, EpiStore, true>(q, e, N * T, st);
+            if (ge == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (ge == cudaSuccess) {
+            TR();
+            gx_done = true;
+        } else if (ge != cudaErrorNotSupported) {
+            CK(ge);
+        }
+    }
+    if (!gx_done) {
         p.B = Wg; p.ldb = 2 * H; p.N = 2 * H; p.sB1 = (long long)K * I * 2 * H; p.sB2 = 0; p.sBk = (long long)I * 2 * H;
         if (bf) { p.A16 = PX16; p.B16 = WG16; }
         p.need16 = skip32x ? 1 : 0;
@@ -1186,7 +1266,26 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     memset(&p, 0, sizeof(p));
     p.splits = 1; p.Z2 = 1; p.KB = 1;
     p.A = PX; p.lda = Cin; p.sA1 = K * UX; p.M = N * B; p.K = Cin;
-    {
+    bool rx_done = false;
+    if (tc && Cin >= 8) {
+        // fast modes: all 3H columns in one contraction against the packed operand (x is streamed once)
+        GemmP q = p;
+        q.B = R3X; q.ldb = Cin; q.N = 3 * H;
+        EpiStore e = epi_store(RX, 3 * U, 0, 3 * H);
+        e.bias = RB3; e.bias_s1 = 0;
+        cudaError_t re = launch_store_lean<ES_BIAS, 128, true, true, false>(q, e, T, st);
+        if (re == cudaErrorNotSupported) {
+            re = launch_gemm_tc<128, true, true, EpiStore>(q, e, T, st);
+            if (re == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (re == cudaSuccess) {
+            TR();
+            rx_done = true;
+        } else if (re != cudaErrorNotSupported) {
+            CK(re);
+        }
+    }
+    if (!rx_done) {
         p.B = Rgw; p.ldb = I; p.N = 2 * H;
         EpiStore e = epi_store(RX, 3 * U, 0, 3 * H);
         e.bias = Rgb; e.bias_s1 = 0;
@@ -1590,13 +1689,10 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         CK(cudaGetLastError());
         // DPX[t,k,n] = DG[t,n][:,0:2H] * Wg[n,k,0:Cin,:]^T + DG[t,n][:,2H:] * Wu[n,k,0:Cin,:]^T     per k: z = (t, n)
         bool dpx_done = false;
-        if (bf && !(Cin & 7)) {
+        if (bf && !(Cin & 7) && !(H & 3)) {
             // bf16 mode: one contraction over all 3H pre-activation gradients per support, against the packed input-row weights
-            __nv_bfloat16* WX16 = reinterpret_cast<__nv_bfloat16*>(bws + bw.WX16);
-            pack_wx16_kernel<<<148 * 8, 256, 0, st>>>(Wg, Wu, N * K, Cin, I, H, WX16);
-            count_launch();
-            TR();
-            CK(cudaGetLastError());
+            // (the packed input-row weights WX16 [N, K, Cin, 3H] were written by the forward pass)
+            const __nv_bfloat16* WX16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.WX16);
             dpx_done = false;
             if (!(Cin & 31)) {
                 // all K supports in ONE launch: the output columns are K blocks of Cin (EpiBlocks), DG is streamed once
@@ -1662,7 +1758,9 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     {
         EpiStore e = epi_store(dx, UX, 0, B * Cin);
         e.add = DPX; e.add_s1 = K * UX; e.add_ld = B * Cin;
-        CK((gemm_any<CfgBig, false, false>(tc, p, e, T, st)));
+        const cudaError_t le = tc ? launch_store_lean<ES_ADD, 128, false, false, true>(p, e, T, st) : cudaErrorNotSupported;
+        if (le == cudaErrorNotSupported) CK((gemm_any<CfgBig, false, false>(tc, p, e, T, st)));
+        else CK(le);
         TR();
     }
     memset(&p, 0, sizeof(p));
@@ -1670,16 +1768,15 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.A = DR; p.lda = 3 * H; p.sA1 = 3 * U; p.M = NB; p.K = 2 * H;
     p.B = Rgw; p.ldb = I; p.N = Cin;
     if (!small_x) {
-        // one pass over DR (475 MB per layer at the Baltimore shape) instead of two: [Rgw[:, 0:Cin]; Ruw[:, 0:Cin]] packed into
-        // one [3H, Cin] operand (DRES is free once the recurrence is done)
-        float* R3 = DRES;
-        CK(cudaMemcpy2DAsync(R3, sizeof(float) * Cin, Rgw, sizeof(float) * I, sizeof(float) * Cin, 2 * H, cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpy2DAsync(R3 + (size_t)2 * H * Cin, sizeof(float) * Cin, Ruw, sizeof(float) * I, sizeof(float) * Cin, H,
-                             cudaMemcpyDeviceToDevice, st));
+        // one pass over DR (475 MB per layer at the Baltimore shape) instead of two: [Rgw[:, 0:Cin]; Ruw[:, 0:Cin]] as one
+        // [3H, Cin] operand
+        const float* R3 = ws + w.R3X;   // (packed by the forward pass)
         p.K = 3 * H; p.B = R3; p.ldb = Cin;
         EpiStore e = epi_store(dx, UX, 0, Cin);
         e.accumulate = 1;
-        CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
+        const cudaError_t le = (tc && Cin <= 64) ? launch_store_lean<ES_ACC, 64, true, false, false>(p, e, T, st) : cudaErrorNotSupported;
+        if (le == cudaErrorNotSupported) CK((gemm_any<CfgMid, true, false>(tc, p, e, T, st)));
+        else CK(le);
         TR();
     }
     // dM[a] = sum_t DPHA[t,a] PH[t,0]^T + DPZA[t,a] PZ[t,0]^T + DPX[t,a+1] PX[t,0]^T     (split-K, atomics)
