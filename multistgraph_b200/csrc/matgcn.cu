@@ -468,6 +468,73 @@ __global__ void xside_fwd_small_kernel(const float* __restrict__ PX, const float
     }
 }
 
+// The same with four output columns per thread (3H % 4 == 0, 16-byte aligned operands): the scalar form above issues ~35
+// instructions per output element and is bound by instruction issue (80 % of the issue slots, 40 % of the DRAM bandwidth:
+// profiles/r2h_xside_ncu.txt); here the 14 shared-memory reads of a row serve four columns and the stores are 16 bytes.
+// grid (N, T), thread = (column quad q, row group rg of 4): rows b = rg, rg + 4, ...
+constexpr int XS_RG = 4;
+__global__ void __launch_bounds__(256) xside_fwd_small4_kernel(const float* __restrict__ PX, const float* __restrict__ Wg,
+                                                               const float* __restrict__ bg, const float* __restrict__ Wu,
+                                                               const float* __restrict__ bu, const float* __restrict__ Rgw,
+                                                               const float* __restrict__ Rgb, const float* __restrict__ Ruw,
+                                                               const float* __restrict__ Rub, int T, int N, int B, int Cin, int H, int K,
+                                                               float* __restrict__ GX, float* __restrict__ RX) {
+    extern __shared__ float xs[];  // [K][B][Cin]
+    const int n = blockIdx.x, t = blockIdx.y;
+    const int Q = 3 * H / 4;
+    const int q = threadIdx.x % Q, rg = threadIdx.x / Q, o = 4 * q;
+    const int I = Cin + H, KC = K * Cin;
+    const long long UX = (long long)N * B * Cin;
+    for (int j = threadIdx.x; j < K * B * Cin; j += blockDim.x) {
+        const int k = j / (B * Cin), r = j - k * (B * Cin);
+        xs[j] = PX[((long long)t * K + k) * UX + (long long)n * B * Cin + r];
+    }
+    const bool gate = o < 2 * H;
+    float4 w[XS_KC], rw[4];
+    int xo[XS_KC];
+#pragma unroll
+    for (int kc = 0; kc < XS_KC; ++kc) {
+        const int k = kc / Cin, i = kc - k * Cin;
+        if (kc < KC) {
+            xo[kc] = k * B * Cin + i;
+            w[kc] = gate ? ld4(Wg + (((long long)n * K + k) * I + i) * 2 * H + o) : ld4(Wu + (((long long)n * K + k) * I + i) * H + o - 2 * H);
+        } else {
+            xo[kc] = 0;  // weight 0: any valid slot
+            w[kc] = f4(0.f);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rw[i] = f4(0.f);
+        if (i < Cin) {
+            const float* r0 = gate ? Rgw + (long long)o * I + i : Ruw + (long long)(o - 2 * H) * I + i;
+            rw[i] = make_float4(r0[0], r0[I], r0[2 * I], r0[3 * I]);
+        }
+    }
+    const float4 bias = gate ? ld4(bg + (long long)n * 2 * H + o) : ld4(bu + (long long)n * H + o - 2 * H);
+    const float4 rb = gate ? ld4(Rgb + o) : ld4(Rub + o - 2 * H);
+    __syncthreads();
+    float* gx = GX + (((long long)t * N + n) * B) * 3 * H + o;
+    float* rx = RX + (((long long)t * N + n) * B) * 3 * H + o;
+    const int cin_m1 = Cin - 1;
+    for (int b = rg; b < B; b += XS_RG) {
+        const float* xb = xs + b * Cin;
+        float4 g = bias, r = rb;
+#pragma unroll
+        for (int kc = 0; kc < XS_KC; ++kc) {
+            const float x = xb[xo[kc]];
+            g.x = fmaf(w[kc].x, x, g.x); g.y = fmaf(w[kc].y, x, g.y); g.z = fmaf(w[kc].z, x, g.z); g.w = fmaf(w[kc].w, x, g.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x = xb[min(i, cin_m1)];
+            r.x = fmaf(rw[i].x, x, r.x); r.y = fmaf(rw[i].y, x, r.y); r.z = fmaf(rw[i].z, x, r.z); r.w = fmaf(rw[i].w, x, r.w);
+        }
+        st4(gx + (long long)b * 3 * H, g);
+        st4(rx + (long long)b * 3 * H, r);
+    }
+}
+
 // One pass over DG[:, n]: weight gradient of the input rows, bias gradient, and the input-side data gradient
 //   dW3[n,k,i,o] = sum_{t,b} PX[t,k,n,b,i] * DG[t,n,b,o]     db3[n,o] = sum_{t,b} DG[t,n,b,o]
 //   DPX[t,k,n,b,i] = sum_o DG[t,n,b,o] * W3[n,k,i,o]
@@ -1202,8 +1269,13 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
         // tiny channel count (layer 0): one streaming kernel writes GX and RX
         dim3 grid(N, T);
         const int threads = (3 * H + 31) / 32 * 32;
-        xside_fwd_small_kernel<<<grid, threads, sizeof(float) * (size_t)K * B * Cin, st>>>(PX, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, T, N,
-                                                                                      B, Cin, H, K, GX, RX);
+        if (!(H & 3) && 3 * H / 4 * XS_RG <= 256 && aligned16(Wg) && aligned16(Wu) && aligned16(bg) && aligned16(bu) && aligned16(Rgb) &&
+            aligned16(Rub) && aligned16(GX) && aligned16(RX))
+            xside_fwd_small4_kernel<<<grid, 3 * H / 4 * XS_RG, sizeof(float) * (size_t)K * B * Cin, st>>>(PX, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub,
+                                                                                                  T, N, B, Cin, H, K, GX, RX);
+        else
+            xside_fwd_small_kernel<<<grid, threads, sizeof(float) * (size_t)K * B * Cin, st>>>(PX, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, T, N,
+                                                                                          B, Cin, H, K, GX, RX);
         count_launch();
         TR();
         CK(cudaGetLastError());
