@@ -67,6 +67,10 @@ static int& dr_pass_flag() {
     return f;
 }
 static bool dr_pass_enabled() { return dr_pass_flag() != 0; }
+static bool dg32_forced() {
+    static const bool on = []() { const char* e = getenv("MATGCN_DG32"); return e && e[0] == '1'; }();
+    return on;
+}
 extern "C" int matgcn_set_dr_pass(int on) {
     const int prev = dr_pass_flag();
     dr_pass_flag() = on ? 1 : 0;
@@ -313,6 +317,58 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ 
             const int col = 4 * c4 + u;
             if (col < split) atomicAdd(out1 + (long long)z * ld1 + col, vals[u]);
             else atomicAdd(out2 + (long long)z * ld2 + col - split, vals[u]);
+        }
+    }
+}
+// The same over a bf16 array (the bf16 twin of DG when the persistent reverse kernel wrote no fp32 copy): eight columns per thread.
+__global__ void __launch_bounds__(256) colsum8_bf16_kernel(const __nv_bfloat16* __restrict__ src, int T, long long st, long long sz, int rows,
+                                                           int ncol, int split, float* __restrict__ out1, int ld1,
+                                                           float* __restrict__ out2, int ld2) {
+    extern __shared__ float4 cs_red[];  // [lanes][ncol / 8][2]
+    const int nc8 = ncol >> 3;
+    const int lanes = blockDim.x / nc8;
+    const int c8 = threadIdx.x % nc8, lane = threadIdx.x / nc8;
+    const int z = blockIdx.x;
+    const int chunks_per_t = (rows + 63) >> 6;
+    const int nchunks = T * chunks_per_t;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (lane < lanes) {
+        for (int ch = blockIdx.y; ch < nchunks; ch += gridDim.y) {
+            const int t = ch / chunks_per_t, r0 = (ch - t * chunks_per_t) << 6;
+            const int r1 = min(rows, r0 + 64);
+            const __nv_bfloat16* base = src + (long long)t * st + (long long)z * sz + 8 * c8;
+            for (int r = r0 + lane; r < r1; r += 4 * lanes) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ru = r + u * lanes;
+                    v[u] = ru < r1 ? *reinterpret_cast<const uint4*>(base + (long long)ru * ncol) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {   // bf16 -> fp32: the 16 bits are the high half of the float
+                        s[2 * j] += __uint_as_float(w4[j] << 16);
+                        s[2 * j + 1] += __uint_as_float(w4[j] & 0xffff0000u);
+                    }
+                }
+            }
+        }
+        cs_red[(lane * nc8 + c8) * 2] = make_float4(s[0], s[1], s[2], s[3]);
+        cs_red[(lane * nc8 + c8) * 2 + 1] = make_float4(s[4], s[5], s[6], s[7]);
+    }
+    __syncthreads();
+    if (lane == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            const float4 a = cs_red[(l * nc8 + c8) * 2], b = cs_red[(l * nc8 + c8) * 2 + 1];
+            s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w; s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int col = 8 * c8 + u;
+            if (col < split) atomicAdd(out1 + (long long)z * ld1 + col, s[u]);
+            else atomicAdd(out2 + (long long)z * ld2 + col - split, s[u]);
         }
     }
 }
@@ -1522,14 +1578,17 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     // same rule as the forward pass: in bf16 mode the propagated slots k >= 1 (PH / PZ / PX there, DPT here) exist only as bf16 twins
     const bool skip32 = bf && !use_multi && !(H & 7) && !(ldm & 7) && B >= 8;
     const bool warm = l2_warm_layer(N, K, Cin, H, B);
-    bool rec_done = false;
+    bool rec_done = false, dg16_only = false;
     if (skip32 && H == 64 && rec_flag() && fused_tail_enabled()) {
         // the whole reverse-time recurrence as one persistent cooperative launch (rec_bwd.cuh)
         CK(cudaMemsetAsync(DH1, 0, sizeof(float) * U, st));    // DHD2: DHD + DPT[0] of the step after (none yet)
         CK(cudaMemsetAsync(DRES, 0, sizeof(float) * U, st));   // DZ / DC: the dense phases' output (no carry yet)
+        // inner layers in bf16 mode: every consumer of the main cell's pre-activation gradients reads the bf16 twin, and the
+        // reverse kernel is bound in part by its store traffic - no fp32 copy then (MATGCN_DG32=1 keeps it)
+        dg16_only = !xside_small_ok(Cin, H, K) && !(Cin & 7) && !(H & 7) && 3 * H / 8 <= 256 && !dg32_forced();
         RecBwdArgs ra{T, N, B, Cin, K, ldm, n_adp, dy, dy_tstride, M16, WG16, WU16,
                       PH, ws + w.Z, ws + w.R, ws + w.HC, ws + w.H1, ws + w.Z2, ws + w.R2, ws + w.HC2,
-                      ws + w.RGH, ws + w.RUH, mix, DG, DR, DG16T, DPT, DPT16, DHD, DH1, DRES,
+                      ws + w.RGH, ws + w.RUH, mix, dg16_only ? nullptr : DG, DR, DG16T, DPT, DPT16, DHD, DH1, DRES,
                       reinterpret_cast<__nv_bfloat16*>(DPZA), reinterpret_cast<__nv_bfloat16*>(DPHA), DHC, dmix,
                       reinterpret_cast<unsigned int*>(bws + bw.MPH)};
         const cudaError_t re = launch_rec_bwd(ra, st);
@@ -1540,6 +1599,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         } else if (re != cudaErrorNotSupported) {
             return fail(__func__, cudaGetErrorString(re));
         }
+        if (!rec_done) dg16_only = false;
     }
     if (!rec_done) {
         for (int t = T - 1; t >= 0; --t) {
@@ -1743,7 +1803,9 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
         TR();
         const size_t cs_smem = sizeof(float4) * (256 / (3 * H / 4 > 0 ? 3 * H / 4 : 1)) * (3 * H / 4);
         dim3 g1(N, 8);
-        if (colsum4_ok(DG, 3 * U, (long long)B * 3 * H, 3 * H))
+        if (dg16_only)
+            colsum8_bf16_kernel<<<g1, 256, cs_smem * 2, st>>>(DG16T, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
+        else if (colsum4_ok(DG, 3 * U, (long long)B * 3 * H, 3 * H))
             colsum4_kernel<<<g1, 256, cs_smem, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
         else
             colsum_kernel<<<g1, cs_threads, 0, st>>>(DG, T, 3 * U, (long long)B * 3 * H, B, 3 * H, 3 * H, 2 * H, dbg, 2 * H, dbu, H);
@@ -1802,6 +1864,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
                 TR();
             }
         }
+        REQUIRE(dpx_done || !dg16_only, "the input-gradient contraction needs the fp32 pre-activation gradients, which were not written");
         for (int k = 0; k < K && !dpx_done; ++k) {
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = N; p.KB = 1;

@@ -26,7 +26,7 @@ struct RecBwdArgs {
     // saved by the forward pass: PH (slot 0 of step t = h_{t-1}), Z, R, HC, H1, Z2, R2, HC2  [T, N*B, H]
     const float* PH; const float* Z; const float* R; const float* HC; const float* H1; const float* Z2; const float* R2; const float* HC2;
     const float* RgH; const float* RuH; const float* mix;
-    float* DG; float* DR;            // [T, N*B, 3H] out (in place of GX / RX)
+    float* DG; float* DR;            // [T, N*B, 3H] out (in place of GX / RX); DG may be null: only the bf16 twin is written
     __nv_bfloat16* DG16;             // [T, N*B, 3H] out: bf16 twin of DG
     float* DPT0;                     // [N*B*H] scratch: slot 0 of the per-node products
     __nv_bfloat16* DPT16;            // [K, N*B*H] scratch: slots 1.. of the per-node products (bf16)

@@ -544,8 +544,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 if (ok[w]) {
                                     const long long o = o0 + w * 8 * H + 16 * m2, x = x0 + w * 8 * 3 * H + 16 * m2;
                                     st4(p.DHD + o, d * rr[e]);
-                                    st4(p.DG + 3 * tU + x + 2 * H, gu);
-                                    st4(p.DG + 3 * tU + x + H, gr);
+                                    if (p.DG) {   // (null: every consumer of DG reads the bf16 twin)
+                                        st4(p.DG + 3 * tU + x + 2 * H, gu);
+                                        st4(p.DG + 3 * tU + x + H, gr);
+                                    }
                                     st4_bf16(p.DG16 + 3 * tU + x + 2 * H, gu);
                                     st4_bf16(p.DG16 + 3 * tU + x + H, gr);
                                 }
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 const float4 gz = dzh * hp[e] * zz[e] * one_minus(zz[e]);
                                 if (ok[w]) {
                                     const long long x = x0 + w * 8 * 3 * H + 16 * m2;
-                                    st4(p.DG + 3 * tU + x, gz);
+                                    if (p.DG) st4(p.DG + 3 * tU + x, gz);
                                     st4_bf16(p.DG16 + 3 * tU + x, gz);
                                 }
                                 if (ok[w]) st4(p.DHD + o0 + w * 8 * H + 16 * m2, dk[e]);   // DHD += dzh z (read back after the products)
@@ -770,10 +772,11 @@ cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
         const char* e = getenv("MATGCN_REC_PF");
         p.prefetch = (e && e[0] == '1');   // off by default: the fill traffic costs the dense phase more than the head gains
     }
-    const void* al[] = {a.dy, a.PH, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.RgH, a.RuH, a.DG, a.DR, a.DG16, a.DPT0, a.DPT16, a.DHD,
+    const void* al[] = {a.dy, a.PH, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.RgH, a.RuH, a.DR, a.DG16, a.DPT0, a.DPT16, a.DHD,
                         a.DHD2, a.DZC, a.DHC};
     for (const void* q : al)
         if (!q || (reinterpret_cast<uintptr_t>(q) & 31)) return cudaErrorNotSupported;
+    if (reinterpret_cast<uintptr_t>(a.DG) & 31) return cudaErrorNotSupported;   // (DG may be null: no fp32 copy of the pre-activation gradients)
     if ((a.dy_tstride & 7) || (a.n_adp > 0 && (!a.DPZA || !a.DPHA || (reinterpret_cast<uintptr_t>(a.DPZA) & 15) || (reinterpret_cast<uintptr_t>(a.DPHA) & 15))))
         return cudaErrorNotSupported;
 
