@@ -272,7 +272,10 @@ def recurrence_roofline(model, batches, opt, train_step, lib, n_nodes, batch, k_
     u = n_nodes * batch * H
     flops = t_steps * (2 * 2.0 * kp * n_nodes * n_nodes * batch * H + 2.0 * n_nodes * batch * k_supports * H * 3 * H + 2.0 * n_nodes * batch * H * 3 * H)
     w_bytes = 2.0 * n_nodes * k_supports * H * 3 * H
-    bytes_bwd = t_steps * (9 * u * 4.0 + (3 * u * 4.0) * 2 + 3 * u * 2.0 + 2 * n_adp * u * 2.0 + w_bytes)
+    # (the fp32 copy of the main-cell pre-activation gradients DG is written by the first layer only - the inner layers' consumers
+    # all read the bf16 twin - and the launches of all layers are averaged below)
+    dg32_share = 1.0 / max(1, int(getattr(model, "num_layers", 2)))
+    bytes_bwd = t_steps * (9 * u * 4.0 + 3 * u * 4.0 * (1.0 + dg32_share) + 3 * u * 2.0 + 2 * n_adp * u * 2.0 + w_bytes)
     bytes_fwd = t_steps * (7 * u * 4.0 + 10 * u * 4.0 + 2 * k_supports * u * 2.0 + w_bytes)
     lib.matgcn_rec_timing(1)
     for i in range(steps):
