@@ -69,6 +69,15 @@ class _NodeWeightsFn(torch.autograd.Function):
         d2, k, i, o = pool.shape
         if d2 != d or bias_pool.shape != (d, o) or c.shape != (k,):
             raise _cabi.MatgcnError("node_weights: inconsistent shapes")
+        ctx.d = d
+        if (ctx.flags & _cabi.FLAG_TF32) and d % 4:
+            # embed_dim 10 (MultiATGCN.json default for the DC runs): rows of 40 bytes do not meet TMA's 16-byte pitch rule and the
+            # two big products would fall back to the fp32 SIMT kernels; zero-padded to a multiple of 4 they stay on tensor cores
+            dp = (d + 3) // 4 * 4
+            E = torch.nn.functional.pad(E, (0, dp - d))
+            pool = torch.nn.functional.pad(pool, (0, 0, 0, 0, 0, 0, 0, dp - d))
+            bias_pool = torch.nn.functional.pad(bias_pool, (0, 0, 0, dp - d))
+            d = dp
         W = torch.empty(n, k, i, o, device=E.device, dtype=torch.float32)
         b = torch.empty(n, o, device=E.device, dtype=torch.float32)
         _cabi.check(_cabi.lib().matgcn_nodeweights_fwd_ex(_ptr(E), _ptr(pool), _ptr(bias_pool), _ptr(c),
@@ -91,6 +100,8 @@ class _NodeWeightsFn(torch.autograd.Function):
                                                            _ptr(db), n, d, k, i, o, _ptr(dE), _ptr(dpool),
                                                            _ptr(dbias_pool), _ptr(dc), ctx.flags, _stream()),
                     "matgcn_nodeweights_bwd")
+        if d != ctx.d:   # drop the zero padding of the embedding dimension
+            dE, dpool, dbias_pool = dE[:, :ctx.d].contiguous(), dpool[:ctx.d].contiguous(), dbias_pool[:ctx.d].contiguous()
         return dE, dpool, dbias_pool, dc, None
 
 
