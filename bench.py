@@ -319,7 +319,7 @@ def run_ours(args):
     from multistgraph_b200.dp import broadcast_parameters
     from multistgraph_b200.model import MultiATGCN
     from multistgraph_b200.synthetic import WORKLOADS, make_batch, workload
-    from multistgraph_b200.train import DeviceWindowBank, FusedClipAdam, fused_train_step
+    from multistgraph_b200.train import DeviceWindowBank, FusedClipAdam, GraphedTrainStep, fused_train_step
 
     world, rank, local = _dist_setup(args.gpus)
     if not torch.cuda.is_available():
@@ -402,7 +402,9 @@ def run_ours(args):
             ev.record(copy_stream)
         return batch, ev
 
-    def e2e_run(n_steps):
+    def e2e_run(n_steps, step_fn=None):
+        if step_fn is None:
+            step_fn = lambda b: train_step(model, b, opt, bucket)   # noqa: E731
         seen = []
         nxt = upload(0)
         prev_ev = None
@@ -411,7 +413,7 @@ def run_ours(args):
             torch.cuda.current_stream().wait_event(ev)
             if i + 1 < n_steps:
                 nxt = upload(i + 1)
-            loss = train_step(model, batch, opt, bucket)
+            loss = step_fn(batch)
             for v in batch.values():
                 v.record_stream(torch.cuda.current_stream())
             loss_host[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
@@ -457,6 +459,43 @@ def run_ours(args):
     e5.record()
     barrier()
     ms_win = e4.elapsed_time(e5) / args.steps
+    # ---- the same step captured once as a CUDA graph and replayed (train.GraphedTrainStep) -------------
+    graph_leg = None
+    if not args.no_graph_leg:
+        gstep = GraphedTrainStep(model, opt, resident[0])
+        lg1 = lib.matgcn_launch_count()
+        for i in range(max(args.warmup, 1)):
+            gstep(resident[i % n_host])
+        barrier()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record()
+        for i in range(args.steps):
+            loss = gstep(resident[i % n_host])
+        e7.record()
+        barrier()
+        ms_graph = e6.elapsed_time(e7) / args.steps
+        graph_loss = float(loss.item())
+        eager_extra = lib.matgcn_launch_count() - lg1   # launches issued outside the graph while replaying (data parallel: the update)
+        torch.cuda.synchronize()
+        h0 = time.perf_counter()
+        for i in range(3):
+            gstep(resident[i % n_host])
+        host_ms_graph = (time.perf_counter() - h0) * 1e3 / 3
+        torch.cuda.synchronize()
+        e2e_run(2, gstep)
+        barrier()
+        e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e8.record()
+        gl = e2e_run(args.steps, gstep)
+        e9.record()
+        barrier()
+        assert len(gl) == args.steps and all(l == l for l in gl)
+        ms_graph_e2e = e8.elapsed_time(e9) / args.steps
+        graph_leg = {"ms_per_step": ms_graph, "e2e_ms_per_step": ms_graph_e2e, "host_enqueue_ms_per_step": host_ms_graph,
+                     "library_kernel_nodes": gstep.library_kernel_nodes, "loss": graph_loss,
+                     "gpu_launches": int(gstep.library_kernel_nodes * args.steps + eager_extra * args.steps // (args.steps + max(args.warmup, 1)))}
+        gstep.close()
+        del gstep
     clocks = sampler.stop() if rank == 0 else {}
     strong = None
     if not args.no_strong_leg and args.workload == DEFAULT_WORKLOAD:
@@ -466,9 +505,12 @@ def run_ours(args):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e, ms_win], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_dev, ms_e2e, ms_win] + ([graph_leg["ms_per_step"], graph_leg["e2e_ms_per_step"]] if graph_leg else []),
+                         device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_dev, ms_e2e, ms_win = float(t[0]), float(t[1]), float(t[2])
+        if graph_leg:
+            graph_leg["ms_per_step"], graph_leg["e2e_ms_per_step"] = float(t[3]), float(t[4])
     global_batch = per_gpu_batch * world
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
@@ -477,6 +519,11 @@ def run_ours(args):
     roof = None
     if model.matgcn_flags == 3 and per_gpu_batch <= 64:
         roof = recurrence_roofline(model, resident, opt, train_step, lib, w["N"], per_gpu_batch, 5, 1, 24, peaks)
+    # headline: the captured step when it was measured (it is the same work, issued as one cudaGraphLaunch), else the eager one
+    eager = {"ms_per_step": ms_dev, "e2e_ms_per_step": ms_e2e, "host_enqueue_ms_per_step": host_ms, "gpu_launches": int(launches)}
+    if graph_leg is not None and not args.eager_headline:
+        ms_dev, ms_e2e, host_ms, launches, last_loss = (graph_leg["ms_per_step"], graph_leg["e2e_ms_per_step"],
+                                                        graph_leg["host_enqueue_ms_per_step"], graph_leg["gpu_launches"], graph_leg["loss"])
     if rank == 0:
         if roof is None:   # modes / shapes that run one launch per phase: the support-propagation GEMM is the dominant kernel
             roof = propagation_roofline(w["N"], per_gpu_batch, 64, 4, model.ldm, dev, peaks, model.matgcn_flags)
@@ -484,7 +531,9 @@ def run_ours(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "tf32", 3: "bf16+tf32"}.get(model.matgcn_flags, "tf32"), "data": "synthetic",
                 "config": {"workload": _workload_desc(args.workload, w, per_gpu_batch), "global_batch": global_batch,
-                           "step": "zero_grad+forward+backward+allreduce+clip_grad_norm(5)+Adam (clip+Adam fused over one flat bucket)",
+                           "step": "zero_grad+forward+backward+allreduce+clip_grad_norm(5)+Adam (clip+Adam fused over one flat bucket)"
+                                   + ("; captured once as a CUDA graph and replayed (train.GraphedTrainStep)"
+                                      if graph_leg is not None and not args.eager_headline else ""),
                            "parallelism": "dp%d (batch-sharded, one flat-bucket all-reduce)" % world,
                            "l2": "per-step working set (several GB of saved activations) is far larger than the 126 MB L2",
                            "mode": {0: "exact: fp32 FFMA kernels (1e-4 parity)",
@@ -508,6 +557,18 @@ def run_ours(args):
             t_roof = max(2.77e12 / (peaks["bf16_tflops_sustained"] * 1e12), 3 * (4.51e9 if model.matgcn_flags == 3 else 9.00e9) / (peaks["hbm_gbs"] * 1e9))
             line["step_roofline"] = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms_dev,
                                      "model": "SURVEY.md 8d: max(algorithmic FLOPs / sustained bf16 peak, algorithmic bytes / HBM peak) per step"}
+        if graph_leg is not None:
+            # one cudaGraphLaunch per step (step count, dropout key and learning rate live on the device)
+            graph_leg["value"] = global_batch / (graph_leg["ms_per_step"] * 1e-3)
+            graph_leg["e2e_value"] = global_batch / (graph_leg["e2e_ms_per_step"] * 1e-3)
+            graph_leg["unit"] = UNIT
+            eager["value"] = global_batch / (eager["ms_per_step"] * 1e-3)
+            eager["e2e_value"] = global_batch / (eager["e2e_ms_per_step"] * 1e-3)
+            eager["note"] = "the same step issued launch by launch (train.fused_train_step)"
+            line["eager"] = eager
+            graph_leg["note"] = ("train.GraphedTrainStep: zero_grad .. Adam captured once and replayed" +
+                                 ("; data parallel: the graph ends after the backward, all-reduce + update follow eagerly" if world > 1 else ""))
+            line["cuda_graph"] = graph_leg
         if strong is not None:
             line["strong_scaling"] = strong
         if world == 1 and model.matgcn_flags != 0 and not args.no_exact_leg:
@@ -615,6 +676,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work allowed for the baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact-leg", action="store_true", help="skip the few exact-mode steps reported as exact_mode")
+    ap.add_argument("--no-graph-leg", action="store_true", help="skip the CUDA-graph replay of the step (cuda_graph key)")
+    ap.add_argument("--eager-headline", action="store_true", help="report the launch-by-launch step as value / e2e")
     ap.add_argument("--no-strong-leg", action="store_true",
                     help="skip the strong-scaling leg (BASELINE config 4: N=883, global batch 256 sharded over the ranks)")
     args = ap.parse_args()

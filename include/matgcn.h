@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MATGCN_ABI_VERSION 3
+#define MATGCN_ABI_VERSION 4
 
 /* flags of the contraction-heavy entry points */
 #define MATGCN_FLAG_EXACT 0 /* fp32 FFMA kernels: 1e-4 parity with the reference */
@@ -232,6 +232,16 @@ int matgcn_grad_sumsq(const float* grad, long long n, double* sumsq, void* strea
 int matgcn_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, const double* sumsq,
                           float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay,
                           long long step, int write_grad, float* norm_out, void* stream);
+/* The same step with the two values that change from step to step resident in device memory, so that ONE captured CUDA graph of
+ * the whole loop body (executor:413-422) can be replayed for every step (train.GraphedTrainStep):
+ *   matgcn_adam_clip_step_dev: lr_dev (device float) is read by the kernel (an lr scheduler, executor:155-197, writes it between
+ *                          replays), step_dev (device int64, >= 1 when the kernel runs) yields the bias corrections;
+ *   matgcn_step_tick:      first node of the captured step: *step_dev += 1 (torch.optim.Adam increments before the update) and
+ *                          *seed_dev moves to the next dropout key (either pointer may be NULL). */
+int matgcn_adam_clip_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, const double* sumsq,
+                              float max_norm, float grad_scale, const float* lr_dev, float beta1, float beta2, float eps,
+                              float weight_decay, const long long* step_dev, int write_grad, float* norm_out, void* stream);
+int matgcn_step_tick(unsigned long long* seed_dev, long long* step_dev, void* stream);
 
 /* f2 - batch assembly: replaces MTHDataset._get_sample_indices / _generate_input_data
  *      (libcity/data/dataset/dataset_subclass/mth_dataset.py:31-60, 62-158) plus the per-batch collate and upload
@@ -266,6 +276,13 @@ int matgcn_head_fwd(const float* y, long long y_tstride, int Tc, long long rows,
 int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, int O, float p_drop,
                     unsigned long long seed, const float* dout, float* dy, float* dw, float* dbias, void* stream);
 int matgcn_head_dropout_mask(long long n, float p_drop, unsigned long long seed, float* mult, void* stream);
+/* Same two operators with the mask keyed by `seed ^ *seed_dev` (device uint64 advanced by matgcn_step_tick): the form a captured
+ * train step uses, so that a replay draws a new mask (MA.py:416: F.dropout draws a new mask every call). */
+int matgcn_head_fwd_dev(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, const float* bias, int O,
+                        float p_drop, unsigned long long seed, const unsigned long long* seed_dev, float* out, void* stream);
+int matgcn_head_bwd_dev(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, int O, float p_drop,
+                        unsigned long long seed, const unsigned long long* seed_dev, const float* dout, float* dy, float* dw,
+                        float* dbias, void* stream);
 
 /* f3, second half - calculate_loss (MultiATGCN.py:422-427): StandardScaler.inverse_transform (libcity/utils/normalization.py:62-76)
  *      of forecast and target, then masked_mae_torch(pred, true, 0) (libcity/model/loss.py:17-29), as one streaming pass.

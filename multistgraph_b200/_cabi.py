@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmatgcn.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_EXACT = 0
 FLAG_TF32 = 1
 FLAG_BF16 = 2
@@ -65,6 +65,9 @@ _SIGNATURES = {
     "matgcn_grad_sumsq": (c_int, [_F, c_longlong, c_void_p, c_void_p]),
     "matgcn_adam_clip_step": (c_int, [_F, _F, _F, _F, c_longlong, c_void_p] + [ctypes.c_float] * 7
                               + [c_longlong, c_int, _F, c_void_p]),
+    "matgcn_adam_clip_step_dev": (c_int, [_F, _F, _F, _F, c_longlong, c_void_p, ctypes.c_float, ctypes.c_float, c_void_p]
+                                  + [ctypes.c_float] * 4 + [c_void_p, c_int, _F, c_void_p]),
+    "matgcn_step_tick": (c_int, [c_void_p, c_void_p, c_void_p]),
     "matgcn_assemble_windows": (c_int, [_F, c_longlong, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, _F, _F,
                                         c_void_p, c_void_p]),
     "matgcn_head_dropout_scale": (ctypes.c_float, [ctypes.c_float]),
@@ -72,6 +75,10 @@ _SIGNATURES = {
                                 c_void_p]),
     "matgcn_head_bwd": (c_int, [_F, c_longlong, c_int, c_longlong, c_int, _F, c_int, ctypes.c_float, ctypes.c_ulonglong, _F, _F, _F,
                                 _F, c_void_p]),
+    "matgcn_head_fwd_dev": (c_int, [_F, c_longlong, c_int, c_longlong, c_int, _F, _F, c_int, ctypes.c_float, ctypes.c_ulonglong,
+                                    c_void_p, _F, c_void_p]),
+    "matgcn_head_bwd_dev": (c_int, [_F, c_longlong, c_int, c_longlong, c_int, _F, c_int, ctypes.c_float, ctypes.c_ulonglong,
+                                    c_void_p, _F, _F, _F, _F, c_void_p]),
     "matgcn_head_dropout_mask": (c_int, [c_longlong, ctypes.c_float, ctypes.c_ulonglong, _F, c_void_p]),
     "matgcn_masked_mae_fwd": (c_int, [_F, _F, c_void_p, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p,
                                       _F, c_void_p]),

@@ -82,6 +82,8 @@ struct AdamP {
     float lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale;
     float bc1, bc2_sqrt;  // 1 - beta1^t, sqrt(1 - beta2^t)
     int write_grad;
+    const long long* step_dev;   // optional device-resident step count / learning rate (a captured step replays with new values):
+    const float* lr_dev;         // the kernel derives the bias corrections from *step_dev itself
 };
 
 __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float coef, const AdamP& a) {
@@ -97,6 +99,12 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, long long n, const double* __restrict__ sumsq,
                                                         AdamP a, float* __restrict__ norm_out) {
+    if (a.step_dev) {   // same double-precision expressions as the host form (matgcn_adam_clip_step)
+        const double st = (double)__ldg(a.step_dev);
+        a.bc1 = (float)(1.0 - pow((double)a.beta1, st));
+        a.bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, st));
+    }
+    if (a.lr_dev) a.lr = __ldg(a.lr_dev);
     // clip coefficient: torch.nn.utils.clip_grad_norm_ -> clamp(max_norm / (total_norm + 1e-6), max=1)
     float coef = a.grad_scale;
     if (sumsq) {
@@ -179,7 +187,12 @@ struct DropP {
     unsigned long long seed;
     uint32_t thr;   // 0: no dropout
     float scale;    // 1 / (1 - thr/65536)
+    const unsigned long long* seed_dev;   // optional device-resident key, XORed into `seed` by the kernel (CUDA-graph replays)
 };
+// the key a kernel uses: the host half XOR the device half (advanced by matgcn_step_tick between replays of a captured step)
+__device__ __forceinline__ void drop_resolve(DropP& d) {
+    if (d.seed_dev) d.seed ^= __ldg(d.seed_dev);
+}
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
     uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
@@ -255,6 +268,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_fwd_kernel(const float* __res
                                                               const float* __restrict__ w, const float* __restrict__ bias, int O, int o0,
                                                               DropP dp, float* __restrict__ out) {
     __shared__ __align__(16) float wsm[2][OW * HD_LD];
+    drop_resolve(dp);
     const int tid = threadIdx.x, rg = tid >> 4, hg = tid & 15;
     const long long r0 = (long long)blockIdx.x * HD_RT;
     const int ow = min(O - o0, OW);
@@ -338,6 +352,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_bwd_kernel(const float* __res
     __shared__ __align__(16) float wsm[OW * HD_LD];            // w_t [o][h]
     __shared__ __align__(16) float ds[OW * HD_LD];             // dout tile transposed [o][row] (32 rows used)
     __shared__ __align__(16) float red[4 * 8 * HD_H];          // end-of-block reduction: [warp][8 outputs][h]
+    drop_resolve(dp);
     const int tid = threadIdx.x, t = blockIdx.y, rg = tid >> 4, hg = tid & 15, warp = tid >> 5, lane = tid & 31;
     const int ow = min(O - o0, OW);
     for (int idx = tid; idx < OW * 16; idx += HD_THREADS) {
@@ -448,13 +463,21 @@ __global__ void __launch_bounds__(256) head_dbias_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) dropout_mask_kernel(long long n4, DropP dp, float* __restrict__ mult) {
+    drop_resolve(dp);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
         reinterpret_cast<float4*>(mult)[i] = drop_mult4(dp, (unsigned long long)i * 4);
 }
 
-DropP make_drop(float p, unsigned long long seed) {
+__global__ void step_tick_kernel(unsigned long long* seed_dev, long long* step_dev) {
+    if (threadIdx.x != 0) return;
+    if (step_dev) *step_dev += 1;
+    if (seed_dev) *seed_dev += 0x9E3779B97F4A7C15ull;   // Weyl sequence: 2^64 distinct keys; Philox decorrelates neighbouring keys
+}
+
+DropP make_drop(float p, unsigned long long seed, const unsigned long long* seed_dev = nullptr) {
     DropP d;
     d.seed = seed;
+    d.seed_dev = seed_dev;
     d.thr = p > 0.f ? (uint32_t)lrintf(p * 65536.f) : 0u;
     if (d.thr > 65535u) d.thr = 65535u;
     d.scale = 65536.f / (float)(65536u - d.thr);
@@ -482,25 +505,54 @@ extern "C" int matgcn_grad_sumsq(const float* grad, long long n, double* sumsq, 
     return 0;
 }
 
-extern "C" int matgcn_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+static int adam_clip_step_impl(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                                      const double* sumsq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
-                                     float eps, float weight_decay, long long step, int write_grad, float* norm_out, void* stream) {
+                                     float eps, float weight_decay, long long step, const long long* step_dev, const float* lr_dev,
+                                     int write_grad, float* norm_out, void* stream) {
     TS_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0, "null pointer or negative length");
     TS_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), "buffers must be 16-byte aligned");
-    TS_REQUIRE(step >= 1, "step counts from 1 (torch.optim.Adam increments before the update)");
+    TS_REQUIRE(step_dev || step >= 1, "step counts from 1 (torch.optim.Adam increments before the update)");
     TS_REQUIRE(max_norm <= 0.f || sumsq, "clipping needs the sum of squares from matgcn_grad_sumsq");
     if (n == 0) return 0;
     AdamP a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
     a.grad_scale = grad_scale;
-    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    a.bc1 = step_dev ? 1.f : (float)(1.0 - pow((double)beta1, (double)step));
+    a.bc2_sqrt = step_dev ? 1.f : (float)sqrt(1.0 - pow((double)beta2, (double)step));
     a.write_grad = write_grad;
+    a.step_dev = step_dev;
+    a.lr_dev = lr_dev;
     long long blocks = (n / 4 + 255) / 256;
     const long long cap = 8LL * sm_count_ts();
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     adam_clip_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, sumsq, a, norm_out);
+    matgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
+    TS_CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int matgcn_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                     const double* sumsq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                                     float eps, float weight_decay, long long step, int write_grad, float* norm_out, void* stream) {
+    return adam_clip_step_impl(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, weight_decay,
+                               step, nullptr, nullptr, write_grad, norm_out, stream);
+}
+
+extern "C" int matgcn_adam_clip_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                         const double* sumsq, float max_norm, float grad_scale, const float* lr_dev, float beta1,
+                                         float beta2, float eps, float weight_decay, const long long* step_dev, int write_grad,
+                                         float* norm_out, void* stream) {
+    TS_REQUIRE(lr_dev && step_dev, "device-resident learning rate and step count required");
+    return adam_clip_step_impl(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, grad_scale, 0.f, beta1, beta2, eps, weight_decay,
+                               0, step_dev, lr_dev, write_grad, norm_out, stream);
+}
+
+// Start of a captured train step: the Adam step count advances by one and the dropout key moves to the next value of a
+// Weyl sequence, both in device memory, so that every replay of the same CUDA graph is a NEW step.
+extern "C" int matgcn_step_tick(unsigned long long* seed_dev, long long* step_dev, void* stream) {
+    TS_REQUIRE(seed_dev || step_dev, "null pointer");
+    step_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(seed_dev, step_dev);
     matgcn::g_launches.fetch_add(1, std::memory_order_relaxed);
     TS_CK(cudaGetLastError());
     return 0;
@@ -536,14 +588,14 @@ extern "C" int matgcn_assemble_windows(const float* series, long long T_total, i
 
 extern "C" float matgcn_head_dropout_scale(float p_drop) { return make_drop(p_drop, 0).scale; }
 
-extern "C" int matgcn_head_fwd(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, const float* bias,
-                               int O, float p_drop, unsigned long long seed, float* out, void* stream) {
+static int head_fwd_impl(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, const float* bias,
+                               int O, float p_drop, unsigned long long seed, const unsigned long long* seed_dev, float* out, void* stream) {
     TS_REQUIRE(y && w && bias && out, "null pointer");
     TS_REQUIRE(Tc > 0 && rows >= 0 && O > 0 && p_drop >= 0.f && p_drop < 1.f, "bad dimensions or dropout probability");
     TS_REQUIRE(H == HD_H, "the head kernels are written for rnn_units = 64");
     TS_REQUIRE(aligned16(y) && aligned16(w) && !(y_tstride & 3), "y and w must be 16-byte aligned");
     if (rows == 0) return 0;
-    const DropP dp = make_drop(p_drop, seed);
+    const DropP dp = make_drop(p_drop, seed, seed_dev);
     const unsigned grid = (unsigned)((rows + HD_RT - 1) / HD_RT);
     cudaStream_t st = (cudaStream_t)stream;
     for (int o0 = 0; o0 < O; o0 += HD_OMAX) {
@@ -557,8 +609,20 @@ extern "C" int matgcn_head_fwd(const float* y, long long y_tstride, int Tc, long
     return 0;
 }
 
-extern "C" int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, int O, float p_drop,
-                               unsigned long long seed, const float* dout, float* dy, float* dw, float* dbias, void* stream) {
+extern "C" int matgcn_head_fwd(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, const float* bias,
+                               int O, float p_drop, unsigned long long seed, float* out, void* stream) {
+    return head_fwd_impl(y, y_tstride, Tc, rows, H, w, bias, O, p_drop, seed, nullptr, out, stream);
+}
+extern "C" int matgcn_head_fwd_dev(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, const float* bias,
+                                   int O, float p_drop, unsigned long long seed, const unsigned long long* seed_dev, float* out,
+                                   void* stream) {
+    TS_REQUIRE(seed_dev, "null device seed");
+    return head_fwd_impl(y, y_tstride, Tc, rows, H, w, bias, O, p_drop, seed, seed_dev, out, stream);
+}
+
+static int head_bwd_impl(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, int O, float p_drop,
+                               unsigned long long seed, const unsigned long long* seed_dev, const float* dout, float* dy, float* dw,
+                               float* dbias, void* stream) {
     TS_REQUIRE(y && w && dout && dy && dw && dbias, "null pointer");
     TS_REQUIRE(Tc > 0 && rows >= 0 && O > 0 && p_drop >= 0.f && p_drop < 1.f, "bad dimensions or dropout probability");
     TS_REQUIRE(H == HD_H, "the head kernels are written for rnn_units = 64");
@@ -567,7 +631,7 @@ extern "C" int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long
     TS_CK(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)O * Tc * H, st));
     TS_CK(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)O, st));
     if (rows == 0) return 0;
-    const DropP dp = make_drop(p_drop, seed);
+    const DropP dp = make_drop(p_drop, seed, seed_dev);
     const long long ntiles = (rows + HD_RT - 1) / HD_RT;
     long long chunks = (3LL * sm_count_ts() + Tc - 1) / Tc;      // ~3 resident blocks per SM in total
     if (chunks > ntiles) chunks = ntiles;
@@ -590,6 +654,17 @@ extern "C" int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long
     }
     TS_CK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int matgcn_head_bwd(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, int O, float p_drop,
+                               unsigned long long seed, const float* dout, float* dy, float* dw, float* dbias, void* stream) {
+    return head_bwd_impl(y, y_tstride, Tc, rows, H, w, O, p_drop, seed, nullptr, dout, dy, dw, dbias, stream);
+}
+extern "C" int matgcn_head_bwd_dev(const float* y, long long y_tstride, int Tc, long long rows, int H, const float* w, int O, float p_drop,
+                                   unsigned long long seed, const unsigned long long* seed_dev, const float* dout, float* dy, float* dw,
+                                   float* dbias, void* stream) {
+    TS_REQUIRE(seed_dev, "null device seed");
+    return head_bwd_impl(y, y_tstride, Tc, rows, H, w, O, p_drop, seed, seed_dev, dout, dy, dw, dbias, stream);
 }
 
 extern "C" int matgcn_head_dropout_mask(long long n, float p_drop, unsigned long long seed, float* mult, void* stream) {

@@ -338,11 +338,17 @@ class MultiATGCN(nn.Module):
             # sits in the layer workspace; the backward writes dy straight in the layout the layer backward consumes.  The seed is
             # drawn from torch's CPU generator, so torch.manual_seed reproduces a run.
             drop = 0.1 if self.training else 0.0
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop > 0 else 0
+            seed_dev = getattr(self, "_dropout_key_dev", None) if drop > 0 else None
+            if seed_dev is not None:
+                # inside a captured train step (train.GraphedTrainStep): the key lives on the device and is advanced by the
+                # graph's first node, the host half was drawn once when the step was captured
+                seed = int(self._dropout_key_host)
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop > 0 else 0
             if drop > 0 and torch.distributed.is_available() and torch.distributed.is_initialized():
                 # data-parallel ranks are usually seeded identically: give each shard its own mask stream
                 seed = (seed ^ (torch.distributed.get_rank() * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
-            out = ops.output_head(y_nm, w, self.end_conv.bias, drop, seed).reshape(n_nodes, n_batch, -1).permute(1, 2, 0)
+            out = ops.output_head(y_nm, w, self.end_conv.bias, drop, seed, seed_dev).reshape(n_nodes, n_batch, -1).permute(1, 2, 0)
         else:
             y_nm = F.dropout(y_nm, p=0.1, training=self.training)
             # end_conv = Conv2d(T -> T_out*C, kernel (1, H)) (MA.py:340-344, 417): time steps are the channels, so it is a

@@ -261,9 +261,11 @@ class _OutputHeadFn(torch.autograd.Function):
     The dropout mask is regenerated in the backward from the seed; nothing but (y, w) is saved."""
 
     @staticmethod
-    def forward(ctx, y, w, bias, p_drop, seed):
+    def forward(ctx, y, w, bias, p_drop, seed, seed_dev):
         if not y.is_cuda or y.dtype != torch.float32:
             raise _cabi.MatgcnError("output_head: y must be a float32 CUDA tensor (no CPU path)")
+        if seed_dev is not None and (not seed_dev.is_cuda or seed_dev.dtype != torch.int64 or seed_dev.numel() != 1):
+            raise _cabi.MatgcnError("output_head: seed_dev must be a one-element int64 CUDA tensor")
         Tc, N, B, H = y.shape
         if y.stride(3) != 1 or y.stride(2) != H or y.stride(1) != B * H or (y.stride(0) & 3):
             y = y.contiguous()
@@ -272,10 +274,14 @@ class _OutputHeadFn(torch.autograd.Function):
         if w.shape != (O, Tc, H) or bias.shape != (O,):
             raise _cabi.MatgcnError("output_head: inconsistent shapes")
         out = torch.empty(N * B, O, device=y.device, dtype=torch.float32)
-        _cabi.check(_cabi.lib().matgcn_head_fwd(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), _ptr(bias), O, float(p_drop),
-                                                int(seed), _ptr(out), _stream()), "matgcn_head_fwd")
+        if seed_dev is None:
+            _cabi.check(_cabi.lib().matgcn_head_fwd(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), _ptr(bias), O, float(p_drop),
+                                                    int(seed), _ptr(out), _stream()), "matgcn_head_fwd")
+        else:
+            _cabi.check(_cabi.lib().matgcn_head_fwd_dev(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), _ptr(bias), O, float(p_drop),
+                                                        int(seed), _ptr(seed_dev), _ptr(out), _stream()), "matgcn_head_fwd_dev")
         ctx.save_for_backward(y, w)
-        ctx.p_drop, ctx.seed = float(p_drop), int(seed)
+        ctx.p_drop, ctx.seed, ctx.seed_dev = float(p_drop), int(seed), seed_dev
         return out
 
     @staticmethod
@@ -287,9 +293,14 @@ class _OutputHeadFn(torch.autograd.Function):
         dy = torch.empty(Tc, N, B, H, device=y.device, dtype=torch.float32)
         dw = torch.empty(O, Tc, H, device=y.device, dtype=torch.float32)
         db = torch.empty(O, device=y.device, dtype=torch.float32)
-        _cabi.check(_cabi.lib().matgcn_head_bwd(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), O, ctx.p_drop, ctx.seed, _ptr(dout),
-                                                _ptr(dy), _ptr(dw), _ptr(db), _stream()), "matgcn_head_bwd")
-        return dy, dw, db, None, None
+        if ctx.seed_dev is None:
+            _cabi.check(_cabi.lib().matgcn_head_bwd(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), O, ctx.p_drop, ctx.seed, _ptr(dout),
+                                                    _ptr(dy), _ptr(dw), _ptr(db), _stream()), "matgcn_head_bwd")
+        else:
+            _cabi.check(_cabi.lib().matgcn_head_bwd_dev(_ptr(y), y.stride(0), Tc, N * B, H, _ptr(w), O, ctx.p_drop, ctx.seed,
+                                                        _ptr(ctx.seed_dev), _ptr(dout), _ptr(dy), _ptr(dw), _ptr(db), _stream()),
+                        "matgcn_head_bwd_dev")
+        return dy, dw, db, None, None, None
 
 
 class _MaskedMaeFn(torch.autograd.Function):
@@ -335,9 +346,10 @@ def masked_mae_loss(pred, y, mean, std, min_s=1e-4):
 HEAD_HIDDEN = 64  # rnn_units the fused head kernels are written for
 
 
-def output_head(y, w, bias, p_drop=0.0, seed=0):
-    """out[n*B + b, o] = bias[o] + sum_t sum_h dropout(y[t, n, b, h]) * w[o, t, h]   (y node-major [Tc, N, B, H])."""
-    return _OutputHeadFn.apply(y, w, bias, p_drop, seed)
+def output_head(y, w, bias, p_drop=0.0, seed=0, seed_dev=None):
+    """out[n*B + b, o] = bias[o] + sum_t sum_h dropout(y[t, n, b, h]) * w[o, t, h]   (y node-major [Tc, N, B, H]).
+    ``seed_dev`` (one int64 on the device) is XORed into ``seed`` by the kernels: the form a captured train step uses."""
+    return _OutputHeadFn.apply(y, w, bias, p_drop, seed, seed_dev)
 
 
 def dropout_multipliers(n, p_drop, seed, device):

@@ -78,6 +78,9 @@ class FusedClipAdam(torch.optim.Optimizer):
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.grad_norm = torch.zeros(1, device=dev)      # total norm of the last step (what clip_grad_norm_ returns)
         self.step_count = 0
+        self._step_dev = None   # device-resident step count / learning rate (set by GraphedTrainStep: see enable_device_state)
+        self._lr_dev = None
+        self._lr_dev_value = None
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
                 self.param[o:o + p.numel()].copy_(p.data.reshape(-1))
@@ -127,6 +130,28 @@ class FusedClipAdam(torch.optim.Optimizer):
                 return 1.0 / world
         return 1.0
 
+    # -- device-resident step state (CUDA-graph replays) -------------------------------------------
+    def enable_device_state(self):
+        """Moves the two values that change between steps - Adam's step count and the learning rate - into device memory
+        (``matgcn_adam_clip_step_dev``), so that a captured step can be replayed: ``matgcn_step_tick`` advances the count on the
+        device, ``sync_lr`` pushes a scheduler's new ``param_groups[0]['lr']`` (executor:155-197) when it changed."""
+        if self._step_dev is None:
+            dev = self.param.device
+            self._step_dev = torch.tensor([self.step_count], device=dev, dtype=torch.int64)
+            self._lr_dev = torch.tensor([self.lr], device=dev, dtype=torch.float32)
+            self._lr_dev_value = self.lr
+        return self._step_dev
+
+    def disable_device_state(self):
+        if self._step_dev is not None:
+            self.step_count = int(self._step_dev.item())
+        self._step_dev = self._lr_dev = self._lr_dev_value = None
+
+    def sync_lr(self):
+        if self._lr_dev is not None and self.lr != self._lr_dev_value:
+            self._lr_dev.fill_(self.lr)
+            self._lr_dev_value = self.lr
+
     # -- update ----------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -141,10 +166,18 @@ class FusedClipAdam(torch.optim.Optimizer):
                 self.grad[o:o + p.numel()].copy_(p.grad.reshape(-1))
                 p.grad = self.grad[o:o + p.numel()].view_as(p)
         g = self.param_groups[0]
-        self.step_count += 1
         st = _stream()
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
         _cabi.check(self._lib.matgcn_grad_sumsq(self.grad.data_ptr(), self.total, self._sumsq.data_ptr(), st), "grad_sumsq")
+        if self._step_dev is not None:
+            # the count was advanced on the device (matgcn_step_tick); the learning rate is read from device memory
+            _cabi.check(self._lib.matgcn_adam_clip_step_dev(
+                self.param.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.total,
+                self._sumsq.data_ptr(), float(self.max_grad_norm) if clip else 0.0, float(grad_scale), self._lr_dev.data_ptr(),
+                float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self._step_dev.data_ptr(), 1,
+                self.grad_norm.data_ptr(), st), "adam_clip_step_dev")
+            return loss
+        self.step_count += 1
         _cabi.check(self._lib.matgcn_adam_clip_step(
             self.param.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.total,
             self._sumsq.data_ptr(), float(self.max_grad_norm) if clip else 0.0, float(grad_scale), float(g["lr"]),
@@ -193,6 +226,13 @@ def fused_train_step(model, batch, opt: FusedClipAdam, micro_batches: int = 1):
     of the samples, and accumulates their gradients in the flat bucket before the single update: the saved activations of only
     one slice are alive at a time (the N = 8192 shape at 64 samples per GPU needs it).  The result equals the one-shot step
     whenever the loss is a mean over samples with equal mask density per slice (the same caveat as batch sharding)."""
+    if opt._step_dev is not None:
+        raise MatgcnError("fused_train_step: the optimiser's step state lives on the device (a GraphedTrainStep owns it); "
+                          "call that object, or its close(), instead")
+    return _train_step_body(model, batch, opt, micro_batches)
+
+
+def _train_step_body(model, batch, opt: FusedClipAdam, micro_batches: int = 1):
     opt.zero_grad()
     if micro_batches <= 1:
         loss = model.calculate_loss(batch)
@@ -211,6 +251,116 @@ def fused_train_step(model, batch, opt: FusedClipAdam, micro_batches: int = 1):
     scale = opt.all_reduce()
     opt.step(grad_scale=scale)
     return loss
+
+
+class GraphedTrainStep:
+    """``fused_train_step`` captured ONCE as a CUDA graph and replayed for every step: the loop body of
+    ``TrafficStateExecutor._train_epoch`` (executor:413-422) becomes one ``cudaGraphLaunch`` - ~80 launches of this library, the
+    ~80 small torch kernels of the view fusion / gradient accumulation, the memsets and copies, with their launch gaps and
+    2.6 - 3.2 ms of host enqueue time per step gone.
+
+    What changes from step to step lives in device memory and is advanced by the graph's first node (``matgcn_step_tick``):
+    Adam's step count (bias corrections) and the dropout key (a replay draws a new mask, as ``F.dropout`` does, MA.py:416).  The
+    learning rate is a device scalar too; ``__call__`` pushes ``param_groups[0]['lr']`` when a scheduler changed it.  The batch
+    is copied into static buffers (``self.batch``) before the replay; the returned loss is a static device scalar.
+
+    Data-parallel runs capture zero_grad .. backward and issue the all-reduce and the update eagerly after the replay (three
+    more launches) unless ``capture_collective=True``.
+
+    Not capturable (raises): ``add_static`` models - the reference re-draws a randomised ``torch.pca_lowrank`` on the host in
+    every forward (MA.py:405-409).  Semantics are those of ``fused_train_step``; tests/test_gpu_train.py compares the two step
+    by step."""
+
+    def __init__(self, model, opt: FusedClipAdam, example_batch, micro_batches: int = 1, warmup: int = 2,
+                 capture_collective: bool = False):
+        if getattr(model, "static", None) is not None:
+            raise MatgcnError("GraphedTrainStep: add_static models draw a host-side randomised PCA in every forward and cannot "
+                              "be captured; use fused_train_step")
+        if not model.training:
+            raise MatgcnError("GraphedTrainStep captures a TRAIN step: call model.train() first")
+        self.model, self.opt, self.micro_batches = model, opt, int(micro_batches)
+        dev = opt.param.device
+        self.batch = {k: torch.empty_like(v, device=dev).copy_(v) for k, v in example_batch.items() if torch.is_tensor(v)}
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._split = world > 1 and not capture_collective
+        self._lib = _cabi.lib()
+        # device-resident step state
+        self._step_dev = opt.enable_device_state()
+        self._key_dev = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(dev)
+        model._dropout_key_dev = self._key_dev
+        model._dropout_key_host = int(torch.randint(0, 2 ** 62, (1,)).item())
+        # warm-up on a side stream (lazy initialisation inside torch / the library), then put the training state back
+        keep = [t.clone() for t in (opt.param, opt.exp_avg, opt.exp_avg_sq, self._step_dev, self._key_dev)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._body(eager=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.no_grad():
+            for t, k in zip((opt.param, opt.exp_avg, opt.exp_avg_sq, self._step_dev, self._key_dev), keep):
+                t.copy_(k)
+        torch.cuda.synchronize(dev)
+        n0 = self._lib.matgcn_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body(eager=False)
+        self.library_kernel_nodes = int(self._lib.matgcn_launch_count() - n0)   # this library's kernels inside one replay
+
+    def _body(self, eager: bool):
+        opt = self.opt
+        _cabi.check(self._lib.matgcn_step_tick(self._key_dev.data_ptr(), self._step_dev.data_ptr(), _stream()), "step_tick")
+        if self._split and not eager:
+            # data parallel: the graph ends after the backward; all-reduce + update follow eagerly in __call__
+            opt.zero_grad()
+            return self._fwd_bwd()
+        loss = _train_step_body(self.model, self.batch, opt, self.micro_batches)
+        return loss
+
+    def _fwd_bwd(self):
+        model, batch, mb = self.model, self.batch, self.micro_batches
+        if mb <= 1:
+            loss = model.calculate_loss(batch)
+            loss.backward()
+            return loss.detach()
+        total = next(iter(batch.values())).shape[0]
+        bounds = [total * i // mb for i in range(mb + 1)]
+        loss = None
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            if hi == lo:
+                continue
+            part = model.calculate_loss({k: v[lo:hi] for k, v in batch.items()}) * ((hi - lo) / total)
+            part.backward()
+            loss = part.detach() if loss is None else loss + part.detach()
+        return loss
+
+    def load_batch(self, batch, non_blocking: bool = True):
+        """Copies a batch (host or device tensors of the captured shapes) into the static input buffers."""
+        for k, dst in self.batch.items():
+            src = batch[k]
+            if src.shape != dst.shape:
+                raise MatgcnError("GraphedTrainStep: batch['%s'] has shape %s, the captured step has %s (capture another one for "
+                                  "a ragged last batch)" % (k, tuple(src.shape), tuple(dst.shape)))
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=non_blocking)
+
+    def __call__(self, batch=None):
+        """One train step; ``batch=None`` reuses whatever ``self.batch`` holds.  Returns the (static) device loss tensor."""
+        if batch is not None:
+            self.load_batch(batch)
+        self.opt.sync_lr()
+        self.graph.replay()
+        if self._split:
+            scale = self.opt.all_reduce()
+            self.opt.step(grad_scale=scale)
+        self.opt.step_count += 1   # host mirror (checkpoints: state_dict reads it)
+        return self.loss
+
+    def close(self):
+        """Hands the step state back to the host side of the optimiser (eager ``fused_train_step`` works again)."""
+        self.opt.disable_device_state()
+        self.model._dropout_key_dev = None
+        self.graph = None
 
 
 class DeviceWindowBank:

@@ -392,3 +392,92 @@ def test_fused_loss_matches_masked_mae_of_the_reference(mean, std):
     l0 = ops.masked_mae_loss(p0, y0, mean, std)
     l0.backward()
     assert l0.item() == 0.0 and p0.grad.abs().max().item() == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# f1: the whole loop body (executor:413-422) as ONE captured CUDA graph
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,n,b", [("exact", 23, 4), ("bf16", 40, 16)])
+def test_graphed_train_step_replays_match_eager_steps(mode, n, b):
+    """train.GraphedTrainStep: capture once, replay five times (new batch, new dropout mask, advancing Adam step count, a
+    learning-rate change on the way) against five eager ``fused_train_step`` calls that are handed the same dropout keys.
+    bf16 case: B = 16, H = 64 takes the persistent cooperative recurrence kernels, i.e. cooperative launches inside the graph."""
+    from multistgraph_b200 import _cabi
+    from multistgraph_b200.model import MultiATGCN
+    from multistgraph_b200.synthetic import make_batch, make_config, make_data_feature
+    from multistgraph_b200.train import FusedClipAdam, GraphedTrainStep, fused_train_step
+
+    dev = _dev()
+    cfg = make_config(adjtype="multi", adpadj="bidirection", embed_dim=8, output_window=6, batch_size=b, device=dev, matgcn_mode=mode)
+    df = make_data_feature(n, seed=3)
+    torch.manual_seed(0)
+    me = MultiATGCN(dict(cfg), df).to(dev).train()
+    torch.manual_seed(0)
+    mg = MultiATGCN(dict(cfg), df).to(dev).train()
+    mg.load_state_dict(me.state_dict())
+    oe = FusedClipAdam(me.parameters(), lr=0.003, max_grad_norm=5.0)
+    og = FusedClipAdam(mg.parameters(), lr=0.003, max_grad_norm=5.0)
+    batches = [{k: v.to(dev) for k, v in make_batch(n, b, 6, seed=20 + i).items()} for i in range(5)]
+    step = GraphedTrainStep(mg, og, batches[0])
+    assert step.library_kernel_nodes > 10
+    # the warm-up steps inside the constructor must leave no trace in the training state
+    for (k, p), (_, q) in zip(me.named_parameters(), mg.named_parameters()):
+        assert torch.equal(p, q), k
+    assert int(step._step_dev.item()) == 0 and float(og.exp_avg.abs().max()) == 0.0
+    # eager arm: same key sequence (host half XOR a device half advanced by the same tick), host-side step count
+    me._dropout_key_host = mg._dropout_key_host
+    me._dropout_key_dev = step._key_dev.clone()
+    lib = _cabi.lib()
+    tol = 1e-4 if mode == "exact" else 2e-2
+    losses = []
+    for i, batch in enumerate(batches):
+        if i == 3:
+            oe.lr = og.lr = 0.0015     # what MultiStepLR does between epochs (executor:155-197)
+        _cabi.check(lib.matgcn_step_tick(me._dropout_key_dev.data_ptr(), None, torch.cuda.current_stream().cuda_stream), "tick")
+        le = float(fused_train_step(me, {k: v.clone() for k, v in batch.items()}, oe))
+        lg = float(step({k: v.clone() for k, v in batch.items()}))
+        losses.append(lg)
+        assert abs(le - lg) <= tol * abs(le), (i, le, lg)
+        assert abs(float(oe.grad_norm) - float(og.grad_norm)) <= 10 * tol * float(oe.grad_norm), i
+    assert torch.equal(me._dropout_key_dev, step._key_dev)
+    assert int(step._step_dev.item()) == 5 and og.step_count == 5 and oe.step_count == 5
+    probe = {k: v.to(dev) for k, v in make_batch(n, b, 6, seed=99).items()}
+    me.eval(); mg.eval()
+    with torch.no_grad():
+        ye, yg = me.predict(probe), mg.predict(probe)
+    assert (ye - yg).abs().max() <= 20 * tol * ye.abs().max()
+    # a replay with a frozen model draws a NEW dropout mask: same batch, lr = 0, different loss
+    mg.train()
+    og.lr = 0.0
+    l1, l2 = float(step(batches[0])), float(step())
+    assert l1 != l2 and abs(l1 - l2) < 0.2 * abs(l1)
+    # checkpoints keep working: the state dict carries the host mirror of the step count; close() returns to eager stepping
+    assert float(og.state_dict()["state"][0]["step"]) == 7.0
+    step.close()
+    og.lr = 0.003
+    fused_train_step(mg, batches[1], og)
+    assert og.step_count == 8
+
+
+def test_graphed_train_step_refuses_what_it_cannot_capture():
+    from multistgraph_b200._cabi import MatgcnError
+    from multistgraph_b200.model import MultiATGCN
+    from multistgraph_b200.synthetic import make_batch, make_config, make_data_feature
+    from multistgraph_b200.train import FusedClipAdam, GraphedTrainStep, fused_train_step
+
+    dev = _dev()
+    n, b = 11, 4
+    cfg = make_config(adjtype="multi", adpadj="bidirection", embed_dim=6, output_window=6, batch_size=b, device=dev)
+    model = MultiATGCN(dict(cfg), make_data_feature(n, seed=3)).to(dev).eval()
+    opt = FusedClipAdam(model.parameters(), lr=0.003, max_grad_norm=5.0)
+    batch = {k: v.to(dev) for k, v in make_batch(n, b, 6, seed=1).items()}
+    with pytest.raises(MatgcnError):
+        GraphedTrainStep(model, opt, batch)          # eval mode
+    model.train()
+    step = GraphedTrainStep(model, opt, batch)
+    with pytest.raises(MatgcnError):
+        fused_train_step(model, batch, opt)          # the step state lives on the device now
+    with pytest.raises(MatgcnError):
+        step({k: v[:2] for k, v in batch.items()})   # ragged batch
+    step.close()
+    fused_train_step(model, batch, opt)
