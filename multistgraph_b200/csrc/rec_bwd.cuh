@@ -55,7 +55,9 @@ struct RecBwdP {
     float* DHC; float* dmix;
     unsigned int* gbar;
     long long* dbg;      // optional phase timeline of CTA 0 (tools/rec_timeline.py)
-    int prefetch;        // warp 3 pulls the next step's saved activations into L2 during the dense phase B
+    int prefetch;        // warp 3, during the dense phases: bit 0 pulls the next step's saved activations into L2 (phase B), bit 1 the
+                         // hidden-row weight blocks of this CTA's nodes for the per-node products that follow (MATGCN_REC_BWD_PF)
+    const __nv_bfloat16* WG16; const __nv_bfloat16* WU16;
 };
 
 __device__ __forceinline__ float4 rb2_ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -363,16 +365,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         // ================================ L2 prefetch ================================
         // the saved activations the head of the NEXT reverse step (t - 1) reads on this CTA, requested while the dense phase B
         // of step t runs
+        const int I = p.Cin + H;
+        auto pf_weights = [&](const __nv_bfloat16* W, int ow) {   // per node and support one contiguous block of 64 rows x ow bf16
+            const int units = ((node_tiles - (int)blockIdx.x + G - 1) / G) * K;
+            for (int u = lane; u < units; u += 32) {
+                const int n = blockIdx.x + (u / K) * G, k = u - (u / K) * K;
+                const __nv_bfloat16* src = W + (((long long)n * K + k) * I + p.Cin) * ow;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(H * ow * 2) : "memory");
+            }
+        };
         uint32_t nb = 1;   // barriers passed when phase B of the first step begins
-        for (int t = T - 1; t >= 1 && p.prefetch; --t, nb += 4) {
+        for (int t = T - 1; t >= 0 && p.prefetch; --t, nb += 4) {
             while (*phase_cnt < nb) __nanosleep(256);
-            const long long tU = (long long)(t - 1) * p.U;
-            const float* arr[9] = {p.H1 + tU, p.R2 + tU, p.HC2 + tU, p.Z2 + tU, p.R + tU, p.HC + tU, p.Z + tU,
-                                   p.PH + (long long)(t - 1) * K * p.U, p.dy + (long long)(t - 1) * p.dy_tstride};
-            for (int n = blockIdx.x; n < node_tiles; n += G) {
-                const long long base = (long long)n * p.B * H;
-                for (int a = 0; a < 9; ++a)
-                    for (int idx = lane; idx < p.B * 2; idx += 32) pf_l2(arr[a] + base + idx * 32);
+            if (p.prefetch & 2) pf_weights(p.WG16, 2 * H);   // phase C: [gz | gr] Wg^T
+            if ((p.prefetch & 1) && t >= 1) {
+                const long long tU = (long long)(t - 1) * p.U;
+                const float* arr[9] = {p.H1 + tU, p.R2 + tU, p.HC2 + tU, p.Z2 + tU, p.R + tU, p.HC + tU, p.Z + tU,
+                                       p.PH + (long long)(t - 1) * K * p.U, p.dy + (long long)(t - 1) * p.dy_tstride};
+                for (int n = blockIdx.x; n < node_tiles; n += G) {
+                    const long long base = (long long)n * p.B * H;
+                    for (int a = 0; a < 9; ++a)
+                        for (int idx = lane; idx < p.B * 2; idx += 32) pf_l2(arr[a] + base + idx * 32);
+                }
+            }
+            if ((p.prefetch & 2) && t >= 1) {
+                while (*phase_cnt < nb + 2) __nanosleep(256);   // phase D of this step: the next step's phase A multiplies with Wu^T
+                pf_weights(p.WU16, H);
             }
         }
     } else if (warp >= 4) {
@@ -767,10 +785,11 @@ cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
     p.DPZA = a.DPZA; p.DPHA = a.DPHA;
     p.DHC = a.DHC; p.dmix = a.dmix;
     p.gbar = a.gbar;
+    p.WG16 = a.WG16; p.WU16 = a.WU16;
     p.dbg = tc_debug_buffer();
     {
-        const char* e = getenv("MATGCN_REC_PF");
-        p.prefetch = (e && e[0] == '1');   // off by default: the fill traffic costs the dense phase more than the head gains
+        const char* e = getenv("MATGCN_REC_BWD_PF");
+        p.prefetch = e ? atoi(e) & 3 : 0;   // bit 0 off by default: the fill traffic costs the dense phase more than the head gains
     }
     const void* al[] = {a.dy, a.PH, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.RgH, a.RuH, a.DR, a.DG16, a.DPT0, a.DPT16, a.DHD,
                         a.DHD2, a.DZC, a.DHC};

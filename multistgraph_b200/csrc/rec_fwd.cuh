@@ -70,7 +70,9 @@ struct RecFwdP {
     __nv_bfloat16* PH16; __nv_bfloat16* PZ16;
     unsigned int* gbar;  // zeroed grid-barrier counter
     long long* dbg;      // optional timeline of CTA 0 (tools/rec_timeline.py)
-    int prefetch;        // warp 3 pulls GX[t] / RX[t] into L2 during the propagation phases (MATGCN_REC_PF=1 turns it on)
+    int prefetch;        // warp 3, during the propagation phases (L2 -> SM bound, HBM idle): bit 0 pulls GX[t] / RX[t] into L2, bit 1 the
+                         // hidden-row weight blocks of this CTA's nodes that the per-node phase after it streams (MATGCN_REC_PF)
+    const __nv_bfloat16* WG16; const __nv_bfloat16* WU16;   // raw pointers of the weight twins (for the prefetch)
 };
 
 __device__ __forceinline__ unsigned int rf_ld_acquire(const unsigned int* p) {
@@ -409,13 +411,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
         // ================================ L2 prefetch of epilogue inputs ================================
         // While a propagation phase runs (L2 -> SM bound, HBM idle) pull the pre-activation rows the per-node phase after it
         // reads on this CTA: GX[t] during M*h, RX[t] during M*(z*h).
+        const int I = p.Cin + H;
         for (int t = 0; t < T && p.prefetch; ++t) {
             for (int part = 0; part < 2; ++part) {
                 const float* X = (part == 0 ? p.GX : p.RX) + (long long)t * 3 * p.U;
                 while (*phase_cnt < (uint32_t)(4 * t + 2 * part)) __nanosleep(256);
-                for (int n = blockIdx.x; n < node_tiles; n += G) {
-                    const float* base = X + (long long)n * p.B * 3 * H;
-                    for (int idx = lane; idx < p.B * 6; idx += 32) pf_l2(base + idx * 32);   // rows of 3H floats = 6 lines
+                if (p.prefetch & 2) {
+                    // per node and support one contiguous block: gate 64 rows x 128 bf16 = 16 KB, candidate 64 x 64 = 8 KB
+                    const int ow = part == 0 ? 2 * H : H;
+                    const __nv_bfloat16* W = part == 0 ? p.WG16 : p.WU16;
+                    const int units = ((node_tiles - (int)blockIdx.x + G - 1) / G) * K;
+                    for (int u = lane; u < units; u += 32) {
+                        const int n = blockIdx.x + (u / K) * G, k = u - (u / K) * K;
+                        const __nv_bfloat16* src = W + (((long long)n * K + k) * I + p.Cin) * ow;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(H * ow * 2) : "memory");
+                    }
+                }
+                if (p.prefetch & 1) {
+                    for (int n = blockIdx.x; n < node_tiles; n += G) {
+                        const float* base = X + (long long)n * p.B * 3 * H;
+                        for (int idx = lane; idx < p.B * 6; idx += 32) pf_l2(base + idx * 32);   // rows of 3H floats = 6 lines
+                    }
                 }
             }
         }
@@ -815,8 +831,9 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
     p.dbg = tc_debug_buffer();
     {
         const char* e = getenv("MATGCN_REC_PF");
-        p.prefetch = (e && e[0] == '1');   // off by default: measured within noise (the fill traffic costs the propagation what the epilogues gain)
+        p.prefetch = e ? atoi(e) & 3 : 0;   // bit 0 (GX / RX) measured within noise: the fill traffic costs the propagation what the epilogues gain
     }
+    p.WG16 = a.WG16; p.WU16 = a.WU16;
     const float* al[] = {a.GX, a.RX, a.PH, a.PZ, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.ZH2, a.RgH, a.RuH};
     for (const float* q : al)
         if (reinterpret_cast<uintptr_t>(q) & 31) return cudaErrorNotSupported;
