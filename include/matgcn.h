@@ -197,6 +197,24 @@ int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int K, int ldm
                              float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
                              int flags, void* stream);
 
+/* Layer chaining (fast bf16 mode, Cin == H): an inner ATGRUEncoder layer (MA.py:200-211: layer l+1 consumes layer l's output
+ * sequence) reads its input where the previous layer left it instead of copying and re-propagating it.  x must be the previous
+ * layer's output view (ws_prev + matgcn_encoder_layer_y_offset, time stride matgcn_encoder_layer_y_tstride) and x16_chain the
+ * address of the previous layer's bf16 state twin one step in: (char*)ws_prev + 4*matgcn_encoder_layer_slot_offset("PH16", prev dims)
+ * + 2*K*N*B*H.  The previous layer's PH16[t+1, 1..K) = M h_t IS this layer's M x_t; only the last step is propagated, into the
+ * spare slots PH16_prev[T, 1..K).  matgcn_encoder_layer_chain_ok tells whether the shape / mode qualifies (the _chained entry
+ * points fail otherwise); the previous layer's workspace must stay alive and unchanged until this layer's backward has run. */
+int matgcn_encoder_layer_chain_ok(int T, int N, int B, int Cin, int H, int K, int ldm, int flags);
+int matgcn_encoder_layer_fwd_chained(int T, int N, int B, int Cin, int H, int K, int ldm, const float* x, long long x_tstride,
+                                     void* x16_chain, const float* h0, const float* M, const float* Wg, const float* bg,
+                                     const float* Wu, const float* bu, const float* Rgw, const float* Rgb, const float* Ruw,
+                                     const float* Rub, const float* mix, float* ws, int flags, void* stream);
+int matgcn_encoder_layer_bwd_chained(int T, int N, int B, int Cin, int H, int K, int ldm, int n_adp, const float* dy,
+                                     long long dy_tstride, const float* M, const float* Wg, const float* Wu, const float* Rgw,
+                                     const float* Ruw, const float* mix, float* ws, float* bws, float* dx, float* dh0, float* dM,
+                                     float* dWg, float* dbg, float* dWu, float* dbu, float* dRgw, float* dRgb, float* dRuw,
+                                     float* dRub, float* dmix, int flags, const float* x_chain, const void* x16_chain, void* stream);
+
 /* -------------------------------------------------------------------------------------------
  * gcn_off ablation layer: a plain GRU whose nn.Linear weights are shared by all nodes,
  * replaces GRUCell.forward MA.py:142-150 used as the main cell (MA.py:187-192, 204) over the whole window.

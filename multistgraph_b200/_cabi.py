@@ -56,6 +56,12 @@ _SIGNATURES = {
                                                        _F, _F, c_int, c_void_p]),
     "matgcn_encoder_layer_bwd": (c_int, [c_int] * 8 + [_F, c_longlong, _F, _F, _F, _F, _F, _F, _F, _F,
                                                        _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_int, c_void_p]),
+    "matgcn_encoder_layer_chain_ok": (c_int, [c_int] * 8),
+    "matgcn_encoder_layer_fwd_chained": (c_int, [c_int] * 7 + [_F, c_longlong, c_void_p, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F,
+                                                               _F, _F, c_int, c_void_p]),
+    "matgcn_encoder_layer_bwd_chained": (c_int, [c_int] * 8 + [_F, c_longlong, _F, _F, _F, _F, _F, _F, _F, _F,
+                                                               _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_int, _F, c_void_p,
+                                                               c_void_p]),
     "matgcn_dense_gru_layer_fwd_ws_bytes": (c_size_t, [c_int] * 5),
     "matgcn_dense_gru_layer_bwd_ws_bytes": (c_size_t, [c_int] * 5),
     "matgcn_dense_gru_layer_y_offset": (c_size_t, [c_int] * 5),

@@ -1063,7 +1063,7 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     // bf16 twins (sizes in floats = elements / 2): base matrices, PH / PZ / PX (same layouts as the fp32 arrays: slot 0 =
     // the state itself, slots 1.. = its propagated copies) and the per-node weights
     w.M16 = take(((size_t)(K - 1) * N * 8 * ((N + 7) / 8 + 1)) / 2 + 64);
-    w.PH16 = take((((size_t)T * K + 1) * w.U) / 2 + 64);
+    w.PH16 = take((((size_t)T * K + K) * w.U) / 2 + 64);   // (+ slots [T, 1..K): written by a chained next layer, see encoder_layer_fwd_impl)
     w.PZ16 = take(((size_t)T * K * w.U) / 2 + 64);
     w.PX16 = take(((size_t)T * K * w.UX) / 2 + 64);
     w.WG16 = take(((size_t)N * K * (Cin + H) * 2 * H) / 2 + 64);
@@ -1114,7 +1114,7 @@ extern "C" size_t matgcn_encoder_layer_slot_offset(const char* name, int T, int 
     const LayerWs w = layer_ws(T, N, B, Cin, H, K);
     struct { const char* n; size_t v; } tab[] = {{"PX", w.PX}, {"GX", w.GX}, {"RX", w.RX}, {"PH", w.PH}, {"PZ", w.PZ},
                                                  {"Z", w.Z}, {"R", w.R}, {"HC", w.HC}, {"H1", w.H1}, {"Z2", w.Z2},
-                                                 {"R2", w.R2}, {"HC2", w.HC2}, {"ZH2", w.ZH2}};
+                                                 {"R2", w.R2}, {"HC2", w.HC2}, {"ZH2", w.ZH2}, {"PH16", w.PH16}};
     for (auto& e : tab)
         if (strcmp(e.n, name) == 0) return e.v;
     return (size_t)-1;
@@ -1261,11 +1261,28 @@ extern "C" int matgcn_gemm_debug_bf16(int a_kc, int b_kc, int M, int N, int K, c
 // ------------------------------------------------------------------------------------------
 // encoder layer forward
 // ------------------------------------------------------------------------------------------
-extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int K, int ldm,
+// Layer chaining (bf16 mode, Cin == H): the input of an inner layer is the previous layer's output, and its propagated copies
+// M x_t are what the previous layer's recurrence already computed for its OWN next step (PH16[t+1, 1..K) = M h_t, same bf16
+// operands).  With x16_chain = &PH16_prev[1, 0] the layer reads x (fp32: slot 0 of the previous PH, same time stride) and its
+// bf16 slots where they sit: no copy, and only the last time step is propagated (into PH16_prev[T, 1..K), which exists for this).
+static bool chain_ok(int T, int N, int B, int Cin, int H, int K, int ldm, int flags) {
+    const char* e = getenv("MATGCN_CHAIN");
+    if (e && e[0] == '0') return false;
+    const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
+    const size_t m16_cap = ((size_t)(K - 1) * N * 8 * ((N + 7) / 8 + 1));
+    const bool bf = tc && (flags & MATGCN_FLAG_BF16) != 0 && (size_t)(K - 1) * N * ldm <= m16_cap;
+    const bool skip32 = bf && !(H & 7) && !(ldm & 7) && B >= 8;
+    return T >= 1 && skip32 && Cin == H && !xside_small_ok(Cin, H, K) && !(Cin & 7);
+}
+extern "C" int matgcn_encoder_layer_chain_ok(int T, int N, int B, int Cin, int H, int K, int ldm, int flags) {
+    return chain_ok(T, N, B, Cin, H, K, ldm, flags) ? 1 : 0;
+}
+
+static int encoder_layer_fwd_impl(int T, int N, int B, int Cin, int H, int K, int ldm,
                                         const float* x, long long x_tstride, const float* h0, const float* M,
                                         const float* Wg, const float* bg, const float* Wu, const float* bu,
                                         const float* Rgw, const float* Rgb, const float* Ruw, const float* Rub,
-                                        const float* mix, float* ws, int flags, void* stream) {
+                                        const float* mix, float* ws, int flags, void* x16_chain, void* stream) {
     const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     REQUIRE(x && M && Wg && bg && Wu && bu && Rgw && Rgb && Ruw && Rub && mix && ws, "null pointer");
     if (check_layer_dims(T, N, B, Cin, H, K, ldm)) return -1;
@@ -1285,9 +1302,18 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     __nv_bfloat16* PX16 = reinterpret_cast<__nv_bfloat16*>(ws + w.PX16);
     __nv_bfloat16* WG16 = reinterpret_cast<__nv_bfloat16*>(ws + w.WG16);
     __nv_bfloat16* WU16 = reinterpret_cast<__nv_bfloat16*>(ws + w.WU16);
+    const bool chained = x16_chain != nullptr;
+    if (chained) {
+        REQUIRE(chain_ok(T, N, B, Cin, H, K, ldm, flags) && x_tstride == K * UX && aligned16(x) && aligned16(x16_chain),
+                "chained input does not qualify (matgcn_encoder_layer_chain_ok)");
+        PX = const_cast<float*>(x);   // read only from here on: slot 0 of the previous layer's PH, time stride K*U
+        PX16 = reinterpret_cast<__nv_bfloat16*>(x16_chain);
+    }
     // x -> slot 0 of PX[t] (and of its bf16 twin: one pass over x when the rows allow 16-byte accesses)
     const bool twin_copy = bf && !(UX & 3) && !(x_tstride & 3) && aligned16(x) && aligned16(PX) && aligned16(PX16);
-    if (twin_copy) {
+    if (chained) {
+        // nothing to copy
+    } else if (twin_copy) {
         copy_twin_kernel<<<148 * 16, 256, 0, st>>>(x, x_tstride, PX, PX16, K * UX, UX >> 2, T);
         count_launch();
         CK(cudaGetLastError());
@@ -1297,7 +1323,7 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     }
     if (bf) {
         CK(to_bf16(M, 0, M16, 0, (long long)Kp * N * ldm, 1, st));
-        if (!twin_copy) CK(to_bf16(x, x_tstride, PX16, K * UX, UX, T, st));
+        if (!twin_copy && !chained) CK(to_bf16(x, x_tstride, PX16, K * UX, UX, T, st));
         // per-node weights: 2-byte twins are what the step contractions stream (and, marked evict-last, what stays in L2
         // across the 24 steps: 49 MB per layer at the Baltimore size instead of 99 MB of fp32 from HBM every step)
         CK(to_bf16(Wg, 0, WG16, 0, (long long)N * K * I * 2 * H, 1, st));
@@ -1309,14 +1335,16 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     const bool skip32 = bf && !(H & 7) && !(ldm & 7) && B >= 8;  // (B = reduction length of the weight gradients)
     const bool skip32x = skip32 && !xside_small_ok(Cin, H, K) && !(Cin & 7);
     const bool warm = l2_warm_layer(N, K, Cin, H, B);
-    // PX[t, 1..K) = M * x_t  (all t at once)
+    // PX[t, 1..K) = M * x_t  (all t at once; a chained layer finds t < T-1 in place and propagates the last step only)
     {
-        GemmP pp = prop_params(M, ldm, N, Kp, PX, B * Cin);
+        const long long t0 = chained ? (long long)(T - 1) * K * UX : 0;
+        GemmP pp = prop_params(M, ldm, N, Kp, PX + t0, B * Cin);
         pp.sB1 = K * UX;
-        EpiPlain e = epi_plain(PX + UX, K * UX, 0, B * Cin);
-        if (bf) { pp.A16 = M16; pp.B16 = PX16; e.C16 = PX16 + UX; }
+        EpiPlain e = epi_plain(PX + t0 + UX, K * UX, 0, B * Cin);
+        if (bf) { pp.A16 = M16; pp.B16 = PX16 + t0; e.C16 = PX16 + t0 + UX; }
         if (skip32x) e.c_z2_hi = 0;   // every consumer of PX[t, k >= 1] reads the bf16 twin
-        CK((gemm_any<CfgBig, true, false>(tc, pp, e, T, st)));
+        if (chained) pp.need16 = 1;   // (the fp32 slots k >= 1 do not exist behind a chained input)
+        CK((gemm_any<CfgBig, true, false>(tc, pp, e, chained ? 1 : T, st)));
     }
     TR();
 
@@ -1533,18 +1561,35 @@ extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int
     tr.report("encoder_layer_fwd");
     return 0;
 }
+extern "C" int matgcn_encoder_layer_fwd(int T, int N, int B, int Cin, int H, int K, int ldm,
+                                        const float* x, long long x_tstride, const float* h0, const float* M,
+                                        const float* Wg, const float* bg, const float* Wu, const float* bu,
+                                        const float* Rgw, const float* Rgb, const float* Ruw, const float* Rub,
+                                        const float* mix, float* ws, int flags, void* stream) {
+    return encoder_layer_fwd_impl(T, N, B, Cin, H, K, ldm, x, x_tstride, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, ws, flags,
+                                  nullptr, stream);
+}
+extern "C" int matgcn_encoder_layer_fwd_chained(int T, int N, int B, int Cin, int H, int K, int ldm,
+                                                const float* x, long long x_tstride, void* x16_chain, const float* h0, const float* M,
+                                                const float* Wg, const float* bg, const float* Wu, const float* bu,
+                                                const float* Rgw, const float* Rgb, const float* Ruw, const float* Rub,
+                                                const float* mix, float* ws, int flags, void* stream) {
+    REQUIRE(x16_chain, "null chain pointer");
+    return encoder_layer_fwd_impl(T, N, B, Cin, H, K, ldm, x, x_tstride, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, ws, flags,
+                                  x16_chain, stream);
+}
 
 // ------------------------------------------------------------------------------------------
 // encoder layer backward
 // ------------------------------------------------------------------------------------------
-extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int K, int ldm, int n_adp,
+static int encoder_layer_bwd_impl(int T, int N, int B, int Cin, int H, int K, int ldm, int n_adp,
                                         const float* dy, long long dy_tstride, const float* M,
                                         const float* Wg, const float* Wu, const float* Rgw, const float* Ruw,
                                         const float* mix, float* ws, float* bws,
                                         float* dx, float* dh0, float* dM,
                                         float* dWg, float* dbg, float* dWu, float* dbu,
                                         float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
-                                        int flags, void* stream) {
+                                        int flags, const float* x_chain, const void* x16_chain, void* stream) {
     const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     REQUIRE(dy && M && Wg && Wu && Rgw && Ruw && mix && ws && bws, "null pointer");
     REQUIRE(dx && dM && dWg && dbg && dWu && dbu && dRgw && dRgb && dRuw && dRub && dmix, "null output pointer");
@@ -1557,6 +1602,10 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     const int Kp = K - 1, I = Cin + H;
     const long long U = (long long)w.U, UX = (long long)w.UX;
     float* PX = ws + w.PX; float* DG = ws + w.GX; float* DR = ws + w.RX; float* PH = ws + w.PH; float* PZ = ws + w.PZ;
+    if (x16_chain) {   // the forward pass read its input where the previous layer left it (encoder_layer_fwd_impl)
+        REQUIRE(x_chain && chain_ok(T, N, B, Cin, H, K, ldm, flags), "chained input does not qualify");
+        PX = const_cast<float*>(x_chain);   // read only
+    }
     float* DPX = bws + bw.DPX; float* DPT = bws + bw.DPT; float* DPHA = bws + bw.DPHA; float* DPZA = bws + bw.DPZA;
     float* DH1 = bws + bw.DH1; float* DHD = bws + bw.DHD; float* DHC = bws + bw.DHC; float* DRES = bws + bw.DRES;
     const int NB = N * B;
@@ -1724,7 +1773,7 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     p.A = PH; p.B = DG; p.N = 2 * H;
     const __nv_bfloat16* PH16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PH16);  // bf16 twins written by the forward pass
     const __nv_bfloat16* PZ16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PZ16);
-    const __nv_bfloat16* PX16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.PX16);
+    const __nv_bfloat16* PX16 = x16_chain ? reinterpret_cast<const __nv_bfloat16*>(x16_chain) : reinterpret_cast<const __nv_bfloat16*>(ws + w.PX16);
     if (bf) { p.A16 = PH16; p.B16 = DG16T; }   // these contractions stream the saved state: half the bytes with the twins
     p.need16 = skip32 ? 1 : 0;                 // (and in that case the forward never wrote the fp32 PH / PZ slots k >= 1)
     CK((gemm_any<CfgMid, false, false>(tc, p, epi_store(dWg + (long long)Cin * 2 * H, (long long)K * I * 2 * H, (long long)I * 2 * H, 2 * H), N * K, st)));
@@ -1972,6 +2021,29 @@ extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int
     }
     tr.report("encoder_layer_bwd");
     return 0;
+}
+extern "C" int matgcn_encoder_layer_bwd(int T, int N, int B, int Cin, int H, int K, int ldm, int n_adp,
+                                        const float* dy, long long dy_tstride, const float* M,
+                                        const float* Wg, const float* Wu, const float* Rgw, const float* Ruw,
+                                        const float* mix, float* ws, float* bws,
+                                        float* dx, float* dh0, float* dM,
+                                        float* dWg, float* dbg, float* dWu, float* dbu,
+                                        float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
+                                        int flags, void* stream) {
+    return encoder_layer_bwd_impl(T, N, B, Cin, H, K, ldm, n_adp, dy, dy_tstride, M, Wg, Wu, Rgw, Ruw, mix, ws, bws, dx, dh0, dM, dWg, dbg,
+                                  dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, flags, nullptr, nullptr, stream);
+}
+extern "C" int matgcn_encoder_layer_bwd_chained(int T, int N, int B, int Cin, int H, int K, int ldm, int n_adp,
+                                                const float* dy, long long dy_tstride, const float* M,
+                                                const float* Wg, const float* Wu, const float* Rgw, const float* Ruw,
+                                                const float* mix, float* ws, float* bws,
+                                                float* dx, float* dh0, float* dM,
+                                                float* dWg, float* dbg, float* dWu, float* dbu,
+                                                float* dRgw, float* dRgb, float* dRuw, float* dRub, float* dmix,
+                                                int flags, const float* x_chain, const void* x16_chain, void* stream) {
+    REQUIRE(x_chain && x16_chain, "null chain pointer");
+    return encoder_layer_bwd_impl(T, N, B, Cin, H, K, ldm, n_adp, dy, dy_tstride, M, Wg, Wu, Rgw, Ruw, mix, ws, bws, dx, dh0, dM, dWg, dbg,
+                                  dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, flags, x_chain, x16_chain, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -107,7 +107,7 @@ class _NodeWeightsFn(torch.autograd.Function):
 
 class _EncoderLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags):
+    def forward(ctx, x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags, prev):
         if not x.is_cuda or x.dtype != torch.float32:
             raise _cabi.MatgcnError("encoder_layer: x must be a float32 CUDA tensor (no CPU path)")
         T, N, B, Cin = x.shape
@@ -129,14 +129,30 @@ class _EncoderLayerFn(torch.autograd.Function):
         L = _cabi.lib()
         dims = (T, N, B, Cin, H, K)
         ws = torch.empty(L.matgcn_encoder_layer_fwd_ws_bytes(*dims) // 4, device=x.device, dtype=torch.float32)
-        _cabi.check(L.matgcn_encoder_layer_fwd(*dims, ldm, _ptr(x), x.stride(0), _ptr(h0), _ptr(M), _ptr(Wg), _ptr(bg),
-                                               _ptr(Wu), _ptr(bu), _ptr(Rgw), _ptr(Rgb), _ptr(Ruw), _ptr(Rub),
-                                               _ptr(mix), _ptr(ws), int(flags), _stream()), "matgcn_encoder_layer_fwd")
+        # layer chaining (include/matgcn.h): x is the previous layer's output view inside ITS workspace -> read it (and the bf16
+        # propagated copies the previous recurrence already produced) in place
+        ctx.chain = None
+        if prev is not None and L.matgcn_encoder_layer_chain_ok(*dims, ldm, int(flags)):
+            pws, pdims = prev
+            if (pdims[0], pdims[1], pdims[2], pdims[4], pdims[5]) == (T, N, B, H, K) and pdims[4] == Cin \
+                    and x.data_ptr() == pws.data_ptr() + 4 * L.matgcn_encoder_layer_y_offset(*pdims) \
+                    and x.stride(0) == L.matgcn_encoder_layer_y_tstride(*pdims):
+                x16 = pws.data_ptr() + 4 * L.matgcn_encoder_layer_slot_offset(b"PH16", *pdims) + 2 * K * N * B * H
+                ctx.chain = (pws, x.data_ptr(), x16)     # (the tensor keeps the previous workspace alive until our backward)
+        if ctx.chain is not None:
+            _cabi.check(L.matgcn_encoder_layer_fwd_chained(*dims, ldm, _ptr(x), x.stride(0), ctx.chain[2], _ptr(h0), _ptr(M), _ptr(Wg),
+                                                           _ptr(bg), _ptr(Wu), _ptr(bu), _ptr(Rgw), _ptr(Rgb), _ptr(Ruw), _ptr(Rub),
+                                                           _ptr(mix), _ptr(ws), int(flags), _stream()), "matgcn_encoder_layer_fwd_chained")
+        else:
+            _cabi.check(L.matgcn_encoder_layer_fwd(*dims, ldm, _ptr(x), x.stride(0), _ptr(h0), _ptr(M), _ptr(Wg), _ptr(bg),
+                                                   _ptr(Wu), _ptr(bu), _ptr(Rgw), _ptr(Rgb), _ptr(Ruw), _ptr(Rub),
+                                                   _ptr(mix), _ptr(ws), int(flags), _stream()), "matgcn_encoder_layer_fwd")
         y = torch.as_strided(ws, (T, N, B, H), (L.matgcn_encoder_layer_y_tstride(*dims), B * H, H, 1),
                              L.matgcn_encoder_layer_y_offset(*dims))
         ctx.save_for_backward(M, Wg, Wu, Rgw, Ruw, mix)
         ctx.ws = ws
         ctx.dims, ctx.ldm, ctx.n_adp, ctx.has_h0, ctx.flags = dims, ldm, int(n_adp), h0 is not None, int(flags)
+        _EncoderLayerFn._last_ws = (ws, dims)   # picked up by ops.encoder_layer (a Function cannot return a python tuple)
         return y
 
     @staticmethod
@@ -156,13 +172,22 @@ class _EncoderLayerFn(torch.autograd.Function):
         dh0 = new(N, B, H) if ctx.has_h0 else None
         dWg, dbg, dWu, dbu = new(N, K, I, 2 * H), new(N, 2 * H), new(N, K, I, H), new(N, H)
         dRgw, dRgb, dRuw, dRub, dmix = new(2 * H, I), new(2 * H), new(H, I), new(H), new(T)
-        _cabi.check(L.matgcn_encoder_layer_bwd(T, N, B, Cin, H, K, ctx.ldm, ctx.n_adp, _ptr(dy), dy.stride(0), _ptr(M),
-                                               _ptr(Wg), _ptr(Wu), _ptr(Rgw), _ptr(Ruw), _ptr(mix), _ptr(ctx.ws),
-                                               _ptr(bws), _ptr(dx), _ptr(dh0), _ptr(dM), _ptr(dWg), _ptr(dbg),
-                                               _ptr(dWu), _ptr(dbu), _ptr(dRgw), _ptr(dRgb), _ptr(dRuw), _ptr(dRub),
-                                               _ptr(dmix), ctx.flags, _stream()), "matgcn_encoder_layer_bwd")
+        if ctx.chain is not None:
+            _cabi.check(L.matgcn_encoder_layer_bwd_chained(T, N, B, Cin, H, K, ctx.ldm, ctx.n_adp, _ptr(dy), dy.stride(0), _ptr(M),
+                                                           _ptr(Wg), _ptr(Wu), _ptr(Rgw), _ptr(Ruw), _ptr(mix), _ptr(ctx.ws),
+                                                           _ptr(bws), _ptr(dx), _ptr(dh0), _ptr(dM), _ptr(dWg), _ptr(dbg),
+                                                           _ptr(dWu), _ptr(dbu), _ptr(dRgw), _ptr(dRgb), _ptr(dRuw), _ptr(dRub),
+                                                           _ptr(dmix), ctx.flags, ctx.chain[1], ctx.chain[2], _stream()),
+                        "matgcn_encoder_layer_bwd_chained")
+        else:
+            _cabi.check(L.matgcn_encoder_layer_bwd(T, N, B, Cin, H, K, ctx.ldm, ctx.n_adp, _ptr(dy), dy.stride(0), _ptr(M),
+                                                   _ptr(Wg), _ptr(Wu), _ptr(Rgw), _ptr(Ruw), _ptr(mix), _ptr(ctx.ws),
+                                                   _ptr(bws), _ptr(dx), _ptr(dh0), _ptr(dM), _ptr(dWg), _ptr(dbg),
+                                                   _ptr(dWu), _ptr(dbu), _ptr(dRgw), _ptr(dRgb), _ptr(dRuw), _ptr(dRub),
+                                                   _ptr(dmix), ctx.flags, _stream()), "matgcn_encoder_layer_bwd")
         ctx.ws = None  # GX/RX slots now hold gradients: the workspace is spent
-        return dx, dh0, dM, dWg, dbg, dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, None, None
+        ctx.chain = None
+        return dx, dh0, dM, dWg, dbg, dWu, dbu, dRgw, dRgb, dRuw, dRub, dmix, None, None, None
 
 
 class _DenseGRULayerFn(torch.autograd.Function):
@@ -372,7 +397,12 @@ def node_weights(E, pool, bias_pool, c, flags=0):
 def encoder_layer(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags=0):
     """x [T,N,B,Cin] node-major -> y [T,N,B,H] (a strided view into the layer's workspace).
     flags: _cabi.FLAG_EXACT (fp32 FFMA) or _cabi.FLAG_TF32 (tcgen05 tensor cores)."""
-    return _EncoderLayerFn.apply(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags)
+    y = _EncoderLayerFn.apply(x, h0, M, Wg, bg, Wu, bu, Rgw, Rgb, Ruw, Rub, mix, n_adp, flags, getattr(x, "_matgcn_layer", None))
+    ws = getattr(_EncoderLayerFn, "_last_ws", None)
+    _EncoderLayerFn._last_ws = None
+    if ws is not None:
+        y._matgcn_layer = ws     # (workspace tensor, dims) of the layer that produced y: lets the next layer chain onto it
+    return y
 
 
 MODES = {"exact": _cabi.FLAG_EXACT, "fp32": _cabi.FLAG_EXACT, "fast": _cabi.FLAG_TF32, "tf32": _cabi.FLAG_TF32,

@@ -124,3 +124,39 @@ def test_persistent_kernels_stay_inside_their_workspaces():
     for name, big, n in (("forward", big_ws, nws), ("reverse", big_bws, nbws)):
         assert (big[:guard] == sentinel).all() and (big[guard + n:] == sentinel).all(), "%s workspace overrun" % name
     assert torch.isfinite(ws).all() and all(torch.isfinite(o).all() for o in outs if o is not None)
+
+
+@pytest.mark.parametrize("N,B,rec", [(70, 16, True), (45, 8, False), (403, 64, True)])
+def test_chained_inner_layer_matches_copy_and_repropagate(N, B, rec):
+    """Layer chaining (include/matgcn.h, matgcn_encoder_layer_fwd_chained): layer 1 reads its input and the propagated bf16
+    copies M x_t where layer 0's recurrence left them (PH16[t+1, 1..K) = M h_t) instead of copying x and propagating all T
+    steps again.  Same operands, same products: forecasts and every gradient agree with the unchained path (MATGCN_CHAIN=0)
+    far inside the bf16 mode's bound.  rec=False: the one-launch-per-phase path produces the same twins."""
+    import os
+
+    cfg = make_config(adjtype="multi", adpadj="bidirection", embed_dim=10, output_window=6, batch_size=B,
+                      device=torch.device(DEV), matgcn_mode="bf16")
+    df = make_data_feature(N, seed=5)
+    batch = make_batch(N, B, 6, seed=5)
+    torch.manual_seed(4)
+    model = MultiATGCN(dict(cfg), df).to(DEV).eval()
+    lib = _cabi.lib()
+    old = os.environ.get("MATGCN_CHAIN")
+    try:
+        os.environ["MATGCN_CHAIN"] = "0"
+        y0, g0, n0 = _run(model, batch, lib, rec)
+        os.environ["MATGCN_CHAIN"] = "1"
+        y1, g1, n1 = _run(model, batch, lib, rec)
+    finally:
+        if old is None:
+            os.environ.pop("MATGCN_CHAIN", None)
+        else:
+            os.environ["MATGCN_CHAIN"] = old
+    assert n1 < n0, "the chained layer should drop the input copy (%d vs %d launches)" % (n1, n0)
+    errs = {"forecast": max_rel_err(y1, y0)}
+    for k in g0:
+        errs[k] = max_rel_err(g1[k], g0[k])
+    print("[chained vs unchained N=%d B=%d] worst %.2e (%s), forecast %.2e" % (N, B, max(errs.values()), max(errs, key=errs.get), errs["forecast"]))
+    assert errs["forecast"] < 2e-3
+    bad = {k: v for k, v in errs.items() if not (v < 5e-3)}
+    assert not bad, bad
