@@ -58,6 +58,7 @@ struct RecBwdP {
     int prefetch;        // warp 3, during the dense phases: bit 0 pulls the next step's saved activations into L2 (phase B), bit 1 the
                          // hidden-row weight blocks of this CTA's nodes for the per-node products that follow (MATGCN_REC_BWD_PF)
     const __nv_bfloat16* WG16; const __nv_bfloat16* WU16;
+    int stream_hint;     // 1: saved activations (read once) and DG / DR (written once) carry the L2 evict-first hint (MATGCN_REC_BWD_HINT)
 };
 
 __device__ __forceinline__ float4 rb2_ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
         const uint32_t s_off = (uint32_t)(half * 8192 + b0 * 128);   // tf32 tiles: slab `half` (+ 2 for the dar2 columns)
         const uint32_t s_x = (uint32_t)(b0 & 7);
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const uint64_t pol = rf_policy_stream(p.stream_hint);
         for (int t = T - 1; t >= 0; --t) {
             for (int ph = 0; ph < 4; ++ph) {
                 long long tl = t;
@@ -459,12 +461,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                             for (int m2 = 0; m2 < 2; ++m2) {
                                 const long long o = o0 + rd[w] * H + 16 * m2;
                                 const int e = 2 * w + m2;
-                                dyv[e] = ld4(dYt + o);
+                                dyv[e] = ld4h(dYt + o, pol);
                                 cv[e] = rb2_ldcg4(p.DZC + o);
                                 dv[e] = ld4(p.DHD2 + o);
-                                h1[e] = ld4(p.H1 + tU + o);
-                                r2v[e] = ld4(p.R2 + tU + o);
-                                hc2[e] = ld4(p.HC2 + tU + o);
+                                h1[e] = ld4h(p.H1 + tU + o, pol);
+                                r2v[e] = ld4h(p.R2 + tU + o, pol);
+                                hc2[e] = ld4h(p.HC2 + tU + o, pol);
                             }
                         }
                     };
@@ -490,8 +492,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 if (ok[w]) {
                                     dmix_part += (pr.x + pr.y) + (pr.z + pr.w);
                                     const long long x = x0 + w * 8 * 3 * H + 16 * m2;
-                                    st4(p.DR + 3 * tU + x + 2 * H, da3);
-                                    st4(p.DR + 3 * tU + x + H, dar);
+                                    st4h(p.DR + 3 * tU + x + 2 * H, da3, pol);
+                                    st4h(p.DR + 3 * tU + x + H, dar, pol);
                                 }
                                 const uint32_t so = s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4);
                                 rf_sts4(a1_s + so, da3);
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int m2 = 0; m2 < 2; ++m2) z2[2 * w + m2] = ld4(p.Z2 + tU + o0 + rd[w] * H + 16 * m2);
+                            for (int m2 = 0; m2 < 2; ++m2) z2[2 * w + m2] = ld4h(p.Z2 + tU + o0 + rd[w] * H + 16 * m2, pol);
                         }
                         float4 rr[4], hc[4], hp[4];
 #pragma unroll
@@ -514,8 +516,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
 #pragma unroll
                             for (int m2 = 0; m2 < 2; ++m2) {
                                 const long long o = o0 + rd[w] * H + 16 * m2;
-                                rr[2 * w + m2] = ld4(p.R + tU + o);
-                                hc[2 * w + m2] = ld4(p.HC + tU + o);
+                                rr[2 * w + m2] = ld4h(p.R + tU + o, pol);
+                                hc[2 * w + m2] = ld4h(p.HC + tU + o, pol);
                                 hp[2 * w + m2] = ld4(Hp + o);
                             }
                         }
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 const int e = 2 * w + m2;
                                 const float4 daz = fa[e] * h1[e] * z2[e] * one_minus(z2[e]);
                                 dh1[e] = dh1[e] + fa[e] * z2[e];
-                                if (ok[w]) st4(p.DR + 3 * tU + x0 + w * 8 * 3 * H + 16 * m2, daz);
+                                if (ok[w]) st4h(p.DR + 3 * tU + x0 + w * 8 * 3 * H + 16 * m2, daz, pol);
                                 rf_sts4(a2_s + s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4), daz);
                             }
                         }
@@ -563,8 +565,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                     const long long o = o0 + w * 8 * H + 16 * m2, x = x0 + w * 8 * 3 * H + 16 * m2;
                                     st4(p.DHD + o, d * rr[e]);
                                     if (p.DG) {   // (null: every consumer of DG reads the bf16 twin)
-                                        st4(p.DG + 3 * tU + x + 2 * H, gu);
-                                        st4(p.DG + 3 * tU + x + H, gr);
+                                        st4h(p.DG + 3 * tU + x + 2 * H, gu, pol);
+                                        st4h(p.DG + 3 * tU + x + H, gr, pol);
                                     }
                                     st4_bf16(p.DG16 + 3 * tU + x + 2 * H, gu);
                                     st4_bf16(p.DG16 + 3 * tU + x + H, gr);
@@ -638,7 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 const int e = 2 * w + m2;
                                 dz[e] = rb2_ldcg4(p.DZC + o);
                                 d0[e] = ld4(p.DPT0 + o);
-                                zz[e] = ld4(p.Z + tU + o);
+                                zz[e] = ld4h(p.Z + tU + o, pol);
                                 hp[e] = ld4(Hp + o);
                                 dd[e] = ld4(p.DHD + o);
                             }
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                                 const float4 gz = dzh * hp[e] * zz[e] * one_minus(zz[e]);
                                 if (ok[w]) {
                                     const long long x = x0 + w * 8 * 3 * H + 16 * m2;
-                                    if (p.DG) st4(p.DG + 3 * tU + x, gz);
+                                    if (p.DG) st4h(p.DG + 3 * tU + x, gz, pol);
                                     st4_bf16(p.DG16 + 3 * tU + x, gz);
                                 }
                                 if (ok[w]) st4(p.DHD + o0 + w * 8 * H + 16 * m2, dk[e]);   // DHD += dzh z (read back after the products)
@@ -786,6 +788,10 @@ cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
     p.DHC = a.DHC; p.dmix = a.dmix;
     p.gbar = a.gbar;
     p.WG16 = a.WG16; p.WU16 = a.WU16;
+    {
+        const char* e = getenv("MATGCN_REC_BWD_HINT");
+        p.stream_hint = e ? (atoi(e) & 1) : 1;   // measured: forward launch -1.3 %, reverse launch -3.3 % (profiles/r2k_ab_l2_hints.txt)
+    }
     p.dbg = tc_debug_buffer();
     {
         const char* e = getenv("MATGCN_REC_BWD_PF");

@@ -73,6 +73,8 @@ struct RecFwdP {
     int prefetch;        // warp 3, during the propagation phases (L2 -> SM bound, HBM idle): bit 0 pulls GX[t] / RX[t] into L2, bit 1 the
                          // hidden-row weight blocks of this CTA's nodes that the per-node phase after it streams (MATGCN_REC_PF)
     const __nv_bfloat16* WG16; const __nv_bfloat16* WU16;   // raw pointers of the weight twins (for the prefetch)
+    int stream_hint;     // bit 0: read-once inputs / write-once outputs carry the L2 evict-first hint, bit 1: so do the TMA reads of the
+                         // propagated state rows (MATGCN_REC_HINT, default 3)
 };
 
 __device__ __forceinline__ unsigned int rf_ld_acquire(const unsigned int* p) {
@@ -145,6 +147,22 @@ __device__ __forceinline__ void rf_st8(void* p, const uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ float2 rf_ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void rf_st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+// L2 eviction hints for the data that is touched once per launch (pre-activation inputs read, saved activations written): marked
+// evict-first so that what IS reused every step - the per-node weight blocks (evict-last), the state twins - stays in the 126 MB L2
+__device__ __forceinline__ uint64_t rf_policy_stream(int on) {
+    uint64_t pol;
+    if (on) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld4h(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st4h(float* p, const float4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void rf_proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // fine-grained timeline of CTA 0 at the middle time step: slot s of tile i (first four tiles of the CTA) of phase ph
@@ -228,6 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0, nbar = 0;
             const uint64_t pol = l2_policy_evict_last();
+            const uint64_t pol_once = rf_policy_stream(p.stream_hint & 2);   // propagated state rows: dead (for this launch) once read here
             for (int t = 0; t < T; ++t) {
                 for (int ph = 0; ph < 4; ++ph) {
                     const bool prop = ph == 0 || ph == 2, gate = ph == 1;
@@ -255,7 +274,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                             tma_load_5d(sa + RF_A_BYTES, tb, fb, tn * 128, kt * 64, slot, 0, 0);
                             tma_load_5d(sa + RF_A_BYTES + 8192, tb, fb, tn * 128 + 64, kt * 64, slot, 0, 0);
                         } else {
-                            tma_load_5d(sa, ta, fb, 0, 0, tile, slot + kt, 0);
+                            if (kt > 0) tma_load_5d_hint(sa, ta, fb, 0, 0, tile, slot + kt, 0, pol_once);
+                            else tma_load_5d(sa, ta, fb, 0, 0, tile, slot + kt, 0);   // (slot 0 = the state itself: the dense phase's operand)
                         }
                     };
                     // before the grid barrier: arm the first stages of this CTA's first tile and request their constant operands
@@ -456,6 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
         const uint32_t s_off = (uint32_t)(half * 8192 + b0 * 128);
         const uint32_t s_x = (uint32_t)(b0 & 7);
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const uint64_t pol = rf_policy_stream(p.stream_hint & 1);
         for (int t = 0; t < T; ++t) {
             for (int ph = 0; ph < 4; ++ph) {
                 if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[(t * 4 + ph) * 4 + 0] = clock64();
@@ -518,9 +539,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
 #pragma unroll
                             for (int m2 = 0; m2 < 2; ++m2) {
                                 const long long o = o0 + rd[w] * H + 16 * m2, x = x0 + rd[w] * 3 * H + 16 * m2;
-                                gz[2 * w + m2] = ld4(GXt + x);
+                                gz[2 * w + m2] = ld4h(GXt + x, pol);
                                 hz[2 * w + m2] = ld4(PHt + o);
-                                gr[2 * w + m2] = ld4(GXt + x + H);
+                                gr[2 * w + m2] = ld4h(GXt + x + H, pol);
                             }
                         }
                     };
@@ -561,7 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                                 if (ok[w]) {
                                     const int e = 2 * w + m2;
                                     const long long o = o0 + w * 8 * H + 16 * m2;
-                                    st4(Zt + o, fz[e]);
+                                    st4h(Zt + o, fz[e], pol);
                                     st4_bf16(PZ16t + o, zh[e]);   // (every consumer of z*h reads the bf16 twin: no fp32 copy)
                                     st4(Rt + o, fr[e]);
                                 }
@@ -590,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
 #pragma unroll
                             for (int m2 = 0; m2 < 2; ++m2) {
                                 const long long o = o0 + rd[w] * H + 16 * m2, x = x0 + rd[w] * 3 * H + 16 * m2;
-                                gc[2 * w + m2] = ld4(GXt + x + 2 * H);
+                                gc[2 * w + m2] = ld4h(GXt + x + 2 * H, pol);
                                 rr[2 * w + m2] = ld4(Rt + o);
                                 hh[2 * w + m2] = ld4(PHt + o);
                             }
@@ -618,8 +639,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
 #pragma unroll
                             for (int m2 = 0; m2 < 2; ++m2) {
                                 const long long x = x0 + rd[w] * 3 * H + 16 * m2;
-                                xz[2 * w + m2] = ld4(RXt + x);
-                                xr[2 * w + m2] = ld4(RXt + x + H);
+                                xz[2 * w + m2] = ld4h(RXt + x, pol);
+                                xr[2 * w + m2] = ld4h(RXt + x + H, pol);
                             }
                         }
                         // stage 1: hc = tanh(acc + GX[:, 2H:]); h1 = r*h + (1-r)*hc -> HC, H1, operand tile S1
@@ -633,8 +654,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                                 h1[e] = rr[e] * hh[e] + one_minus(rr[e]) * hc;
                                 if (ok[w]) {
                                     const long long o = o0 + w * 8 * H + 16 * m2;
-                                    st4(p.HC + tU + o, hc);
-                                    st4(p.H1 + tU + o, h1[e]);
+                                    st4h(p.HC + tU + o, hc, pol);
+                                    st4h(p.H1 + tU + o, h1[e], pol);
                                 }
                                 rf_sts4(s1_s + s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4), h1[e]);
                             }
@@ -654,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {
 #pragma unroll
-                            for (int m2 = 0; m2 < 2; ++m2) xu[2 * w + m2] = ld4(RXt + x0 + rd[w] * 3 * H + 16 * m2 + 2 * H);
+                            for (int m2 = 0; m2 < 2; ++m2) xu[2 * w + m2] = ld4h(RXt + x0 + rd[w] * 3 * H + 16 * m2 + 2 * H, pol);
                         }
                         rf_quad4(a, fa, odd);
                         rf_quad4(c2, fc, odd);
@@ -668,9 +689,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                                 const float4 zh2 = z2 * h1[e];
                                 if (ok[w]) {
                                     const long long o = o0 + w * 8 * H + 16 * m2;
-                                    st4(p.Z2 + tU + o, z2);
-                                    st4(p.R2 + tU + o, r2[e]);
-                                    st4(p.ZH2 + tU + o, zh2);
+                                    st4h(p.Z2 + tU + o, z2, pol);
+                                    st4h(p.R2 + tU + o, r2[e], pol);
+                                    st4h(p.ZH2 + tU + o, zh2, pol);
                                 }
                                 rf_sts4(s2_s + s_off + (uint32_t)(w * 1024) + ((((uint32_t)(4 * m2 + pc)) ^ s_x) << 4), zh2);
                             }
@@ -698,7 +719,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                                     const float4 hc2 = tanh4(fa[e] + xu[e], 1);
                                     const float4 res = r2[e] * h1[e] + one_minus(r2[e]) * hc2;
                                     const float4 y = m * h1[e] + (1.f - m) * res;
-                                    st4(p.HC2 + tU + o, hc2);
+                                    st4h(p.HC2 + tU + o, hc2, pol);
                                     st4(Yt + o, y);
                                     st4_bf16(Y16t + o, y);
                                 }
@@ -834,6 +855,10 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
         p.prefetch = e ? atoi(e) & 3 : 0;   // bit 0 (GX / RX) measured within noise: the fill traffic costs the propagation what the epilogues gain
     }
     p.WG16 = a.WG16; p.WU16 = a.WU16;
+    {
+        const char* e = getenv("MATGCN_REC_HINT");
+        p.stream_hint = e ? (atoi(e) & 3) : 3;   // measured: forward launch -1.3 %, reverse launch -3.3 % (profiles/r2k_ab_l2_hints.txt)
+    }
     const float* al[] = {a.GX, a.RX, a.PH, a.PZ, a.Z, a.R, a.HC, a.H1, a.Z2, a.R2, a.HC2, a.ZH2, a.RgH, a.RuH};
     for (const float* q : al)
         if (reinterpret_cast<uintptr_t>(q) & 31) return cudaErrorNotSupported;
