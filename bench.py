@@ -289,7 +289,7 @@ def recurrence_roofline(model, batches, opt, train_step, lib, n_nodes, batch, k_
         return None
     fwd_ms, bwd_ms = f_ms.value / f_n.value, b_ms.value / b_n.value
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r2_rec_bwd_ncu.json")
+    prof = os.path.join(ROOT, "profiles", "r2m_rec_bwd_ncu.json")
     if os.path.exists(prof):
         with open(prof) as f:
             pj = json.load(f)
