@@ -815,6 +815,58 @@ static cudaError_t to_bf16(const float* src, long long spitch, __nv_bfloat16* ds
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// 3xTF32 (exact mode on the tensor cores, dense propagations only): x = hi + lo with hi = x truncated to TF32 (10 explicit
+// mantissa bits; the tensor core then reads it exactly) and lo = x - hi (exact in fp32, |lo| < 2^-10 |x|, read by the tensor core
+// to 10 bits: relative error 2^-20 of x).  a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (the dropped lo*lo term is 2^-20 relative) as
+// THREE k-batches of one TF32 contraction accumulated in fp32 in TMEM: operand slabs [hi, hi, lo] (pattern 0) against [hi, lo, hi]
+// (pattern 1).  src: n contiguous floats (n % 4 == 0, 16-byte aligned); dst: three slabs `slab` floats apart.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, long long n4, float* __restrict__ dst, long long slab,
+                                                     int pattern) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = ld4(src + 4 * i);
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
+        hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
+        hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
+        hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
+        st4(dst + 4 * i, hi);
+        st4(dst + slab + 4 * i, pattern == 0 ? hi : lo);
+        st4(dst + 2 * slab + 4 * i, pattern == 0 ? lo : hi);
+    }
+}
+static cudaError_t split3(const float* src, long long n, float* dst, long long slab, int pattern, cudaStream_t st) {
+    const long long n4 = n >> 2;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    split3_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n4, dst, slab, pattern);
+    count_launch();
+    return cudaGetLastError();
+}
+// MATGCN_EXACT_TC=0 keeps every contraction of the exact mode on the fp32 FFMA kernels (A/B comparisons, tests)
+static bool exact_tc_enabled() {
+    const char* e = getenv("MATGCN_EXACT_TC");
+    return !(e && e[0] == '0');
+}
+constexpr int EXACT_TC_MAX_N = 2048;   // the split copies of the base matrices are 3 (K-1) N ldm floats: kept for N up to here
+// One dense propagation of the exact mode as a 3-k-batch TF32 contraction on the tensor-core engine.  A3: the [hi, hi, lo] slabs of
+// the base matrices (slab stride sa), B: the fp32 operand (nb contiguous floats) whose [hi, lo, hi] slabs go to B3.
+// cudaErrorNotSupported: shape / alignment does not qualify - the caller runs the FFMA kernel.
+template <bool A_KC, class Epi>
+static cudaError_t prop_3xtf32(GemmP p, const Epi& epi, const float* A3, long long sa, float* B3, long long nb, cudaStream_t st) {
+    if (!A3 || !B3 || (nb & 3) || !aligned16(p.B) || !aligned16(B3) || !aligned16(A3) || (p.lda & 3) || (p.ldb & 3) || p.KB != 1)
+        return cudaErrorNotSupported;
+    cudaError_t e = split3(p.B, nb, B3, nb, 1, st);
+    if (e != cudaSuccess) return e;
+    p.A = A3; p.sAk = sa; p.B = B3; p.sBk = nb; p.KB = 3;
+    p.A16 = nullptr; p.B16 = nullptr; p.need16 = 0; p.npf = 0;
+    e = launch_gemm_tc<128, A_KC, false, Epi>(p, epi, 1, st);
+    if (e == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    return e;
+}
+
 // bf16 [N*K, Cin, 3H] concatenation of the input rows of the gate and candidate weights: WX[nk, i, 0:2H] = Wg[nk, i, :],
 // WX[nk, i, 2H:3H] = Wu[nk, i, :] (i < Cin) - lets the time-batched input gradient run as ONE contraction over 3H per support.
 // (H % 4 == 0: four columns per thread, 16-byte loads and 8-byte stores)
@@ -1031,7 +1083,7 @@ static GemmP prop_params(const float* M, int ldm, int N, int Kp, const float* sl
 // encoder layer: workspace layout
 // ------------------------------------------------------------------------------------------
 struct LayerWs {
-    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, R3X, RB3, BX3, MPH, M16, PH16, PZ16, PX16, WG16, WU16, WX16, total;
+    size_t PX, GX, RX, PH, PZ, Z, R, HC, H1, Z2, R2, HC2, ZH2, RGH, RUH, R3X, RB3, BX3, MPH, M16, PH16, PZ16, PX16, WG16, WU16, WX16, M3, X3, total;
     size_t U, UX;  // floats of one [N,B,H] / [N,B,Cin] block
 };
 static size_t align64(size_t v) { return (v + 63) / 64 * 64; }
@@ -1044,7 +1096,7 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.PX = take((size_t)T * K * w.UX);
     w.GX = take((size_t)T * 3 * w.U);
     w.RX = take((size_t)T * 3 * w.U);
-    w.PH = take(((size_t)T * K + 1) * w.U);
+    w.PH = take(((size_t)T * K + K) * w.U);   // (+ slots [T, 1..K): written by a chained next layer in the fp32-slot modes)
     w.PZ = take((size_t)T * K * w.U);
     w.Z = take((size_t)T * w.U);
     w.R = take((size_t)T * w.U);
@@ -1069,11 +1121,16 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     w.WG16 = take(((size_t)N * K * (Cin + H) * 2 * H) / 2 + 64);
     w.WU16 = take(((size_t)N * K * (Cin + H) * H) / 2 + 64);
     w.WX16 = take(((size_t)N * K * Cin * 3 * H) / 2 + 64);  // bf16 [N, K, Cin, 3H]: gate | candidate input-row weights (forward GX, backward DPX)
+    // exact mode, dense propagations as 3xTF32 (prop_3xtf32): [hi, hi, lo] slabs of the base matrices (kept for the backward) and the
+    // [hi, lo, hi] slabs of one step's state
+    const bool x3 = N <= EXACT_TC_MAX_N;
+    w.M3 = take(x3 ? (size_t)3 * (K - 1) * N * 8 * ((N + 7) / 8 + 1) : 0);
+    w.X3 = take(x3 ? (size_t)3 * w.U : 0);
     w.total = o;
     return w;
 }
 struct LayerBws {
-    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, total;
+    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, DPT3, total;
 };
 static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp) {
     LayerBws w;
@@ -1092,6 +1149,7 @@ static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp)
     w.DPT16 = take(((size_t)K * U) / 2 + 64);
     w.DPX16 = take(((size_t)T * K * UX) / 2 + 64);
     w.DG16 = take(((size_t)T * 3 * U) / 2 + 64);  // bf16 twin of the pre-activation gradients DG [T, N*B, 3H]
+    w.DPT3 = take(N <= EXACT_TC_MAX_N ? (size_t)3 * (K - 1) * U : 0);   // exact mode: [hi, lo, hi] slabs of DPT[1..K) (prop_3xtf32)
     w.total = o;
     return w;
 }
@@ -1261,18 +1319,21 @@ extern "C" int matgcn_gemm_debug_bf16(int a_kc, int b_kc, int M, int N, int K, c
 // ------------------------------------------------------------------------------------------
 // encoder layer forward
 // ------------------------------------------------------------------------------------------
-// Layer chaining (bf16 mode, Cin == H): the input of an inner layer is the previous layer's output, and its propagated copies
+// Layer chaining (Cin == H): the input of an inner layer is the previous layer's output, and its propagated copies
 // M x_t are what the previous layer's recurrence already computed for its OWN next step (PH16[t+1, 1..K) = M h_t, same bf16
 // operands).  With x16_chain = &PH16_prev[1, 0] the layer reads x (fp32: slot 0 of the previous PH, same time stride) and its
 // bf16 slots where they sit: no copy, and only the last time step is propagated (into PH16_prev[T, 1..K), which exists for this).
+// The exact and tf32 modes keep the propagated slots in fp32 (PH_prev[t+1, 1..K), same layout as PX) and chain onto those.
 static bool chain_ok(int T, int N, int B, int Cin, int H, int K, int ldm, int flags) {
     const char* e = getenv("MATGCN_CHAIN");
     if (e && e[0] == '0') return false;
+    if (T < 1 || Cin != H || xside_small_ok(Cin, H, K)) return false;
     const bool tc = (flags & MATGCN_FLAG_TF32) != 0;
     const size_t m16_cap = ((size_t)(K - 1) * N * 8 * ((N + 7) / 8 + 1));
     const bool bf = tc && (flags & MATGCN_FLAG_BF16) != 0 && (size_t)(K - 1) * N * ldm <= m16_cap;
-    const bool skip32 = bf && !(H & 7) && !(ldm & 7) && B >= 8;
-    return T >= 1 && skip32 && Cin == H && !xside_small_ok(Cin, H, K) && !(Cin & 7);
+    if (!bf) return true;   // fp32 slots (exact and tf32 modes): PH_prev[t+1, 1..K) = M h_t is this layer's PX[t, 1..K) as it stands
+    const bool skip32 = !(H & 7) && !(ldm & 7) && B >= 8;
+    return skip32 && !(Cin & 7);
 }
 extern "C" int matgcn_encoder_layer_chain_ok(int T, int N, int B, int Cin, int H, int K, int ldm, int flags) {
     return chain_ok(T, N, B, Cin, H, K, ldm, flags) ? 1 : 0;
@@ -1335,6 +1396,13 @@ static int encoder_layer_fwd_impl(int T, int N, int B, int Cin, int H, int K, in
     const bool skip32 = bf && !(H & 7) && !(ldm & 7) && B >= 8;  // (B = reduction length of the weight gradients)
     const bool skip32x = skip32 && !xside_small_ok(Cin, H, K) && !(Cin & 7);
     const bool warm = l2_warm_layer(N, K, Cin, H, B);
+    // exact mode: the dense propagations of the recurrence run as 3xTF32 on the tensor-core engine (prop_3xtf32)
+    const long long m3_slab = (long long)Kp * N * ldm;
+    const bool x3 = !tc && exact_tc_enabled() && N <= EXACT_TC_MAX_N && !(ldm & 3) && !((B * H) & 3) && aligned16(M) &&
+                    (size_t)m3_slab <= (size_t)Kp * N * 8 * ((N + 7) / 8 + 1);
+    float* M3 = x3 ? ws + w.M3 : nullptr;
+    float* X3 = x3 ? ws + w.X3 : nullptr;
+    if (x3) CK(split3(M, m3_slab, M3, m3_slab, 0, st));
     // PX[t, 1..K) = M * x_t  (all t at once; a chained layer finds t < T-1 in place and propagates the last step only)
     {
         const long long t0 = chained ? (long long)(T - 1) * K * UX : 0;
@@ -1343,7 +1411,7 @@ static int encoder_layer_fwd_impl(int T, int N, int B, int Cin, int H, int K, in
         EpiPlain e = epi_plain(PX + t0 + UX, K * UX, 0, B * Cin);
         if (bf) { pp.A16 = M16; pp.B16 = PX16 + t0; e.C16 = PX16 + t0 + UX; }
         if (skip32x) e.c_z2_hi = 0;   // every consumer of PX[t, k >= 1] reads the bf16 twin
-        if (chained) pp.need16 = 1;   // (the fp32 slots k >= 1 do not exist behind a chained input)
+        if (chained && skip32x) pp.need16 = 1;   // (bf16 mode: the fp32 slots k >= 1 do not exist behind a chained input)
         CK((gemm_any<CfgBig, true, false>(tc, pp, e, chained ? 1 : T, st)));
     }
     TR();
@@ -1503,7 +1571,10 @@ static int encoder_layer_fwd_impl(int T, int N, int B, int Cin, int H, int K, in
                     add_pf(p, WG16 + (long long)Cin * 2 * H, (long long)I * 2 * H * 2, (long long)H * 2 * H * 2, N * K);
                     if (l2_warm_level() >= 2) add_pf(p, GXt, 0, (long long)3 * U * 4, 1);   // its epilogue reads GX[t] (and the tail after it)
                 }
-                STEP_GEMM(0, CfgBig, true, false, p, e, 1);
+                cudaError_t xe = x3 ? prop_3xtf32<true>(p, e, M3, m3_slab, X3, U, st) : cudaErrorNotSupported;
+                if (xe == cudaSuccess) { TR(); }
+                else if (xe != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(xe));
+                else STEP_GEMM(0, CfgBig, true, false, p, e, 1);
             }
             // (b) gate: per node [B, K*H] x [K*H, 2H]
             memset(&p, 0, sizeof(p));
@@ -1523,7 +1594,10 @@ static int encoder_layer_fwd_impl(int T, int N, int B, int Cin, int H, int K, in
                     add_pf(pp, WU16 + (long long)Cin * H, (long long)I * H * 2, (long long)H * H * 2, N * K);
                     if (l2_warm_level() >= 2) add_pf(pp, RXt, 0, (long long)3 * U * 4, 1);  // the fused tail reads RX[t]
                 }
-                STEP_GEMM(2, CfgBig, true, false, pp, e, 1);
+                cudaError_t xe = x3 ? prop_3xtf32<true>(pp, e, M3, m3_slab, X3, U, st) : cudaErrorNotSupported;
+                if (xe == cudaSuccess) { TR(); }
+                else if (xe != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(xe));
+                else STEP_GEMM(2, CfgBig, true, false, pp, e, 1);
             }
             // (d) candidate
             p.A = PZt;
@@ -1627,6 +1701,12 @@ static int encoder_layer_bwd_impl(int T, int N, int B, int Cin, int H, int K, in
     // same rule as the forward pass: in bf16 mode the propagated slots k >= 1 (PH / PZ / PX there, DPT here) exist only as bf16 twins
     const bool skip32 = bf && !use_multi && !(H & 7) && !(ldm & 7) && B >= 8;
     const bool warm = l2_warm_layer(N, K, Cin, H, B);
+    // exact mode: the dense transposed propagations B4 / B6 as 3xTF32 against the [hi, hi, lo] slabs the forward pass left in ws
+    const long long m3_slab = (long long)Kp * N * ldm;
+    const bool x3 = !tc && exact_tc_enabled() && N <= EXACT_TC_MAX_N && !(ldm & 3) && !((B * H) & 3) && aligned16(M) &&
+                    (size_t)m3_slab <= (size_t)Kp * N * 8 * ((N + 7) / 8 + 1);
+    const float* M3 = x3 ? ws + w.M3 : nullptr;
+    float* DPT3 = x3 ? bws + bw.DPT3 : nullptr;
     bool rec_done = false, dg16_only = false;
     if (skip32 && H == 64 && rec_flag() && fused_tail_enabled()) {
         // the whole reverse-time recurrence as one persistent cooperative launch (rec_bwd.cuh)
@@ -1724,7 +1804,13 @@ static int encoder_layer_bwd_impl(int T, int N, int B, int Cin, int H, int K, in
             if (bf && warm) {   // B5 streams Wg16[n, k, Cin:, :]
                 add_pf(p, WG16 + (long long)Cin * 2 * H, (long long)I * 2 * H * 2, (long long)H * 2 * H * 2, N * K);
             }
-            STEP_GEMM(3, CfgBig, false, false, p, (EpiB4{DPT, PHt, Zt, DHD, DGt, H, B * H, DG16}), 1);
+            {
+                const EpiB4 e4{DPT, PHt, Zt, DHD, DGt, H, B * H, DG16};
+                cudaError_t xe = x3 ? prop_3xtf32<false>(p, e4, M3, m3_slab, DPT3, (long long)Kp * U, st) : cudaErrorNotSupported;
+                if (xe == cudaSuccess) { TR(); }
+                else if (xe != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(xe));
+                else STEP_GEMM(3, CfgBig, false, false, p, e4, 1);
+            }
             // B5: DPT[k][n] = dag[n] [B,2H] * Wg[n,k,Cin:,:]^T
             memset(&p, 0, sizeof(p));
             p.splits = 1; p.Z2 = K; p.KB = 1;
@@ -1759,7 +1845,13 @@ static int encoder_layer_bwd_impl(int T, int N, int B, int Cin, int H, int K, in
                     add_pf(p, ws + w.HC + (t - 1) * U, 0, ub, 1);
                 }
             }
-            STEP_GEMM(5, CfgBig, false, false, p, (EpiB6{DPT, DHD, DHC, B * H}), 1);
+            {
+                const EpiB6 e6{DPT, DHD, DHC, B * H};
+                cudaError_t xe = x3 ? prop_3xtf32<false>(p, e6, M3, m3_slab, DPT3, (long long)Kp * U, st) : cudaErrorNotSupported;
+                if (xe == cudaSuccess) { TR(); }
+                else if (xe != cudaErrorNotSupported) return fail(__func__, cudaGetErrorString(xe));
+                else STEP_GEMM(5, CfgBig, false, false, p, e6, 1);
+            }
         }
     }
     if (dh0) CK(cudaMemcpyAsync(dh0, DHC, sizeof(float) * U, cudaMemcpyDeviceToDevice, st));
