@@ -822,26 +822,30 @@ static cudaError_t to_bf16(const float* src, long long spitch, __nv_bfloat16* ds
 // THREE k-batches of one TF32 contraction accumulated in fp32 in TMEM: operand slabs [hi, hi, lo] (pattern 0) against [hi, lo, hi]
 // (pattern 1).  src: n contiguous floats (n % 4 == 0, 16-byte aligned); dst: three slabs `slab` floats apart.
 // ------------------------------------------------------------------------------------------
+// (rows x n floats, source row pitch `spitch`; the three destination slabs are dense [rows, n] blocks `slab` floats apart)
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, long long n4, float* __restrict__ dst, long long slab,
-                                                     int pattern) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 x = ld4(src + 4 * i);
+                                                     int pattern, int rows, long long spitch) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n4 * rows; j += (long long)gridDim.x * blockDim.x) {
+        const long long r = j / n4, i = j - r * n4;
+        const float4 x = ld4(src + r * spitch + 4 * i);
+        float* __restrict__ d = dst + r * (n4 * 4);
         float4 hi, lo;
         hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
         hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
         hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
         hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
-        st4(dst + 4 * i, hi);
-        st4(dst + slab + 4 * i, pattern == 0 ? hi : lo);
-        st4(dst + 2 * slab + 4 * i, pattern == 0 ? lo : hi);
+        st4(d + 4 * i, hi);
+        st4(d + slab + 4 * i, pattern == 0 ? hi : lo);
+        st4(d + 2 * slab + 4 * i, pattern == 0 ? lo : hi);
     }
 }
-static cudaError_t split3(const float* src, long long n, float* dst, long long slab, int pattern, cudaStream_t st) {
+static cudaError_t split3(const float* src, long long n, float* dst, long long slab, int pattern, cudaStream_t st, int rows = 1,
+                          long long spitch = 0) {
     const long long n4 = n >> 2;
-    long long blocks = (n4 + 255) / 256;
+    long long blocks = (n4 * rows + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    split3_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n4, dst, slab, pattern);
+    split3_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n4, dst, slab, pattern, rows, spitch);
     count_launch();
     return cudaGetLastError();
 }
@@ -865,6 +869,37 @@ static cudaError_t prop_3xtf32(GemmP p, const Epi& epi, const float* A3, long lo
     e = launch_gemm_tc<128, A_KC, false, Epi>(p, epi, 1, st);
     if (e == cudaSuccess) g_tc_launches.fetch_add(1, std::memory_order_relaxed);
     return e;
+}
+
+// A time-batched split-K contraction of the exact mode (dM: both operands K-major, one dense [M, K] / [N, K] block per time step,
+// KB = T k-batches, atomic epilogue) as 3xTF32: chunks of tc time steps, operand copies [term][tt][block] so that the k-batch
+// index (term, tt) keeps ONE stride; the chunks accumulate through the atomic epilogue.  scratch: >= 6 * tc * max(nA, nB) floats.
+template <class Epi>
+static cudaError_t tb_3xtf32(const GemmP& p, const Epi& epi, float* scratch, long long scratch_floats, cudaStream_t st) {
+    const long long nA = (long long)p.M * p.lda, nB = (long long)p.N * p.ldb;
+    if (!scratch || p.lda != p.K || p.ldb != p.K || (nA & 3) || (nB & 3) || (p.sAk & 3) || (p.sBk & 3) || !aligned16(p.A) || !aligned16(p.B) ||
+        !aligned16(scratch) || p.KB < 1)
+        return cudaErrorNotSupported;
+    long long tc = scratch_floats / (3 * (nA + nB));
+    if (tc > p.KB) tc = p.KB;
+    if (tc > 8) tc = 8;
+    if (tc < 1) return cudaErrorNotSupported;
+    float* A3 = scratch;
+    float* B3 = scratch + 3 * tc * nA;
+    for (int t0 = 0; t0 < p.KB; t0 += (int)tc) {
+        const int c = (int)((p.KB - t0) < tc ? (p.KB - t0) : tc);
+        cudaError_t e = split3(p.A + (long long)t0 * p.sAk, nA, A3, (long long)c * nA, 0, st, c, p.sAk);
+        if (e != cudaSuccess) return e;
+        e = split3(p.B + (long long)t0 * p.sBk, nB, B3, (long long)c * nB, 1, st, c, p.sBk);
+        if (e != cudaSuccess) return e;
+        GemmP q = p;
+        q.A = A3; q.sAk = nA; q.B = B3; q.sBk = nB; q.KB = 3 * c; q.splits = 3 * c;
+        q.A16 = nullptr; q.B16 = nullptr; q.need16 = 0; q.npf = 0;
+        e = launch_gemm_tc<128, true, true, Epi>(q, epi, 1, st);
+        if (e != cudaSuccess) return e;   // (NotSupported can only come from the first chunk: nothing has been accumulated yet)
+        g_tc_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return cudaSuccess;
 }
 
 // bf16 [N*K, Cin, 3H] concatenation of the input rows of the gate and candidate weights: WX[nk, i, 0:2H] = Wg[nk, i, :],
@@ -1130,7 +1165,7 @@ static LayerWs layer_ws(int T, int N, int B, int Cin, int H, int K) {
     return w;
 }
 struct LayerBws {
-    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, DPT3, total;
+    size_t DPX, DPT, DPHA, DPZA, DH1, DHD, DHC, DRES, MPH, DPT16, DPX16, DG16, DPT3, TB3, TB3_floats, total;
 };
 static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp) {
     LayerBws w;
@@ -1150,6 +1185,16 @@ static LayerBws layer_bws(int T, int N, int B, int Cin, int H, int K, int n_adp)
     w.DPX16 = take(((size_t)T * K * UX) / 2 + 64);
     w.DG16 = take(((size_t)T * 3 * U) / 2 + 64);  // bf16 twin of the pre-activation gradients DG [T, N*B, 3H]
     w.DPT3 = take(N <= EXACT_TC_MAX_N ? (size_t)3 * (K - 1) * U : 0);   // exact mode: [hi, lo, hi] slabs of DPT[1..K) (prop_3xtf32)
+    // exact mode: operand copies of the dM contractions (tb_3xtf32): up to eight time steps per chunk, at most 256 MB
+    w.TB3_floats = 0;
+    if (N <= EXACT_TC_MAX_N && n_adp > 0) {
+        const size_t um = U > UX ? U : UX;
+        size_t tcn = ((size_t)64 << 20) / (6 * um);
+        if (tcn > 8) tcn = 8;
+        if (tcn > (size_t)T) tcn = (size_t)T;
+        w.TB3_floats = tcn * 6 * um;
+    }
+    w.TB3 = take(w.TB3_floats);
     w.total = o;
     return w;
 }
@@ -2068,18 +2113,24 @@ static int encoder_layer_bwd_impl(int T, int N, int B, int Cin, int H, int K, in
         if (skip32) {   // the per-step adaptive slices were kept as bf16 (D2h above); h_t has its bf16 twin in slot 0 of PH16
             p.A16 = reinterpret_cast<const __nv_bfloat16*>(DPHA) + (long long)a * U; p.B16 = PH16; p.need16 = 1;
         }
-        CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
+        // (exact mode: 3xTF32 on the tensor-core engine when the shape qualifies, else the FFMA kernel)
+        auto dm_term = [&](const GemmP& q) -> cudaError_t {
+            cudaError_t xe = (x3 && bw.TB3_floats) ? tb_3xtf32(q, ea, bws + bw.TB3, (long long)bw.TB3_floats, st) : cudaErrorNotSupported;
+            if (xe == cudaErrorNotSupported) xe = gemm_any<CfgBig, true, true>(tc, q, ea, 1, st);
+            return xe;
+        };
+        CK(dm_term(p));
         TR();
         p.A = DPZA + (long long)a * U; p.B = PZ;
         if (skip32) { p.A16 = reinterpret_cast<const __nv_bfloat16*>(DPZA) + (long long)a * U; p.B16 = PZ16; }
-        CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
+        CK(dm_term(p));
         TR();
         p.K = B * Cin; p.lda = B * Cin; p.ldb = B * Cin;
         p.A = DPX + (long long)(a + 1) * UX; p.sAk = K * UX; p.B = PX; p.sBk = K * UX;
         p.A16 = nullptr; p.B16 = nullptr; p.need16 = 0;
         if (bf && !small_x && !(Cin & 7)) { p.A16 = DPX16 + (long long)(a + 1) * UX; p.B16 = PX16; }
         p.need16 = dpx16_only ? 1 : 0;
-        CK((gemm_any<CfgBig, true, true>(tc, p, ea, 1, st)));
+        CK(dm_term(p));
         TR();
     }
     // residual GRU weights: dRgw[:, Cin:] = sum DR[:,0:2H]^T H1 ; dRgw[:, 0:Cin] = sum DR[:,0:2H]^T x ; same for Ruw
