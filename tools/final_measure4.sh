@@ -4,8 +4,10 @@
 TAG=${1:-final}
 O=gpurun_out
 python -m pytest tests -m gpu -q > $O/gpu_tests_$TAG.log 2>&1; tail -2 $O/gpu_tests_$TAG.log
+python __graft_entry__.py --smoke > $O/smoke_$TAG.log 2>&1; tail -4 $O/smoke_$TAG.log
 python bench.py > $O/bench_${TAG}_bf16.json 2> $O/bench_${TAG}.err
 python bench.py --mode tf32 --no-cpu-baseline --no-exact-leg --no-strong-leg > $O/bench_${TAG}_tf32.json 2>> $O/bench_${TAG}.err
+python bench.py --mode exact --no-cpu-baseline --no-exact-leg --no-strong-leg --steps 5 --warmup 2 > $O/bench_${TAG}_exact.json 2>> $O/bench_${TAG}.err
 for w in dc_multi dc_adaptive_only pems07_scale; do
   python bench.py --workload $w --no-cpu-baseline --no-exact-leg --no-strong-leg > $O/bench_${TAG}_$w.json 2>> $O/bench_${TAG}.err
 done
