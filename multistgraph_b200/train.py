@@ -272,7 +272,7 @@ class GraphedTrainStep:
     by step."""
 
     def __init__(self, model, opt: FusedClipAdam, example_batch, micro_batches: int = 1, warmup: int = 2,
-                 capture_collective: bool = False):
+                 capture_collective: bool = False, input_slots: int = 1):
         if getattr(model, "static", None) is not None:
             raise MatgcnError("GraphedTrainStep: add_static models draw a host-side randomised PCA in every forward and cannot "
                               "be captured; use fused_train_step")
@@ -280,7 +280,13 @@ class GraphedTrainStep:
             raise MatgcnError("GraphedTrainStep captures a TRAIN step: call model.train() first")
         self.model, self.opt, self.micro_batches = model, opt, int(micro_batches)
         dev = opt.param.device
-        self.batch = {k: torch.empty_like(v, device=dev).copy_(v) for k, v in example_batch.items() if torch.is_tensor(v)}
+        # input_slots > 1: that many sets of static input buffers, one captured graph each (they share one memory pool: the graphs
+        # are replayed one after the other, never concurrently), used round-robin - the host batch of step i+1 can then be uploaded
+        # on a copy stream straight into the buffers of the NEXT graph while step i runs, with no staging copy on the compute stream
+        self.batches = [{k: torch.empty_like(v, device=dev).copy_(v) for k, v in example_batch.items() if torch.is_tensor(v)}
+                        for _ in range(max(1, int(input_slots)))]
+        self.batch = self.batches[0]
+        self._next = 0
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._split = world > 1 and not capture_collective
         self._lib = _cabi.lib()
@@ -302,23 +308,28 @@ class GraphedTrainStep:
                 t.copy_(k)
         torch.cuda.synchronize(dev)
         n0 = self._lib.matgcn_launch_count()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._body(eager=False)
-        self.library_kernel_nodes = int(self._lib.matgcn_launch_count() - n0)   # this library's kernels inside one replay
+        self.graphs, self.losses = [], []
+        for s in range(len(self.batches)):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, **({"pool": self.graphs[0].pool()} if s else {})):
+                loss = self._body(eager=False, slot=s)
+            self.graphs.append(g)
+            self.losses.append(loss)
+        self.graph, self.loss = self.graphs[0], self.losses[0]
+        self.library_kernel_nodes = int(self._lib.matgcn_launch_count() - n0) // len(self.graphs)   # this library's kernels per replay
 
-    def _body(self, eager: bool):
+    def _body(self, eager: bool, slot: int = 0):
         opt = self.opt
         _cabi.check(self._lib.matgcn_step_tick(self._key_dev.data_ptr(), self._step_dev.data_ptr(), _stream()), "step_tick")
         if self._split and not eager:
             # data parallel: the graph ends after the backward; all-reduce + update follow eagerly in __call__
             opt.zero_grad()
-            return self._fwd_bwd()
-        loss = _train_step_body(self.model, self.batch, opt, self.micro_batches)
+            return self._fwd_bwd(slot)
+        loss = _train_step_body(self.model, self.batches[slot], opt, self.micro_batches)
         return loss
 
-    def _fwd_bwd(self):
-        model, batch, mb = self.model, self.batch, self.micro_batches
+    def _fwd_bwd(self, slot: int = 0):
+        model, batch, mb = self.model, self.batches[slot], self.micro_batches
         if mb <= 1:
             loss = model.calculate_loss(batch)
             loss.backward()
@@ -334,9 +345,15 @@ class GraphedTrainStep:
             loss = part.detach() if loss is None else loss + part.detach()
         return loss
 
-    def load_batch(self, batch, non_blocking: bool = True):
-        """Copies a batch (host or device tensors of the captured shapes) into the static input buffers."""
-        for k, dst in self.batch.items():
+    def next_slot(self) -> int:
+        """The input slot the next ``__call__`` without an explicit slot will read."""
+        return self._next
+
+    def load_batch(self, batch, non_blocking: bool = True, slot: int = 0):
+        """Copies a batch (host or device tensors of the captured shapes) into the static input buffers of ``slot``, on the current
+        stream.  With ``input_slots > 1`` a caller may do this on a copy stream for the NEXT slot while the current replay runs, as long
+        as that stream has waited for the replay that last read the slot (bench.py's e2e loop shows the event pattern)."""
+        for k, dst in self.batches[slot].items():
             src = batch[k]
             if src.shape != dst.shape:
                 raise MatgcnError("GraphedTrainStep: batch['%s'] has shape %s, the captured step has %s (capture another one for "
@@ -344,23 +361,28 @@ class GraphedTrainStep:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=non_blocking)
 
-    def __call__(self, batch=None):
-        """One train step; ``batch=None`` reuses whatever ``self.batch`` holds.  Returns the (static) device loss tensor."""
+    def __call__(self, batch=None, slot=None):
+        """One train step from input slot ``slot`` (default: round-robin); ``batch=None`` reuses whatever the slot's buffers hold.
+        Returns the (static, per slot) device loss tensor."""
+        if slot is None:
+            slot = self._next
         if batch is not None:
-            self.load_batch(batch)
+            self.load_batch(batch, slot=slot)
         self.opt.sync_lr()
-        self.graph.replay()
+        self.graphs[slot].replay()
+        self._next = (slot + 1) % len(self.graphs)
         if self._split:
             scale = self.opt.all_reduce()
             self.opt.step(grad_scale=scale)
         self.opt.step_count += 1   # host mirror (checkpoints: state_dict reads it)
-        return self.loss
+        return self.losses[slot]
 
     def close(self):
         """Hands the step state back to the host side of the optimiser (eager ``fused_train_step`` works again)."""
         self.opt.disable_device_state()
         self.model._dropout_key_dev = None
         self.graph = None
+        self.graphs = []
 
 
 class DeviceWindowBank:

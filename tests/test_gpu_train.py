@@ -397,11 +397,12 @@ def test_fused_loss_matches_masked_mae_of_the_reference(mean, std):
 # ------------------------------------------------------------------------------------------------
 # f1: the whole loop body (executor:413-422) as ONE captured CUDA graph
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode,n,b", [("exact", 23, 4), ("bf16", 40, 16)])
-def test_graphed_train_step_replays_match_eager_steps(mode, n, b):
+@pytest.mark.parametrize("mode,n,b,slots", [("exact", 23, 4, 1), ("bf16", 40, 16, 2)])
+def test_graphed_train_step_replays_match_eager_steps(mode, n, b, slots):
     """train.GraphedTrainStep: capture once, replay five times (new batch, new dropout mask, advancing Adam step count, a
     learning-rate change on the way) against five eager ``fused_train_step`` calls that are handed the same dropout keys.
-    bf16 case: B = 16, H = 64 takes the persistent cooperative recurrence kernels, i.e. cooperative launches inside the graph."""
+    bf16 case: B = 16, H = 64 takes the persistent cooperative recurrence kernels, i.e. cooperative launches inside the graph, and
+    two input slots (two graphs over one memory pool, replayed alternately: the double-buffered upload path of bench.py's e2e)."""
     from multistgraph_b200 import _cabi
     from multistgraph_b200.model import MultiATGCN
     from multistgraph_b200.synthetic import make_batch, make_config, make_data_feature
@@ -418,8 +419,8 @@ def test_graphed_train_step_replays_match_eager_steps(mode, n, b):
     oe = FusedClipAdam(me.parameters(), lr=0.003, max_grad_norm=5.0)
     og = FusedClipAdam(mg.parameters(), lr=0.003, max_grad_norm=5.0)
     batches = [{k: v.to(dev) for k, v in make_batch(n, b, 6, seed=20 + i).items()} for i in range(5)]
-    step = GraphedTrainStep(mg, og, batches[0])
-    assert step.library_kernel_nodes > 10
+    step = GraphedTrainStep(mg, og, batches[0], input_slots=slots)
+    assert step.library_kernel_nodes > 10 and len(step.graphs) == slots
     # the warm-up steps inside the constructor must leave no trace in the training state
     for (k, p), (_, q) in zip(me.named_parameters(), mg.named_parameters()):
         assert torch.equal(p, q), k
@@ -449,14 +450,16 @@ def test_graphed_train_step_replays_match_eager_steps(mode, n, b):
     # a replay with a frozen model draws a NEW dropout mask: same batch, lr = 0, different loss
     mg.train()
     og.lr = 0.0
-    l1, l2 = float(step(batches[0])), float(step())
+    l1, l2 = float(step(batches[0])), float(step(batches[0]))
     assert l1 != l2 and abs(l1 - l2) < 0.2 * abs(l1)
+    step.load_batch(batches[0], slot=0)
+    assert float(step(slot=0)) != l2            # batch=None: the slot's buffers as they stand, again a new mask
     # checkpoints keep working: the state dict carries the host mirror of the step count; close() returns to eager stepping
-    assert float(og.state_dict()["state"][0]["step"]) == 7.0
+    assert float(og.state_dict()["state"][0]["step"]) == 8.0
     step.close()
     og.lr = 0.003
     fused_train_step(mg, batches[1], og)
-    assert og.step_count == 8
+    assert og.step_count == 9
 
 
 def test_graphed_train_step_refuses_what_it_cannot_capture():
