@@ -44,6 +44,7 @@ struct RecBwdMaps {
 struct RecBwdP {
     int T, N, B, K, Cin, n_adp;
     int prop_tiles_m, prop_tiles_n, prop_kt;
+    int tn_fast;         // dense-phase tile order: 1 = column tiles fastest (see rf_tile_decode)
     long long U, dy_tstride;
     const float* dy;
     const float* PH; const float* Z; const float* R; const float* HC; const float* H1; const float* Z2; const float* R2; const float* HC2;
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         mbar_wait(nempty0, (wuse0 & 1u) ^ 1u);
                         mbar_wait(nempty0 + 8u, (wuse1 & 1u) ^ 1u);
                         if ((int)blockIdx.x < prop_tiles) {
-                            const int tn = blockIdx.x / p.prop_tiles_m, tm = blockIdx.x - tn * p.prop_tiles_m;
+                            int tm, tn;
+                            rf_tile_decode(blockIdx.x, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
                             int s2 = stage;
                             uint32_t p2 = phase;
                             for (; pre < p.prop_kt && pre < RB2_STAGES; ++pre) {
@@ -195,7 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                         ++nbar;
                         asm volatile("fence.proxy.async;" ::: "memory");
                         for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
-                            const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                            int tm, tn;
+                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
                             for (int kt = 0; kt < p.prop_kt; ++kt) {
                                 const uint32_t sa = smem_u32(stage_base + stage * RF_STAGE_BYTES);
                                 const uint32_t fb = full0 + 8u * stage;
@@ -423,7 +426,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_bwd_kernel(const __grid_con
                 if (ph == 1 || ph == 3) {
                     // ---- dense phases: plain fp32 store of the 128 x 128 tile (lane = node row) ----
                     for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
-                        const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                        int tm, tn;
+                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
                         const long long row = (long long)tm * 128 + q * 32 + lane;
                         mbar_wait(tfull0 + 8u * acc, acc_phase);
                         tc_fence_after();
@@ -788,6 +792,7 @@ cudaError_t launch_rec_bwd(const RecBwdArgs& a, cudaStream_t st) {
     p.DHC = a.DHC; p.dmix = a.dmix;
     p.gbar = a.gbar;
     p.WG16 = a.WG16; p.WU16 = a.WU16;
+    p.tn_fast = rec_tn_fast(a.K - 1, a.N);
     {
         const char* e = getenv("MATGCN_REC_BWD_HINT");
         p.stream_hint = e ? (atoi(e) & 1) : 1;   // measured: forward launch -1.3 %, reverse launch -3.3 % (profiles/r2k_ab_l2_hints.txt)

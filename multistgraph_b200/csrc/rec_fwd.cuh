@@ -62,6 +62,7 @@ struct RecMaps {
 struct RecFwdP {
     int T, N, B, K, Cin;
     int prop_tiles_m, prop_tiles_n, prop_kt;
+    int tn_fast;         // dense-phase tile order: 1 = column tiles fastest (see rf_tile_decode)
     long long U;        // N * B * 64
     const float* GX; const float* RX;      // [T, N*B, 3H]
     float* PH; float* PZ;                  // fp32 slot arrays (only slot 0 of every step is written)
@@ -163,6 +164,19 @@ __device__ __forceinline__ float4 ld4h(const float* p, uint64_t pol) {
 __device__ __forceinline__ void st4h(float* p, const float4& v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
+// Dense-phase tile -> (row tile tm, column tile tn).  Row tiles fastest (the default at the BASELINE shapes: everything fits L2) makes
+// the CTAs of a wave share one column block of the state and stream DIFFERENT row bands of the base-matrix stack; once that stack
+// exceeds L2 (N = 8192: 537 MB of bf16) it would be re-read from HBM once per column tile.  Column tiles fastest lets the CTAs that
+// run together share a row band and keeps the (small) state slab in L2: the stack is read once per phase.
+__device__ __forceinline__ void rf_tile_decode(int tile, int tiles_m, int tiles_n, int tn_fast, int& tm, int& tn) {
+    if (tn_fast) { tm = tile / tiles_n; tn = tile - tm * tiles_n; }
+    else { tn = tile / tiles_m; tm = tile - tn * tiles_m; }
+}
+inline int rec_tn_fast(int Kp, int N) {
+    const char* e = getenv("MATGCN_REC_TN_FAST");
+    if (e) return atoi(e) != 0;
+    return (long long)Kp * N * N * 2 > (48LL << 20);   // bf16 base-matrix stack larger than ~half of what L2 can keep
+}
 __device__ __forceinline__ void rf_proxy_fence_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // fine-grained timeline of CTA 0 at the middle time step: slot s of tile i (first four tiles of the CTA) of phase ph
@@ -260,7 +274,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     // the operand of a k-block that does NOT depend on the previous phase (base matrices / per-node weights)
                     auto issue_const = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
                         if (prop) {
-                            const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                            int tm, tn;
+                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
                             tma_load_5d_hint(sa, &maps.M, fb, kt * 64, tm * 128, 0, 0, 0, pol);
                         } else {
                             tma_load_5d_hint(sa + RF_A_BYTES, tw, fb, 0, p.Cin, kt, tile, 0, pol);
@@ -270,7 +285,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     // ... and the one that does (the state written by the other CTAs in the previous phase)
                     auto issue_state = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
                         if (prop) {
-                            const int tn = tile / p.prop_tiles_m;
+                            int tm, tn;
+                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
+                            (void)tm;
                             tma_load_5d(sa + RF_A_BYTES, tb, fb, tn * 128, kt * 64, slot, 0, 0);
                             tma_load_5d(sa + RF_A_BYTES + 8192, tb, fb, tn * 128 + 64, kt * 64, slot, 0, 0);
                         } else {
@@ -484,7 +501,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     // ---- propagation (128-row tiles, lane = row): bf16 twin of the accumulator -> slots 1.. of PH16 / PZ16 ----
                     __nv_bfloat16* dst = (ph == 0 ? p.PH16 : p.PZ16) + ((long long)t * K + 1) * p.U;
                     for (int tile = blockIdx.x; tile < prop_tiles; tile += G) {
-                        const int tn = tile / p.prop_tiles_m, tm = tile - tn * p.prop_tiles_m;
+                        int tm, tn;
+                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
                         const long long row = (long long)tm * 128 + q * 32 + lane;
                         RF_STAMP_E(ph, tile / G, 5);
                         mbar_wait(tfull0 + 8u * acc, acc_phase);
@@ -855,6 +873,7 @@ cudaError_t launch_rec_fwd(const RecFwdArgs& a, cudaStream_t st) {
         p.prefetch = e ? atoi(e) & 3 : 0;   // bit 0 (GX / RX) measured within noise: the fill traffic costs the propagation what the epilogues gain
     }
     p.WG16 = a.WG16; p.WU16 = a.WU16;
+    p.tn_fast = rec_tn_fast(Kp, a.N);
     {
         const char* e = getenv("MATGCN_REC_HINT");
         p.stream_hint = e ? (atoi(e) & 3) : 3;   // measured: forward launch -1.3 %, reverse launch -3.3 % (profiles/r2k_ab_l2_hints.txt)

@@ -165,3 +165,20 @@ def test_chained_inner_layer_matches_copy_and_repropagate(N, B, rec, mode):
     assert errs["forecast"] < 2e-3
     bad = {k: v for k, v in errs.items() if not (v < 5e-3)}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("N,B", [(150, 64), (300, 16)])
+def test_persistent_kernels_with_column_fastest_tile_order(N, B):
+    """Dense-phase tile order of the persistent kernels (rf_tile_decode): column tiles fastest is what graphs whose base-matrix stack
+    exceeds L2 (N = 8192) select; forced here at shapes with several row AND column tiles, against the one-launch-per-phase path."""
+    import os
+
+    old = os.environ.get("MATGCN_REC_TN_FAST")
+    os.environ["MATGCN_REC_TN_FAST"] = "1"
+    try:
+        test_persistent_forward_matches_per_phase_launches(N, B, "multi", 10, 6)
+    finally:
+        if old is None:
+            os.environ.pop("MATGCN_REC_TN_FAST", None)
+        else:
+            os.environ["MATGCN_REC_TN_FAST"] = old
