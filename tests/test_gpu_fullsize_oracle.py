@@ -58,9 +58,10 @@ def test_baseline_shape_matches_oracle(wl, mode):
     torch.cuda.synchronize()
     used_tc = lib.matgcn_tc_launch_count() - before
     if mode == "exact":
-        # the only tensor-core launches of the exact mode are the dense propagations as 3xTF32 (hi / lo operand split, three
-        # k-batches accumulated in fp32: csrc/matgcn.cu prop_3xtf32); everything else is fp32 FFMA
-        assert used_tc <= 3 * 4 * 24 * 2, "exact mode may only send its dense propagations to the tensor-core engine (%d launches)" % used_tc
+        # the only tensor-core launches of the exact mode are its dense contractions as 3xTF32 (hi / lo operand split, three
+        # k-batches accumulated in fp32: csrc/matgcn.cu prop_3xtf32 - two propagations per step, layer and pass, two forward passes
+        # and one backward here - and tb_3xtf32 - the chunked dM contractions); everything else is fp32 FFMA
+        assert used_tc <= 3 * (2 * 24 * 2) + 2 * 3 * 24, "exact mode sent other contractions to the tensor-core engine (%d launches)" % used_tc
     else:
         assert used_tc > 20, "fast mode did not run on the tensor-core kernels"
     g_tol, y_tol, y_elem_tol = BOUNDS[mode]
