@@ -272,11 +272,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     const CUtensorMap* tb = ph == 0 ? &maps.Hs : &maps.Zs;
                     const int slot = t * K;
                     // the operand of a k-block that does NOT depend on the previous phase (base matrices / per-node weights)
+                    // (row / column tile of a dense tile: decoded once per tile, not once per k-block - this thread's latency is on the
+                    // critical path of the operand stream)
+                    int c_tile = -1, c_tm = 0, c_tn = 0;
+                    auto decode = [&](int tile) {
+                        if (tile != c_tile) {
+                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, c_tm, c_tn);
+                            c_tile = tile;
+                        }
+                    };
                     auto issue_const = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
                         if (prop) {
-                            int tm, tn;
-                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
-                            tma_load_5d_hint(sa, &maps.M, fb, kt * 64, tm * 128, 0, 0, 0, pol);
+                            decode(tile);
+                            tma_load_5d_hint(sa, &maps.M, fb, kt * 64, c_tm * 128, 0, 0, 0, pol);
                         } else {
                             tma_load_5d_hint(sa + RF_A_BYTES, tw, fb, 0, p.Cin, kt, tile, 0, pol);
                             if (gate) tma_load_5d_hint(sa + RF_A_BYTES + 8192, tw, fb, 64, p.Cin, kt, tile, 0, pol);
@@ -285,11 +293,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rec_fwd_kernel(const __grid_con
                     // ... and the one that does (the state written by the other CTAs in the previous phase)
                     auto issue_state = [&](int tile, int kt, uint32_t sa, uint32_t fb) {
                         if (prop) {
-                            int tm, tn;
-                            rf_tile_decode(tile, p.prop_tiles_m, p.prop_tiles_n, p.tn_fast, tm, tn);
-                            (void)tm;
-                            tma_load_5d(sa + RF_A_BYTES, tb, fb, tn * 128, kt * 64, slot, 0, 0);
-                            tma_load_5d(sa + RF_A_BYTES + 8192, tb, fb, tn * 128 + 64, kt * 64, slot, 0, 0);
+                            decode(tile);
+                            tma_load_5d(sa + RF_A_BYTES, tb, fb, c_tn * 128, kt * 64, slot, 0, 0);
+                            tma_load_5d(sa + RF_A_BYTES + 8192, tb, fb, c_tn * 128 + 64, kt * 64, slot, 0, 0);
                         } else {
                             if (kt > 0) tma_load_5d_hint(sa, ta, fb, 0, 0, tile, slot + kt, 0, pol_once);
                             else tma_load_5d(sa, ta, fb, 0, 0, tile, slot + kt, 0);   // (slot 0 = the state itself: the dense phase's operand)
